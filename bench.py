@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Benchmark of the sparch SNN hot path (BASELINE.json metric: train samples/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg4] [--impl ours|reference]
+
+A "step" is one training step of the reference's loop (sparch/exp.py:355-377): forward through
+SNN, cross-entropy, backward (BPTT), Adam update, on one batch of synthetic data of the
+configured shape.  Default workload: cfg4 = RadLIF [1024,1024,35] + batchnorm + dropout 0.1 on
+SC-shaped input (batch 256 per GPU, 100 steps, 40 features, 35 classes) -- BASELINE.json
+configs[3], the one the metric is quoted on.
+
+Prints ONE JSON line (rank 0).  `value` = whole-job samples/s with inputs resident in HBM;
+`e2e` = the same through the public module API with the batch copied from pinned host memory
+and the loss read back every step; `roofline` = the membrane-recurrence kernels (the dominant
+part of the step) against the measured HBM peak; `cpu_baseline` = the oracle's torch-CPU
+restatement of the reference timed on this box's host cores.
+
+`--impl reference` times the reference's CPU implementation of the same step (the oracle's
+op-for-op restatement; the reference itself is pure Python/PyTorch and /root/reference does not
+exist on the GPU box) with all host threads, on a bounded per-step batch.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    "cfg1": dict(desc="LIF [128,128,20], SHD-shaped (B128,T100,F700)", neuron_type="LIF",
+                 layer_sizes=[128, 128, 20], dropout=0.0, normalization="none", B=128, T=100, F=700,
+                 data="spikes"),
+    "cfg2": dict(desc="adLIF [128,128,20] + batchnorm, SHD-shaped (B128,T100,F700)",
+                 neuron_type="adLIF", layer_sizes=[128, 128, 20], dropout=0.0,
+                 normalization="batchnorm", B=128, T=100, F=700, data="spikes"),
+    "cfg3": dict(desc="RLIF [512,512,35], SSC-shaped (B128,T100,F700)", neuron_type="RLIF",
+                 layer_sizes=[512, 512, 35], dropout=0.0, normalization="batchnorm", B=128, T=100,
+                 F=700, data="spikes"),
+    "cfg4": dict(desc="RadLIF [1024,1024,35] + batchnorm + dropout 0.1, SC-shaped (B256,T100,F40)",
+                 neuron_type="RadLIF", layer_sizes=[1024, 1024, 35], dropout=0.1,
+                 normalization="batchnorm", B=256, T=100, F=40, data="randn"),
+}
+
+
+def make_batch(cfg, B, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    if cfg["data"] == "spikes":
+        x = (torch.rand(B, cfg["T"], cfg["F"], generator=g) < 0.03).float()
+    else:
+        x = torch.randn(B, cfg["T"], cfg["F"], generator=g)
+    y = torch.randint(0, cfg["layer_sizes"][-1], (B,), generator=g)
+    return x, y
+
+
+def model_kwargs(cfg):
+    return dict(layer_sizes=cfg["layer_sizes"], neuron_type=cfg["neuron_type"], dropout=cfg["dropout"],
+                normalization=cfg["normalization"])
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [z.strip() for z in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- reference arm (CPU)
+def cpu_reference_steps(cfg, B, steps, warmup):
+    """Oracle restatement of the reference train step on the host cores; returns samples/s."""
+    import torch
+    from oracle import snn_oracle as orc
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(0)
+    net = orc.build_oracle_snn((B, None, cfg["F"]), **model_kwargs(cfg))
+    opt = torch.optim.Adam(net.parameters(), 1e-2)
+    x, y = make_batch(cfg, B, 1234)
+    net.train()
+    for _ in range(warmup):
+        orc.oracle_train_step(net, opt, x, y)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.oracle_train_step(net, opt, x, y)
+    dt = time.perf_counter() - t0
+    return B * steps / dt, dt / steps
+
+
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return
+    # bounded per-step sample: shrink the per-step batch so K+W steps end within ~2 minutes
+    B = min(cfg["B"], 32)
+    _, t32 = cpu_reference_steps(cfg, B, 1, 1)
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    scale = max(1.0, budget / max(t32, 1e-3))
+    Bs = int(min(cfg["B"], max(16, (int(B * scale) // 16) * 16)))
+    sps, t = cpu_reference_steps(cfg, Bs, args.steps, args.warmup)
+    cores = os.cpu_count()
+    sample = (f"{args.steps} train steps of the same model at per-step batch {Bs} "
+              f"(config batch {cfg['B']}), T={cfg['T']}")
+    line = {
+        "impl": "reference", "metric": "train samples/sec", "value": sps, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": cfg["desc"], "bench_config": args.config,
+                                        "per_step_batch": Bs},
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm (B200)
+def run_ours(args, cfg, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import sparch_b200
+    from sparch_b200 import functional as F
+    from sparch_b200 import parallel
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = cfg["B"]
+    torch.manual_seed(0)
+    net = sparch_b200.SNN((B, None, cfg["F"]), **model_kwargs(cfg)).to(dev)
+    net.train()
+    opt = torch.optim.Adam(net.parameters(), 1e-2)            # exp.py:89
+    sync = parallel.GradSync(net) if world > 1 else None
+    x_h, y_h = make_batch(cfg, B, 1234 + rank)
+    x_h, y_h = x_h.pin_memory(), y_h.pin_memory()
+    x_d, y_d = x_h.to(dev), y_h.to(dev)
+    loss_fn = torch.nn.CrossEntropyLoss()                     # exp.py:100
+
+    def step(x, y):
+        out, _ = net(x)                                       # exp.py:359
+        loss = loss_fn(out, y)
+        opt.zero_grad()
+        loss.backward()                                       # exp.py:376
+        if sync is not None:
+            sync.finish()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step(x_d, y_d)
+    # ---- device-resident number ------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    F.timers_enable(True)
+    n0 = F.native_launches()
+    ms = timed(lambda: step(x_d, y_d), args.steps)
+    launches = F.native_launches() - n0
+    rec_ms = F.timers_collect()                               # {"recurrence_fwd": ms, ...} totals
+    F.timers_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end to end: pinned host batch -> device, loss read back every step ------------------
+    def e2e_step():
+        x_d.copy_(x_h, non_blocking=True)
+        y_d.copy_(y_h, non_blocking=True)
+        return float(step(x_d, y_d).item())                   # exp.py:363 loss.item()
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        return
+    # ---- roofline of the recurrence kernels (16.5 B per (b,t,h) per spiking layer)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    n_spiking = len(cfg["layer_sizes"]) - 1
+    elts = sum(B * cfg["T"] * h for h in cfg["layer_sizes"][:n_spiking])
+    alg_bytes = 16.5 * elts
+    rec_total_ms = (rec_ms.get("recurrence_fwd", 0.0) + rec_ms.get("recurrence_bwd", 0.0)) / args.steps
+    achieved = alg_bytes / (rec_total_ms * 1e-3) / 1e9 if rec_total_ms > 0 else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "kernel": "membrane recurrence fwd+bwd (all launches of one train step)",
+                "ms_per_step": rec_total_ms, "algorithmic_bytes_per_step": alg_bytes,
+                "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                "share_of_step": rec_total_ms / (ms / args.steps) if rec_total_ms else None}
+
+    # ---- CPU baseline beside it (bounded sample: the full config batch, 2 timed steps) --------
+    cpu = None
+    if not args.no_cpu_baseline:
+        Bc = cfg["B"]
+        sps, t = cpu_reference_steps(cfg, Bc, 2, 1)
+        cpu = {"value": sps, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"2 timed train steps (1 warm-up) of the full config at batch {Bc}, "
+                         f"{t:.2f} s/step"}
+
+    line = {
+        "metric": "train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": cfg["desc"], "bench_config": args.config, "per_gpu_batch": B,
+                   "global_batch": B * world, "parallelism": f"dp{world}",
+                   "l2": "per-step working set (>=1 GB of activations/tapes) exceeds the 126 MB L2"},
+        "e2e": {"value": e2e_value, "unit": "samples/s",
+                "h2d_bytes_per_step": x_h.numel() * 4 + y_h.numel() * 8, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="cfg4", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+               f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port",
+               str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
+    run_ours(args, cfg, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

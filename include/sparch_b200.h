@@ -1,0 +1,128 @@
+/* sparch_b200.h -- C ABI of libsparch_b200.so (hand-written sm_100a CUDA kernels).
+ *
+ * This is the drop-in boundary for sparch's surrogate-gradient SNN hot path.  The
+ * reference has NO native interface for this path: it is Python calling PyTorch ATen
+ * (sparch/models/snns.py, whole file).  Each entry point below therefore cites the
+ * reference Python lines whose ATen call sequence it replaces.  The binding a
+ * maintainer adds on the reference side is a ctypes stub; the
+ * repo's own stub is sparch_b200/_lib.py.
+ *
+ * Conventions:
+ *  - every pointer is a DEVICE pointer into caller-owned memory; the library never
+ *    allocates or frees persistent memory; tensors are contiguous row-major fp32
+ *    unless a parameter says otherwise; activations are (Be, T, H) exactly as the
+ *    reference lays them out (batch, time, neuron);
+ *  - work is enqueued on the caller's CUDA stream `st` (a cudaStream_t), no sync;
+ *  - return 0 on success, negative sparch_status on failure; sparch_last_error()
+ *    gives a thread-local message;
+ *  - CUDA only: there is no host fallback in this library.
+ *
+ * Neuron kinds (snns.py:109): 0 LIF, 1 adLIF, 2 RLIF, 3 RadLIF.
+ *   bit0 = adaptive (w state, beta/a/b), bit1 = recurrent (V).
+ */
+#ifndef SPARCH_B200_H
+#define SPARCH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* sparch_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define SPARCH_API __attribute__((visibility("default")))
+#else
+#define SPARCH_API
+#endif
+
+enum sparch_status {
+  SPARCH_OK = 0,
+  SPARCH_ERR_ARG = -1,     /* bad argument (shape, null pointer, unsupported size) */
+  SPARCH_ERR_CUDA = -2,    /* a CUDA runtime call or launch failed                 */
+  SPARCH_ERR_DEVICE = -3,  /* device is not sm_100 class / attribute unavailable   */
+  SPARCH_ERR_TIMEOUT = -4  /* a persistent kernel's bounded spin expired           */
+};
+
+enum sparch_kind { SPARCH_LIF = 0, SPARCH_ADLIF = 1, SPARCH_RLIF = 2, SPARCH_RADLIF = 3 };
+
+SPARCH_API const char* sparch_last_error(void);
+SPARCH_API int sparch_abi_version(void);
+
+/* ---- SpikeFunctionBoxcar (snns.py:20-36) ---------------------------------- */
+/* s = (x > 0) as fp32                                         snns.py:29       */
+SPARCH_API int sparch_boxcar_fwd(const float* x, float* s, int64_t n, sparch_stream_t st);
+/* gx = gs where -0.5 < x <= 0.5 else 0                        snns.py:33-35    */
+SPARCH_API int sparch_boxcar_bwd(const float* x, const float* gs, float* gx, int64_t n, sparch_stream_t st);
+
+/* ---- BatchNorm1d(H, momentum=0.05) folded to scale/shift (snns.py:678-680) - */
+/* sum[h] = sum_m Z[m,h], sumsq[h] = sum_m Z[m,h]^2 in fp64 (outputs are zeroed here). */
+SPARCH_API int sparch_col_stats(const float* Z, int64_t M, int H, double* sum, double* sumsq,
+                     sparch_stream_t st);
+/* sum1[h] = sum_m A[m,h]; sum2[h] = sum_m A[m,h]*(Zn[m,h]-mean[h])*rstd[h]  (BN backward
+ * reductions, autograd of snns.py:679).  mean/rstd may be NULL => sum2 = sum A*Zn.       */
+SPARCH_API int sparch_col_dot(const float* A, const float* Zn, const float* mean, const float* rstd,
+                   int64_t M, int H, double* sum1, double* sum2, sparch_stream_t st);
+/* train-mode fold: mean, biased var -> rstd; scale = gamma*rstd; shift = beta-mean*scale;
+ * running stats updated with the unbiased variance (momentum form of ATen). gamma/beta or
+ * running_* may be NULL.                                                                 */
+SPARCH_API int sparch_bn_fold_train(const double* sum, const double* sumsq, int64_t M, const float* gamma,
+                         const float* beta, float eps, float momentum, float* running_mean,
+                         float* running_var, float* mean, float* rstd, float* scale,
+                         float* shift, int H, sparch_stream_t st);
+/* dZ[m,h] = scale[h]*(dI[m,h] - sum1[h]/M - xhat[m,h]*sum2[h]/M), in place on dI.        */
+SPARCH_API int sparch_bn_bwd_apply(float* dI, const float* Z, const float* mean, const float* rstd,
+                        const float* scale, const double* sum1, const double* sum2, int64_t M,
+                        int H, sparch_stream_t st);
+
+/* ---- membrane recurrence, forward (snns.py:282-303, 419-445, 554-578, 696-727) ------- */
+/* Non-recurrent kinds (LIF, adLIF): whole time loop in one streaming kernel, state in
+ * registers.  I_t = Z[b,t,h]*scale[h]+shift[h] (scale/shift NULL => I = Z).  alpha..b are the
+ * CLAMPED parameters.  Writes spikes S (fp32 {0,1}), membrane tape U and adaptation tape W
+ * (W may be NULL for LIF).                                                               */
+SPARCH_API int sparch_cell_fwd(int kind, const float* Z, const float* scale, const float* shift,
+                    const float* alpha, const float* beta, const float* a, const float* b,
+                    const float* u0, const float* w0, const float* s0, float theta, float* S,
+                    float* U, float* W, int Be, int T, int H, sparch_stream_t st);
+/* One timestep t of any kind; `rec` (Be,H) is s_{t-1}@V0 for recurrent kinds (else NULL).
+ * Previous state is read from the tapes at t-1 (from u0/w0/s0 when t == 0).              */
+SPARCH_API int sparch_cell_step_fwd(int kind, int t, const float* Z, const float* scale,
+                         const float* shift, const float* alpha, const float* beta,
+                         const float* a, const float* b, const float* rec, const float* u0,
+                         const float* w0, const float* s0, float theta, float* S, float* U,
+                         float* W, int Be, int T, int H, sparch_stream_t st);
+
+/* ---- membrane recurrence, reverse-time BPTT (autograd of the above) ----- */
+/* Non-recurrent kinds: whole reverse loop.  G = dL/dS (Be,T,H).  Writes dI (Be,T,H) and the
+ * per-(b,h) partial parameter gradients pa,pb,pc,pd (Be,H each; pb..pd NULL for LIF) which
+ * the caller reduces over b (sparch_col_stats-style) and masks by the clamp window.      */
+SPARCH_API int sparch_cell_bwd(int kind, const float* G, const float* U, const float* W,
+                    const float* alpha, const float* beta, const float* a, const float* b,
+                    const float* u0, const float* w0, const float* s0, float theta, float* dI,
+                    float* p_alpha, float* p_beta, float* p_a, float* p_b, int Be, int T, int H,
+                    sparch_stream_t st);
+/* One reverse step t of any kind.  recb (Be,H) = dI_{t+1}@V0^T (NULL for t == T-1 or
+ * non-recurrent).  du_next/dw_next (Be,H) carry the adjoint state across calls (zero them
+ * before t == T-1); p_* are accumulated (+=).                                            */
+SPARCH_API int sparch_cell_step_bwd(int kind, int t, const float* G, const float* U, const float* W,
+                         const float* alpha, const float* beta, const float* a, const float* b,
+                         const float* recb, const float* u0, const float* w0, const float* s0,
+                         float theta, float* dI, float* du_next, float* dw_next, float* p_alpha,
+                         float* p_beta, float* p_a, float* p_b, int Be, int T, int H,
+                         sparch_stream_t st);
+
+/* ---- ReadoutLayer cell (snns.py:807-825) ---------------------------------------------- */
+/* u_t = alpha*u_{t-1} + (1-alpha)*I_t ; out = sum_t softmax(u_t, dim=1).  U (B,T,C) tape.  */
+SPARCH_API int sparch_readout_fwd(const float* Z, const float* scale, const float* shift,
+                       const float* alpha, const float* u0, float* out, float* U, int B, int T,
+                       int C, sparch_stream_t st);
+/* gout (B,C) -> dI (B,T,C), p_alpha (B,C) partials.                                       */
+SPARCH_API int sparch_readout_bwd(const float* gout, const float* U, const float* alpha, const float* u0,
+                       float* dI, float* p_alpha, int B, int T, int C, sparch_stream_t st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPARCH_B200_H */

@@ -144,12 +144,37 @@ def boxcar_kat(snns):
     print("boxcar_kat", s.tolist(), x.grad.tolist(), lim.grad.tolist())
 
 
+INIT_CASES = [
+    ("LIF", dict(layer_sizes=[8, 6, 3], neuron_type="LIF")),
+    ("adLIF", dict(layer_sizes=[8, 6, 3], neuron_type="adLIF", use_bias=True)),
+    ("RLIF", dict(layer_sizes=[8, 6, 3], neuron_type="RLIF", bidirectional=True)),
+    ("RadLIF", dict(layer_sizes=[8, 6, 3], neuron_type="RadLIF", normalization="layernorm")),
+    ("RadLIF_noreadout", dict(layer_sizes=[8, 6], neuron_type="RadLIF", use_readout_layer=False)),
+]
+
+
+def init_contract(SNN):
+    """RNG / state_dict contract: the reference's parameters right after
+    construction under torch.manual_seed(0), plus the initial-state draws of one forward."""
+    blob = {}
+    for name, kw in INIT_CASES:
+        torch.manual_seed(0)
+        net = SNN(input_shape=(2, None, 5), **kw)
+        blob[name + ".keys"] = np.array(json.dumps(list(net.state_dict().keys())))
+        blob[name + ".kwargs"] = np.array(json.dumps(kw))
+        for k, v in net.state_dict().items():
+            blob[name + ".sd." + k] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "init_contract.npz"), **blob)
+    print("init_contract", [n for n, _ in INIT_CASES])
+
+
 def main():
     sys.path.insert(0, REF)
     from sparch.models import snns  # the untouched reference
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
     boxcar_kat(snns)
+    init_contract(snns.SNN)
     for name, kw, xshape, ncls, stable in CASES:
         run_case(snns.SNN, name, kw, xshape, ncls, stable)
     run_case(snns.SNN, "radlif_bn", CASES[3][1], CASES[3][2], 5, False, eval_mode=True)

@@ -1,0 +1,302 @@
+"""torch.autograd.Function wrappers over the C ABI (include/sparch_b200.h).
+
+These replace the autograd tape the reference builds op by op inside its Python time
+loops (sparch/models/snns.py:282-303, 419-445, 554-578, 696-727, 807-825) and its
+``SpikeFunctionBoxcar`` (snns.py:20-36).  Inputs must be CUDA fp32 tensors: there is no
+CPU path (``RuntimeError`` otherwise).
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+
+KINDS = {"LIF": 0, "adLIF": 1, "RLIF": 2, "RadLIF": 3}
+
+# parameter limits, snns.py:229 / 356-359
+ALPHA_LIM = (math.exp(-1 / 5), math.exp(-1 / 25))
+BETA_LIM = (math.exp(-1 / 30), math.exp(-1 / 120))
+A_LIM = (-1.0, 1.0)
+B_LIM = (0.0, 2.0)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# Optional CUDA-event timers around named regions (bench.py's roofline leg).  Events are recorded
+# on the current stream; nothing synchronises until timers_collect().
+_TIMERS = {"on": False, "events": []}
+
+
+def timers_enable(flag):
+    _TIMERS["on"] = bool(flag)
+    _TIMERS["events"] = []
+
+
+class _region:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _TIMERS["on"]:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _TIMERS["on"]:
+            self.e1.record()
+            _TIMERS["events"].append((self.name, self.e0, self.e1))
+        return False
+
+
+def timers_collect():
+    """Total milliseconds per region name since timers_enable(True)."""
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in _TIMERS["events"]:
+        out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+    _TIMERS["events"] = []
+    return out
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("sparch_b200 runs on CUDA tensors only (no CPU fallback); "
+                               "move the module and its inputs to a B200 device")
+
+
+def _f32c(t):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _clamp_mask(p, lim):
+    """clamp backward: gradient flows on the closed interval [lo, hi]."""
+    return ((p >= lim[0]) & (p <= lim[1])).to(p.dtype)
+
+
+class SpikeFunctionBoxcar(torch.autograd.Function):
+    """snns.py:20-36.  forward: x.gt(0).float(); backward: pass-through on -0.5 < x <= 0.5."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x)
+        x = _f32c(x)
+        ctx.save_for_backward(x)
+        s = torch.empty_like(x)
+        call("sparch_boxcar_fwd", ptr(x), ptr(s), x.numel(), _stream())
+        return s
+
+    @staticmethod
+    def backward(ctx, grad_spikes):
+        (x,) = ctx.saved_tensors
+        g = _f32c(grad_spikes)
+        gx = torch.empty_like(x)
+        call("sparch_boxcar_bwd", ptr(x), ptr(g), ptr(gx), x.numel(), _stream())
+        return gx
+
+
+class NormState:
+    """How the (Be*T, H) pre-activations are normalised before the recurrence.
+
+    mode: 'bn_train' (batch statistics, running stats updated in place), 'bn_eval'
+    (running statistics), or 'none'.  LayerNorm is applied by the caller.
+    """
+
+    def __init__(self, mode="none", running_mean=None, running_var=None, eps=1e-5, momentum=0.05):
+        self.mode = mode
+        self.running_mean = running_mean
+        self.running_var = running_var
+        self.eps = eps
+        self.momentum = momentum
+
+
+def _fold_norm(Z2d, gamma, bn_beta, norm):
+    """Returns (scale, shift, mean, rstd); all None when there is no normalisation."""
+    M, H = Z2d.shape
+    dev = Z2d.device
+    if norm.mode == "none":
+        return None, None, None, None
+    if norm.mode == "bn_eval":
+        rstd = torch.rsqrt(norm.running_var + norm.eps)
+        scale = rstd if gamma is None else gamma * rstd
+        shift = -norm.running_mean * scale
+        if bn_beta is not None:
+            shift = shift + bn_beta
+        return scale.contiguous(), shift.contiguous(), norm.running_mean.contiguous(), rstd
+    if norm.mode != "bn_train":
+        raise ValueError(f"unknown normalisation mode {norm.mode}")
+    if M <= 1:
+        raise ValueError("Expected more than 1 value per channel when training")
+    sums = torch.empty(2, H, dtype=torch.float64, device=dev)
+    call("sparch_col_stats", ptr(Z2d), M, H, ptr(sums[0]), ptr(sums[1]), _stream())
+    out = torch.empty(4, H, dtype=torch.float32, device=dev)
+    call("sparch_bn_fold_train", ptr(sums[0]), ptr(sums[1]), M, ptr(gamma), ptr(bn_beta),
+         float(norm.eps), float(norm.momentum), ptr(norm.running_mean), ptr(norm.running_var),
+         ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]), H, _stream())
+    return out[2], out[3], out[0], out[1]
+
+
+def _norm_backward(dI2d, Z2d, gamma, bn_beta, norm, scale, mean, rstd):
+    """dI -> dZ in place; returns (dgamma, dbn_beta)."""
+    if norm.mode == "none":
+        return None, None
+    M, H = dI2d.shape
+    sums = torch.empty(2, H, dtype=torch.float64, device=dI2d.device)
+    call("sparch_col_dot", ptr(dI2d), ptr(Z2d), ptr(mean), ptr(rstd), M, H, ptr(sums[0]),
+         ptr(sums[1]), _stream())
+    dgamma = sums[1].float() if gamma is not None else None
+    dbeta = sums[0].float() if bn_beta is not None else None
+    if norm.mode == "bn_train":
+        call("sparch_bn_bwd_apply", ptr(dI2d), ptr(Z2d), ptr(mean), ptr(rstd), ptr(scale),
+             ptr(sums[0]), ptr(sums[1]), M, H, _stream())
+    else:
+        dI2d.mul_(scale)
+    return dgamma, dbeta
+
+
+class SpikingCellFunction(torch.autograd.Function):
+    """Normalisation fold + membrane recurrence of one spiking layer.
+
+    forward(Z, gamma, bn_beta, alpha, beta, a, b, V, u0, w0, s0, kind, theta, norm) -> S
+      Z (Be,T,H) pre-activations W x (snns.py:675); gamma/bn_beta BatchNorm affine (or None);
+      alpha..b raw (unclamped) neuron parameters; V raw recurrent weight (H,H) or None;
+      u0,w0,s0 (Be,H) initial states (snns.py:700-702).  S (Be,T,H) fp32 spikes.
+    """
+
+    @staticmethod
+    def forward(ctx, Z, gamma, bn_beta, alpha, beta, a, b, V, u0, w0, s0, kind, theta, norm):
+        _require_cuda(Z, alpha, u0, s0)
+        k = KINDS[kind]
+        adaptive, recurrent = bool(k & 1), bool(k & 2)
+        Z = _f32c(Z)
+        Be, T, H = Z.shape
+        dev = Z.device
+        st = _stream()
+        with torch.no_grad():
+            al = alpha.clamp(*ALPHA_LIM)
+            be = beta.clamp(*BETA_LIM) if adaptive else None
+            aa = a.clamp(*A_LIM) if adaptive else None
+            bb = b.clamp(*B_LIM) if adaptive else None
+            V0 = V.detach().clone().fill_diagonal_(0) if recurrent else None  # snns.py:712
+            u0, w0, s0 = _f32c(u0), _f32c(w0) if adaptive else None, _f32c(s0)
+            Z2d = Z.view(Be * T, H)
+            scale, shift, mean, rstd = _fold_norm(Z2d, gamma, bn_beta, norm)
+            S = torch.empty_like(Z)
+            U = torch.empty_like(Z)
+            Wt = torch.empty_like(Z) if adaptive else None
+            region = _region("recurrence_fwd").__enter__()
+            if not recurrent:
+                call("sparch_cell_fwd", k, ptr(Z), ptr(scale), ptr(shift), ptr(al), ptr(be), ptr(aa),
+                     ptr(bb), ptr(u0), ptr(w0), ptr(s0), float(theta), ptr(S), ptr(U), ptr(Wt), Be, T,
+                     H, st)
+            else:
+                rec = torch.empty(Be, H, device=dev, dtype=torch.float32)
+                for t in range(T):
+                    torch.matmul(s0 if t == 0 else S[:, t - 1, :], V0, out=rec)  # snns.py:720
+                    call("sparch_cell_step_fwd", k, t, ptr(Z), ptr(scale), ptr(shift), ptr(al),
+                         ptr(be), ptr(aa), ptr(bb), ptr(rec), ptr(u0), ptr(w0), ptr(s0), float(theta),
+                         ptr(S), ptr(U), ptr(Wt), Be, T, H, st)
+            region.__exit__()
+        ctx.k, ctx.theta, ctx.norm = k, float(theta), norm
+        ctx.has = (gamma is not None, bn_beta is not None)
+        ctx.save_for_backward(Z, gamma, bn_beta, alpha, beta, a, b, V0, u0, w0, s0, S, U, Wt, al, be,
+                              aa, bb, scale, mean, rstd)
+        return S
+
+    @staticmethod
+    def backward(ctx, gS):
+        (Z, gamma, bn_beta, alpha, beta, a, b, V0, u0, w0, s0, S, U, Wt, al, be, aa, bb, scale, mean,
+         rstd) = ctx.saved_tensors
+        k, theta, norm = ctx.k, ctx.theta, ctx.norm
+        adaptive, recurrent = bool(k & 1), bool(k & 2)
+        Be, T, H = Z.shape
+        dev = Z.device
+        st = _stream()
+        G = _f32c(gS)
+        dI = torch.empty_like(Z)
+        npart = 4 if adaptive else 1
+        part = torch.zeros(npart, Be, H, device=dev, dtype=torch.float32)
+        pp = [ptr(part[i]) if i < npart else None for i in range(4)]
+        region = _region("recurrence_bwd").__enter__()
+        if not recurrent:
+            call("sparch_cell_bwd", k, ptr(G), ptr(U), ptr(Wt), ptr(al), ptr(be), ptr(aa), ptr(bb),
+                 ptr(u0), ptr(w0), ptr(s0), theta, ptr(dI), pp[0], pp[1], pp[2], pp[3], Be, T, H, st)
+            region.__exit__()
+            dV = None
+        else:
+            carry = torch.zeros(2, Be, H, device=dev, dtype=torch.float32)
+            recb = torch.empty(Be, H, device=dev, dtype=torch.float32)
+            V0t = V0.t()
+            for t in range(T - 1, -1, -1):
+                if t < T - 1:
+                    torch.matmul(dI[:, t + 1, :], V0t, out=recb)
+                call("sparch_cell_step_bwd", k, t, ptr(G), ptr(U), ptr(Wt), ptr(al), ptr(be), ptr(aa),
+                     ptr(bb), ptr(recb) if t < T - 1 else None, ptr(u0), ptr(w0), ptr(s0), theta,
+                     ptr(dI), ptr(carry[0]), ptr(carry[1]) if adaptive else None, pp[0], pp[1], pp[2],
+                     pp[3], Be, T, H, st)
+            region.__exit__()
+            # dV = sum_t s_{t-1}^T dI_t, diagonal masked (clone().fill_diagonal_(0) backward)
+            dV = s0.t() @ dI[:, 0, :]
+            if T > 1:
+                dV += torch.einsum("bti,btj->ij", S[:, :-1, :], dI[:, 1:, :])
+            dV.fill_diagonal_(0)
+        psum = part.sum(dim=1)
+        dalpha = psum[0] * _clamp_mask(alpha, ALPHA_LIM)
+        dbeta = da = db = None
+        if adaptive:
+            dbeta = psum[1] * _clamp_mask(beta, BETA_LIM)
+            da = psum[2] * _clamp_mask(a, A_LIM)
+            db = psum[3] * _clamp_mask(b, B_LIM)
+        dgamma, dbnb = _norm_backward(dI.view(Be * T, H), Z.view(Be * T, H), gamma, bn_beta, norm,
+                                      scale, mean, rstd)
+        return (dI, dgamma, dbnb, dalpha, dbeta, da, db, dV, None, None, None, None, None, None)
+
+
+class ReadoutCellFunction(torch.autograd.Function):
+    """Normalisation fold + ReadoutLayer cell (snns.py:807-825): out = sum_t softmax(u_t)."""
+
+    @staticmethod
+    def forward(ctx, Z, gamma, bn_beta, alpha, u0, norm):
+        _require_cuda(Z, alpha, u0)
+        Z = _f32c(Z)
+        B, T, C = Z.shape
+        st = _stream()
+        with torch.no_grad():
+            al = alpha.clamp(*ALPHA_LIM)
+            u0 = _f32c(u0)
+            scale, shift, mean, rstd = _fold_norm(Z.view(B * T, C), gamma, bn_beta, norm)
+            out = torch.empty(B, C, device=Z.device, dtype=torch.float32)
+            U = torch.empty_like(Z)
+            call("sparch_readout_fwd", ptr(Z), ptr(scale), ptr(shift), ptr(al), ptr(u0), ptr(out),
+                 ptr(U), B, T, C, st)
+        ctx.norm = norm
+        ctx.save_for_backward(Z, gamma, bn_beta, alpha, u0, U, al, scale, mean, rstd)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        Z, gamma, bn_beta, alpha, u0, U, al, scale, mean, rstd = ctx.saved_tensors
+        B, T, C = Z.shape
+        st = _stream()
+        g = _f32c(gout)
+        dI = torch.empty_like(Z)
+        part = torch.empty(B, C, device=Z.device, dtype=torch.float32)
+        call("sparch_readout_bwd", ptr(g), ptr(U), ptr(al), ptr(u0), ptr(dI), ptr(part), B, T, C, st)
+        dalpha = part.sum(dim=0) * _clamp_mask(alpha, ALPHA_LIM)
+        dgamma, dbnb = _norm_backward(dI.view(B * T, C), Z.view(B * T, C), gamma, bn_beta, ctx.norm,
+                                      scale, mean, rstd)
+        return dI, dgamma, dbnb, dalpha, None, None
+
+
+def native_launches():
+    """Number of C-ABI calls made so far by this process."""
+    return _lib.launches

@@ -1,0 +1,76 @@
+"""Data-parallel gradient synchronisation (one process per GPU, torch.distributed).
+
+The reference is single-process (sparch/exp.py:81); batch rows are independent inside every
+layer, so the path shards over the batch with ONE exchange per train step: a
+sum all-reduce of the parameter gradients, averaged over ranks.  Gradients are bucketed per
+layer of ``SNN.snn`` and each bucket's all-reduce is launched asynchronously from a
+post-accumulate-grad hook as soon as the last gradient of that layer exists, so the transfer
+over NVLink overlaps the BPTT of the layers below it.  BatchNorm uses local (per-rank) batch
+statistics -- plain data-parallel semantics.
+
+Works with any backend ("nccl" on GPUs; "gloo" in the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+class GradSync:
+    def __init__(self, module, group=None, broadcast=True):
+        if not dist.is_initialized():
+            raise RuntimeError("GradSync needs an initialised torch.distributed process group")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.buckets = []
+        layers = list(module.snn) if hasattr(module, "snn") else [module]
+        seen = set()
+        for lay in layers:
+            ps = [p for p in lay.parameters() if p.requires_grad and id(p) not in seen]
+            seen.update(id(p) for p in ps)
+            if ps:
+                self._add_bucket(ps)
+        rest = [p for p in module.parameters() if p.requires_grad and id(p) not in seen]
+        if rest:
+            self._add_bucket(rest)
+        if broadcast:
+            with torch.no_grad():
+                for t in list(module.parameters()) + list(module.buffers()):
+                    dist.broadcast(t, src=0, group=group)
+        self._handles = []
+
+    def _add_bucket(self, params):
+        n = sum(p.numel() for p in params)
+        flat = torch.zeros(n, dtype=params[0].dtype, device=params[0].device)
+        b = {"params": params, "flat": flat, "pending": len(params), "work": None, "views": []}
+        off = 0
+        for p in params:
+            b["views"].append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+            p.register_post_accumulate_grad_hook(self._make_hook(b, len(b["views"]) - 1))
+        self.buckets.append(b)
+
+    def _make_hook(self, b, i):
+        def hook(p):
+            b["views"][i].copy_(p.grad)
+            b["pending"] -= 1
+            if b["pending"] == 0:
+                b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group,
+                                            async_op=True)
+        return hook
+
+    def finish(self):
+        """Wait for the outstanding all-reduces, average, and point .grad at the reduced values."""
+        for b in self.buckets:
+            if b["pending"] != 0:
+                # a parameter received no gradient this step: reduce what there is
+                for v, p in zip(b["views"], b["params"]):
+                    if p.grad is None:
+                        v.zero_()
+                b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group,
+                                            async_op=True)
+        for b in self.buckets:
+            b["work"].wait()
+            b["flat"].div_(self.world)
+            for v, p in zip(b["views"], b["params"]):
+                p.grad = v
+            b["pending"] = len(b["params"])
+            b["work"] = None

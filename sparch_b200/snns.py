@@ -1,0 +1,267 @@
+"""B200-native stand-in for ``sparch.models.snns`` (reference: sparch/models/snns.py).
+
+Same public classes, constructor arguments, attribute names, parameter registration order
+(=> identical ``state_dict`` keys and whole-module pickles) and RNG draw order as the
+reference, so ``sparch/exp.py:305-314`` can construct ``SNN`` unchanged.  The per-timestep
+Python loops of the reference (snns.py:282-303, 419-445, 554-578, 696-727, 807-825) are replaced
+by ``torch.autograd.Function`` wrappers over hand-written sm_100a kernels
+(``sparch_b200.functional`` -> ``libsparch_b200.so``).  CUDA only: a forward pass on CPU
+tensors raises ``RuntimeError``.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .functional import (NormState, ReadoutCellFunction, SpikeFunctionBoxcar,
+                         SpikingCellFunction)
+
+__all__ = ["SpikeFunctionBoxcar", "SNN", "LIFLayer", "adLIFLayer", "RLIFLayer", "RadLIFLayer",
+           "ReadoutLayer"]
+
+
+def _norm_args(layer):
+    """(Z-transform, gamma, beta, NormState) for the layer's normalisation (snns.py:652-658)."""
+    if not layer.normalize:
+        return None, None, NormState("none")
+    norm = layer.norm
+    if isinstance(norm, nn.BatchNorm1d):
+        use_batch = norm.training or norm.running_mean is None
+        if use_batch:
+            if norm.training and norm.num_batches_tracked is not None:
+                norm.num_batches_tracked.add_(1)
+            track = norm.training and norm.running_mean is not None
+            st = NormState("bn_train", norm.running_mean if track else None,
+                           norm.running_var if track else None, norm.eps, norm.momentum)
+        else:
+            st = NormState("bn_eval", norm.running_mean, norm.running_var, norm.eps, norm.momentum)
+        return norm.weight, norm.bias, st
+    return None, None, None  # LayerNorm: applied by torch before the cell
+
+
+class _SpikingLayerBase(nn.Module):
+    """Shared constructor / forward of the four spiking layers (snns.py:179-727).
+
+    Parameter creation and initialisation follow the reference line by line so that a given
+    ``torch.manual_seed`` produces the same weights: W (Linear), [V (Linear)], alpha
+    [, beta, a, b] ``uniform_`` in that order, then ``orthogonal_`` on V.
+    """
+
+    _kind = None
+    _adaptive = False
+    _recurrent = False
+
+    def __init__(self, input_size, hidden_size, batch_size, threshold=1.0, dropout=0.0,
+                 normalization="batchnorm", use_bias=False, bidirectional=False):
+        super().__init__()
+        self.input_size = int(input_size)
+        self.hidden_size = int(hidden_size)
+        self.batch_size = batch_size
+        self.threshold = threshold
+        self.dropout = dropout
+        self.normalization = normalization
+        self.use_bias = use_bias
+        self.bidirectional = bidirectional
+        self.batch_size = self.batch_size * (1 + self.bidirectional)
+        self.alpha_lim = [np.exp(-1 / 5), np.exp(-1 / 25)]
+        if self._adaptive:
+            self.beta_lim = [np.exp(-1 / 30), np.exp(-1 / 120)]
+            self.a_lim = [-1.0, 1.0]
+            self.b_lim = [0.0, 2.0]
+        self.spike_fct = SpikeFunctionBoxcar.apply
+
+        self.W = nn.Linear(self.input_size, self.hidden_size, bias=use_bias)
+        if self._recurrent:
+            self.V = nn.Linear(self.hidden_size, self.hidden_size, bias=False)
+        self.alpha = nn.Parameter(torch.Tensor(self.hidden_size))
+        if self._adaptive:
+            self.beta = nn.Parameter(torch.Tensor(self.hidden_size))
+            self.a = nn.Parameter(torch.Tensor(self.hidden_size))
+            self.b = nn.Parameter(torch.Tensor(self.hidden_size))
+        nn.init.uniform_(self.alpha, self.alpha_lim[0], self.alpha_lim[1])
+        if self._adaptive:
+            nn.init.uniform_(self.beta, self.beta_lim[0], self.beta_lim[1])
+            nn.init.uniform_(self.a, self.a_lim[0], self.a_lim[1])
+            nn.init.uniform_(self.b, self.b_lim[0], self.b_lim[1])
+        if self._recurrent:
+            nn.init.orthogonal_(self.V.weight)
+
+        self.normalize = False
+        if normalization == "batchnorm":
+            self.norm = nn.BatchNorm1d(self.hidden_size, momentum=0.05)
+            self.normalize = True
+        elif normalization == "layernorm":
+            self.norm = nn.LayerNorm(self.hidden_size)
+            self.normalize = True
+        self.drop = nn.Dropout(p=dropout)
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("sparch_b200 layers run on CUDA only (no CPU fallback)")
+        if self.bidirectional:                                   # snns.py:666-668
+            x = torch.cat([x, x.flip(1)], dim=0)
+        if self.batch_size != x.shape[0]:                        # snns.py:671-672
+            self.batch_size = x.shape[0]
+        Wx = self.W(x)                                           # snns.py:675
+        gamma, bn_beta, norm = _norm_args(self)
+        if norm is None:                                         # layernorm, snns.py:678-680
+            Wx = self.norm(Wx)
+            norm = NormState("none")
+        s = self._cell(Wx, gamma, bn_beta, norm)
+        if self.bidirectional:                                   # snns.py:686-689
+            s_f, s_b = s.chunk(2, dim=0)
+            s = torch.cat([s_f, s_b.flip(1)], dim=2)
+        return self.drop(s)                                      # snns.py:692
+
+    def _cell(self, Wx, gamma, bn_beta, norm):
+        device = Wx.device
+        Be, H = Wx.shape[0], Wx.shape[2]
+        # initial states from the CPU generator in the reference's order (snns.py:700-702)
+        ut = torch.rand(Be, H).to(device)
+        wt = torch.rand(Be, H).to(device) if self._adaptive else None
+        st = torch.rand(Be, H).to(device)
+        return SpikingCellFunction.apply(
+            Wx, gamma, bn_beta, self.alpha, getattr(self, "beta", None), getattr(self, "a", None),
+            getattr(self, "b", None), self.V.weight if self._recurrent else None, ut, wt, st,
+            self._kind, self.threshold, norm)
+
+
+class LIFLayer(_SpikingLayerBase):
+    """Leaky integrate-and-fire layer (snns.py:179-303)."""
+    _kind = "LIF"
+
+    def _lif_cell(self, Wx):
+        return self._cell(Wx, None, None, NormState("none"))
+
+
+class adLIFLayer(_SpikingLayerBase):
+    """Adaptive LIF layer (snns.py:306-445)."""
+    _kind = "adLIF"
+    _adaptive = True
+
+    def _adlif_cell(self, Wx):
+        return self._cell(Wx, None, None, NormState("none"))
+
+
+class RLIFLayer(_SpikingLayerBase):
+    """LIF layer with layer-wise recurrent connections (snns.py:448-578)."""
+    _kind = "RLIF"
+    _recurrent = True
+
+    def _rlif_cell(self, Wx):
+        return self._cell(Wx, None, None, NormState("none"))
+
+
+class RadLIFLayer(_SpikingLayerBase):
+    """Adaptive LIF layer with recurrent connections (snns.py:581-727)."""
+    _kind = "RadLIF"
+    _adaptive = True
+    _recurrent = True
+
+    def _radlif_cell(self, Wx):
+        return self._cell(Wx, None, None, NormState("none"))
+
+
+class ReadoutLayer(nn.Module):
+    """Non-spiking LIF readout: out = sum_t softmax(u_t) (snns.py:730-825)."""
+
+    def __init__(self, input_size, hidden_size, batch_size, dropout=0.0, normalization="batchnorm",
+                 use_bias=False):
+        super().__init__()
+        self.input_size = int(input_size)
+        self.hidden_size = int(hidden_size)
+        self.batch_size = batch_size
+        self.dropout = dropout
+        self.normalization = normalization
+        self.use_bias = use_bias
+        self.alpha_lim = [np.exp(-1 / 5), np.exp(-1 / 25)]
+
+        self.W = nn.Linear(self.input_size, self.hidden_size, bias=use_bias)
+        self.alpha = nn.Parameter(torch.Tensor(self.hidden_size))
+        nn.init.uniform_(self.alpha, self.alpha_lim[0], self.alpha_lim[1])
+
+        self.normalize = False
+        if normalization == "batchnorm":
+            self.norm = nn.BatchNorm1d(self.hidden_size, momentum=0.05)
+            self.normalize = True
+        elif normalization == "layernorm":
+            self.norm = nn.LayerNorm(self.hidden_size)
+            self.normalize = True
+        self.drop = nn.Dropout(p=dropout)  # constructed but never applied, as in the reference
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("sparch_b200 layers run on CUDA only (no CPU fallback)")
+        Wx = self.W(x)                                           # snns.py:796
+        gamma, bn_beta, norm = _norm_args(self)
+        if norm is None:
+            Wx = self.norm(Wx)
+            norm = NormState("none")
+        return self._readout_cell(Wx, gamma, bn_beta, norm)
+
+    def _readout_cell(self, Wx, gamma=None, bn_beta=None, norm=None):
+        ut = torch.rand(Wx.shape[0], Wx.shape[2]).to(Wx.device)  # snns.py:812
+        return ReadoutCellFunction.apply(Wx, gamma, bn_beta, self.alpha, ut,
+                                         norm if norm is not None else NormState("none"))
+
+
+_LAYER_CLASSES = {"LIF": LIFLayer, "adLIF": adLIFLayer, "RLIF": RLIFLayer, "RadLIF": RadLIFLayer}
+
+
+class SNN(nn.Module):
+    """Multi-layered spiking network (snns.py:39-176): same arguments, same
+    ``forward(x) -> (outputs, firing_rates)`` contract."""
+
+    def __init__(self, input_shape, layer_sizes, neuron_type="LIF", threshold=1.0, dropout=0.0,
+                 normalization="batchnorm", use_bias=False, bidirectional=False,
+                 use_readout_layer=True):
+        super().__init__()
+        self.reshape = True if len(input_shape) > 3 else False
+        self.input_size = float(torch.prod(torch.tensor(input_shape[2:])))
+        self.batch_size = input_shape[0]
+        self.layer_sizes = layer_sizes
+        self.num_layers = len(layer_sizes)
+        self.num_outputs = layer_sizes[-1]
+        self.neuron_type = neuron_type
+        self.threshold = threshold
+        self.dropout = dropout
+        self.normalization = normalization
+        self.use_bias = use_bias
+        self.bidirectional = bidirectional
+        self.use_readout_layer = use_readout_layer
+        self.is_snn = True
+
+        if neuron_type not in ["LIF", "adLIF", "RLIF", "RadLIF"]:
+            raise ValueError(f"Invalid neuron type {neuron_type}")
+
+        self.snn = self._init_layers()
+
+    def _init_layers(self):
+        snn = nn.ModuleList([])
+        input_size = self.input_size
+        layer_cls = _LAYER_CLASSES[self.neuron_type]
+        num_hidden = self.num_layers - 1 if self.use_readout_layer else self.num_layers
+        for i in range(num_hidden):
+            snn.append(layer_cls(input_size=input_size, hidden_size=self.layer_sizes[i],
+                                 batch_size=self.batch_size, threshold=self.threshold,
+                                 dropout=self.dropout, normalization=self.normalization,
+                                 use_bias=self.use_bias, bidirectional=self.bidirectional))
+            input_size = self.layer_sizes[i] * (1 + self.bidirectional)
+        if self.use_readout_layer:
+            snn.append(ReadoutLayer(input_size=input_size, hidden_size=self.layer_sizes[-1],
+                                    batch_size=self.batch_size, dropout=self.dropout,
+                                    normalization=self.normalization, use_bias=self.use_bias))
+        return snn
+
+    def forward(self, x):
+        if self.reshape:                                         # snns.py:160-164
+            if x.ndim == 4:
+                x = x.reshape(x.shape[0], x.shape[1], x.shape[2] * x.shape[3])
+            else:
+                raise NotImplementedError
+        all_spikes = []
+        for i, snn_lay in enumerate(self.snn):
+            x = snn_lay(x)
+            if not (self.use_readout_layer and i == self.num_layers - 1):
+                all_spikes.append(x)
+        firing_rates = torch.cat(all_spikes, dim=2).mean(dim=(0, 1))   # snns.py:174
+        return x, firing_rates

@@ -1,0 +1,119 @@
+"""CPU tests of the host side: drop-in contract of sparch_b200.snns (constructor, state_dict
+layout, RNG draw order, pickling, error behaviour) and the C-ABI library surface.  No kernel is
+launched here (there is no GPU in the build container)."""
+import ctypes
+import io
+import json
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import snn_oracle as orc
+from tests.helpers import GOLDEN_DIR, Golden, golden_names
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = []
+    inc = os.path.join(ROOT, "include")
+    for fn in sorted(os.listdir(inc)):
+        if fn.endswith(".h"):
+            src = open(os.path.join(inc, fn)).read()
+            names += re.findall(r"SPARCH_API\s+[\w\s\*]+?\b(sparch_\w+)\s*\(", src)
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    from sparch_b200 import _lib, build
+    build.build()
+    names = _declared_symbols()
+    assert len(names) >= 14
+    h = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(h, n), f"{n} declared in include/ but not exported"
+    # every declared entry point has a ctypes prototype (and nothing undeclared is bound)
+    bound = set(_lib._PROTOS) | {"sparch_last_error"}
+    assert bound == set(names), (sorted(bound ^ set(names)))
+    assert _lib.lib().sparch_abi_version() >= 1
+
+
+def test_init_rng_and_state_dict_contract():
+    """Same seed -> same parameters, in the same state_dict order, as the reference."""
+    import sparch_b200
+    z = np.load(os.path.join(GOLDEN_DIR, "init_contract.npz"))
+    cases = sorted({k.split(".")[0] for k in z.files})
+    assert len(cases) == 5
+    for name in cases:
+        kw = json.loads(str(z[name + ".kwargs"]))
+        keys = json.loads(str(z[name + ".keys"]))
+        torch.manual_seed(0)
+        net = sparch_b200.SNN(input_shape=(2, None, 5), **kw)
+        sd = net.state_dict()
+        assert list(sd.keys()) == keys, name
+        for k in keys:
+            np.testing.assert_array_equal(sd[k].numpy(), z[f"{name}.sd.{k}"], err_msg=f"{name}:{k}")
+        # the oracle module obeys the same contract
+        torch.manual_seed(0)
+        ref = orc.build_oracle_snn((2, None, 5), **kw)
+        assert list(ref.state_dict().keys()) == keys
+        for k in keys:
+            np.testing.assert_array_equal(ref.state_dict()[k].numpy(), z[f"{name}.sd.{k}"])
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_state_dict_of_fixtures_loads(name):
+    import sparch_b200
+    g = Golden(name)
+    net = sparch_b200.SNN(g.input_shape, **g.kwargs)
+    net.load_state_dict(g.state_dict())  # strict: keys and shapes must match the reference's
+    assert net.is_snn and len(net.snn) == len(g.kwargs["layer_sizes"])
+
+
+def test_constructor_contract_and_errors():
+    import sparch_b200
+    with pytest.raises(ValueError, match="Invalid neuron type"):
+        sparch_b200.SNN((4, None, 7), [8, 3], neuron_type="LSTM")
+    net = sparch_b200.SNN((4, None, 7), [8, 8, 3], neuron_type="RadLIF", bidirectional=True,
+                          dropout=0.1, use_bias=True)
+    lay0, lay1, ro = net.snn
+    assert type(lay0).__name__ == "RadLIFLayer" and type(ro).__name__ == "ReadoutLayer"
+    assert lay0.W.weight.shape == (8, 7) and lay1.W.weight.shape == (8, 16)   # snns.py:140
+    assert ro.W.weight.shape == (3, 16) and lay0.batch_size == 8
+    assert lay0.V.weight.shape == (8, 8) and lay0.norm.momentum == 0.05
+    assert callable(lay0.spike_fct) and lay0.drop.p == 0.1
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        net(torch.zeros(4, 5, 7))           # no CPU fallback
+    net4 = sparch_b200.SNN((4, None, 7, 2), [8, 3])
+    assert net4.reshape
+    with pytest.raises(NotImplementedError):
+        net4(torch.zeros(4, 5, 14))
+
+
+def test_whole_module_pickle_round_trip():
+    """exp.py:462 saves the whole module with torch.save; it must survive a round trip."""
+    import sparch_b200
+    torch.manual_seed(3)
+    net = sparch_b200.SNN((4, None, 7), [8, 8, 3], neuron_type="adLIF")
+    buf = io.BytesIO()
+    torch.save(net, buf)
+    buf.seek(0)
+    net2 = torch.load(buf, weights_only=False)
+    for (k1, v1), (k2, v2) in zip(net.state_dict().items(), net2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+    assert pickle.loads(pickle.dumps(net.snn[0].spike_fct)) is not None
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under sparch_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "sparch_b200")
+    for dp, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|snn_oracle", src, re.M), \
+                    os.path.join(dp, fn)
