@@ -218,6 +218,18 @@ def run_ours(args, cfg, rank, local_rank, world):
             ms = float(t.item())
         return ms
 
+    if args.profile:
+        for _ in range(args.warmup):
+            step(x_d, y_d)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for _ in range(args.steps):
+            step(x_d, y_d)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "steps": args.steps, "warmup": args.warmup}))
+        return
     for _ in range(max(args.warmup, 3)):
         step(x_d, y_d)
     # ---- device-resident number ------------------------------------------------------------
@@ -300,6 +312,9 @@ def main():
     ap.add_argument("--config", default="cfg4", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="profiling run (under ncu): exactly --warmup warm-up and --steps timed steps of "
+                         "the device-resident loop, no e2e leg, no CPU baseline; prints no bench value")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", 0))

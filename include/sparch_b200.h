@@ -113,6 +113,24 @@ SPARCH_API int sparch_cell_step_bwd(int kind, int t, const float* G, const float
                          float* p_beta, float* p_a, float* p_b, int Be, int T, int H,
                          sparch_stream_t st);
 
+/* ---- recurrent kinds on the tensor pipe (snns.py:554-578, 696-727) --------------------- */
+/* Hidden size rounded up to a multiple of 32 (spike words / V0 slices are padded to it).    */
+SPARCH_API int sparch_recur_padded(int H);
+/* Build the fragment-ordered fp16 hi/lo images of V0 = V with zero diagonal (snns.py:566, 712):
+ * img_fwd for s @ V0, img_bwd for dI @ V0^T (either may be NULL).  Each image is Hp*Hp uint32
+ * words; meta is 2 ints (meta[0] = E with max|V0| < 2^E).                                    */
+SPARCH_API int sparch_recur_prepare(const float* V, int H, uint32_t* img_fwd, uint32_t* img_bwd,
+                                    int* meta, sparch_stream_t st);
+/* All T steps of an RLIF/RadLIF layer.  rec0 (Be,H) = s0 @ V0 (s0 is real-valued, snns.py:702);
+ * later steps take s_{t-1} from the packed spike planes `bits` [T][Be][Hp/32] this call writes.
+ * Also writes the fp32 tapes S, U (and W for RadLIF).                                        */
+SPARCH_API int sparch_recur_fwd(int kind, const float* Z, const float* scale, const float* shift,
+                                const float* alpha, const float* beta, const float* a,
+                                const float* b, const float* rec0, const uint32_t* img_fwd,
+                                const int* meta, const float* u0, const float* w0,
+                                const float* s0, float theta, float* S, float* U, float* W,
+                                uint32_t* bits, int Be, int T, int H, sparch_stream_t st);
+
 /* ---- ReadoutLayer cell (snns.py:807-825) ---------------------------------------------- */
 /* u_t = alpha*u_{t-1} + (1-alpha)*I_t ; out = sum_t softmax(u_t, dim=1).  U (B,T,C) tape.  */
 SPARCH_API int sparch_readout_fwd(const float* Z, const float* scale, const float* shift,

@@ -25,6 +25,9 @@ _PROTOS = {
     "sparch_cell_step_fwd": "ii" + "p" * 11 + "f" + "ppp" + "iii" + "p",
     "sparch_cell_bwd": "i" + "p" * 10 + "f" + "p" * 5 + "iii" + "p",
     "sparch_cell_step_bwd": "ii" + "p" * 11 + "f" + "p" * 7 + "iii" + "p",
+    "sparch_recur_padded": "i",
+    "sparch_recur_prepare": "pipppp",
+    "sparch_recur_fwd": "i" + "p" * 13 + "f" + "pppp" + "iii" + "p",
     "sparch_readout_fwd": "p" * 7 + "iii" + "p",
     "sparch_readout_bwd": "p" * 6 + "iii" + "p",
 }

@@ -1,0 +1,337 @@
+// Recurrent kinds (RLIF, RadLIF): the per-timestep product s_{t-1} @ V0 on the tensor pipe, fused
+// with the membrane update (snns.py:572, 718-724).
+//
+// Decomposition: CTA (slice, group) owns 32 neurons (columns of V0) and 64 batch rows.  Its slice
+// of V0 (Hp x 32) sits in shared memory as fp16 hi + fp16 lo (V0 * 2^k split in two, 22 mantissa
+// bits: products with a spike are exact, accumulation is fp32), already arranged in
+// mma.m16n8k16 B-fragment order so a warp loads its fragments with conflict-free 16-byte reads.
+// The A operand is never materialised: spikes travel as 1-bit planes (32 neurons per word) and
+// each thread synthesises its A fragments from the words with one rotate and one mask per
+// register.  A spike is encoded as 2.0 (fp16 pattern 0x4000, a single set bit), and the K order
+// inside a 32-neuron word is permuted so that the two halves of every fragment register are 16
+// bits apart in the word (the same permutation is baked into the V0 image; the factor 2 into its
+// scale).  8 warps = 4 K-quarters x 2 column halves; the K-quarters are reduced through shared
+// memory, then 256 threads apply the neuron update to the 64 x 32 block and emit the new spike
+// words, the fp32 spike/membrane/adaptation tapes.
+#include <cuda_fp16.h>
+
+#include "cell_math.cuh"
+#include "common.cuh"
+
+namespace sparch {
+
+constexpr int RB = 64;       // batch rows per CTA
+constexpr int RC = 32;       // neurons (V0 columns) per CTA
+constexpr int RED_RS = 40;   // row stride (floats) of the K-quarter reduction buffer: conflict-free float2 stores
+constexpr int VSCALE_EXP = 13;
+
+// meta[0] = E with max|V0| < 2^E (int), set by vmax_kernel.
+__global__ void vmax_kernel(const float* __restrict__ V, int H, int* __restrict__ meta) {
+  float m = 0.f;
+  int64_t n = (int64_t)H * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(i / H), c = (int)(i % H);
+    if (r != c) m = fmaxf(m, fabsf(V[i]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(&meta[1], __float_as_int(m));
+}
+
+__global__ void vmax_finish_kernel(int* meta) {
+  float m = __int_as_float(meta[1]);
+  int e = 0;
+  if (m > 0.f && isfinite(m)) frexpf(m, &e);  // m = f * 2^e, f in [0.5, 1)
+  meta[0] = e;
+}
+
+// Physical bit (neuron index inside a 32-neuron word) feeding logical K position `kpos` (0..15) of
+// k-step `ks` (0/1) of that word.  kpos = 2q + 8hs + e.
+__host__ __device__ __forceinline__ int spike_bit_of(int ks, int kpos) {
+  int e = kpos & 1, hs = (kpos >> 3) & 1, q = (kpos >> 1) & 3;
+  return (14 + 16 * e + 4 * q + 2 * ks + hs) & 31;
+}
+
+// Build the fragment-ordered fp16 hi/lo image of V0 (diagonal zeroed, snns.py:566/712).
+//   transposed == 0 (forward):  B[k = presynaptic j][n = neuron c] = V[j][c], K bit-permuted
+//   transposed == 1 (backward): B[k = neuron c][n = presynaptic j] = V[j][c], natural K order
+// Image words per slice: (((kk*2 + nh)*2 + blk)*32 + lane)*4 + wd, kk < Hp/16.
+__global__ void vprep_kernel(const float* __restrict__ V, int H, int Hp, int transposed,
+                             const int* __restrict__ meta, uint32_t* __restrict__ img) {
+  const int KK = Hp / 16;
+  const int64_t words_per_slice = (int64_t)KK * 512;
+  const int64_t total = words_per_slice * (Hp / RC);
+  const int E = meta[0];
+  const float sc = ldexpf(1.0f, (transposed ? VSCALE_EXP : VSCALE_EXP - 1) - E);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int slice = (int)(i / words_per_slice);
+    int r = (int)(i % words_per_slice);
+    int wd = r & 3, lane = (r >> 2) & 31, blk = (r >> 7) & 1, nh = (r >> 8) & 1, kk = r >> 9;
+    int part = wd >> 1, reg = wd & 1, g = lane >> 2, q = lane & 3;
+    int n = slice * RC + 8 * (2 * nh + blk) + g;
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      int kpos = 2 * q + 8 * reg + e;
+      int k = transposed ? 16 * kk + kpos : 32 * (kk >> 1) + spike_bit_of(kk & 1, kpos);
+      int row = transposed ? n : k, col = transposed ? k : n;  // V[row][col], row = presynaptic j
+      float x = 0.f;
+      if (row < H && col < H && row != col) x = V[(int64_t)row * H + col] * sc;
+      __half hi = __float2half_rn(x);
+      v[e] = part ? (x - __half2float(hi)) : __half2float(hi);
+    }
+    __half2 h2 = __floats2half2_rn(v[0], v[1]);
+    img[i] = *reinterpret_cast<uint32_t*>(&h2);
+  }
+}
+
+struct RecFwdArgs {
+  const float *Z, *scale, *shift, *alpha, *beta, *a, *b, *rec0, *u0, *w0, *s0;
+  const uint32_t* img;
+  const int* meta;
+  float theta;
+  float *S, *U, *W;
+  uint32_t* bits;  // [T][Be][Hp/32]
+  int Be, T, H, Hp;
+};
+
+__device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// 8 consecutive floats: two 16-byte accesses when aligned, scalar with a bound otherwise.
+__device__ __forceinline__ void load8(const float* __restrict__ p, float (&v)[8], bool vec, int nv) {
+  if (vec) {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = i < nv ? p[i] : 0.f;
+  }
+}
+__device__ __forceinline__ void store8(float* __restrict__ p, const float (&v)[8], bool vec, int nv) {
+  if (vec) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) p[i] = v[i];
+  }
+}
+
+template <bool ADAPT>
+__global__ void __launch_bounds__(256, 1) rec_fwd_step_kernel(const RecFwdArgs p, const int t) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int NW = p.Hp / 32;          // spike words per row
+  const int RSB = NW + 1;            // padded row stride of the spike-word tile
+  uint32_t* simg = reinterpret_cast<uint32_t*>(smem_raw);
+  float* red = reinterpret_cast<float*>(smem_raw + (size_t)p.Hp * 128);
+  uint32_t* sbits = reinterpret_cast<uint32_t*>(red + 4 * RB * RED_RS);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slice = blockIdx.x, row0 = blockIdx.y * RB;
+  const int kq = warp >> 1, nh = warp & 1, g = lane >> 2, q = lane & 3;
+
+  if (t > 0) {
+    const uint4* src = reinterpret_cast<const uint4*>(p.img + (size_t)slice * p.Hp * 32);
+    uint4* dst = reinterpret_cast<uint4*>(simg);
+    for (int i = tid; i < p.Hp * 8; i += 256) cp_async16(dst + i, src + i);
+    const uint32_t* bsrc = p.bits + (size_t)(t - 1) * p.Be * NW;
+    for (int i = tid; i < RB * NW; i += 256) {
+      int r = i / NW, wi = i - r * NW;
+      int row = row0 + r;
+      sbits[r * RSB + wi] = row < p.Be ? bsrc[(size_t)row * NW + wi] : 0u;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    float acc[4][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+
+    const uint4* bimg = reinterpret_cast<const uint4*>(simg);
+    for (int wi = kq; wi < NW; wi += 4) {
+      uint32_t wa[4], wb[4];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        wa[mt] = __funnelshift_r(sbits[(16 * mt + g) * RSB + wi], sbits[(16 * mt + g) * RSB + wi], 4 * q);
+        wb[mt] = __funnelshift_r(sbits[(16 * mt + g + 8) * RSB + wi], sbits[(16 * mt + g + 8) * RSB + wi], 4 * q);
+      }
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int kk = 2 * wi + ks;
+        const uint4 f0 = bimg[((kk * 2 + nh) * 2 + 0) * 32 + lane];
+        const uint4 f1 = bimg[((kk * 2 + nh) * 2 + 1) * 32 + lane];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          const uint32_t M = 0x40004000u;
+          uint32_t a0 = __funnelshift_r(wa[mt], wa[mt], 2 * ks) & M;
+          uint32_t a1 = __funnelshift_r(wb[mt], wb[mt], 2 * ks) & M;
+          uint32_t a2 = __funnelshift_r(wa[mt], wa[mt], 2 * ks + 1) & M;
+          uint32_t a3 = __funnelshift_r(wb[mt], wb[mt], 2 * ks + 1) & M;
+          mma16816(acc[mt][0], a0, a1, a2, a3, f0.x, f0.y);
+          mma16816(acc[mt][0], a0, a1, a2, a3, f0.z, f0.w);
+          mma16816(acc[mt][1], a0, a1, a2, a3, f1.x, f1.y);
+          mma16816(acc[mt][1], a0, a1, a2, a3, f1.z, f1.w);
+        }
+      }
+    }
+    float* myred = red + kq * RB * RED_RS;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        int col = 16 * nh + 8 * nt + 2 * q;
+        *reinterpret_cast<float2*>(&myred[(16 * mt + g) * RED_RS + col]) =
+            make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+        *reinterpret_cast<float2*>(&myred[(16 * mt + g + 8) * RED_RS + col]) =
+            make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+      }
+    __syncthreads();
+  }
+
+  // ---- neuron update for 8 consecutive neurons of one row per thread
+  const int r = tid >> 2, cg = tid & 3;
+  const int row = row0 + r;
+  const int col0 = slice * RC + cg * 8;
+  uint32_t my = 0;
+  if (row < p.Be && col0 < p.H) {
+    const bool vec = ((p.H & 3) == 0) && (col0 + 8 <= p.H);
+    const int nv = min(8, p.H - col0);
+    const int64_t idx0 = (int64_t)row * p.H + col0;
+    const int64_t o0 = ((int64_t)row * p.T + t) * p.H + col0;
+    float z[8], u[8], w[8], s[8], rec[8];
+    load8(p.Z + o0, z, vec, nv);
+    if (t > 0) {
+      const float rs = ldexpf(1.0f, p.meta[0] - VSCALE_EXP);
+      const uint32_t prevw = sbits[r * RSB + slice] >> (cg * 8);
+      load8(p.U + o0 - p.H, u, vec, nv);
+      if (ADAPT) load8(p.W + o0 - p.H, w, vec, nv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = cg * 8 + i;
+        rec[i] = ((red[(0 * RB + r) * RED_RS + c] + red[(1 * RB + r) * RED_RS + c]) +
+                  (red[(2 * RB + r) * RED_RS + c] + red[(3 * RB + r) * RED_RS + c])) * rs;
+        s[i] = (float)((prevw >> i) & 1u);
+      }
+    } else {
+      load8(p.rec0 + idx0, rec, vec, nv);
+      load8(p.u0 + idx0, u, vec, nv);
+      load8(p.s0 + idx0, s, vec, nv);
+      if (ADAPT) load8(p.w0 + idx0, w, vec, nv);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < nv) {
+        const int col = col0 + i;
+        const NeuronParams np = load_params<ADAPT>(p.alpha, p.beta, p.a, p.b, col);
+        float cur = z[i];
+        if (p.scale) cur = __fmaf_rn(cur, p.scale[col], p.shift[col]);
+        cur = __fadd_rn(cur, rec[i]);
+        float wi_ = ADAPT ? w[i] : 0.f;
+        step_fwd<ADAPT>(np, cur, p.theta, u[i], wi_, s[i]);
+        w[i] = wi_;
+        my |= (s[i] > 0.f ? 1u : 0u) << (cg * 8 + i);
+      }
+    }
+    store8(p.S + o0, s, vec, nv);
+    store8(p.U + o0, u, vec, nv);
+    if (ADAPT) store8(p.W + o0, w, vec, nv);
+  }
+  my |= __shfl_xor_sync(0xffffffffu, my, 1);
+  my |= __shfl_xor_sync(0xffffffffu, my, 2);
+  if (cg == 0 && row < p.Be) p.bits[((size_t)t * p.Be + row) * NW + slice] = my;
+}
+
+static size_t rec_fwd_smem(int Hp) {
+  return (size_t)Hp * 128 + (size_t)4 * RB * RED_RS * sizeof(float) + (size_t)RB * (Hp / 32 + 1) * 4;
+}
+
+}  // namespace sparch
+
+using namespace sparch;
+
+extern "C" {
+
+int sparch_recur_padded(int H) { return ((H + 31) / 32) * 32; }
+
+int sparch_recur_prepare(const float* V, int H, uint32_t* img_fwd, uint32_t* img_bwd, int* meta,
+                         sparch_stream_t st_) {
+  SPARCH_REQUIRE(V && H > 0 && meta && (img_fwd || img_bwd), "null pointer");
+  cudaStream_t st = as_stream(st_);
+  const int Hp = sparch_recur_padded(H);
+  SPARCH_CUDA(cudaMemsetAsync(meta, 0, 2 * sizeof(int), st));
+  int nb = (int)(((int64_t)H * H + 255) / 256);
+  if (nb > sm_count() * 8) nb = sm_count() * 8;
+  vmax_kernel<<<nb, 256, 0, st>>>(V, H, meta);
+  SPARCH_LAUNCH_OK();
+  vmax_finish_kernel<<<1, 1, 0, st>>>(meta);
+  SPARCH_LAUNCH_OK();
+  int64_t total = (int64_t)Hp * Hp;  // words
+  int pb = (int)((total + 255) / 256);
+  if (pb > sm_count() * 16) pb = sm_count() * 16;
+  if (img_fwd) {
+    vprep_kernel<<<pb, 256, 0, st>>>(V, H, Hp, 0, meta, img_fwd);
+    SPARCH_LAUNCH_OK();
+  }
+  if (img_bwd) {
+    vprep_kernel<<<pb, 256, 0, st>>>(V, H, Hp, 1, meta, img_bwd);
+    SPARCH_LAUNCH_OK();
+  }
+  return SPARCH_OK;
+}
+
+int sparch_recur_fwd(int kind, const float* Z, const float* scale, const float* shift,
+                     const float* alpha, const float* beta, const float* a, const float* b,
+                     const float* rec0, const uint32_t* img_fwd, const int* meta, const float* u0,
+                     const float* w0, const float* s0, float theta, float* S, float* U, float* W,
+                     uint32_t* bits, int Be, int T, int H, sparch_stream_t st_) {
+  SPARCH_REQUIRE(kind == SPARCH_RLIF || kind == SPARCH_RADLIF, "recurrent kinds only");
+  SPARCH_REQUIRE(Be >= 0 && T >= 0 && H > 0, "bad shape");
+  SPARCH_REQUIRE((scale == nullptr) == (shift == nullptr), "scale and shift go together");
+  if (Be == 0 || T == 0) return SPARCH_OK;
+  SPARCH_REQUIRE(Z && alpha && rec0 && img_fwd && meta && u0 && s0 && S && U && bits, "null pointer");
+  const bool adapt = kind & 1;
+  SPARCH_REQUIRE(!adapt || (beta && a && b && w0 && W), "adaptive kind needs beta, a, b, w0, W");
+  const int Hp = sparch_recur_padded(H);
+  const size_t smem = rec_fwd_smem(Hp);
+  SPARCH_REQUIRE(smem <= 227 * 1024, "hidden size too large for the resident V0 slice (H <= 1408)");
+  static bool attr_set = false;
+  if (!attr_set) {
+    SPARCH_CUDA(cudaFuncSetAttribute(rec_fwd_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SPARCH_CUDA(cudaFuncSetAttribute(rec_fwd_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  RecFwdArgs p{Z, scale, shift, alpha, beta, a, b, rec0, u0, w0, s0, img_fwd, meta, theta, S, U, W, bits, Be, T, H, Hp};
+  dim3 grid(Hp / RC, (Be + RB - 1) / RB);
+  cudaStream_t st = as_stream(st_);
+  for (int t = 0; t < T; ++t) {
+    if (adapt)
+      rec_fwd_step_kernel<true><<<grid, 256, smem, st>>>(p, t);
+    else
+      rec_fwd_step_kernel<false><<<grid, 256, smem, st>>>(p, t);
+  }
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+}  // extern "C"

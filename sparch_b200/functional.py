@@ -199,12 +199,17 @@ class SpikingCellFunction(torch.autograd.Function):
                      ptr(bb), ptr(u0), ptr(w0), ptr(s0), float(theta), ptr(S), ptr(U), ptr(Wt), Be, T,
                      H, st)
             else:
-                rec = torch.empty(Be, H, device=dev, dtype=torch.float32)
-                for t in range(T):
-                    torch.matmul(s0 if t == 0 else S[:, t - 1, :], V0, out=rec)  # snns.py:720
-                    call("sparch_cell_step_fwd", k, t, ptr(Z), ptr(scale), ptr(shift), ptr(al),
-                         ptr(be), ptr(aa), ptr(bb), ptr(rec), ptr(u0), ptr(w0), ptr(s0), float(theta),
-                         ptr(S), ptr(U), ptr(Wt), Be, T, H, st)
+                # tensor-core step kernels: s_{t-1} @ V0 from packed spike planes (csrc/recur.cu)
+                Hp = _lib.lib().sparch_recur_padded(H)
+                img_f = torch.empty(Hp * Hp, device=dev, dtype=torch.int32)
+                meta = torch.empty(2, device=dev, dtype=torch.int32)
+                call("sparch_recur_prepare", ptr(V.detach().contiguous()), H, ptr(img_f), None,
+                     ptr(meta), st)
+                rec0 = torch.matmul(s0, V0)        # t = 0: s_{-1} is real-valued (snns.py:702)
+                bits = torch.empty(T, Be, Hp // 32, device=dev, dtype=torch.int32)
+                call("sparch_recur_fwd", k, ptr(Z), ptr(scale), ptr(shift), ptr(al), ptr(be), ptr(aa),
+                     ptr(bb), ptr(rec0), ptr(img_f), ptr(meta), ptr(u0), ptr(w0), ptr(s0),
+                     float(theta), ptr(S), ptr(U), ptr(Wt), ptr(bits), Be, T, H, st)
             region.__exit__()
         ctx.k, ctx.theta, ctx.norm = k, float(theta), norm
         ctx.has = (gamma is not None, bn_beta is not None)
