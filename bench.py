@@ -273,7 +273,9 @@ def run_ours(args, cfg, rank, local_rank, world):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": None,
                 "kernel": "membrane recurrence fwd+bwd (all launches of one train step)",
-                "ms_per_step": rec_total_ms, "algorithmic_bytes_per_step": alg_bytes,
+                "ms_per_step": rec_total_ms,
+                "ms_fwd": rec_ms.get("recurrence_fwd", 0.0) / args.steps,
+                "ms_bwd": rec_ms.get("recurrence_bwd", 0.0) / args.steps, "algorithmic_bytes_per_step": alg_bytes,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "share_of_step": rec_total_ms / (ms / args.steps) if rec_total_ms else None}
 

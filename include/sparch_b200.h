@@ -131,6 +131,19 @@ SPARCH_API int sparch_recur_fwd(int kind, const float* Z, const float* scale, co
                                 const float* s0, float theta, float* S, float* U, float* W,
                                 uint32_t* bits, int Be, int T, int H, sparch_stream_t st);
 
+/* Reverse pass of an RLIF/RadLIF layer, all T steps: dI (Be,T,H) and the per-(b,h) partial
+ * parameter gradients (as sparch_cell_step_bwd: du_next/dw_next/p_* are (Be,H), zeroed by the
+ * caller).  img_bwd from sparch_recur_prepare; workspace of sparch_recur_bwd_workspace() bytes
+ * holds the block-floating-point dI panels exchanged between consecutive steps.              */
+SPARCH_API size_t sparch_recur_bwd_workspace(int Be, int H);
+SPARCH_API int sparch_recur_bwd(int kind, const float* G, const float* U, const float* W,
+                                const float* alpha, const float* beta, const float* a,
+                                const float* b, const uint32_t* img_bwd, const int* meta,
+                                const float* u0, const float* w0, const float* s0, float theta,
+                                float* dI, float* du_next, float* dw_next, float* p_alpha,
+                                float* p_beta, float* p_a, float* p_b, void* workspace, int Be,
+                                int T, int H, sparch_stream_t st);
+
 /* ---- ReadoutLayer cell (snns.py:807-825) ---------------------------------------------- */
 /* u_t = alpha*u_{t-1} + (1-alpha)*I_t ; out = sum_t softmax(u_t, dim=1).  U (B,T,C) tape.  */
 SPARCH_API int sparch_readout_fwd(const float* Z, const float* scale, const float* shift,

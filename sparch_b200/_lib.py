@@ -28,6 +28,8 @@ _PROTOS = {
     "sparch_recur_padded": "i",
     "sparch_recur_prepare": "pipppp",
     "sparch_recur_fwd": "i" + "p" * 13 + "f" + "pppp" + "iii" + "p",
+    "sparch_recur_bwd_workspace": "ii",
+    "sparch_recur_bwd": "i" + "p" * 12 + "f" + "p" * 8 + "iii" + "p",
     "sparch_readout_fwd": "p" * 7 + "iii" + "p",
     "sparch_readout_bwd": "p" * 6 + "iii" + "p",
 }
@@ -55,7 +57,7 @@ def lib():
         h.sparch_last_error.argtypes = []
         for name, sig in _PROTOS.items():
             fn = getattr(h, name)
-            fn.restype = _I
+            fn.restype = ctypes.c_size_t if name.endswith("_workspace") else _I
             fn.argtypes = [_CT[c] for c in sig]
         _lib = h
     return _lib

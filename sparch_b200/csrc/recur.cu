@@ -262,6 +262,236 @@ __global__ void __launch_bounds__(256, 1) rec_fwd_step_kernel(const RecFwdArgs p
   if (cg == 0 && row < p.Be) p.bits[((size_t)t * p.Be + row) * NW + slice] = my;
 }
 
+// ------------------------------------------------------------------ reverse step
+// recb[b, j] = sum_c dI_{t+1}[b, c] * V0[j, c] for the CTA's 32 presynaptic neurons j, then the
+// BPTT update of SURVEY.md 8a for its 64 x 32 block.  The A operand is real-valued here, so the
+// producer (the same block of step t+1) hands it over already split for the tensor pipe as
+// block floating point: per (row, 32-column chunk) a power-of-two scale brings the chunk's
+// largest |dI| into [8, 16), then hi = fp16(x), lo = fp16(x - hi) (22 mantissa bits inside the
+// chunk, full fp32 range across chunks), stored in mma A-fragment order so the consumer's loads
+// are linear 16-byte copies.  hi*Vhi + hi*Vlo + lo*Vhi are accumulated per chunk and folded into
+// the fp32 accumulators with the chunk's inverse scale.  A panels and V0^T image stream through a
+// 4-stage cp.async ring (48 KB per stage: 4 chunks of A + the 8 matching k-steps of V0^T).
+struct RecBwdArgs {
+  const float *G, *U, *W, *alpha, *beta, *a, *b, *u0, *w0, *s0;
+  const uint32_t* img;  // V0^T image (vprep transposed = 1)
+  const int* meta;
+  float theta;
+  float *dI, *du_next, *dw_next, *p_alpha, *p_beta, *p_a, *p_b;
+  uint32_t* panel;  // 2 x [groups][Hp/32 chunks][2048 words]
+  float* pscale;    // 2 x [groups][Hp/32][64]
+  int Be, T, H, Hp;
+};
+
+constexpr int BW_STAGES = 4;
+constexpr int BW_STAGE_WORDS = 4 * 2048 + 8 * 512;  // 4 chunks of A + 8 k-steps of V0^T = 48 KB
+
+template <bool ADAPT>
+__global__ void __launch_bounds__(256, 1) rec_bwd_step_kernel(const RecBwdArgs p, const int t) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int NCH = p.Hp / 32;
+  uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw);
+  float* sscale = reinterpret_cast<float*>(smem_raw + (size_t)BW_STAGES * BW_STAGE_WORDS * 4);
+  float* red = reinterpret_cast<float*>(smem_raw);  // aliases the ring after the K loop
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slice = blockIdx.x, group = blockIdx.y, row0 = group * RB;
+  const int kq = warp >> 1, nh = warp & 1, g = lane >> 2, q = lane & 3;
+  const int ngroups = gridDim.y;
+  const bool have_next = t < p.T - 1;
+  const int rbuf = (t + 1) & 1, wbuf = t & 1;
+
+  if (have_next) {
+    const uint32_t* apanel = p.panel + ((size_t)rbuf * ngroups + group) * NCH * 2048;
+    const uint32_t* vimg = p.img + (size_t)slice * p.Hp * 32;
+    const float* gsc = p.pscale + ((size_t)rbuf * ngroups + group) * NCH * 64;
+    const int NSC = (NCH + 3) / 4;
+
+    auto issue = [&](int sc) {
+      if (sc < NSC) {
+        uint32_t* dst = ring + (size_t)(sc % BW_STAGES) * BW_STAGE_WORDS;
+        const int nch = min(4, NCH - 4 * sc);
+        const uint4* sa = reinterpret_cast<const uint4*>(apanel + (size_t)4 * sc * 2048);
+        uint4* da = reinterpret_cast<uint4*>(dst);
+        for (int i = tid; i < nch * 512; i += 256) cp_async16(da + i, sa + i);
+        const uint4* sv = reinterpret_cast<const uint4*>(vimg + (size_t)8 * sc * 512);
+        uint4* dv = reinterpret_cast<uint4*>(dst + 4 * 2048);
+        for (int i = tid; i < nch * 256; i += 256) cp_async16(dv + i, sv + i);
+      }
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+
+    for (int i = tid; i < NCH * 64; i += 256) sscale[i] = gsc[i];
+    for (int s = 0; s < BW_STAGES - 1; ++s) issue(s);
+
+    float acc[4][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+
+    for (int sc = 0; sc < NSC; ++sc) {
+      issue(sc + BW_STAGES - 1);
+      asm volatile("cp.async.wait_group %0;\n" ::"n"(BW_STAGES - 1) : "memory");
+      __syncthreads();
+      const int c = 4 * sc + kq;
+      if (c < NCH) {
+        const uint4* st4 = reinterpret_cast<const uint4*>(ring + (size_t)(sc % BW_STAGES) * BW_STAGE_WORDS);
+        const uint4* a4 = st4 + kq * 512;
+        const uint4* b4 = st4 + 4 * 512;
+        float tacc[4][2][4];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tacc[mt][nt][i] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const int kl = 2 * kq + ks;
+          const uint4 f0 = b4[((kl * 2 + nh) * 2 + 0) * 32 + lane];
+          const uint4 f1 = b4[((kl * 2 + nh) * 2 + 1) * 32 + lane];
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) {
+            const uint4 ah = a4[((mt * 2 + ks) * 2 + 0) * 32 + lane];
+            const uint4 al = a4[((mt * 2 + ks) * 2 + 1) * 32 + lane];
+            mma16816(tacc[mt][0], ah.x, ah.y, ah.z, ah.w, f0.x, f0.y);
+            mma16816(tacc[mt][0], ah.x, ah.y, ah.z, ah.w, f0.z, f0.w);
+            mma16816(tacc[mt][0], al.x, al.y, al.z, al.w, f0.x, f0.y);
+            mma16816(tacc[mt][1], ah.x, ah.y, ah.z, ah.w, f1.x, f1.y);
+            mma16816(tacc[mt][1], ah.x, ah.y, ah.z, ah.w, f1.z, f1.w);
+            mma16816(tacc[mt][1], al.x, al.y, al.z, al.w, f1.x, f1.y);
+          }
+        }
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          const float s_lo = sscale[c * 64 + 16 * mt + g], s_hi = sscale[c * 64 + 16 * mt + g + 8];
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            acc[mt][nt][0] = fmaf(tacc[mt][nt][0], s_lo, acc[mt][nt][0]);
+            acc[mt][nt][1] = fmaf(tacc[mt][nt][1], s_lo, acc[mt][nt][1]);
+            acc[mt][nt][2] = fmaf(tacc[mt][nt][2], s_hi, acc[mt][nt][2]);
+            acc[mt][nt][3] = fmaf(tacc[mt][nt][3], s_hi, acc[mt][nt][3]);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    float* myred = red + kq * RB * RED_RS;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        int col = 16 * nh + 8 * nt + 2 * q;
+        *reinterpret_cast<float2*>(&myred[(16 * mt + g) * RED_RS + col]) =
+            make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+        *reinterpret_cast<float2*>(&myred[(16 * mt + g + 8) * RED_RS + col]) =
+            make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+      }
+    __syncthreads();
+  }
+
+  // ---- BPTT update for 8 consecutive neurons of one row per thread
+  const int r = tid >> 2, cg = tid & 3;
+  const int row = row0 + r;
+  const int col0 = slice * RC + cg * 8;
+  float d[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d[i] = 0.f;
+  if (row < p.Be && col0 < p.H) {
+    const bool vec = ((p.H & 3) == 0) && (col0 + 8 <= p.H);
+    const int nv = min(8, p.H - col0);
+    const int64_t idx0 = (int64_t)row * p.H + col0;
+    const int64_t o0 = ((int64_t)row * p.T + t) * p.H + col0;
+    float gq[8], ut[8], up[8], wp[8], sp[8], du[8], dw[8], pa[8], pb[8], pc[8], pd[8], recb[8];
+    load8(p.G + o0, gq, vec, nv);
+    load8(p.U + o0, ut, vec, nv);
+    load8(p.du_next + idx0, du, vec, nv);
+    load8(p.p_alpha + idx0, pa, vec, nv);
+    if (ADAPT) {
+      load8(p.dw_next + idx0, dw, vec, nv);
+      load8(p.p_beta + idx0, pb, vec, nv);
+      load8(p.p_a + idx0, pc, vec, nv);
+      load8(p.p_b + idx0, pd, vec, nv);
+    }
+    if (t > 0) {
+      load8(p.U + o0 - p.H, up, vec, nv);
+      if (ADAPT) load8(p.W + o0 - p.H, wp, vec, nv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sp[i] = spike_of(__fsub_rn(up[i], p.theta));
+    } else {
+      load8(p.u0 + idx0, up, vec, nv);
+      load8(p.s0 + idx0, sp, vec, nv);
+      if (ADAPT) load8(p.w0 + idx0, wp, vec, nv);
+    }
+    if (have_next) {
+      const float rs = ldexpf(1.0f, p.meta[0] - VSCALE_EXP);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = cg * 8 + i;
+        recb[i] = ((red[(0 * RB + r) * RED_RS + c] + red[(1 * RB + r) * RED_RS + c]) +
+                   (red[(2 * RB + r) * RED_RS + c] + red[(3 * RB + r) * RED_RS + c])) * rs;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) recb[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < nv) {
+        const int col = col0 + i;
+        const NeuronParams np = load_params<ADAPT>(p.alpha, p.beta, p.a, p.b, col);
+        const float inv_oma = 1.0f / np.oma;
+        float dwi = ADAPT ? dw[i] : 0.f, pbi = 0.f, pci = 0.f, pdi = 0.f;
+        if (ADAPT) { pbi = pb[i]; pci = pc[i]; pdi = pd[i]; }
+        d[i] = step_bwd<ADAPT>(np, inv_oma, p.theta, gq[i], recb[i], ut[i], up[i], sp[i],
+                               ADAPT ? wp[i] : 0.f, du[i], dwi, pa[i], pbi, pci, pdi);
+        if (ADAPT) { dw[i] = dwi; pb[i] = pbi; pc[i] = pci; pd[i] = pdi; }
+      }
+    }
+    store8(p.dI + o0, d, vec, nv);
+    store8(p.du_next + idx0, du, vec, nv);
+    store8(p.p_alpha + idx0, pa, vec, nv);
+    if (ADAPT) {
+      store8(p.dw_next + idx0, dw, vec, nv);
+      store8(p.p_beta + idx0, pb, vec, nv);
+      store8(p.p_a + idx0, pc, vec, nv);
+      store8(p.p_b + idx0, pd, vec, nv);
+    }
+  }
+  // ---- hand dI_t to step t-1 as block-floating-point fp16 hi/lo in A-fragment order
+  if (t > 0) {
+    float m = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m = fmaxf(m, fabsf(d[i]));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    int e = 0;
+    if (m > 0.f && m <= 3.0e38f) frexpf(m, &e);
+    e = max(e, -100);
+    const float up_scale = ldexpf(1.0f, 4 - e), inv_scale = ldexpf(1.0f, e - 4);
+    uint32_t* wpanel = p.panel + (((size_t)wbuf * ngroups + group) * NCH + slice) * 2048;
+    const int mt = r >> 4, rr = r & 15, gg = rr & 7, upper = rr >> 3, ks = cg >> 1, hs = cg & 1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x0 = d[2 * j] * up_scale, x1 = d[2 * j + 1] * up_scale;
+      __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+      __half2 hi = __halves2half2(h0, h1);
+      __half2 lo = __floats2half2_rn(x0 - __half2float(h0), x1 - __half2float(h1));
+      const int w = ((mt * 2 + ks) * 2 * 32 + (4 * gg + j)) * 4 + upper + 2 * hs;
+      wpanel[w] = *reinterpret_cast<uint32_t*>(&hi);
+      wpanel[w + 128] = *reinterpret_cast<uint32_t*>(&lo);
+    }
+    if (cg == 0) p.pscale[(((size_t)wbuf * ngroups + group) * NCH + slice) * 64 + r] = inv_scale;
+  }
+}
+
+static size_t rec_bwd_smem(int Hp) {
+  return (size_t)BW_STAGES * BW_STAGE_WORDS * 4 + (size_t)(Hp / 32) * 64 * 4;
+}
+
 static size_t rec_fwd_smem(int Hp) {
   return (size_t)Hp * 128 + (size_t)4 * RB * RED_RS * sizeof(float) + (size_t)RB * (Hp / 32 + 1) * 4;
 }
@@ -329,6 +559,52 @@ int sparch_recur_fwd(int kind, const float* Z, const float* scale, const float* 
       rec_fwd_step_kernel<true><<<grid, 256, smem, st>>>(p, t);
     else
       rec_fwd_step_kernel<false><<<grid, 256, smem, st>>>(p, t);
+  }
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+size_t sparch_recur_bwd_workspace(int Be, int H) {
+  const int Hp = sparch_recur_padded(H);
+  const size_t groups = (size_t)(Be + RB - 1) / RB;
+  return 2 * groups * (Hp / 32) * 2048 * 4 + 2 * groups * (Hp / 32) * 64 * 4;
+}
+
+int sparch_recur_bwd(int kind, const float* G, const float* U, const float* W, const float* alpha,
+                     const float* beta, const float* a, const float* b, const uint32_t* img_bwd,
+                     const int* meta, const float* u0, const float* w0, const float* s0, float theta,
+                     float* dI, float* du_next, float* dw_next, float* p_alpha, float* p_beta,
+                     float* p_a, float* p_b, void* workspace, int Be, int T, int H,
+                     sparch_stream_t st_) {
+  SPARCH_REQUIRE(kind == SPARCH_RLIF || kind == SPARCH_RADLIF, "recurrent kinds only");
+  SPARCH_REQUIRE(Be >= 0 && T >= 0 && H > 0, "bad shape");
+  if (Be == 0 || T == 0) return SPARCH_OK;
+  SPARCH_REQUIRE(G && U && alpha && img_bwd && meta && u0 && s0 && dI && du_next && p_alpha && workspace,
+                 "null pointer");
+  const bool adapt = kind & 1;
+  SPARCH_REQUIRE(!adapt || (W && beta && a && b && w0 && dw_next && p_beta && p_a && p_b),
+                 "adaptive kind needs W, beta, a, b, w0, dw_next and the partial buffers");
+  const int Hp = sparch_recur_padded(H);
+  const size_t smem = rec_bwd_smem(Hp);
+  SPARCH_REQUIRE(smem <= 227 * 1024, "hidden size too large");
+  static bool attr_set = false;
+  if (!attr_set) {
+    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const size_t groups = (size_t)(Be + RB - 1) / RB;
+  uint32_t* panel = reinterpret_cast<uint32_t*>(workspace);
+  float* pscale = reinterpret_cast<float*>(panel + 2 * groups * (Hp / 32) * 2048);
+  RecBwdArgs p{G, U, W, alpha, beta, a, b, u0, w0, s0, img_bwd, meta, theta, dI, du_next, dw_next,
+               p_alpha, p_beta, p_a, p_b, panel, pscale, Be, T, H, Hp};
+  dim3 grid(Hp / RC, (unsigned)groups);
+  cudaStream_t st = as_stream(st_);
+  for (int t = T - 1; t >= 0; --t) {
+    if (adapt)
+      rec_bwd_step_kernel<true><<<grid, 256, smem, st>>>(p, t);
+    else
+      rec_bwd_step_kernel<false><<<grid, 256, smem, st>>>(p, t);
   }
   SPARCH_LAUNCH_OK();
   return SPARCH_OK;

@@ -202,9 +202,11 @@ class SpikingCellFunction(torch.autograd.Function):
                 # tensor-core step kernels: s_{t-1} @ V0 from packed spike planes (csrc/recur.cu)
                 Hp = _lib.lib().sparch_recur_padded(H)
                 img_f = torch.empty(Hp * Hp, device=dev, dtype=torch.int32)
+                img_b = torch.empty(Hp * Hp, device=dev, dtype=torch.int32)
                 meta = torch.empty(2, device=dev, dtype=torch.int32)
-                call("sparch_recur_prepare", ptr(V.detach().contiguous()), H, ptr(img_f), None,
+                call("sparch_recur_prepare", ptr(V.detach().contiguous()), H, ptr(img_f), ptr(img_b),
                      ptr(meta), st)
+                ctx.rec = (img_b, meta)
                 rec0 = torch.matmul(s0, V0)        # t = 0: s_{-1} is real-valued (snns.py:702)
                 bits = torch.empty(T, Be, Hp // 32, device=dev, dtype=torch.int32)
                 call("sparch_recur_fwd", k, ptr(Z), ptr(scale), ptr(shift), ptr(al), ptr(be), ptr(aa),
@@ -239,15 +241,11 @@ class SpikingCellFunction(torch.autograd.Function):
             dV = None
         else:
             carry = torch.zeros(2, Be, H, device=dev, dtype=torch.float32)
-            recb = torch.empty(Be, H, device=dev, dtype=torch.float32)
-            V0t = V0.t()
-            for t in range(T - 1, -1, -1):
-                if t < T - 1:
-                    torch.matmul(dI[:, t + 1, :], V0t, out=recb)
-                call("sparch_cell_step_bwd", k, t, ptr(G), ptr(U), ptr(Wt), ptr(al), ptr(be), ptr(aa),
-                     ptr(bb), ptr(recb) if t < T - 1 else None, ptr(u0), ptr(w0), ptr(s0), theta,
-                     ptr(dI), ptr(carry[0]), ptr(carry[1]) if adaptive else None, pp[0], pp[1], pp[2],
-                     pp[3], Be, T, H, st)
+            img_b, meta = ctx.rec
+            ws = torch.empty(_lib.lib().sparch_recur_bwd_workspace(Be, H), device=dev, dtype=torch.uint8)
+            call("sparch_recur_bwd", k, ptr(G), ptr(U), ptr(Wt), ptr(al), ptr(be), ptr(aa), ptr(bb),
+                 ptr(img_b), ptr(meta), ptr(u0), ptr(w0), ptr(s0), theta, ptr(dI), ptr(carry[0]),
+                 ptr(carry[1]) if adaptive else None, pp[0], pp[1], pp[2], pp[3], ptr(ws), Be, T, H, st)
             region.__exit__()
             # dV = sum_t s_{t-1}^T dI_t, diagonal masked (clone().fill_diagonal_(0) backward)
             dV = s0.t() @ dI[:, 0, :]
