@@ -113,6 +113,28 @@ SPARCH_API int sparch_cell_step_bwd(int kind, int t, const float* G, const float
                          float* p_beta, float* p_a, float* p_b, int Be, int T, int H,
                          sparch_stream_t st);
 
+/* ---- time-parallel GEMMs on tcgen05/TMEM/TMA (snns.py:675 and its autograd) -------------- */
+/* Split an fp32 matrix X (M, K; row stride ldx) into nparts (1..3) bf16 terms, x = p0+p1+p2,
+ * written row-major with row stride ldp (zero padded; ldp % 8 == 0 for the GEMM).           */
+SPARCH_API int sparch_split_bf16(const float* X, int64_t ldx, int M, int K, int nparts, void* P0,
+                                 void* P1, void* P2, int64_t ldp, sparch_stream_t st);
+/* Transposing split: X (R, C) contiguous -> parts (C, ldp >= R): part[c][r] = term(X[r][c]).
+ * With T > 0 and shift > 0 rows are (b, t) and output column (b, t) takes X[b, t-shift, :],
+ * zero for t < shift (the S_prev operand of dV, autograd of snns.py:720).                    */
+SPARCH_API int sparch_split_bf16_transpose(const float* X, int R, int C, int nparts, int T,
+                                           int shift, void* P0, void* P1, void* P2, int64_t ldp,
+                                           sparch_stream_t st);
+/* C[M,N] (fp32, row stride ldc) = alpha * sum_p A[pair_a[p]] . B[pair_b[p]]^T (+ bias[n]);
+ * A parts are (M, K) and B parts (N, K) bf16 row-major with row strides lda / ldb (multiples of
+ * 8).  `workspace` (sparch_gemm_workspace bytes, may be NULL) enables deterministic split-K
+ * when the output has fewer tiles than the GPU has SMs.                                      */
+SPARCH_API size_t sparch_gemm_workspace(int M, int N, int K);
+SPARCH_API int sparch_gemm_bf16(const void* const* A_parts, int na, const void* const* B_parts,
+                                int nb, int64_t lda, int64_t ldb, const int* pair_a,
+                                const int* pair_b, int npairs, int M, int N, int K, float alpha,
+                                const float* bias, float* C, int64_t ldc, void* workspace,
+                                sparch_stream_t st);
+
 /* ---- recurrent kinds on the tensor pipe (snns.py:554-578, 696-727) --------------------- */
 /* Hidden size rounded up to a multiple of 32 (spike words / V0 slices are padded to it).    */
 SPARCH_API int sparch_recur_padded(int H);

@@ -1,0 +1,439 @@
+// Time-parallel GEMMs of the SNN stack on the 5th-generation tensor cores (tcgen05 + TMEM + TMA):
+//   projection  Z  = X  W^T          (snns.py:675)        M = Be*T, N = H,   K = Fin
+//   data grad   dX = dZ W            (autograd of :675)   M = Be*T, N = Fin, K = H
+//   weight grad dW = dZ^T X          (autograd of :675)   M = H,    N = Fin, K = Be*T
+//   recur. grad dV = S_prev^T dI     (autograd of :720)   M = H,    N = H,   K = Be*T
+// All are computed as C[M,N] = alpha * sum_pairs A_i[M,K] . B_j[N,K]^T with both operands K-major
+// bf16.  fp32 accuracy comes from splitting an fp32 operand into up to three bf16 parts
+// (x = x0 + x1 + x2, 24 mantissa bits); a spike operand is exact in one part.  The products of
+// all requested (i, j) part pairs accumulate into ONE fp32 TMEM accumulator, so the split costs
+// tensor-pipe passes but no extra traffic on C.
+//
+// Kernel: one 128 x 256 output tile per CTA (cta_group::1, UMMA 128x256x16, full-rate shape),
+// 4-stage TMA -> shared (SWIZZLE_128B) ring, warp-specialised: warp 0 TMA producer, warp 1 MMA
+// issuer (one elected lane) + TMEM allocator, warps 2..5 epilogue (tcgen05.ld -> registers ->
+// global).  Split-K over blockIdx.z writes fp32 partial tiles that a small kernel reduces in a
+// fixed order (deterministic).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace sparch {
+
+constexpr int GM = 128, GN = 256, GK = 64, GSTAGES = 4;
+constexpr int G_A_BYTES = GM * GK * 2, G_B_BYTES = GN * GK * 2, G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
+constexpr int G_THREADS = 192;
+constexpr uint32_t G_TMEM_COLS = 256;
+constexpr size_t G_SMEM = (size_t)GSTAGES * G_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct TmapSet {
+  CUtensorMap a[3];
+  CUtensorMap b[3];
+};
+
+struct GemmParams {
+  int M, N, K;
+  int npairs;
+  int pair_a[8], pair_b[8];
+  int kblocks;         // ceil(K / 64)
+  int kb_per_split;    // k-blocks handled by one blockIdx.z
+  float* C;            // final output (splits == 1) or partial buffer [splits][M][ldc]
+  long long ldc;
+  long long split_stride;
+  float alpha;
+  const float* bias;   // per column n, may be NULL (applied only when splits == 1)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a lost arrival traps (context error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address
+  d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset
+  d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+
+// kind::f16, bf16 x bf16 -> fp32, both K-major, M = 128, N = 256
+constexpr uint32_t G_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
+  extern __shared__ unsigned char gsm_raw[];
+  const uint32_t raw = smem_u32(gsm_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024-byte alignment
+  unsigned char* gsm = gsm_raw + (base - raw);
+  const uint32_t bars = base + GSTAGES * G_STAGE_BYTES;         // full[4], empty[4], tmem_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gsm + GSTAGES * G_STAGE_BYTES + 128);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+  const int iters = p.npairs * (kb1 - kb0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < GSTAGES; ++s) {
+      mbar_init(bars + 8 * s, 1);
+      mbar_init(bars + 8 * (GSTAGES + s), 1);
+    }
+    mbar_init(bars + 8 * (2 * GSTAGES), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(G_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int pr = 0; pr < p.npairs; ++pr) {
+        const CUtensorMap* ma = &maps.a[p.pair_a[pr]];
+        const CUtensorMap* mb = &maps.b[p.pair_b[pr]];
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % GSTAGES;
+          const uint32_t ph = (it / GSTAGES) & 1;
+          mbar_wait(bars + 8 * (GSTAGES + s), ph ^ 1);
+          mbar_expect_tx(bars + 8 * s, G_STAGE_BYTES);
+          const uint32_t sa = base + s * G_STAGE_BYTES;
+          tma_load_2d(sa, ma, kb * GK, m0, bars + 8 * s);
+          tma_load_2d(sa + G_A_BYTES, mb, kb * GK, n0, bars + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % GSTAGES;
+        const uint32_t ph = (it / GSTAGES) & 1;
+        mbar_wait(bars + 8 * s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = base + s * G_STAGE_BYTES;
+        const uint64_t da = make_desc_k_sw128(sa), db = make_desc_k_sw128(sa + G_A_BYTES);
+#pragma unroll
+        for (int k = 0; k < GK / 16; ++k)  // 16 bf16 = 32 bytes = 2 descriptor units inside the swizzle atom
+          umma_f16(tmem, da + 2 * k, db + 2 * k, G_IDESC, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(bars + 8 * (GSTAGES + s));   // frees the smem stage when these MMAs retire
+      }
+      umma_commit(bars + 8 * (2 * GSTAGES));     // accumulator complete
+    }
+  } else {
+    // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    const int quarter = warp & 3;
+    const int row = m0 + quarter * 32 + lane;
+    mbar_wait(bars + 8 * (2 * GSTAGES), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* crow = p.C + (size_t)blockIdx.z * p.split_stride + (size_t)row * p.ldc;
+    const bool final_out = gridDim.z == 1;
+    const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    for (int c = 0; c < GN / 32; ++c) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+            "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+            "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+            "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int nb = n0 + c * 32;
+      if (row < p.M && nb < p.N) {
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          f[i] = __uint_as_float(v[i]);
+          if (final_out) {
+            f[i] *= p.alpha;
+            if (p.bias && nb + i < p.N) f[i] += p.bias[nb + i];
+          }
+        }
+        if (vec && nb + 32 <= p.N) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(crow + nb + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (nb + i < p.N) crow[nb + i] = f[i];
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(G_TMEM_COLS) : "memory");
+  }
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, long long split_stride, int M,
+                                     int N, long long ldc_part, float* __restrict__ C, long long ldc, float alpha,
+                                     const float* __restrict__ bias) {
+  long long n = (long long)M * N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int r = (int)(i / N), c = (int)(i % N);
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[z * split_stride + (long long)r * ldc_part + c];
+    s *= alpha;
+    if (bias) s += bias[c];
+    C[(long long)r * ldc + c] = s;
+  }
+}
+
+// ------------------------------------------------------------------ fp32 -> bf16 parts
+// parts[i][r][c] (row stride ldp, zero padded to ldp) = i-th bf16 term of X[r][c].
+__global__ void split_rows_kernel(const float* __restrict__ X, long long ldx, int M, int K, int nparts,
+                                  __nv_bfloat16* __restrict__ P0, __nv_bfloat16* __restrict__ P1,
+                                  __nv_bfloat16* __restrict__ P2, long long ldp) {
+  long long n = (long long)M * ldp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / ldp;
+    int c = (int)(i - r * ldp);
+    float x = c < K ? X[r * ldx + c] : 0.f;
+    __nv_bfloat16 h0 = __float2bfloat16_rn(x);
+    P0[i] = h0;
+    if (nparts > 1) {
+      float r1 = x - __bfloat162float(h0);
+      __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+      P1[i] = h1;
+      if (nparts > 2) P2[i] = __float2bfloat16_rn(r1 - __bfloat162float(h1));
+    }
+  }
+}
+
+// Transposing split: X is (R rows, C cols) fp32 row-major; parts are (C, ldp >= R) bf16 row-major,
+// i.e. parts[i][c][r] = term_i(X[r][c]).  With T > 0 the rows are (b, t) pairs and `shift` delays
+// time: output column (b, t) takes X[b, t - shift, :], zero for t < shift (S_prev for dV).
+__global__ void split_transpose_kernel(const float* __restrict__ X, int R, int C, int nparts, int T, int shift,
+                                       __nv_bfloat16* __restrict__ P0, __nv_bfloat16* __restrict__ P1,
+                                       __nv_bfloat16* __restrict__ P2, long long ldp) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int r = r0 + j, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < R && c < C) {
+      long long src = r;
+      bool ok = true;
+      if (T > 0 && shift > 0) {
+        int t = r % T;
+        ok = t >= shift;
+        src = r - shift;
+      }
+      if (ok) v = X[src * (long long)C + c];
+    }
+    tile[j][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int c = c0 + j, r = r0 + threadIdx.x;
+    if (c < C && r < ldp) {
+      float x = r < R ? tile[threadIdx.x][j] : 0.f;
+      long long o = (long long)c * ldp + r;
+      __nv_bfloat16 h0 = __float2bfloat16_rn(x);
+      P0[o] = h0;
+      if (nparts > 1) {
+        float r1 = x - __bfloat162float(h0);
+        __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+        P1[o] = h1;
+        if (nparts > 2) P2[o] = __float2bfloat16_rn(r1 - __bfloat162float(h1));
+      }
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+
+// bf16 matrix (rows, cols) row-major with row stride ld elements; box = (64 cols, box_rows rows), 128B swizzle.
+static int make_map(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return SPARCH_ERR_DEVICE;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)GK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld);
+    return SPARCH_ERR_CUDA;
+  }
+  return SPARCH_OK;
+}
+
+}  // namespace sparch
+
+using namespace sparch;
+
+extern "C" {
+
+int sparch_split_bf16(const float* X, int64_t ldx, int M, int K, int nparts, void* P0, void* P1, void* P2,
+                      int64_t ldp, sparch_stream_t st) {
+  SPARCH_REQUIRE(M >= 0 && K > 0 && nparts >= 1 && nparts <= 3 && ldp >= K && ldx >= K, "bad shape");
+  SPARCH_REQUIRE(P0 && (nparts < 2 || P1) && (nparts < 3 || P2), "null part pointer");
+  if (M == 0) return SPARCH_OK;
+  SPARCH_REQUIRE(X, "null pointer");
+  int64_t n = (int64_t)M * ldp;
+  int64_t g = (n + 255) / 256, cap = (int64_t)sm_count() * 16;
+  split_rows_kernel<<<(unsigned)(g < cap ? g : cap), 256, 0, as_stream(st)>>>(
+      X, ldx, M, K, nparts, (__nv_bfloat16*)P0, (__nv_bfloat16*)P1, (__nv_bfloat16*)P2, ldp);
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+int sparch_split_bf16_transpose(const float* X, int R, int C, int nparts, int T, int shift, void* P0, void* P1,
+                                void* P2, int64_t ldp, sparch_stream_t st) {
+  SPARCH_REQUIRE(R >= 0 && C > 0 && nparts >= 1 && nparts <= 3 && ldp >= R && shift >= 0, "bad shape");
+  SPARCH_REQUIRE(P0 && (nparts < 2 || P1) && (nparts < 3 || P2), "null part pointer");
+  if (ldp == 0) return SPARCH_OK;
+  SPARCH_REQUIRE(X || R == 0, "null pointer");
+  dim3 grid((C + 31) / 32, (unsigned)((ldp + 31) / 32)), block(32, 8);
+  split_transpose_kernel<<<grid, block, 0, as_stream(st)>>>(X, R, C, nparts, T, shift, (__nv_bfloat16*)P0,
+                                                            (__nv_bfloat16*)P1, (__nv_bfloat16*)P2, ldp);
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+size_t sparch_gemm_workspace(int M, int N, int K) {
+  // room for up to 8 fp32 split-K partial tiles sets
+  return (size_t)8 * M * (((size_t)N + 3) / 4 * 4) * sizeof(float);
+}
+
+int sparch_gemm_bf16(const void* const* A_parts, int na, const void* const* B_parts, int nb, int64_t lda,
+                     int64_t ldb, const int* pair_a, const int* pair_b, int npairs, int M, int N, int K, float alpha,
+                     const float* bias, float* C, int64_t ldc, void* workspace, sparch_stream_t st_) {
+  SPARCH_REQUIRE(M > 0 && N > 0 && K > 0 && na >= 1 && na <= 3 && nb >= 1 && nb <= 3, "bad shape");
+  SPARCH_REQUIRE(npairs >= 1 && npairs <= 8 && A_parts && B_parts && pair_a && pair_b && C, "bad argument");
+  SPARCH_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0 && lda >= K && ldb >= K,
+                 "operand row strides must be multiples of 8 bf16 elements (16 bytes) and >= K");
+  cudaStream_t st = as_stream(st_);
+  TmapSet maps;
+  memset(&maps, 0, sizeof maps);
+  for (int i = 0; i < na; ++i) {
+    SPARCH_REQUIRE(A_parts[i] && (reinterpret_cast<uintptr_t>(A_parts[i]) & 15) == 0, "A part null or unaligned");
+    if (int e = make_map(&maps.a[i], A_parts[i], M, K, lda, GM)) return e;
+  }
+  for (int i = 0; i < nb; ++i) {
+    SPARCH_REQUIRE(B_parts[i] && (reinterpret_cast<uintptr_t>(B_parts[i]) & 15) == 0, "B part null or unaligned");
+    if (int e = make_map(&maps.b[i], B_parts[i], N, K, ldb, GN)) return e;
+  }
+  GemmParams p;
+  memset(&p, 0, sizeof p);
+  p.M = M; p.N = N; p.K = K; p.npairs = npairs;
+  for (int i = 0; i < npairs; ++i) {
+    SPARCH_REQUIRE(pair_a[i] >= 0 && pair_a[i] < na && pair_b[i] >= 0 && pair_b[i] < nb, "pair index out of range");
+    p.pair_a[i] = pair_a[i];
+    p.pair_b[i] = pair_b[i];
+  }
+  p.kblocks = (K + GK - 1) / GK;
+  const int tiles = ((M + GM - 1) / GM) * ((N + GN - 1) / GN);
+  int splits = 1;
+  if (workspace && tiles < sm_count()) {
+    splits = sm_count() / tiles;
+    if (splits > 8) splits = 8;
+    if (splits > p.kblocks) splits = p.kblocks;
+    if (splits < 1) splits = 1;
+  }
+  p.kb_per_split = (p.kblocks + splits - 1) / splits;
+  splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;
+  const long long ldw = ((long long)N + 3) / 4 * 4;
+  if (splits > 1) {
+    p.C = reinterpret_cast<float*>(workspace);
+    p.ldc = ldw;
+    p.split_stride = (long long)M * ldw;
+    p.alpha = 1.f;
+    p.bias = nullptr;
+  } else {
+    p.C = C; p.ldc = ldc; p.split_stride = 0; p.alpha = alpha; p.bias = bias;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    SPARCH_CUDA(cudaFuncSetAttribute(gemm_tn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
+    attr_set = true;
+  }
+  dim3 grid((N + GN - 1) / GN, (M + GM - 1) / GM, splits);
+  gemm_tn_bf16_kernel<<<grid, G_THREADS, G_SMEM, st>>>(maps, p);
+  SPARCH_LAUNCH_OK();
+  if (splits > 1) {
+    long long n = (long long)M * N;
+    long long g = (n + 255) / 256, cap = (long long)sm_count() * 8;
+    splitk_reduce_kernel<<<(unsigned)(g < cap ? g : cap), 256, 0, st>>>(reinterpret_cast<float*>(workspace), splits,
+                                                                        p.split_stride, M, N, ldw, C, ldc, alpha, bias);
+    SPARCH_LAUNCH_OK();
+  }
+  return SPARCH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,61 @@
+"""GPU tests of the tcgen05 GEMM and the bf16 term splitting against fp64 matmul."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ref(A, B):
+    return A.double() @ B.double().t()
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 1024, 40), (256, 35, 1024), (1000, 520, 700),
+                                   (1024, 1024, 5000), (128, 256, 64), (130, 257, 72), (35, 1024, 3000),
+                                   (4096, 1024, 1024)])
+def test_gemm_fp32_accuracy(M, N, K):
+    from sparch_b200 import gemm
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    A = torch.randn(M, K, device=DEV, generator=g) * 3
+    B = torch.randn(N, K, device=DEV, generator=g)
+    bias = torch.randn(N, device=DEV, generator=g)
+    C = gemm.gemm_parts(gemm.split_rows(A, 3), gemm.split_rows(B, 3), K, alpha=0.5, bias=bias)
+    ref = 0.5 * _ref(A, B) + bias.double()
+    err = float((C.double() - ref).abs().max() / ref.abs().max())
+    assert err < 2e-6, err
+    # binary A (spikes): one term is exact
+    S = (torch.rand(M, K, device=DEV, generator=g) < 0.1).float()
+    C = gemm.gemm_parts(gemm.split_rows(S, 1), gemm.split_rows(B, 3), K)
+    ref = _ref(S, B)
+    err = float((C.double() - ref).abs().max() / ref.abs().max())
+    assert err < 2e-6, err
+
+
+def test_split_terms_reconstruct():
+    from sparch_b200 import gemm
+    x = torch.randn(77, 53, device=DEV) * 100
+    x[0, 0] = 0.0
+    x[1, 1] = 1e-30
+    p = gemm.split_rows(x, 3)
+    assert p.shape == (3, 77, 56) and float(p[:, :, 53:].abs().max()) == 0
+    rec = p[0].double() + p[1].double() + p[2].double()
+    assert float((rec[:, :53] - x.double()).abs().max() / 100) < 1e-7
+    pt = gemm.split_transposed(x, 3)
+    assert pt.shape == (3, 53, 80)
+    rect = (pt[0].double() + pt[1].double() + pt[2].double())[:, :77]
+    assert torch.equal(rect, rec[:, :53].t())
+
+
+def test_transposed_gemm_with_time_shift():
+    """dV-style product: S_prev^T @ dI with the spike rows delayed by one step inside each batch."""
+    from sparch_b200 import gemm
+    Be, T, H = 6, 9, 96
+    g = torch.Generator(device=DEV).manual_seed(3)
+    S = (torch.rand(Be, T, H, device=DEV, generator=g) < 0.2).float()
+    dI = torch.randn(Be, T, H, device=DEV, generator=g)
+    Sp = gemm.split_transposed(S.view(Be * T, H), 1, T=T, shift=1)
+    dIt = gemm.split_transposed(dI.view(Be * T, H), 3)
+    dV = gemm.gemm_parts(Sp, dIt, Be * T)
+    ref = torch.einsum("bti,btj->ij", S[:, :-1].double(), dI[:, 1:].double())
+    err = float((dV.double() - ref).abs().max() / ref.abs().max())
+    assert err < 2e-6, err
