@@ -114,16 +114,19 @@ SPARCH_API int sparch_cell_step_bwd(int kind, int t, const float* G, const float
                          sparch_stream_t st);
 
 /* ---- time-parallel GEMMs on tcgen05/TMEM/TMA (snns.py:675 and its autograd) -------------- */
-/* Split an fp32 matrix X (M, K; row stride ldx) into nparts (1..3) bf16 terms, x = p0+p1+p2,
- * written row-major with row stride ldp (zero padded; ldp % 8 == 0 for the GEMM).           */
-SPARCH_API int sparch_split_bf16(const float* X, int64_t ldx, int M, int K, int nparts, void* P0,
-                                 void* P1, void* P2, int64_t ldp, sparch_stream_t st);
+/* Split an fp32 matrix X (M, K; row stride ldx) into nparts (1..3) bf16 terms,
+ * prescale*x = p0+p1+p2, written row-major with row stride ldp (zero padded; ldp % 8 == 0 for
+ * the GEMM).  prescale = (1-p) with nparts = 1 turns dropout-scaled spikes {0, 1/(1-p)} into
+ * the exact bf16 values {0, 1} (the factor goes into the GEMM's alpha).                     */
+SPARCH_API int sparch_split_bf16(const float* X, int64_t ldx, int M, int K, int nparts,
+                                 float prescale, void* P0, void* P1, void* P2, int64_t ldp,
+                                 sparch_stream_t st);
 /* Transposing split: X (R, C) contiguous -> parts (C, ldp >= R): part[c][r] = term(X[r][c]).
  * With T > 0 and shift > 0 rows are (b, t) and output column (b, t) takes X[b, t-shift, :],
  * zero for t < shift (the S_prev operand of dV, autograd of snns.py:720).                    */
 SPARCH_API int sparch_split_bf16_transpose(const float* X, int R, int C, int nparts, int T,
-                                           int shift, void* P0, void* P1, void* P2, int64_t ldp,
-                                           sparch_stream_t st);
+                                           int shift, float prescale, void* P0, void* P1,
+                                           void* P2, int64_t ldp, sparch_stream_t st);
 /* C[M,N] (fp32, row stride ldc) = alpha * sum_p A[pair_a[p]] . B[pair_b[p]]^T (+ bias[n]);
  * A parts are (M, K) and B parts (N, K) bf16 row-major with row strides lda / ldb (multiples of
  * 8).  `workspace` (sparch_gemm_workspace bytes, may be NULL) enables deterministic split-K

@@ -25,8 +25,8 @@ _PROTOS = {
     "sparch_cell_step_fwd": "ii" + "p" * 11 + "f" + "ppp" + "iii" + "p",
     "sparch_cell_bwd": "i" + "p" * 10 + "f" + "p" * 5 + "iii" + "p",
     "sparch_cell_step_bwd": "ii" + "p" * 11 + "f" + "p" * 7 + "iii" + "p",
-    "sparch_split_bf16": "pliiippplp",
-    "sparch_split_bf16_transpose": "piiiiippplp",
+    "sparch_split_bf16": "pliiifppplp",
+    "sparch_split_bf16_transpose": "piiiiifppplp",
     "sparch_gemm_workspace": "iii",
     "sparch_gemm_bf16": "pipillppiiiifppl" + "pp",
     "sparch_recur_padded": "i",

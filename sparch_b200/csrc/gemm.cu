@@ -236,14 +236,14 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
 
 // ------------------------------------------------------------------ fp32 -> bf16 parts
 // parts[i][r][c] (row stride ldp, zero padded to ldp) = i-th bf16 term of X[r][c].
-__global__ void split_rows_kernel(const float* __restrict__ X, long long ldx, int M, int K, int nparts,
+__global__ void split_rows_kernel(const float* __restrict__ X, long long ldx, int M, int K, int nparts, float prescale,
                                   __nv_bfloat16* __restrict__ P0, __nv_bfloat16* __restrict__ P1,
                                   __nv_bfloat16* __restrict__ P2, long long ldp) {
   long long n = (long long)M * ldp;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     long long r = i / ldp;
     int c = (int)(i - r * ldp);
-    float x = c < K ? X[r * ldx + c] : 0.f;
+    float x = c < K ? X[r * ldx + c] * prescale : 0.f;
     __nv_bfloat16 h0 = __float2bfloat16_rn(x);
     P0[i] = h0;
     if (nparts > 1) {
@@ -258,7 +258,7 @@ __global__ void split_rows_kernel(const float* __restrict__ X, long long ldx, in
 // Transposing split: X is (R rows, C cols) fp32 row-major; parts are (C, ldp >= R) bf16 row-major,
 // i.e. parts[i][c][r] = term_i(X[r][c]).  With T > 0 the rows are (b, t) pairs and `shift` delays
 // time: output column (b, t) takes X[b, t - shift, :], zero for t < shift (S_prev for dV).
-__global__ void split_transpose_kernel(const float* __restrict__ X, int R, int C, int nparts, int T, int shift,
+__global__ void split_transpose_kernel(const float* __restrict__ X, int R, int C, int nparts, int T, int shift, float prescale,
                                        __nv_bfloat16* __restrict__ P0, __nv_bfloat16* __restrict__ P1,
                                        __nv_bfloat16* __restrict__ P2, long long ldp) {
   __shared__ float tile[32][33];
@@ -274,7 +274,7 @@ __global__ void split_transpose_kernel(const float* __restrict__ X, int R, int C
         ok = t >= shift;
         src = r - shift;
       }
-      if (ok) v = X[src * (long long)C + c];
+      if (ok) v = X[src * (long long)C + c] * prescale;
     }
     tile[j][threadIdx.x] = v;
   }
@@ -339,8 +339,8 @@ using namespace sparch;
 
 extern "C" {
 
-int sparch_split_bf16(const float* X, int64_t ldx, int M, int K, int nparts, void* P0, void* P1, void* P2,
-                      int64_t ldp, sparch_stream_t st) {
+int sparch_split_bf16(const float* X, int64_t ldx, int M, int K, int nparts, float prescale, void* P0, void* P1,
+                      void* P2, int64_t ldp, sparch_stream_t st) {
   SPARCH_REQUIRE(M >= 0 && K > 0 && nparts >= 1 && nparts <= 3 && ldp >= K && ldx >= K, "bad shape");
   SPARCH_REQUIRE(P0 && (nparts < 2 || P1) && (nparts < 3 || P2), "null part pointer");
   if (M == 0) return SPARCH_OK;
@@ -348,19 +348,19 @@ int sparch_split_bf16(const float* X, int64_t ldx, int M, int K, int nparts, voi
   int64_t n = (int64_t)M * ldp;
   int64_t g = (n + 255) / 256, cap = (int64_t)sm_count() * 16;
   split_rows_kernel<<<(unsigned)(g < cap ? g : cap), 256, 0, as_stream(st)>>>(
-      X, ldx, M, K, nparts, (__nv_bfloat16*)P0, (__nv_bfloat16*)P1, (__nv_bfloat16*)P2, ldp);
+      X, ldx, M, K, nparts, prescale, (__nv_bfloat16*)P0, (__nv_bfloat16*)P1, (__nv_bfloat16*)P2, ldp);
   SPARCH_LAUNCH_OK();
   return SPARCH_OK;
 }
 
-int sparch_split_bf16_transpose(const float* X, int R, int C, int nparts, int T, int shift, void* P0, void* P1,
-                                void* P2, int64_t ldp, sparch_stream_t st) {
+int sparch_split_bf16_transpose(const float* X, int R, int C, int nparts, int T, int shift, float prescale,
+                                void* P0, void* P1, void* P2, int64_t ldp, sparch_stream_t st) {
   SPARCH_REQUIRE(R >= 0 && C > 0 && nparts >= 1 && nparts <= 3 && ldp >= R && shift >= 0, "bad shape");
   SPARCH_REQUIRE(P0 && (nparts < 2 || P1) && (nparts < 3 || P2), "null part pointer");
   if (ldp == 0) return SPARCH_OK;
   SPARCH_REQUIRE(X || R == 0, "null pointer");
   dim3 grid((C + 31) / 32, (unsigned)((ldp + 31) / 32)), block(32, 8);
-  split_transpose_kernel<<<grid, block, 0, as_stream(st)>>>(X, R, C, nparts, T, shift, (__nv_bfloat16*)P0,
+  split_transpose_kernel<<<grid, block, 0, as_stream(st)>>>(X, R, C, nparts, T, shift, prescale, (__nv_bfloat16*)P0,
                                                             (__nv_bfloat16*)P1, (__nv_bfloat16*)P2, ldp);
   SPARCH_LAUNCH_OK();
   return SPARCH_OK;

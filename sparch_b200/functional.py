@@ -9,7 +9,7 @@ import math
 
 import torch
 
-from . import _lib
+from . import _lib, gemm
 from ._lib import call, ptr
 
 KINDS = {"LIF": 0, "adLIF": 1, "RLIF": 2, "RadLIF": 3}
@@ -38,6 +38,7 @@ def timers_enable(flag):
 class _region:
     def __init__(self, name):
         self.name = name
+        self.e0 = self.e1 = None
 
     def __enter__(self):
         if _TIMERS["on"]:
@@ -102,6 +103,58 @@ class SpikeFunctionBoxcar(torch.autograd.Function):
         gx = torch.empty_like(x)
         call("sparch_boxcar_bwd", ptr(x), ptr(g), ptr(gx), x.numel(), _stream())
         return gx
+
+
+class LinearFunction(torch.autograd.Function):
+    """Time-parallel projection ``x @ W^T + b`` over all Be*T frames (snns.py:675) and its
+    autograd, on the tcgen05 GEMM.  ``in_scale``: None for a general fp32 input (three bf16
+    terms); a float c when every input value is exactly 0 or c (spikes, c = 1/(1-p) after
+    dropout) so that one exact bf16 term {0,1} suffices and c moves into the epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, in_scale):
+        _require_cuda(x, weight)
+        K = x.shape[-1]
+        N = weight.shape[0]
+        x2d = _f32c(x).reshape(-1, K)
+        M = x2d.shape[0]
+        with torch.no_grad():
+            with _region("gemm_fwd"):
+                if in_scale is None:
+                    xa, alpha = gemm.split_rows(x2d, 3), 1.0
+                else:
+                    xa, alpha = gemm.split_rows(x2d, 1, prescale=1.0 / in_scale), float(in_scale)
+                wb = gemm.split_rows(_f32c(weight), 3)
+                Z = gemm.gemm_parts(xa, wb, K, alpha=alpha, bias=None if bias is None else _f32c(bias))
+        ctx.in_scale = in_scale
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x2d, weight)
+        ctx.xshape = x.shape
+        return Z.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, gZ):
+        x2d, weight = ctx.saved_tensors
+        M, K = x2d.shape
+        N = weight.shape[0]
+        g2d = _f32c(gZ).reshape(M, N)
+        dx = dw = db = None
+        with _region("gemm_bwd"):
+            if ctx.needs_input_grad[0]:
+                # dX = dZ @ W : contraction over N, B operand = W^T terms (K, N)
+                dx = gemm.gemm_parts(gemm.split_rows(g2d, 3), gemm.split_transposed(_f32c(weight), 3), N)
+                dx = dx.view(ctx.xshape)
+            if ctx.needs_input_grad[1]:
+                # dW = dZ^T @ X : contraction over the Be*T frames
+                gt = gemm.split_transposed(g2d, 3)
+                if ctx.in_scale is None:
+                    xt, alpha = gemm.split_transposed(x2d, 3), 1.0
+                else:
+                    xt, alpha = gemm.split_transposed(x2d, 1, prescale=1.0 / ctx.in_scale), float(ctx.in_scale)
+                dw = gemm.gemm_parts(gt, xt, M, alpha=alpha)
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                db = g2d.sum(dim=0)
+        return dx, dw, db, None
 
 
 class NormState:
@@ -248,10 +301,13 @@ class SpikingCellFunction(torch.autograd.Function):
                  ptr(carry[1]) if adaptive else None, pp[0], pp[1], pp[2], pp[3], ptr(ws), Be, T, H, st)
             region.__exit__()
             # dV = sum_t s_{t-1}^T dI_t, diagonal masked (clone().fill_diagonal_(0) backward)
-            dV = s0.t() @ dI[:, 0, :]
-            if T > 1:
-                dV += torch.einsum("bti,btj->ij", S[:, :-1, :], dI[:, 1:, :])
-            dV.fill_diagonal_(0)
+            with _region("gemm_bwd"):
+                dV = s0.t() @ dI[:, 0, :]              # t = 0: s_{-1} is real-valued
+                if T > 1:
+                    sp = gemm.split_transposed(S.view(Be * T, H), 1, T=T, shift=1)
+                    dit = gemm.split_transposed(dI.view(Be * T, H), 3)
+                    dV += gemm.gemm_parts(sp, dit, Be * T)
+                dV.fill_diagonal_(0)
         psum = part.sum(dim=1)
         dalpha = psum[0] * _clamp_mask(alpha, ALPHA_LIM)
         dbeta = da = db = None

@@ -31,18 +31,18 @@ def _pad8(n):
     return (n + 7) // 8 * 8
 
 
-def split_rows(x2d, nparts):
+def split_rows(x2d, nparts, prescale=1.0):
     """(M, K) fp32 -> nparts bf16 tensors (M, ld) with ld = K rounded up to 8 (zero padded)."""
     x2d = x2d.contiguous() if x2d.stride(-1) != 1 else x2d
     M, K = x2d.shape
     ld = _pad8(K)
     parts = torch.empty(nparts, M, ld, device=x2d.device, dtype=torch.bfloat16)
     p = [ptr(parts[i]) if i < nparts else None for i in range(3)]
-    call("sparch_split_bf16", ptr(x2d), x2d.stride(0), M, K, nparts, p[0], p[1], p[2], ld, _stream())
+    call("sparch_split_bf16", ptr(x2d), x2d.stride(0), M, K, nparts, float(prescale), p[0], p[1], p[2], ld, _stream())
     return parts
 
 
-def split_transposed(x2d, nparts, T=0, shift=0):
+def split_transposed(x2d, nparts, T=0, shift=0, prescale=1.0):
     """(R, C) fp32 contiguous -> nparts bf16 tensors (C, ld >= R): the transposed terms.  T/shift
     delay the time index of rows laid out as (b, t) (zero-filled), see the C header."""
     x2d = x2d.contiguous()
@@ -50,7 +50,7 @@ def split_transposed(x2d, nparts, T=0, shift=0):
     ld = _pad8(R)
     parts = torch.empty(nparts, C, ld, device=x2d.device, dtype=torch.bfloat16)
     p = [ptr(parts[i]) if i < nparts else None for i in range(3)]
-    call("sparch_split_bf16_transpose", ptr(x2d), R, C, nparts, T, shift, p[0], p[1], p[2], ld,
+    call("sparch_split_bf16_transpose", ptr(x2d), R, C, nparts, T, shift, float(prescale), p[0], p[1], p[2], ld,
          _stream())
     return parts
 

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .functional import (NormState, ReadoutCellFunction, SpikeFunctionBoxcar,
+from .functional import (LinearFunction, NormState, ReadoutCellFunction, SpikeFunctionBoxcar,
                          SpikingCellFunction)
 
 __all__ = ["SpikeFunctionBoxcar", "SNN", "LIFLayer", "adLIFLayer", "RLIFLayer", "RadLIFLayer",
@@ -94,14 +94,16 @@ class _SpikingLayerBase(nn.Module):
             self.normalize = True
         self.drop = nn.Dropout(p=dropout)
 
-    def forward(self, x):
+    def forward(self, x, in_scale=None):
+        """``in_scale``: None for a general input; c when every input value is exactly 0 or c
+        (the previous spiking layer's output), which lets the projection use one exact bf16 term."""
         if not x.is_cuda:
             raise RuntimeError("sparch_b200 layers run on CUDA only (no CPU fallback)")
         if self.bidirectional:                                   # snns.py:666-668
             x = torch.cat([x, x.flip(1)], dim=0)
         if self.batch_size != x.shape[0]:                        # snns.py:671-672
             self.batch_size = x.shape[0]
-        Wx = self.W(x)                                           # snns.py:675
+        Wx = LinearFunction.apply(x, self.W.weight, self.W.bias, in_scale)   # snns.py:675
         gamma, bn_beta, norm = _norm_args(self)
         if norm is None:                                         # layernorm, snns.py:678-680
             Wx = self.norm(Wx)
@@ -188,10 +190,10 @@ class ReadoutLayer(nn.Module):
             self.normalize = True
         self.drop = nn.Dropout(p=dropout)  # constructed but never applied, as in the reference
 
-    def forward(self, x):
+    def forward(self, x, in_scale=None):
         if not x.is_cuda:
             raise RuntimeError("sparch_b200 layers run on CUDA only (no CPU fallback)")
-        Wx = self.W(x)                                           # snns.py:796
+        Wx = LinearFunction.apply(x, self.W.weight, self.W.bias, in_scale)   # snns.py:796
         gamma, bn_beta, norm = _norm_args(self)
         if norm is None:
             Wx = self.norm(Wx)
@@ -259,9 +261,13 @@ class SNN(nn.Module):
             else:
                 raise NotImplementedError
         all_spikes = []
+        in_scale = None          # the network input is a general fp32 tensor
         for i, snn_lay in enumerate(self.snn):
-            x = snn_lay(x)
+            x = snn_lay(x, in_scale=in_scale)
             if not (self.use_readout_layer and i == self.num_layers - 1):
                 all_spikes.append(x)
+                # a spiking layer emits exactly {0, 1/(1-p)} in training and {0, 1} otherwise
+                p = snn_lay.drop.p
+                in_scale = 1.0 / (1.0 - p) if (snn_lay.drop.training and 0.0 < p < 1.0) else 1.0
         firing_rates = torch.cat(all_spikes, dim=2).mean(dim=(0, 1))   # snns.py:174
         return x, firing_rates
