@@ -178,6 +178,7 @@ def run_ours(args, cfg, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = cfg["B"]
+    sparch_b200.set_state_init(args.state_init)
     torch.manual_seed(0)
     net = sparch_b200.SNN((B, None, cfg["F"]), **model_kwargs(cfg)).to(dev)
     net.train()
@@ -295,6 +296,9 @@ def run_ours(args, cfg, rank, local_rank, world):
         "data": "synthetic",
         "config": {"workload": cfg["desc"], "bench_config": args.config, "per_gpu_batch": B,
                    "global_batch": B * world, "parallelism": f"dp{world}",
+                   "state_init": args.state_init + (" generator draws of u0/w0/s0 ~ U[0,1) (same distribution "
+                                                    "as the reference's CPU draws)" if args.state_init == "device"
+                                                    else " generator draws, identical to the reference's"),
                    "l2": "per-step working set (>=1 GB of activations/tapes) exceeds the 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "samples/s",
                 "h2d_bytes_per_step": x_h.numel() * 4 + y_h.numel() * 8, "d2h_bytes_per_step": 4,
@@ -314,6 +318,9 @@ def main():
     ap.add_argument("--config", default="cfg4", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--state-init", default="device", choices=["device", "cpu"],
+                    help="where the per-forward initial states ~U[0,1) are drawn: 'device' (CUDA generator) "
+                         "or 'cpu' (the reference's CPU-generator draws, snns.py:700-702; host-bound)")
     ap.add_argument("--profile", action="store_true",
                     help="profiling run (under ncu): exactly --warmup warm-up and --steps timed steps of "
                          "the device-resident loop, no e2e leg, no CPU baseline; prints no bench value")

@@ -146,28 +146,31 @@ SPARCH_API int sparch_recur_padded(int H);
  * words; meta is 2 ints (meta[0] = E with max|V0| < 2^E).                                    */
 SPARCH_API int sparch_recur_prepare(const float* V, int H, uint32_t* img_fwd, uint32_t* img_bwd,
                                     int* meta, sparch_stream_t st);
-/* All T steps of an RLIF/RadLIF layer.  rec0 (Be,H) = s0 @ V0 (s0 is real-valued, snns.py:702);
- * later steps take s_{t-1} from the packed spike planes `bits` [T][Be][Hp/32] this call writes.
- * Also writes the fp32 tapes S, U (and W for RadLIF).                                        */
+/* All T steps of an RLIF/RadLIF layer in ONE persistent cooperative kernel per <= 148-CTA batch
+ * chunk: V0 slices stay in shared memory, neuron state in registers; each step's spike words
+ * cross CTAs through L2 as tagged 64-bit words.  rec0 (Be,H) = s0 @ V0 (s0 is real-valued,
+ * snns.py:702).  Writes the fp32 tapes S, U (and W for RadLIF) and `bits`, the packed spike
+ * planes [T][Be][Hp/32] of 8-byte words {32 spikes, t+1} (2 * T*Be*Hp/32 uint32).               */
 SPARCH_API int sparch_recur_fwd(int kind, const float* Z, const float* scale, const float* shift,
                                 const float* alpha, const float* beta, const float* a,
                                 const float* b, const float* rec0, const uint32_t* img_fwd,
                                 const int* meta, const float* u0, const float* w0,
                                 const float* s0, float theta, float* S, float* U, float* W,
                                 uint32_t* bits, int Be, int T, int H, sparch_stream_t st);
-
-/* Reverse pass of an RLIF/RadLIF layer, all T steps: dI (Be,T,H) and the per-(b,h) partial
- * parameter gradients (as sparch_cell_step_bwd: du_next/dw_next/p_* are (Be,H), zeroed by the
- * caller).  img_bwd from sparch_recur_prepare; workspace of sparch_recur_bwd_workspace() bytes
- * holds the block-floating-point dI panels exchanged between consecutive steps.              */
+/* Reverse pass of an RLIF/RadLIF layer, all T steps in one persistent cooperative kernel: dI
+ * (Be,T,H) and the per-(b,h) partial parameter gradients p_* (Be,H).  img_bwd from
+ * sparch_recur_prepare; workspace of sparch_recur_bwd_workspace() bytes holds the
+ * block-floating-point dI panels handed from step to step; sync_ws is
+ * sparch_recur_sync_words() ints (one arrival counter per 64-row group, zeroed here).          */
+SPARCH_API int sparch_recur_sync_words(int Be);
 SPARCH_API size_t sparch_recur_bwd_workspace(int Be, int H);
 SPARCH_API int sparch_recur_bwd(int kind, const float* G, const float* U, const float* W,
                                 const float* alpha, const float* beta, const float* a,
                                 const float* b, const uint32_t* img_bwd, const int* meta,
                                 const float* u0, const float* w0, const float* s0, float theta,
-                                float* dI, float* du_next, float* dw_next, float* p_alpha,
-                                float* p_beta, float* p_a, float* p_b, void* workspace, int Be,
-                                int T, int H, sparch_stream_t st);
+                                float* dI, float* p_alpha, float* p_beta, float* p_a,
+                                float* p_b, void* workspace, int* sync_ws, int Be, int T, int H,
+                                sparch_stream_t st);
 
 /* ---- ReadoutLayer cell (snns.py:807-825) ---------------------------------------------- */
 /* u_t = alpha*u_{t-1} + (1-alpha)*I_t ; out = sum_t softmax(u_t, dim=1).  U (B,T,C) tape.  */

@@ -6,8 +6,8 @@
 not load the native library; the first kernel call does, and fails loudly if it is absent.
 """
 from .snns import (SNN, LIFLayer, RadLIFLayer, ReadoutLayer, RLIFLayer, SpikeFunctionBoxcar,
-                   adLIFLayer)
+                   adLIFLayer, set_state_init)
 
 __all__ = ["SNN", "LIFLayer", "adLIFLayer", "RLIFLayer", "RadLIFLayer", "ReadoutLayer",
-           "SpikeFunctionBoxcar"]
+           "SpikeFunctionBoxcar", "set_state_init"]
 __version__ = "0.1.0"

@@ -92,7 +92,7 @@ struct RecFwdArgs {
   const int* meta;
   float theta;
   float *S, *U, *W;
-  uint32_t* bits;  // [T][Be][Hp/32]
+  uint2* bits;     // [T][Be][Hp/32] {32 spikes, step tag t+1}: tagged 64-bit words (LL exchange)
   int Be, T, H, Hp;
 };
 
@@ -134,134 +134,6 @@ __device__ __forceinline__ void store8(float* __restrict__ p, const float (&v)[8
   }
 }
 
-template <bool ADAPT>
-__global__ void __launch_bounds__(256, 1) rec_fwd_step_kernel(const RecFwdArgs p, const int t) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int NW = p.Hp / 32;          // spike words per row
-  const int RSB = NW + 1;            // padded row stride of the spike-word tile
-  uint32_t* simg = reinterpret_cast<uint32_t*>(smem_raw);
-  float* red = reinterpret_cast<float*>(smem_raw + (size_t)p.Hp * 128);
-  uint32_t* sbits = reinterpret_cast<uint32_t*>(red + 4 * RB * RED_RS);
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int slice = blockIdx.x, row0 = blockIdx.y * RB;
-  const int kq = warp >> 1, nh = warp & 1, g = lane >> 2, q = lane & 3;
-
-  if (t > 0) {
-    const uint4* src = reinterpret_cast<const uint4*>(p.img + (size_t)slice * p.Hp * 32);
-    uint4* dst = reinterpret_cast<uint4*>(simg);
-    for (int i = tid; i < p.Hp * 8; i += 256) cp_async16(dst + i, src + i);
-    const uint32_t* bsrc = p.bits + (size_t)(t - 1) * p.Be * NW;
-    for (int i = tid; i < RB * NW; i += 256) {
-      int r = i / NW, wi = i - r * NW;
-      int row = row0 + r;
-      sbits[r * RSB + wi] = row < p.Be ? bsrc[(size_t)row * NW + wi] : 0u;
-    }
-    cp_async_wait_all();
-    __syncthreads();
-
-    float acc[4][2][4];
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
-
-    const uint4* bimg = reinterpret_cast<const uint4*>(simg);
-    for (int wi = kq; wi < NW; wi += 4) {
-      uint32_t wa[4], wb[4];
-#pragma unroll
-      for (int mt = 0; mt < 4; ++mt) {
-        wa[mt] = __funnelshift_r(sbits[(16 * mt + g) * RSB + wi], sbits[(16 * mt + g) * RSB + wi], 4 * q);
-        wb[mt] = __funnelshift_r(sbits[(16 * mt + g + 8) * RSB + wi], sbits[(16 * mt + g + 8) * RSB + wi], 4 * q);
-      }
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        const int kk = 2 * wi + ks;
-        const uint4 f0 = bimg[((kk * 2 + nh) * 2 + 0) * 32 + lane];
-        const uint4 f1 = bimg[((kk * 2 + nh) * 2 + 1) * 32 + lane];
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
-          const uint32_t M = 0x40004000u;
-          uint32_t a0 = __funnelshift_r(wa[mt], wa[mt], 2 * ks) & M;
-          uint32_t a1 = __funnelshift_r(wb[mt], wb[mt], 2 * ks) & M;
-          uint32_t a2 = __funnelshift_r(wa[mt], wa[mt], 2 * ks + 1) & M;
-          uint32_t a3 = __funnelshift_r(wb[mt], wb[mt], 2 * ks + 1) & M;
-          mma16816(acc[mt][0], a0, a1, a2, a3, f0.x, f0.y);
-          mma16816(acc[mt][0], a0, a1, a2, a3, f0.z, f0.w);
-          mma16816(acc[mt][1], a0, a1, a2, a3, f1.x, f1.y);
-          mma16816(acc[mt][1], a0, a1, a2, a3, f1.z, f1.w);
-        }
-      }
-    }
-    float* myred = red + kq * RB * RED_RS;
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        int col = 16 * nh + 8 * nt + 2 * q;
-        *reinterpret_cast<float2*>(&myred[(16 * mt + g) * RED_RS + col]) =
-            make_float2(acc[mt][nt][0], acc[mt][nt][1]);
-        *reinterpret_cast<float2*>(&myred[(16 * mt + g + 8) * RED_RS + col]) =
-            make_float2(acc[mt][nt][2], acc[mt][nt][3]);
-      }
-    __syncthreads();
-  }
-
-  // ---- neuron update for 8 consecutive neurons of one row per thread
-  const int r = tid >> 2, cg = tid & 3;
-  const int row = row0 + r;
-  const int col0 = slice * RC + cg * 8;
-  uint32_t my = 0;
-  if (row < p.Be && col0 < p.H) {
-    const bool vec = ((p.H & 3) == 0) && (col0 + 8 <= p.H);
-    const int nv = min(8, p.H - col0);
-    const int64_t idx0 = (int64_t)row * p.H + col0;
-    const int64_t o0 = ((int64_t)row * p.T + t) * p.H + col0;
-    float z[8], u[8], w[8], s[8], rec[8];
-    load8(p.Z + o0, z, vec, nv);
-    if (t > 0) {
-      const float rs = ldexpf(1.0f, p.meta[0] - VSCALE_EXP);
-      const uint32_t prevw = sbits[r * RSB + slice] >> (cg * 8);
-      load8(p.U + o0 - p.H, u, vec, nv);
-      if (ADAPT) load8(p.W + o0 - p.H, w, vec, nv);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = cg * 8 + i;
-        rec[i] = ((red[(0 * RB + r) * RED_RS + c] + red[(1 * RB + r) * RED_RS + c]) +
-                  (red[(2 * RB + r) * RED_RS + c] + red[(3 * RB + r) * RED_RS + c])) * rs;
-        s[i] = (float)((prevw >> i) & 1u);
-      }
-    } else {
-      load8(p.rec0 + idx0, rec, vec, nv);
-      load8(p.u0 + idx0, u, vec, nv);
-      load8(p.s0 + idx0, s, vec, nv);
-      if (ADAPT) load8(p.w0 + idx0, w, vec, nv);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (i < nv) {
-        const int col = col0 + i;
-        const NeuronParams np = load_params<ADAPT>(p.alpha, p.beta, p.a, p.b, col);
-        float cur = z[i];
-        if (p.scale) cur = __fmaf_rn(cur, p.scale[col], p.shift[col]);
-        cur = __fadd_rn(cur, rec[i]);
-        float wi_ = ADAPT ? w[i] : 0.f;
-        step_fwd<ADAPT>(np, cur, p.theta, u[i], wi_, s[i]);
-        w[i] = wi_;
-        my |= (s[i] > 0.f ? 1u : 0u) << (cg * 8 + i);
-      }
-    }
-    store8(p.S + o0, s, vec, nv);
-    store8(p.U + o0, u, vec, nv);
-    if (ADAPT) store8(p.W + o0, w, vec, nv);
-  }
-  my |= __shfl_xor_sync(0xffffffffu, my, 1);
-  my |= __shfl_xor_sync(0xffffffffu, my, 2);
-  if (cg == 0 && row < p.Be) p.bits[((size_t)t * p.Be + row) * NW + slice] = my;
-}
-
 // ------------------------------------------------------------------ reverse step
 // recb[b, j] = sum_c dI_{t+1}[b, c] * V0[j, c] for the CTA's 32 presynaptic neurons j, then the
 // BPTT update of SURVEY.md 8a for its 64 x 32 block.  The A operand is real-valued here, so the
@@ -270,164 +142,364 @@ __global__ void __launch_bounds__(256, 1) rec_fwd_step_kernel(const RecFwdArgs p
 // largest |dI| into [8, 16), then hi = fp16(x), lo = fp16(x - hi) (22 mantissa bits inside the
 // chunk, full fp32 range across chunks), stored in mma A-fragment order so the consumer's loads
 // are linear 16-byte copies.  hi*Vhi + hi*Vlo + lo*Vhi are accumulated per chunk and folded into
-// the fp32 accumulators with the chunk's inverse scale.  A panels and V0^T image stream through a
-// 4-stage cp.async ring (48 KB per stage: 4 chunks of A + the 8 matching k-steps of V0^T).
+// the fp32 accumulators with the chunk's inverse scale.  The V0^T image is resident in shared
+// memory; the A panels stream through a cp.async ring (32 KB per stage: 4 chunks).
 struct RecBwdArgs {
   const float *G, *U, *W, *alpha, *beta, *a, *b, *u0, *w0, *s0;
   const uint32_t* img;  // V0^T image (vprep transposed = 1)
   const int* meta;
   float theta;
-  float *dI, *du_next, *dw_next, *p_alpha, *p_beta, *p_a, *p_b;
+  float *dI, *p_alpha, *p_beta, *p_a, *p_b;
   uint32_t* panel;  // 2 x [groups][Hp/32 chunks][2048 words]
   float* pscale;    // 2 x [groups][Hp/32][64]
   int Be, T, H, Hp;
 };
 
-constexpr int BW_STAGES = 4;
-constexpr int BW_STAGE_WORDS = 4 * 2048 + 8 * 512;  // 4 chunks of A + 8 k-steps of V0^T = 48 KB
+// ------------------------------------------------------------------ persistent variants
+// One cooperative launch runs all T steps.  The V0 image is loaded into shared memory once and the
+// per-neuron state (u, w, previous spike; adjoints and parameter-gradient sums in the reverse
+// kernel) stays in registers across timesteps.  The only inter-CTA traffic per step is the
+// exchange of the step's spike words (forward) or dI panels (reverse) through L2, ordered by one
+// monotonically increasing counter per batch group: every slice of the group adds 1 after its
+// stores (release); a step may start when the counter has reached slices * steps_done (acquire).
+__device__ __forceinline__ void group_wait(const int* ctr, int target) {
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while (true) {
+      int v;
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if (v >= target) break;
+      if (clock64() - t0 > 4000000000LL) __trap();  // a lost arrival must not hang the GPU
+    }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void group_arrive(int* ctr) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ctr) : "memory");
+}
 
 template <bool ADAPT>
-__global__ void __launch_bounds__(256, 1) rec_bwd_step_kernel(const RecBwdArgs p, const int t) {
+__global__ void __launch_bounds__(256, 1)
+rec_fwd_persist_kernel(const RecFwdArgs p, const int group0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int NCH = p.Hp / 32;
-  uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw);
-  float* sscale = reinterpret_cast<float*>(smem_raw + (size_t)BW_STAGES * BW_STAGE_WORDS * 4);
-  float* red = reinterpret_cast<float*>(smem_raw);  // aliases the ring after the K loop
+  const int NW = p.Hp / 32;
+  const int RSB = NW + 1;
+  uint32_t* simg = reinterpret_cast<uint32_t*>(smem_raw);
+  float* red = reinterpret_cast<float*>(smem_raw + (size_t)p.Hp * 128);
+  uint32_t* sbits = reinterpret_cast<uint32_t*>(red + 4 * RB * RED_RS);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int slice = blockIdx.x, group = blockIdx.y, row0 = group * RB;
+  const int slice = blockIdx.x, group = group0 + blockIdx.y, row0 = group * RB;
   const int kq = warp >> 1, nh = warp & 1, g = lane >> 2, q = lane & 3;
-  const int ngroups = gridDim.y;
-  const bool have_next = t < p.T - 1;
-  const int rbuf = (t + 1) & 1, wbuf = t & 1;
 
-  if (have_next) {
-    const uint32_t* apanel = p.panel + ((size_t)rbuf * ngroups + group) * NCH * 2048;
-    const uint32_t* vimg = p.img + (size_t)slice * p.Hp * 32;
-    const float* gsc = p.pscale + ((size_t)rbuf * ngroups + group) * NCH * 64;
-    const int NSC = (NCH + 3) / 4;
-
-    auto issue = [&](int sc) {
-      if (sc < NSC) {
-        uint32_t* dst = ring + (size_t)(sc % BW_STAGES) * BW_STAGE_WORDS;
-        const int nch = min(4, NCH - 4 * sc);
-        const uint4* sa = reinterpret_cast<const uint4*>(apanel + (size_t)4 * sc * 2048);
-        uint4* da = reinterpret_cast<uint4*>(dst);
-        for (int i = tid; i < nch * 512; i += 256) cp_async16(da + i, sa + i);
-        const uint4* sv = reinterpret_cast<const uint4*>(vimg + (size_t)8 * sc * 512);
-        uint4* dv = reinterpret_cast<uint4*>(dst + 4 * 2048);
-        for (int i = tid; i < nch * 256; i += 256) cp_async16(dv + i, sv + i);
-      }
-      asm volatile("cp.async.commit_group;\n" ::: "memory");
-    };
-
-    for (int i = tid; i < NCH * 64; i += 256) sscale[i] = gsc[i];
-    for (int s = 0; s < BW_STAGES - 1; ++s) issue(s);
-
-    float acc[4][2][4];
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
-
-    for (int sc = 0; sc < NSC; ++sc) {
-      issue(sc + BW_STAGES - 1);
-      asm volatile("cp.async.wait_group %0;\n" ::"n"(BW_STAGES - 1) : "memory");
-      __syncthreads();
-      const int c = 4 * sc + kq;
-      if (c < NCH) {
-        const uint4* st4 = reinterpret_cast<const uint4*>(ring + (size_t)(sc % BW_STAGES) * BW_STAGE_WORDS);
-        const uint4* a4 = st4 + kq * 512;
-        const uint4* b4 = st4 + 4 * 512;
-        float tacc[4][2][4];
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-          for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) tacc[mt][nt][i] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const int kl = 2 * kq + ks;
-          const uint4 f0 = b4[((kl * 2 + nh) * 2 + 0) * 32 + lane];
-          const uint4 f1 = b4[((kl * 2 + nh) * 2 + 1) * 32 + lane];
-#pragma unroll
-          for (int mt = 0; mt < 4; ++mt) {
-            const uint4 ah = a4[((mt * 2 + ks) * 2 + 0) * 32 + lane];
-            const uint4 al = a4[((mt * 2 + ks) * 2 + 1) * 32 + lane];
-            mma16816(tacc[mt][0], ah.x, ah.y, ah.z, ah.w, f0.x, f0.y);
-            mma16816(tacc[mt][0], ah.x, ah.y, ah.z, ah.w, f0.z, f0.w);
-            mma16816(tacc[mt][0], al.x, al.y, al.z, al.w, f0.x, f0.y);
-            mma16816(tacc[mt][1], ah.x, ah.y, ah.z, ah.w, f1.x, f1.y);
-            mma16816(tacc[mt][1], ah.x, ah.y, ah.z, ah.w, f1.z, f1.w);
-            mma16816(tacc[mt][1], al.x, al.y, al.z, al.w, f1.x, f1.y);
-          }
-        }
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
-          const float s_lo = sscale[c * 64 + 16 * mt + g], s_hi = sscale[c * 64 + 16 * mt + g + 8];
-#pragma unroll
-          for (int nt = 0; nt < 2; ++nt) {
-            acc[mt][nt][0] = fmaf(tacc[mt][nt][0], s_lo, acc[mt][nt][0]);
-            acc[mt][nt][1] = fmaf(tacc[mt][nt][1], s_lo, acc[mt][nt][1]);
-            acc[mt][nt][2] = fmaf(tacc[mt][nt][2], s_hi, acc[mt][nt][2]);
-            acc[mt][nt][3] = fmaf(tacc[mt][nt][3], s_hi, acc[mt][nt][3]);
-          }
-        }
-      }
-      __syncthreads();
-    }
-    float* myred = red + kq * RB * RED_RS;
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        int col = 16 * nh + 8 * nt + 2 * q;
-        *reinterpret_cast<float2*>(&myred[(16 * mt + g) * RED_RS + col]) =
-            make_float2(acc[mt][nt][0], acc[mt][nt][1]);
-        *reinterpret_cast<float2*>(&myred[(16 * mt + g + 8) * RED_RS + col]) =
-            make_float2(acc[mt][nt][2], acc[mt][nt][3]);
-      }
-    __syncthreads();
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.img + (size_t)slice * p.Hp * 32);
+    uint4* dst = reinterpret_cast<uint4*>(simg);
+    for (int i = tid; i < p.Hp * 8; i += 256) cp_async16(dst + i, src + i);
   }
-
-  // ---- BPTT update for 8 consecutive neurons of one row per thread
   const int r = tid >> 2, cg = tid & 3;
   const int row = row0 + r;
   const int col0 = slice * RC + cg * 8;
-  float d[8];
+  const bool live = row < p.Be && col0 < p.H;
+  const bool vec = ((p.H & 3) == 0) && (col0 + 8 <= p.H);
+  const int nv = live ? min(8, p.H - col0) : 0;
+  const int64_t idx0 = (int64_t)row * p.H + col0;
+  const float rs = ldexpf(1.0f, p.meta[0] - VSCALE_EXP);
+
+  __shared__ float sprm[8][RC];  // alpha, 1-alpha, beta, a, b, 1/(1-alpha), scale, shift of the slice
+  if (tid < RC) {
+    const int col = min(slice * RC + tid, p.H - 1);
+    const NeuronParams q0 = load_params<ADAPT>(p.alpha, p.beta, p.a, p.b, col);
+    sprm[0][tid] = q0.alpha; sprm[1][tid] = q0.oma; sprm[2][tid] = q0.beta; sprm[3][tid] = q0.a;
+    sprm[4][tid] = q0.b; sprm[5][tid] = 1.0f / q0.oma;
+    sprm[6][tid] = p.scale ? p.scale[col] : 1.0f;
+    sprm[7][tid] = p.scale ? p.shift[col] : 0.0f;
+  }
+  float u[8], w[8], s[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) d[i] = 0.f;
-  if (row < p.Be && col0 < p.H) {
-    const bool vec = ((p.H & 3) == 0) && (col0 + 8 <= p.H);
-    const int nv = min(8, p.H - col0);
-    const int64_t idx0 = (int64_t)row * p.H + col0;
+  for (int i = 0; i < 8; ++i) u[i] = w[i] = s[i] = 0.f;
+  if (live) {
+    load8(p.u0 + idx0, u, vec, nv);
+    load8(p.s0 + idx0, s, vec, nv);
+    if (ADAPT) load8(p.w0 + idx0, w, vec, nv);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  const uint4* bimg = reinterpret_cast<const uint4*>(simg);
+  for (int t = 0; t < p.T; ++t) {
     const int64_t o0 = ((int64_t)row * p.T + t) * p.H + col0;
-    float gq[8], ut[8], up[8], wp[8], sp[8], du[8], dw[8], pa[8], pb[8], pc[8], pd[8], recb[8];
-    load8(p.G + o0, gq, vec, nv);
-    load8(p.U + o0, ut, vec, nv);
-    load8(p.du_next + idx0, du, vec, nv);
-    load8(p.p_alpha + idx0, pa, vec, nv);
-    if (ADAPT) {
-      load8(p.dw_next + idx0, dw, vec, nv);
-      load8(p.p_beta + idx0, pb, vec, nv);
-      load8(p.p_a + idx0, pc, vec, nv);
-      load8(p.p_b + idx0, pd, vec, nv);
-    }
-    if (t > 0) {
-      load8(p.U + o0 - p.H, up, vec, nv);
-      if (ADAPT) load8(p.W + o0 - p.H, wp, vec, nv);
+    float z[8], rec[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sp[i] = spike_of(__fsub_rn(up[i], p.theta));
-    } else {
-      load8(p.u0 + idx0, up, vec, nv);
-      load8(p.s0 + idx0, sp, vec, nv);
-      if (ADAPT) load8(p.w0 + idx0, wp, vec, nv);
+    for (int i = 0; i < 8; ++i) z[i] = rec[i] = 0.f;
+    if (live) load8(p.Z + o0, z, vec, nv);  // independent of the exchange: issued before the wait
+    if (t > 0) {
+      // Wait for and fetch the spike words of step t-1 in one go: each word travels with its step
+      // tag in a single 8-byte store, so a matching tag means the data is there (no fence, no
+      // separate flag).  All of a thread's loads are issued before any tag is checked.
+      const uint2* bsrc = p.bits + (size_t)(t - 1) * p.Be * NW;
+      const long long t0 = clock64();
+      for (int base = 0; base < RB * NW; base += 256 * 4) {
+        bool ok;
+        do {
+          ok = true;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = base + k * 256 + tid;
+            if (i < RB * NW) {
+              const int rr = i / NW, wi = i - rr * NW;
+              const int grow = row0 + rr;
+              uint32_t bv = 0;
+              if (grow < p.Be) {
+                uint32_t tag;
+                asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];"
+                             : "=r"(bv), "=r"(tag)
+                             : "l"(bsrc + (size_t)grow * NW + wi)
+                             : "memory");
+                ok = ok && (tag == (uint32_t)t);
+              }
+              sbits[rr * RSB + wi] = bv;
+            }
+          }
+          if (!ok && clock64() - t0 > 4000000000LL) __trap();  // a lost store must not hang the GPU
+        } while (!ok);
+      }
+      __syncthreads();
+      float acc[4][2][4];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+      for (int wi = kq; wi < NW; wi += 4) {
+        uint32_t wa[4], wb[4];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          const uint32_t x0 = sbits[(16 * mt + g) * RSB + wi], x1 = sbits[(16 * mt + g + 8) * RSB + wi];
+          wa[mt] = __funnelshift_r(x0, x0, 4 * q);
+          wb[mt] = __funnelshift_r(x1, x1, 4 * q);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const int kk = 2 * wi + ks;
+          const uint4 f0 = bimg[((kk * 2 + nh) * 2 + 0) * 32 + lane];
+          const uint4 f1 = bimg[((kk * 2 + nh) * 2 + 1) * 32 + lane];
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) {
+            const uint32_t M = 0x40004000u;
+            uint32_t a0 = __funnelshift_r(wa[mt], wa[mt], 2 * ks) & M;
+            uint32_t a1 = __funnelshift_r(wb[mt], wb[mt], 2 * ks) & M;
+            uint32_t a2 = __funnelshift_r(wa[mt], wa[mt], 2 * ks + 1) & M;
+            uint32_t a3 = __funnelshift_r(wb[mt], wb[mt], 2 * ks + 1) & M;
+            mma16816(acc[mt][0], a0, a1, a2, a3, f0.x, f0.y);
+            mma16816(acc[mt][0], a0, a1, a2, a3, f0.z, f0.w);
+            mma16816(acc[mt][1], a0, a1, a2, a3, f1.x, f1.y);
+            mma16816(acc[mt][1], a0, a1, a2, a3, f1.z, f1.w);
+          }
+        }
+      }
+      float* myred = red + kq * RB * RED_RS;
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          int col = 16 * nh + 8 * nt + 2 * q;
+          *reinterpret_cast<float2*>(&myred[(16 * mt + g) * RED_RS + col]) =
+              make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+          *reinterpret_cast<float2*>(&myred[(16 * mt + g + 8) * RED_RS + col]) =
+              make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+        }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = cg * 8 + i;
+        rec[i] = ((red[(0 * RB + r) * RED_RS + c] + red[(1 * RB + r) * RED_RS + c]) +
+                  (red[(2 * RB + r) * RED_RS + c] + red[(3 * RB + r) * RED_RS + c])) * rs;
+      }
+    } else if (live) {
+      load8(p.rec0 + idx0, rec, vec, nv);
     }
-    if (have_next) {
-      const float rs = ldexpf(1.0f, p.meta[0] - VSCALE_EXP);
+    uint32_t my = 0;
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i < nv) {
+          const int lc = cg * 8 + i;
+          NeuronParams npi;
+          npi.alpha = sprm[0][lc]; npi.oma = sprm[1][lc]; npi.beta = sprm[2][lc]; npi.a = sprm[3][lc];
+          npi.b = sprm[4][lc];
+          float cur = p.scale ? __fmaf_rn(z[i], sprm[6][lc], sprm[7][lc]) : z[i];
+          cur = __fadd_rn(cur, rec[i]);
+          float wi_ = ADAPT ? w[i] : 0.f;
+          step_fwd<ADAPT>(npi, cur, p.theta, u[i], wi_, s[i]);
+          w[i] = wi_;
+          my |= (s[i] > 0.f ? 1u : 0u) << (cg * 8 + i);
+        }
+      }
+    }
+    my |= __shfl_xor_sync(0xffffffffu, my, 1);
+    my |= __shfl_xor_sync(0xffffffffu, my, 2);
+    if (cg == 0 && row < p.Be)   // publish first: this store is what the other slices wait for
+      asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p.bits + ((size_t)t * p.Be + row) * NW + slice),
+                   "r"(my), "r"((uint32_t)(t + 1))
+                   : "memory");
+    if (live) {                  // tapes are only read after the kernel: off the critical path
+      store8(p.S + o0, s, vec, nv);
+      store8(p.U + o0, u, vec, nv);
+      if (ADAPT) store8(p.W + o0, w, vec, nv);
+    }
+    __syncthreads();             // sbits / red are rewritten by the next step
+  }
+}
+
+constexpr int PB_STAGE_WORDS = 4 * 2048;  // 4 chunks of the A panel = 32 KB
+constexpr int PB_STAGES = 2;
+
+template <bool ADAPT>
+__global__ void __launch_bounds__(256, 1)
+rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_total, int* __restrict__ counters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int NCH = p.Hp / 32;
+  uint32_t* simg = reinterpret_cast<uint32_t*>(smem_raw);                                   // V0^T image
+  uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw + (size_t)p.Hp * 128);               // A stages
+  float* sscale = reinterpret_cast<float*>(smem_raw + (size_t)p.Hp * 128 + (size_t)PB_STAGES * PB_STAGE_WORDS * 4);
+  float* red = reinterpret_cast<float*>(ring);                                              // aliases the ring
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slice = blockIdx.x, group = group0 + blockIdx.y, row0 = group * RB;
+  const int nslices = gridDim.x;
+  const int kq = warp >> 1, nh = warp & 1, g = lane >> 2, q = lane & 3;
+  int* ctr = counters + group;
+
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.img + (size_t)slice * p.Hp * 32);
+    uint4* dst = reinterpret_cast<uint4*>(simg);
+    for (int i = tid; i < p.Hp * 8; i += 256) cp_async16(dst + i, src + i);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
+  const int r = tid >> 2, cg = tid & 3;
+  const int row = row0 + r;
+  const int col0 = slice * RC + cg * 8;
+  const bool live = row < p.Be && col0 < p.H;
+  const bool vec = ((p.H & 3) == 0) && (col0 + 8 <= p.H);
+  const int nv = live ? min(8, p.H - col0) : 0;
+  const int64_t idx0 = (int64_t)row * p.H + col0;
+  const float rs = ldexpf(1.0f, p.meta[0] - VSCALE_EXP);
+
+  __shared__ float sprm[6][RC];  // alpha, 1-alpha, beta, a, b, 1/(1-alpha) of the slice
+  if (tid < RC) {
+    const int col = min(slice * RC + tid, p.H - 1);
+    const NeuronParams q0 = load_params<ADAPT>(p.alpha, p.beta, p.a, p.b, col);
+    sprm[0][tid] = q0.alpha; sprm[1][tid] = q0.oma; sprm[2][tid] = q0.beta; sprm[3][tid] = q0.a;
+    sprm[4][tid] = q0.b; sprm[5][tid] = 1.0f / q0.oma;
+  }
+  float du[8], dw[8], pa[8], pb[8], pc[8], pd[8], ut[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) du[i] = dw[i] = pa[i] = pb[i] = pc[i] = pd[i] = ut[i] = 0.f;
+  if (live && p.T > 0) load8(p.U + ((int64_t)row * p.T + (p.T - 1)) * p.H + col0, ut, vec, nv);
+  const uint4* bimg = reinterpret_cast<const uint4*>(simg);
+  const int NSC = (NCH + 3) / 4;
+
+  for (int t = p.T - 1; t >= 0; --t) {
+    const int64_t o0 = ((int64_t)row * p.T + t) * p.H + col0;
+    const int rbuf = (t + 1) & 1, wbuf = t & 1;
+    float gq[8], up[8], wp[8], sp[8], recb[8], d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gq[i] = up[i] = wp[i] = sp[i] = recb[i] = d[i] = 0.f;
+    if (live) {  // tape reads are independent of the exchange: issued before the wait
+      load8(p.G + o0, gq, vec, nv);
+      if (t > 0) {
+        load8(p.U + o0 - p.H, up, vec, nv);
+        if (ADAPT) load8(p.W + o0 - p.H, wp, vec, nv);
+      } else {
+        load8(p.u0 + idx0, up, vec, nv);
+        load8(p.s0 + idx0, sp, vec, nv);
+        if (ADAPT) load8(p.w0 + idx0, wp, vec, nv);
+      }
+    }
+    if (t < p.T - 1) {
+      group_wait(ctr, nslices * (p.T - 1 - t));
+      const uint32_t* apanel = p.panel + ((size_t)rbuf * ngroups_total + group) * NCH * 2048;
+      const float* gsc = p.pscale + ((size_t)rbuf * ngroups_total + group) * NCH * 64;
+      auto issue = [&](int sc) {
+        if (sc < NSC) {
+          uint32_t* dst = ring + (size_t)(sc % PB_STAGES) * PB_STAGE_WORDS;
+          const int nch = min(4, NCH - 4 * sc);
+          const uint4* sa = reinterpret_cast<const uint4*>(apanel + (size_t)4 * sc * 2048);
+          uint4* da = reinterpret_cast<uint4*>(dst);
+          for (int i = tid; i < nch * 512; i += 256) cp_async16(da + i, sa + i);
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+      };
+      for (int i = tid; i < NCH * 64; i += 256) sscale[i] = __ldcg(&gsc[i]);
+      issue(0);
+      float acc[4][2][4];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+      for (int sc = 0; sc < NSC; ++sc) {
+        issue(sc + 1);
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        __syncthreads();
+        const int c = 4 * sc + kq;
+        if (c < NCH) {
+          const uint4* a4 = reinterpret_cast<const uint4*>(ring + (size_t)(sc % PB_STAGES) * PB_STAGE_WORDS) + kq * 512;
+          float tacc[4][2][4];
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) tacc[mt][nt][i] = 0.f;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const int kk = 2 * c + ks;
+            const uint4 f0 = bimg[((kk * 2 + nh) * 2 + 0) * 32 + lane];
+            const uint4 f1 = bimg[((kk * 2 + nh) * 2 + 1) * 32 + lane];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+              const uint4 ah = a4[((mt * 2 + ks) * 2 + 0) * 32 + lane];
+              const uint4 al = a4[((mt * 2 + ks) * 2 + 1) * 32 + lane];
+              mma16816(tacc[mt][0], ah.x, ah.y, ah.z, ah.w, f0.x, f0.y);
+              mma16816(tacc[mt][0], ah.x, ah.y, ah.z, ah.w, f0.z, f0.w);
+              mma16816(tacc[mt][0], al.x, al.y, al.z, al.w, f0.x, f0.y);
+              mma16816(tacc[mt][1], ah.x, ah.y, ah.z, ah.w, f1.x, f1.y);
+              mma16816(tacc[mt][1], ah.x, ah.y, ah.z, ah.w, f1.z, f1.w);
+              mma16816(tacc[mt][1], al.x, al.y, al.z, al.w, f1.x, f1.y);
+            }
+          }
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) {
+            const float s_lo = sscale[c * 64 + 16 * mt + g], s_hi = sscale[c * 64 + 16 * mt + g + 8];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+              acc[mt][nt][0] = fmaf(tacc[mt][nt][0], s_lo, acc[mt][nt][0]);
+              acc[mt][nt][1] = fmaf(tacc[mt][nt][1], s_lo, acc[mt][nt][1]);
+              acc[mt][nt][2] = fmaf(tacc[mt][nt][2], s_hi, acc[mt][nt][2]);
+              acc[mt][nt][3] = fmaf(tacc[mt][nt][3], s_hi, acc[mt][nt][3]);
+            }
+          }
+        }
+        __syncthreads();
+      }
+      float* myred = red + kq * RB * RED_RS;
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          int col = 16 * nh + 8 * nt + 2 * q;
+          *reinterpret_cast<float2*>(&myred[(16 * mt + g) * RED_RS + col]) =
+              make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+          *reinterpret_cast<float2*>(&myred[(16 * mt + g + 8) * RED_RS + col]) =
+              make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+        }
+      __syncthreads();
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int c = cg * 8 + i;
@@ -435,61 +507,68 @@ __global__ void __launch_bounds__(256, 1) rec_bwd_step_kernel(const RecBwdArgs p
                    (red[(2 * RB + r) * RED_RS + c] + red[(3 * RB + r) * RED_RS + c])) * rs;
       }
     } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) recb[i] = 0.f;
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");  // V0^T image resident before first use
+      __syncthreads();
     }
+    if (live) {
+      if (t > 0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (i < nv) {
-        const int col = col0 + i;
-        const NeuronParams np = load_params<ADAPT>(p.alpha, p.beta, p.a, p.b, col);
-        const float inv_oma = 1.0f / np.oma;
-        float dwi = ADAPT ? dw[i] : 0.f, pbi = 0.f, pci = 0.f, pdi = 0.f;
-        if (ADAPT) { pbi = pb[i]; pci = pc[i]; pdi = pd[i]; }
-        d[i] = step_bwd<ADAPT>(np, inv_oma, p.theta, gq[i], recb[i], ut[i], up[i], sp[i],
-                               ADAPT ? wp[i] : 0.f, du[i], dwi, pa[i], pbi, pci, pdi);
-        if (ADAPT) { dw[i] = dwi; pb[i] = pbi; pc[i] = pci; pd[i] = pdi; }
+        for (int i = 0; i < 8; ++i) sp[i] = spike_of(__fsub_rn(up[i], p.theta));
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i < nv) {
+          const int lc = cg * 8 + i;
+          NeuronParams npi;
+          npi.alpha = sprm[0][lc]; npi.oma = sprm[1][lc]; npi.beta = sprm[2][lc]; npi.a = sprm[3][lc];
+          npi.b = sprm[4][lc];
+          float dwi = dw[i], pbi = pb[i], pci = pc[i], pdi = pd[i];
+          d[i] = step_bwd<ADAPT>(npi, sprm[5][lc], p.theta, gq[i], recb[i], ut[i], up[i], sp[i], wp[i],
+                                 du[i], dwi, pa[i], pbi, pci, pdi);
+          dw[i] = dwi; pb[i] = pbi; pc[i] = pci; pd[i] = pdi;
+          ut[i] = up[i];
+        }
       }
     }
-    store8(p.dI + o0, d, vec, nv);
-    store8(p.du_next + idx0, du, vec, nv);
+    if (t > 0) {
+      float m = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m = fmaxf(m, fabsf(d[i]));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      int e = 0;
+      if (m > 0.f && m <= 3.0e38f) frexpf(m, &e);
+      e = max(e, -100);
+      const float up_scale = ldexpf(1.0f, 4 - e), inv_scale = ldexpf(1.0f, e - 4);
+      uint32_t* wpanel = p.panel + (((size_t)wbuf * ngroups_total + group) * NCH + slice) * 2048;
+      const int mt = r >> 4, rr = r & 15, gg = rr & 7, upper = rr >> 3, ks = cg >> 1, hs = cg & 1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float x0 = d[2 * j] * up_scale, x1 = d[2 * j + 1] * up_scale;
+        __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+        __half2 hi = __halves2half2(h0, h1);
+        __half2 lo = __floats2half2_rn(x0 - __half2float(h0), x1 - __half2float(h1));
+        const int wd = ((mt * 2 + ks) * 2 * 32 + (4 * gg + j)) * 4 + upper + 2 * hs;
+        wpanel[wd] = *reinterpret_cast<uint32_t*>(&hi);
+        wpanel[wd + 128] = *reinterpret_cast<uint32_t*>(&lo);
+      }
+      if (cg == 0) p.pscale[(((size_t)wbuf * ngroups_total + group) * NCH + slice) * 64 + r] = inv_scale;
+      group_arrive(ctr);
+    }
+    if (live) store8(p.dI + o0, d, vec, nv);  // tape store after the hand-over: off the critical path
+  }
+  if (live) {
     store8(p.p_alpha + idx0, pa, vec, nv);
     if (ADAPT) {
-      store8(p.dw_next + idx0, dw, vec, nv);
       store8(p.p_beta + idx0, pb, vec, nv);
       store8(p.p_a + idx0, pc, vec, nv);
       store8(p.p_b + idx0, pd, vec, nv);
     }
   }
-  // ---- hand dI_t to step t-1 as block-floating-point fp16 hi/lo in A-fragment order
-  if (t > 0) {
-    float m = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) m = fmaxf(m, fabsf(d[i]));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-    int e = 0;
-    if (m > 0.f && m <= 3.0e38f) frexpf(m, &e);
-    e = max(e, -100);
-    const float up_scale = ldexpf(1.0f, 4 - e), inv_scale = ldexpf(1.0f, e - 4);
-    uint32_t* wpanel = p.panel + (((size_t)wbuf * ngroups + group) * NCH + slice) * 2048;
-    const int mt = r >> 4, rr = r & 15, gg = rr & 7, upper = rr >> 3, ks = cg >> 1, hs = cg & 1;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float x0 = d[2 * j] * up_scale, x1 = d[2 * j + 1] * up_scale;
-      __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-      __half2 hi = __halves2half2(h0, h1);
-      __half2 lo = __floats2half2_rn(x0 - __half2float(h0), x1 - __half2float(h1));
-      const int w = ((mt * 2 + ks) * 2 * 32 + (4 * gg + j)) * 4 + upper + 2 * hs;
-      wpanel[w] = *reinterpret_cast<uint32_t*>(&hi);
-      wpanel[w + 128] = *reinterpret_cast<uint32_t*>(&lo);
-    }
-    if (cg == 0) p.pscale[(((size_t)wbuf * ngroups + group) * NCH + slice) * 64 + r] = inv_scale;
-  }
 }
 
-static size_t rec_bwd_smem(int Hp) {
-  return (size_t)BW_STAGES * BW_STAGE_WORDS * 4 + (size_t)(Hp / 32) * 64 * 4;
+static size_t rec_bwd_persist_smem(int Hp) {
+  return (size_t)Hp * 128 + (size_t)PB_STAGES * PB_STAGE_WORDS * 4 + (size_t)(Hp / 32) * 64 * 4;
 }
 
 static size_t rec_fwd_smem(int Hp) {
@@ -544,25 +623,33 @@ int sparch_recur_fwd(int kind, const float* Z, const float* scale, const float* 
   SPARCH_REQUIRE(!adapt || (beta && a && b && w0 && W), "adaptive kind needs beta, a, b, w0, W");
   const int Hp = sparch_recur_padded(H);
   const size_t smem = rec_fwd_smem(Hp);
-  SPARCH_REQUIRE(smem <= 227 * 1024, "hidden size too large for the resident V0 slice (H <= 1408)");
-  static bool attr_set = false;
-  if (!attr_set) {
-    SPARCH_CUDA(cudaFuncSetAttribute(rec_fwd_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SPARCH_CUDA(cudaFuncSetAttribute(rec_fwd_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  RecFwdArgs p{Z, scale, shift, alpha, beta, a, b, rec0, u0, w0, s0, img_fwd, meta, theta, S, U, W, bits, Be, T, H, Hp};
-  dim3 grid(Hp / RC, (Be + RB - 1) / RB);
+  SPARCH_REQUIRE(smem <= 225 * 1024, "hidden size too large for the resident V0 slice (H <= 1376)");
+  RecFwdArgs p{Z, scale, shift, alpha, beta, a, b, rec0, u0, w0, s0, img_fwd, meta, theta, S, U, W,
+               reinterpret_cast<uint2*>(bits), Be, T, H, Hp};
   cudaStream_t st = as_stream(st_);
-  for (int t = 0; t < T; ++t) {
-    if (adapt)
-      rec_fwd_step_kernel<true><<<grid, 256, smem, st>>>(p, t);
-    else
-      rec_fwd_step_kernel<false><<<grid, 256, smem, st>>>(p, t);
+  static int max_ctas = 0;
+  if (max_ctas == 0) {
+    SPARCH_CUDA(cudaFuncSetAttribute(rec_fwd_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    SPARCH_CUDA(cudaFuncSetAttribute(rec_fwd_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    max_ctas = sm_count();  // one CTA per SM (shared memory bound)
   }
-  SPARCH_LAUNCH_OK();
+  const int slices = Hp / RC, groups = (Be + RB - 1) / RB;
+  SPARCH_REQUIRE(slices <= max_ctas, "hidden size needs more co-resident CTAs than the GPU has SMs");
+  const int gmax = max_ctas / slices;
+  // tags are t+1 >= 1: a zeroed buffer means "nothing published yet"
+  SPARCH_CUDA(cudaMemsetAsync(bits, 0, sizeof(uint2) * (size_t)T * Be * (Hp / 32), st));
+  for (int g0 = 0; g0 < groups; g0 += gmax) {
+    int gn = groups - g0 < gmax ? groups - g0 : gmax;
+    dim3 cgrid(slices, gn);
+    int group0 = g0;
+    void* args[] = {(void*)&p, (void*)&group0};
+    const void* fn = adapt ? (const void*)rec_fwd_persist_kernel<true> : (const void*)rec_fwd_persist_kernel<false>;
+    SPARCH_CUDA(cudaLaunchCooperativeKernel(fn, cgrid, dim3(256), args, smem + 0, st));
+  }
   return SPARCH_OK;
 }
+
+int sparch_recur_sync_words(int Be) { return (Be + RB - 1) / RB + 1; }
 
 size_t sparch_recur_bwd_workspace(int Be, int H) {
   const int Hp = sparch_recur_padded(H);
@@ -573,40 +660,43 @@ size_t sparch_recur_bwd_workspace(int Be, int H) {
 int sparch_recur_bwd(int kind, const float* G, const float* U, const float* W, const float* alpha,
                      const float* beta, const float* a, const float* b, const uint32_t* img_bwd,
                      const int* meta, const float* u0, const float* w0, const float* s0, float theta,
-                     float* dI, float* du_next, float* dw_next, float* p_alpha, float* p_beta,
-                     float* p_a, float* p_b, void* workspace, int Be, int T, int H,
-                     sparch_stream_t st_) {
+                     float* dI, float* p_alpha, float* p_beta, float* p_a, float* p_b, void* workspace,
+                     int* sync_ws, int Be, int T, int H, sparch_stream_t st_) {
   SPARCH_REQUIRE(kind == SPARCH_RLIF || kind == SPARCH_RADLIF, "recurrent kinds only");
   SPARCH_REQUIRE(Be >= 0 && T >= 0 && H > 0, "bad shape");
   if (Be == 0 || T == 0) return SPARCH_OK;
-  SPARCH_REQUIRE(G && U && alpha && img_bwd && meta && u0 && s0 && dI && du_next && p_alpha && workspace,
+  SPARCH_REQUIRE(G && U && alpha && img_bwd && meta && u0 && s0 && dI && p_alpha && workspace && sync_ws,
                  "null pointer");
   const bool adapt = kind & 1;
-  SPARCH_REQUIRE(!adapt || (W && beta && a && b && w0 && dw_next && p_beta && p_a && p_b),
-                 "adaptive kind needs W, beta, a, b, w0, dw_next and the partial buffers");
+  SPARCH_REQUIRE(!adapt || (W && beta && a && b && w0 && p_beta && p_a && p_b),
+                 "adaptive kind needs W, beta, a, b, w0 and the partial buffers");
   const int Hp = sparch_recur_padded(H);
-  const size_t smem = rec_bwd_smem(Hp);
-  SPARCH_REQUIRE(smem <= 227 * 1024, "hidden size too large");
-  static bool attr_set = false;
-  if (!attr_set) {
-    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   const size_t groups = (size_t)(Be + RB - 1) / RB;
   uint32_t* panel = reinterpret_cast<uint32_t*>(workspace);
   float* pscale = reinterpret_cast<float*>(panel + 2 * groups * (Hp / 32) * 2048);
-  RecBwdArgs p{G, U, W, alpha, beta, a, b, u0, w0, s0, img_bwd, meta, theta, dI, du_next, dw_next,
+  RecBwdArgs p{G, U, W, alpha, beta, a, b, u0, w0, s0, img_bwd, meta, theta, dI,
                p_alpha, p_beta, p_a, p_b, panel, pscale, Be, T, H, Hp};
-  dim3 grid(Hp / RC, (unsigned)groups);
   cudaStream_t st = as_stream(st_);
-  for (int t = T - 1; t >= 0; --t) {
-    if (adapt)
-      rec_bwd_step_kernel<true><<<grid, 256, smem, st>>>(p, t);
-    else
-      rec_bwd_step_kernel<false><<<grid, 256, smem, st>>>(p, t);
+  const size_t psmem = rec_bwd_persist_smem(Hp);
+  SPARCH_REQUIRE(psmem <= 225 * 1024, "hidden size too large for the resident V0^T slice");
+  static int max_ctas = 0;
+  if (max_ctas == 0) {
+    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    max_ctas = sm_count();
   }
-  SPARCH_LAUNCH_OK();
+  const int slices = Hp / RC;
+  SPARCH_REQUIRE(slices <= max_ctas, "hidden size needs more co-resident CTAs than the GPU has SMs");
+  const int gmax = max_ctas / slices;
+  SPARCH_CUDA(cudaMemsetAsync(sync_ws, 0, sizeof(int) * groups, st));
+  for (int g0 = 0; g0 < (int)groups; g0 += gmax) {
+    int gn = (int)groups - g0 < gmax ? (int)groups - g0 : gmax;
+    dim3 cgrid(slices, gn);
+    int group0 = g0, ngt = (int)groups;
+    void* args[] = {(void*)&p, (void*)&group0, (void*)&ngt, (void*)&sync_ws};
+    const void* fn = adapt ? (const void*)rec_bwd_persist_kernel<true> : (const void*)rec_bwd_persist_kernel<false>;
+    SPARCH_CUDA(cudaLaunchCooperativeKernel(fn, cgrid, dim3(256), args, psmem, st));
+  }
   return SPARCH_OK;
 }
 

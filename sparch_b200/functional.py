@@ -6,6 +6,7 @@ loops (sparch/models/snns.py:282-303, 419-445, 554-578, 696-727, 807-825) and it
 CPU path (``RuntimeError`` otherwise).
 """
 import math
+import os
 
 import torch
 
@@ -261,7 +262,7 @@ class SpikingCellFunction(torch.autograd.Function):
                      ptr(meta), st)
                 ctx.rec = (img_b, meta)
                 rec0 = torch.matmul(s0, V0)        # t = 0: s_{-1} is real-valued (snns.py:702)
-                bits = torch.empty(T, Be, Hp // 32, device=dev, dtype=torch.int32)
+                bits = torch.empty(T, Be, Hp // 32, 2, device=dev, dtype=torch.int32)
                 call("sparch_recur_fwd", k, ptr(Z), ptr(scale), ptr(shift), ptr(al), ptr(be), ptr(aa),
                      ptr(bb), ptr(rec0), ptr(img_f), ptr(meta), ptr(u0), ptr(w0), ptr(s0),
                      float(theta), ptr(S), ptr(U), ptr(Wt), ptr(bits), Be, T, H, st)
@@ -293,12 +294,12 @@ class SpikingCellFunction(torch.autograd.Function):
             region.__exit__()
             dV = None
         else:
-            carry = torch.zeros(2, Be, H, device=dev, dtype=torch.float32)
             img_b, meta = ctx.rec
             ws = torch.empty(_lib.lib().sparch_recur_bwd_workspace(Be, H), device=dev, dtype=torch.uint8)
+            sync = torch.empty(_lib.lib().sparch_recur_sync_words(Be), device=dev, dtype=torch.int32)
             call("sparch_recur_bwd", k, ptr(G), ptr(U), ptr(Wt), ptr(al), ptr(be), ptr(aa), ptr(bb),
-                 ptr(img_b), ptr(meta), ptr(u0), ptr(w0), ptr(s0), theta, ptr(dI), ptr(carry[0]),
-                 ptr(carry[1]) if adaptive else None, pp[0], pp[1], pp[2], pp[3], ptr(ws), Be, T, H, st)
+                 ptr(img_b), ptr(meta), ptr(u0), ptr(w0), ptr(s0), theta, ptr(dI), pp[0], pp[1], pp[2],
+                 pp[3], ptr(ws), ptr(sync), Be, T, H, st)
             region.__exit__()
             # dV = sum_t s_{t-1}^T dI_t, diagonal masked (clone().fill_diagonal_(0) backward)
             with _region("gemm_bwd"):

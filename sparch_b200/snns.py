@@ -8,12 +8,37 @@ by ``torch.autograd.Function`` wrappers over hand-written sm_100a kernels
 (``sparch_b200.functional`` -> ``libsparch_b200.so``).  CUDA only: a forward pass on CPU
 tensors raises ``RuntimeError``.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
 
 from .functional import (LinearFunction, NormState, ReadoutCellFunction, SpikeFunctionBoxcar,
                          SpikingCellFunction)
+
+# Where the per-forward initial states u_{-1}, w_{-1}, s_{-1} ~ U[0,1) are drawn.
+#   "cpu"    (default): torch.rand on the CPU default generator, then copied to the device --
+#            exactly the reference's draws (snns.py:700-702), so a given torch.manual_seed gives the
+#            reference's states.  The serial CPU generator costs ~2 ms per (256, 1024) draw.
+#   "device": torch.rand on the CUDA generator in the same order: same distribution, different
+#            stream, no host work.
+_STATE_INIT = os.environ.get("SPARCH_B200_STATE_INIT", "cpu")
+
+
+def set_state_init(mode):
+    """Select "cpu" (reference-identical draws) or "device" (fast) initial-state generation."""
+    global _STATE_INIT
+    if mode not in ("cpu", "device"):
+        raise ValueError("state init mode must be 'cpu' or 'device'")
+    _STATE_INIT = mode
+
+
+def _rand_state(rows, cols, device):
+    if _STATE_INIT == "device":
+        return torch.rand(rows, cols, device=device)
+    return torch.rand(rows, cols).to(device)
+
 
 __all__ = ["SpikeFunctionBoxcar", "SNN", "LIFLayer", "adLIFLayer", "RLIFLayer", "RadLIFLayer",
            "ReadoutLayer"]
@@ -118,9 +143,9 @@ class _SpikingLayerBase(nn.Module):
         device = Wx.device
         Be, H = Wx.shape[0], Wx.shape[2]
         # initial states from the CPU generator in the reference's order (snns.py:700-702)
-        ut = torch.rand(Be, H).to(device)
-        wt = torch.rand(Be, H).to(device) if self._adaptive else None
-        st = torch.rand(Be, H).to(device)
+        ut = _rand_state(Be, H, device)
+        wt = _rand_state(Be, H, device) if self._adaptive else None
+        st = _rand_state(Be, H, device)
         return SpikingCellFunction.apply(
             Wx, gamma, bn_beta, self.alpha, getattr(self, "beta", None), getattr(self, "a", None),
             getattr(self, "b", None), self.V.weight if self._recurrent else None, ut, wt, st,
@@ -201,7 +226,7 @@ class ReadoutLayer(nn.Module):
         return self._readout_cell(Wx, gamma, bn_beta, norm)
 
     def _readout_cell(self, Wx, gamma=None, bn_beta=None, norm=None):
-        ut = torch.rand(Wx.shape[0], Wx.shape[2]).to(Wx.device)  # snns.py:812
+        ut = _rand_state(Wx.shape[0], Wx.shape[2], Wx.device)    # snns.py:812
         return ReadoutCellFunction.apply(Wx, gamma, bn_beta, self.alpha, ut,
                                          norm if norm is not None else NormState("none"))
 
