@@ -239,32 +239,52 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
 __global__ void split_rows_kernel(const float* __restrict__ X, long long ldx, int M, int K, int nparts, float prescale,
                                   __nv_bfloat16* __restrict__ P0, __nv_bfloat16* __restrict__ P1,
                                   __nv_bfloat16* __restrict__ P2, long long ldp) {
-  long long n = (long long)M * ldp;
+  // one thread per 8 consecutive output elements (ldp % 8 == 0): 16-byte stores
+  const long long segs_per_row = ldp / 8;
+  const long long n = (long long)M * segs_per_row;
+  const bool vec_in = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    long long r = i / ldp;
-    int c = (int)(i - r * ldp);
-    float x = c < K ? X[r * ldx + c] * prescale : 0.f;
-    __nv_bfloat16 h0 = __float2bfloat16_rn(x);
-    P0[i] = h0;
-    if (nparts > 1) {
-      float r1 = x - __bfloat162float(h0);
-      __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
-      P1[i] = h1;
-      if (nparts > 2) P2[i] = __float2bfloat16_rn(r1 - __bfloat162float(h1));
+    const long long r = i / segs_per_row;
+    const int c = (int)(i - r * segs_per_row) * 8;
+    float x[8];
+    const float* src = X + r * ldx + c;
+    if (vec_in && c + 8 <= K) {
+      float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = c + j < K ? src[j] : 0.f;
     }
+    __align__(16) __nv_bfloat16 h0[8], h1[8], h2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = x[j] * prescale;
+      h0[j] = __float2bfloat16_rn(v);
+      float r1 = v - __bfloat162float(h0[j]);
+      h1[j] = __float2bfloat16_rn(r1);
+      h2[j] = __float2bfloat16_rn(r1 - __bfloat162float(h1[j]));
+    }
+    const long long o = r * ldp + c;
+    *reinterpret_cast<uint4*>(P0 + o) = *reinterpret_cast<const uint4*>(h0);
+    if (nparts > 1) *reinterpret_cast<uint4*>(P1 + o) = *reinterpret_cast<const uint4*>(h1);
+    if (nparts > 2) *reinterpret_cast<uint4*>(P2 + o) = *reinterpret_cast<const uint4*>(h2);
   }
 }
 
 // Transposing split: X is (R rows, C cols) fp32 row-major; parts are (C, ldp >= R) bf16 row-major,
 // i.e. parts[i][c][r] = term_i(X[r][c]).  With T > 0 the rows are (b, t) pairs and `shift` delays
 // time: output column (b, t) takes X[b, t - shift, :], zero for t < shift (S_prev for dV).
-__global__ void split_transpose_kernel(const float* __restrict__ X, int R, int C, int nparts, int T, int shift, float prescale,
-                                       __nv_bfloat16* __restrict__ P0, __nv_bfloat16* __restrict__ P1,
-                                       __nv_bfloat16* __restrict__ P2, long long ldp) {
-  __shared__ float tile[32][33];
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-    int r = r0 + j, c = c0 + threadIdx.x;
+__global__ void __launch_bounds__(256)
+split_transpose_kernel(const float* __restrict__ X, int R, int C, int nparts, int T, int shift, float prescale,
+                       __nv_bfloat16* __restrict__ P0, __nv_bfloat16* __restrict__ P1,
+                       __nv_bfloat16* __restrict__ P2, long long ldp) {
+  // tile: 64 input rows (r) x 32 input columns (c).  Reads are 128-byte rows; every output row c
+  // receives 64 consecutive r = 128 bytes, written as eight 16-byte stores.
+  __shared__ float tile[64][33];
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 64; j += 8) {
+    int r = r0 + j, c = c0 + tx;
     float v = 0.f;
     if (r < R && c < C) {
       long long src = r;
@@ -276,21 +296,31 @@ __global__ void split_transpose_kernel(const float* __restrict__ X, int R, int C
       }
       if (ok) v = X[src * (long long)C + c] * prescale;
     }
-    tile[j][threadIdx.x] = v;
+    tile[j][tx] = v;
   }
   __syncthreads();
-  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-    int c = c0 + j, r = r0 + threadIdx.x;
-    if (c < C && r < ldp) {
-      float x = r < R ? tile[threadIdx.x][j] : 0.f;
-      long long o = (long long)c * ldp + r;
-      __nv_bfloat16 h0 = __float2bfloat16_rn(x);
-      P0[o] = h0;
-      if (nparts > 1) {
-        float r1 = x - __bfloat162float(h0);
-        __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
-        P1[o] = h1;
-        if (nparts > 2) P2[o] = __float2bfloat16_rn(r1 - __bfloat162float(h1));
+  const int cl = threadIdx.x >> 3, seg = threadIdx.x & 7;  // 32 output rows x 8 segments of 8 elements
+  const int c = c0 + cl, rb = r0 + seg * 8;
+  if (c < C && rb < ldp) {
+    __align__(16) __nv_bfloat16 h0[8], h1[8], h2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float x = tile[seg * 8 + i][cl];  // zero beyond R (loaded as 0)
+      h0[i] = __float2bfloat16_rn(x);
+      float r1 = x - __bfloat162float(h0[i]);
+      h1[i] = __float2bfloat16_rn(r1);
+      h2[i] = __float2bfloat16_rn(r1 - __bfloat162float(h1[i]));
+    }
+    const long long o = (long long)c * ldp + rb;  // ldp % 8 == 0 and rb % 8 == 0: 16-byte aligned
+    if (rb + 8 <= ldp) {
+      *reinterpret_cast<uint4*>(P0 + o) = *reinterpret_cast<const uint4*>(h0);
+      if (nparts > 1) *reinterpret_cast<uint4*>(P1 + o) = *reinterpret_cast<const uint4*>(h1);
+      if (nparts > 2) *reinterpret_cast<uint4*>(P2 + o) = *reinterpret_cast<const uint4*>(h2);
+    } else {
+      for (int i = 0; i < 8 && rb + i < ldp; ++i) {
+        P0[o + i] = h0[i];
+        if (nparts > 1) P1[o + i] = h1[i];
+        if (nparts > 2) P2[o + i] = h2[i];
       }
     }
   }
@@ -345,7 +375,8 @@ int sparch_split_bf16(const float* X, int64_t ldx, int M, int K, int nparts, flo
   SPARCH_REQUIRE(P0 && (nparts < 2 || P1) && (nparts < 3 || P2), "null part pointer");
   if (M == 0) return SPARCH_OK;
   SPARCH_REQUIRE(X, "null pointer");
-  int64_t n = (int64_t)M * ldp;
+  SPARCH_REQUIRE((ldp % 8) == 0, "ldp must be a multiple of 8");
+  int64_t n = (int64_t)M * (ldp / 8);
   int64_t g = (n + 255) / 256, cap = (int64_t)sm_count() * 16;
   split_rows_kernel<<<(unsigned)(g < cap ? g : cap), 256, 0, as_stream(st)>>>(
       X, ldx, M, K, nparts, prescale, (__nv_bfloat16*)P0, (__nv_bfloat16*)P1, (__nv_bfloat16*)P2, ldp);
@@ -359,7 +390,8 @@ int sparch_split_bf16_transpose(const float* X, int R, int C, int nparts, int T,
   SPARCH_REQUIRE(P0 && (nparts < 2 || P1) && (nparts < 3 || P2), "null part pointer");
   if (ldp == 0) return SPARCH_OK;
   SPARCH_REQUIRE(X || R == 0, "null pointer");
-  dim3 grid((C + 31) / 32, (unsigned)((ldp + 31) / 32)), block(32, 8);
+  SPARCH_REQUIRE((ldp % 8) == 0, "ldp must be a multiple of 8");
+  dim3 grid((C + 31) / 32, (unsigned)((ldp + 63) / 64)), block(256);
   split_transpose_kernel<<<grid, block, 0, as_stream(st)>>>(X, R, C, nparts, T, shift, prescale, (__nv_bfloat16*)P0,
                                                             (__nv_bfloat16*)P1, (__nv_bfloat16*)P2, ldp);
   SPARCH_LAUNCH_OK();

@@ -1,0 +1,85 @@
+"""World-size-2 CPU test (gloo) of the data-parallel gradient exchange (sparch_b200/parallel.py).
+
+The SNN layers themselves are CUDA-only, so the exchange logic is exercised on a plain torch
+module with an ``snn`` ModuleList of the same shape: per-layer buckets, asynchronous all-reduce
+launched from the post-accumulate-grad hooks, averaging, parameter/buffer broadcast from rank 0,
+and a parameter that receives no gradient.
+"""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+class _Toy(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.snn = torch.nn.ModuleList([torch.nn.Linear(6, 5), torch.nn.Linear(5, 4), torch.nn.Linear(4, 3)])
+        self.unused = torch.nn.Parameter(torch.ones(2))
+        self.register_buffer("stat", torch.zeros(3))
+
+    def forward(self, x):
+        for lay in self.snn:
+            x = torch.tanh(lay(x))
+        return x
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from sparch_b200.parallel import GradSync
+        torch.manual_seed(100 + rank)          # different init per rank: broadcast must fix it
+        net = _Toy()
+        net.stat.fill_(float(rank + 1))
+        sync = GradSync(net)
+        torch.manual_seed(7)
+        ref = _Toy()                            # what rank 0 had (seed 100) is unknown here; compare via gather
+        p0 = [p.detach().clone() for p in net.parameters()]
+        gathered = [torch.zeros_like(p0[0]) for _ in range(world)]
+        dist.all_gather(gathered, p0[0])
+        assert all(torch.equal(g, gathered[0]) for g in gathered), "parameters were not broadcast"
+        assert float(net.stat[0]) == 1.0, "buffers were not broadcast from rank 0"
+        for step in range(2):                   # two steps: hooks must re-arm
+            torch.manual_seed(10 * step + rank)
+            x = torch.randn(8, 6)
+            net.zero_grad()                     # set_to_none=True, like exp.py:375
+            loss = net(x).square().sum()
+            loss.backward()
+            local = [None if p.grad is None else p.grad.detach().clone() for p in net.parameters()]
+            sync.finish()
+            for p, lg in zip(net.parameters(), local):
+                if lg is None:
+                    assert float(p.grad.abs().sum()) == 0.0
+                    continue
+                parts = [torch.zeros_like(lg) for _ in range(world)]
+                dist.all_gather(parts, lg)
+                want = sum(parts) / world
+                assert torch.allclose(p.grad, want, rtol=1e-6, atol=1e-7)
+        out.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        out.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradsync_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
