@@ -264,9 +264,12 @@ def run_ours(args, cfg, rank, local_rank, world):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
-    if rank == 0 and len(sampler.lines) < 8:                  # short runs: keep the GPU loaded until sampled
-        t_end = time.time() + 1.5
-        while time.time() < t_end:
+    # Short runs end before nvidia-smi has produced enough samples: keep the GPU under the same load
+    # for ~1.5 s more.  The step count comes from the rank-reduced timing, so every rank runs the
+    # same number of (collective-bearing) steps.
+    loaded_s = (ms + ms_e2e) * 1e-3
+    if loaded_s < 1.5:
+        for _ in range(int((1.5 - loaded_s) / (ms * 1e-3 / args.steps)) + 1):
             step(x_d, y_d)
         torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None            # samples cover the timed + e2e (+ filler) load
