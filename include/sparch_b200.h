@@ -157,6 +157,10 @@ SPARCH_API int sparch_recur_fwd(int kind, const float* Z, const float* scale, co
                                 const int* meta, const float* u0, const float* w0,
                                 const float* s0, float theta, float* S, float* U, float* W,
                                 uint32_t* bits, int Be, int T, int H, sparch_stream_t st);
+/* Profiling aid: device buffer of T*4 int64 that receives, per timestep, the SM clock of CTA (0,0)
+ * after the spike-word wait, after the MMA loop, after the reduction and at the end of the step
+ * for the following sparch_recur_fwd launches (NULL switches it off).                          */
+SPARCH_API int sparch_recur_debug_clocks(long long* buf);
 /* Reverse pass of an RLIF/RadLIF layer, all T steps in one persistent cooperative kernel: dI
  * (Be,T,H) and the per-(b,h) partial parameter gradients p_* (Be,H).  img_bwd from
  * sparch_recur_prepare; workspace of sparch_recur_bwd_workspace() bytes holds the

@@ -14,6 +14,7 @@
 // memory, then 256 threads apply the neuron update to the 64 x 32 block and emit the new spike
 // words, the fp32 spike/membrane/adaptation tapes.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "cell_math.cuh"
 #include "common.cuh"
@@ -86,6 +87,9 @@ __global__ void vprep_kernel(const float* __restrict__ V, int H, int Hp, int tra
   }
 }
 
+static long long* g_dbg = nullptr;  // see sparch_recur_debug_clocks
+static int g_dbg_flags = 0;
+
 struct RecFwdArgs {
   const float *Z, *scale, *shift, *alpha, *beta, *a, *b, *rec0, *u0, *w0, *s0;
   const uint32_t* img;
@@ -94,6 +98,8 @@ struct RecFwdArgs {
   float *S, *U, *W;
   uint2* bits;     // [T][Be][Hp/32] {32 spikes, step tag t+1}: tagged 64-bit words (LL exchange)
   int Be, T, H, Hp;
+  long long* dbg;  // optional [T][8] phase clocks of CTA (0,0) (profiling aid), normally NULL
+  int dbg_flags;   // profiling experiments (results invalid): 1 no tag wait, 2 no tape stores, 4 no Z loads
 };
 
 __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
@@ -153,6 +159,7 @@ struct RecBwdArgs {
   uint32_t* panel;  // 2 x [groups][Hp/32 chunks][2048 words]
   float* pscale;    // 2 x [groups][Hp/32][64]
   int Be, T, H, Hp;
+  long long* dbg;   // optional [T][8] phase clocks of CTA (0,0) (profiling aid), normally NULL
 };
 
 // ------------------------------------------------------------------ persistent variants
@@ -229,44 +236,65 @@ rec_fwd_persist_kernel(const RecFwdArgs p, const int group0) {
   __syncthreads();
 
   const uint4* bimg = reinterpret_cast<const uint4*>(simg);
+  bool tapes_pending = false;
   for (int t = 0; t < p.T; ++t) {
     const int64_t o0 = ((int64_t)row * p.T + t) * p.H + col0;
     float z[8], rec[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) z[i] = rec[i] = 0.f;
-    if (live) load8(p.Z + o0, z, vec, nv);  // independent of the exchange: issued before the wait
+    const bool dbg_on = p.dbg && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+    if (live && !(p.dbg_flags & 4)) load8(p.Z + o0, z, vec, nv);  // independent of the exchange: issued before the wait
     if (t > 0) {
       // Wait for and fetch the spike words of step t-1 in one go: each word travels with its step
       // tag in a single 8-byte store, so a matching tag means the data is there (no fence, no
       // separate flag).  All of a thread's loads are issued before any tag is checked.
       const uint2* bsrc = p.bits + (size_t)(t - 1) * p.Be * NW;
       const long long t0 = clock64();
-      for (int base = 0; base < RB * NW; base += 256 * 4) {
+      if (dbg_on) p.dbg[t * 8 + 4] = t0;
+      for (int base = 0; base < RB * NW; base += 256 * 8) {
+        // issue every load of the batch before looking at any result (independent L2 round trips)
+        const uint2* src[8];
+        int dst[8];
+        bool need[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int i = base + k * 256 + tid;
+          const int rr = i / NW, wi = i - rr * NW;
+          need[k] = i < RB * NW && row0 + rr < p.Be;
+          dst[k] = i < RB * NW ? rr * RSB + wi : -1;
+          src[k] = bsrc + (size_t)(row0 + rr) * NW + wi;
+        }
+        uint32_t bv[8], tg[8];
         bool ok;
         do {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            bv[k] = 0;
+            tg[k] = (uint32_t)t;
+            if (need[k])
+              asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];"
+                           : "=r"(bv[k]), "=r"(tg[k])
+                           : "l"(src[k])
+                           : "memory");
+          }
+          if (tapes_pending) {  // step t-1's tape stores ride in the shadow of the L2 round trip
+            tapes_pending = false;
+            const int64_t op = o0 - p.H;
+            store8(p.S + op, s, vec, nv);
+            store8(p.U + op, u, vec, nv);
+            if (ADAPT) store8(p.W + op, w, vec, nv);
+          }
           ok = true;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int i = base + k * 256 + tid;
-            if (i < RB * NW) {
-              const int rr = i / NW, wi = i - rr * NW;
-              const int grow = row0 + rr;
-              uint32_t bv = 0;
-              if (grow < p.Be) {
-                uint32_t tag;
-                asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];"
-                             : "=r"(bv), "=r"(tag)
-                             : "l"(bsrc + (size_t)grow * NW + wi)
-                             : "memory");
-                ok = ok && (tag == (uint32_t)t);
-              }
-              sbits[rr * RSB + wi] = bv;
-            }
-          }
+          for (int k = 0; k < 8; ++k) ok = ok && (tg[k] == (uint32_t)t || (p.dbg_flags & 1));
           if (!ok && clock64() - t0 > 4000000000LL) __trap();  // a lost store must not hang the GPU
         } while (!ok);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (dst[k] >= 0) sbits[dst[k]] = bv[k];
       }
       __syncthreads();
+      if (dbg_on) p.dbg[t * 8 + 0] = clock64();
       float acc[4][2][4];
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
@@ -287,20 +315,30 @@ rec_fwd_persist_kernel(const RecFwdArgs p, const int group0) {
           const int kk = 2 * wi + ks;
           const uint4 f0 = bimg[((kk * 2 + nh) * 2 + 0) * 32 + lane];
           const uint4 f1 = bimg[((kk * 2 + nh) * 2 + 1) * 32 + lane];
+          // hi terms of all 8 accumulators first, then the lo terms: consecutive HMMAs never
+          // chain on the same accumulator
+          uint32_t af[4][4];
 #pragma unroll
           for (int mt = 0; mt < 4; ++mt) {
             const uint32_t M = 0x40004000u;
-            uint32_t a0 = __funnelshift_r(wa[mt], wa[mt], 2 * ks) & M;
-            uint32_t a1 = __funnelshift_r(wb[mt], wb[mt], 2 * ks) & M;
-            uint32_t a2 = __funnelshift_r(wa[mt], wa[mt], 2 * ks + 1) & M;
-            uint32_t a3 = __funnelshift_r(wb[mt], wb[mt], 2 * ks + 1) & M;
-            mma16816(acc[mt][0], a0, a1, a2, a3, f0.x, f0.y);
-            mma16816(acc[mt][0], a0, a1, a2, a3, f0.z, f0.w);
-            mma16816(acc[mt][1], a0, a1, a2, a3, f1.x, f1.y);
-            mma16816(acc[mt][1], a0, a1, a2, a3, f1.z, f1.w);
+            af[mt][0] = __funnelshift_r(wa[mt], wa[mt], 2 * ks) & M;
+            af[mt][1] = __funnelshift_r(wb[mt], wb[mt], 2 * ks) & M;
+            af[mt][2] = __funnelshift_r(wa[mt], wa[mt], 2 * ks + 1) & M;
+            af[mt][3] = __funnelshift_r(wb[mt], wb[mt], 2 * ks + 1) & M;
+          }
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) {
+            mma16816(acc[mt][0], af[mt][0], af[mt][1], af[mt][2], af[mt][3], f0.x, f0.y);
+            mma16816(acc[mt][1], af[mt][0], af[mt][1], af[mt][2], af[mt][3], f1.x, f1.y);
+          }
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) {
+            mma16816(acc[mt][0], af[mt][0], af[mt][1], af[mt][2], af[mt][3], f0.z, f0.w);
+            mma16816(acc[mt][1], af[mt][0], af[mt][1], af[mt][2], af[mt][3], f1.z, f1.w);
           }
         }
       }
+      if (dbg_on) p.dbg[t * 8 + 1] = clock64();
       float* myred = red + kq * RB * RED_RS;
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
@@ -319,6 +357,7 @@ rec_fwd_persist_kernel(const RecFwdArgs p, const int group0) {
         rec[i] = ((red[(0 * RB + r) * RED_RS + c] + red[(1 * RB + r) * RED_RS + c]) +
                   (red[(2 * RB + r) * RED_RS + c] + red[(3 * RB + r) * RED_RS + c])) * rs;
       }
+      if (dbg_on) p.dbg[t * 8 + 2] = clock64();
     } else if (live) {
       load8(p.rec0 + idx0, rec, vec, nv);
     }
@@ -346,12 +385,16 @@ rec_fwd_persist_kernel(const RecFwdArgs p, const int group0) {
       asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p.bits + ((size_t)t * p.Be + row) * NW + slice),
                    "r"(my), "r"((uint32_t)(t + 1))
                    : "memory");
-    if (live) {                  // tapes are only read after the kernel: off the critical path
+    // The tapes are only read after the kernel: their stores are deferred until the next step's
+    // spike-word loads are in flight (u, w, s stay unchanged in registers until then).
+    tapes_pending = live && !(p.dbg_flags & 2);
+    if (tapes_pending && t == p.T - 1) {
       store8(p.S + o0, s, vec, nv);
       store8(p.U + o0, u, vec, nv);
       if (ADAPT) store8(p.W + o0, w, vec, nv);
     }
     __syncthreads();             // sbits / red are rewritten by the next step
+    if (dbg_on) p.dbg[t * 8 + 3] = clock64();
   }
 }
 
@@ -420,15 +463,21 @@ rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_t
         if (ADAPT) load8(p.w0 + idx0, wp, vec, nv);
       }
     }
+    const bool dbg_on = p.dbg && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+    if (dbg_on) p.dbg[t * 8 + 0] = clock64();
     if (t < p.T - 1) {
       group_wait(ctr, nslices * (p.T - 1 - t));
+      if (dbg_on) p.dbg[t * 8 + 1] = clock64();
       const uint32_t* apanel = p.panel + ((size_t)rbuf * ngroups_total + group) * NCH * 2048;
       const float* gsc = p.pscale + ((size_t)rbuf * ngroups_total + group) * NCH * 64;
+      // (Starting each CTA's walk over the panel at a different super-chunk was measured: no gain.)
+      const int rot = 0;
       auto issue = [&](int sc) {
         if (sc < NSC) {
           uint32_t* dst = ring + (size_t)(sc % PB_STAGES) * PB_STAGE_WORDS;
-          const int nch = min(4, NCH - 4 * sc);
-          const uint4* sa = reinterpret_cast<const uint4*>(apanel + (size_t)4 * sc * 2048);
+          const int psc = (sc + rot) % NSC;
+          const int nch = min(4, NCH - 4 * psc);
+          const uint4* sa = reinterpret_cast<const uint4*>(apanel + (size_t)4 * psc * 2048);
           uint4* da = reinterpret_cast<uint4*>(dst);
           for (int i = tid; i < nch * 512; i += 256) cp_async16(da + i, sa + i);
         }
@@ -447,7 +496,7 @@ rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_t
         issue(sc + 1);
         asm volatile("cp.async.wait_group 1;\n" ::: "memory");
         __syncthreads();
-        const int c = 4 * sc + kq;
+        const int c = 4 * ((sc + rot) % NSC) + kq;
         if (c < NCH) {
           const uint4* a4 = reinterpret_cast<const uint4*>(ring + (size_t)(sc % PB_STAGES) * PB_STAGE_WORDS) + kq * 512;
           float tacc[4][2][4];
@@ -467,10 +516,10 @@ rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_t
               const uint4 ah = a4[((mt * 2 + ks) * 2 + 0) * 32 + lane];
               const uint4 al = a4[((mt * 2 + ks) * 2 + 1) * 32 + lane];
               mma16816(tacc[mt][0], ah.x, ah.y, ah.z, ah.w, f0.x, f0.y);
-              mma16816(tacc[mt][0], ah.x, ah.y, ah.z, ah.w, f0.z, f0.w);
-              mma16816(tacc[mt][0], al.x, al.y, al.z, al.w, f0.x, f0.y);
               mma16816(tacc[mt][1], ah.x, ah.y, ah.z, ah.w, f1.x, f1.y);
+              mma16816(tacc[mt][0], ah.x, ah.y, ah.z, ah.w, f0.z, f0.w);
               mma16816(tacc[mt][1], ah.x, ah.y, ah.z, ah.w, f1.z, f1.w);
+              mma16816(tacc[mt][0], al.x, al.y, al.z, al.w, f0.x, f0.y);
               mma16816(tacc[mt][1], al.x, al.y, al.z, al.w, f1.x, f1.y);
             }
           }
@@ -488,6 +537,7 @@ rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_t
         }
         __syncthreads();
       }
+      if (dbg_on) p.dbg[t * 8 + 2] = clock64();
       float* myred = red + kq * RB * RED_RS;
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
@@ -553,7 +603,9 @@ rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_t
         wpanel[wd + 128] = *reinterpret_cast<uint32_t*>(&lo);
       }
       if (cg == 0) p.pscale[(((size_t)wbuf * ngroups_total + group) * NCH + slice) * 64 + r] = inv_scale;
+      if (dbg_on) p.dbg[t * 8 + 3] = clock64();
       group_arrive(ctr);
+      if (dbg_on) p.dbg[t * 8 + 4] = clock64();
     }
     if (live) store8(p.dI + o0, d, vec, nv);  // tape store after the hand-over: off the critical path
   }
@@ -582,6 +634,13 @@ using namespace sparch;
 extern "C" {
 
 int sparch_recur_padded(int H) { return ((H + 31) / 32) * 32; }
+
+int sparch_recur_debug_clocks(long long* buf) {
+  g_dbg = buf;
+  const char* f = getenv("SPARCH_B200_DEBUG_FLAGS");
+  g_dbg_flags = (buf && f) ? atoi(f) : 0;
+  return SPARCH_OK;
+}
 
 int sparch_recur_prepare(const float* V, int H, uint32_t* img_fwd, uint32_t* img_bwd, int* meta,
                          sparch_stream_t st_) {
@@ -625,7 +684,7 @@ int sparch_recur_fwd(int kind, const float* Z, const float* scale, const float* 
   const size_t smem = rec_fwd_smem(Hp);
   SPARCH_REQUIRE(smem <= 225 * 1024, "hidden size too large for the resident V0 slice (H <= 1376)");
   RecFwdArgs p{Z, scale, shift, alpha, beta, a, b, rec0, u0, w0, s0, img_fwd, meta, theta, S, U, W,
-               reinterpret_cast<uint2*>(bits), Be, T, H, Hp};
+               reinterpret_cast<uint2*>(bits), Be, T, H, Hp, g_dbg, g_dbg_flags};
   cudaStream_t st = as_stream(st_);
   static int max_ctas = 0;
   if (max_ctas == 0) {
@@ -675,7 +734,7 @@ int sparch_recur_bwd(int kind, const float* G, const float* U, const float* W, c
   uint32_t* panel = reinterpret_cast<uint32_t*>(workspace);
   float* pscale = reinterpret_cast<float*>(panel + 2 * groups * (Hp / 32) * 2048);
   RecBwdArgs p{G, U, W, alpha, beta, a, b, u0, w0, s0, img_bwd, meta, theta, dI,
-               p_alpha, p_beta, p_a, p_b, panel, pscale, Be, T, H, Hp};
+               p_alpha, p_beta, p_a, p_b, panel, pscale, Be, T, H, Hp, g_dbg};
   cudaStream_t st = as_stream(st_);
   const size_t psmem = rec_bwd_persist_smem(Hp);
   SPARCH_REQUIRE(psmem <= 225 * 1024, "hidden size too large for the resident V0^T slice");

@@ -315,3 +315,74 @@ def test_eval_mode_and_dropout_train_mode():
     torch.manual_seed(3)
     o2, _ = net(x)
     assert torch.equal(o1, o2)
+
+
+def _oracle_cell_check(kind, Be, T, H, seed, drive=(3.0, 1.2), stable=True):
+    """Free-running CUDA cell vs the numpy oracle on random inputs: spikes (flip fraction), then the
+    given-mask backward when the spike trains agree exactly."""
+    _, F = _mods()
+    rng = np.random.default_rng(seed)
+    adaptive, recurrent = orc.kind_flags(kind)
+    I = (rng.standard_normal((Be, T, H)) * drive[0] + drive[1]).astype(np.float32)
+    alpha = rng.uniform(0.80, 0.97, H).astype(np.float32)          # some outside the clamp window
+    beta = rng.uniform(0.96, 0.995, H).astype(np.float32)
+    a = rng.uniform(0.0 if stable else -1.2, 1.2, H).astype(np.float32)
+    b = rng.uniform(-0.2, 2.2, H).astype(np.float32)
+    V = (rng.standard_normal((H, H)) / np.sqrt(H)).astype(np.float32)
+    u0, w0, s0 = (rng.uniform(0, 1, (Be, H)).astype(np.float32) for _ in range(3))
+    p = orc.clamp_params(kind, alpha, beta, a, b)
+    V0 = None
+    if recurrent:
+        V0 = V.copy()
+        np.fill_diagonal(V0, 0)
+    r = orc.cell_forward(kind, I, p["alpha"], p.get("beta"), p.get("a"), p.get("b"), V0, u0,
+                         w0 if adaptive else None, s0)
+    t = lambda z, g=False: torch.from_numpy(z).to(DEV).requires_grad_(g)
+    It, al, be, aa, bb, Vt = t(I, True), t(alpha, True), t(beta, True), t(a, True), t(b, True), t(V, True)
+    S = F.SpikingCellFunction.apply(It, None, None, al, be if adaptive else None, aa if adaptive else None,
+                                    bb if adaptive else None, Vt if recurrent else None, t(u0),
+                                    t(w0) if adaptive else None, t(s0), kind, 1.0, F.NormState("none"))
+    s_gpu = S.detach().cpu().numpy()
+    rate = float(r["s"].mean())
+    flips = float((s_gpu != r["s"]).mean())
+    assert Be * T * H < 1000 or 0.005 < rate < 0.95, rate
+    assert flips <= (FLIP_TOL if recurrent else 0.0), (kind, Be, T, H, flips)
+    if flips > 0:
+        return flips
+    gs = rng.standard_normal(s_gpu.shape).astype(np.float32)
+    S.backward(torch.from_numpy(gs).to(DEV))
+    bw = orc.cell_backward(kind, gs, I, p["alpha"], p.get("beta"), p.get("a"), p.get("b"), V0, u0,
+                           w0 if adaptive else None, s0, U=r["u"], W=r["w"], S=r["s"])
+    tol = 5e-5  # longer chains than the fixtures: fp32 accumulation over T*Be terms
+    assert rel_err(It.grad.cpu().numpy(), bw["dI"]) < tol
+    assert rel_err(al.grad.cpu().numpy(), bw["dalpha"] * orc.clamp_grad_mask(alpha, orc.ALPHA_LIM)) < tol
+    if adaptive:
+        for k, g_, raw, lim in (("beta", be, beta, orc.BETA_LIM), ("a", aa, a, orc.A_LIM), ("b", bb, b, orc.B_LIM)):
+            assert rel_err(g_.grad.cpu().numpy(), bw["d" + k] * orc.clamp_grad_mask(raw, lim)) < tol, k
+    if recurrent:
+        assert rel_err(Vt.grad.cpu().numpy(), bw["dV"]) < tol
+    return flips
+
+
+@pytest.mark.parametrize("kind,Be,T,H", [
+    ("RadLIF", 300, 7, 96),     # 5 row groups: ragged last group
+    ("RadLIF", 70, 5, 1000),    # H not a multiple of 32: padded spike words and V0 slices
+    ("RLIF", 3, 1, 40),         # single timestep, tiny batch
+    ("RadLIF", 640, 4, 512),    # 10 groups x 16 slices = 160 CTAs > 148: two cooperative launches
+    ("RLIF", 33, 60, 130),      # longer chain, odd sizes
+    ("adLIF", 65, 33, 77),      # streaming kernels, odd sizes, T not a multiple of the prefetch depth
+    ("LIF", 1, 1, 1),
+])
+def test_cell_edge_shapes_against_oracle(kind, Be, T, H):
+    _oracle_cell_check(kind, Be, T, H, seed=Be + T + H)
+
+
+def test_empty_batch_and_time_are_tolerated():
+    _, F = _mods()
+    for Be, T in ((0, 5), (4, 0)):
+        Z = torch.zeros(Be, T, 8, device=DEV)
+        al = torch.full((8,), 0.9, device=DEV)
+        S = F.SpikingCellFunction.apply(Z, None, None, al, None, None, None, None,
+                                        torch.zeros(Be, 8, device=DEV), None, torch.zeros(Be, 8, device=DEV),
+                                        "LIF", 1.0, F.NormState("none"))
+        assert S.shape == (Be, T, 8)

@@ -36,3 +36,36 @@ for it in range(3):
     print(f"iter {it}: rate {float(S.mean()):.3f} fwd {tm['recurrence_fwd']:.3f} ms "
           f"bwd {tm['recurrence_bwd']:.3f} ms  ({tm['recurrence_fwd'] / T * 1e3:.1f} / "
           f"{tm['recurrence_bwd'] / T * 1e3:.1f} us per step)")
+
+if os.environ.get("SPARCH_PHASES"):
+    from sparch_b200._lib import call, ptr
+    dbg = torch.zeros(T, 8, dtype=torch.int64, device=dev)
+    call("sparch_recur_debug_clocks", ptr(dbg))
+    S = F.SpikingCellFunction.apply(I, None, None, alpha, beta if adaptive else None, a if adaptive else None,
+                                    b if adaptive else None, V if recurrent else None, u0,
+                                    w0 if adaptive else None, s0, kind, 1.0, F.NormState("none"))
+    torch.cuda.synchronize()
+    call("sparch_recur_debug_clocks", None)
+    c = dbg.cpu().double()
+    d, prev_end = c[2:], c[1:-1, 3]
+    m = lambda x: float(x.mean())
+    print("forward phases, cycles/step (CTA 0,0): spike-word wait+load %.0f | mma %.0f | reduce %.0f | "
+          "update+publish %.0f | total %.0f"
+          % (m(d[:, 0] - prev_end), m(d[:, 1] - d[:, 0]), m(d[:, 2] - d[:, 1]), m(d[:, 3] - d[:, 2]),
+             m(d[:, 3] - prev_end)))
+    dbg.zero_()
+    call("sparch_recur_debug_clocks", ptr(dbg))
+    I2 = I.detach().clone().requires_grad_(True)
+    S = F.SpikingCellFunction.apply(I2, None, None, alpha, beta if adaptive else None, a if adaptive else None,
+                                    b if adaptive else None, V if recurrent else None, u0,
+                                    w0 if adaptive else None, s0, kind, 1.0, F.NormState("none"))
+    torch.cuda.synchronize()
+    dbg.zero_()
+    S.backward(g)
+    torch.cuda.synchronize()
+    call("sparch_recur_debug_clocks", None)
+    c = dbg.cpu().double()[2:-2]
+    print("backward phases, cycles/step (CTA 0,0): prefetch issue->wait done %.0f | stream+mma %.0f | "
+          "reduce+update+panel %.0f | fence+arrive %.0f | total %.0f"
+          % (m(c[:, 1] - c[:, 0]), m(c[:, 2] - c[:, 1]), m(c[:, 3] - c[:, 2]), m(c[:, 4] - c[:, 3]),
+             m(c[1:, 0] - c[:-1, 0]) * -1))
