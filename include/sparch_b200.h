@@ -127,16 +127,20 @@ SPARCH_API int sparch_split_bf16(const float* X, int64_t ldx, int M, int K, int 
 SPARCH_API int sparch_split_bf16_transpose(const float* X, int R, int C, int nparts, int T,
                                            int shift, float prescale, void* P0, void* P1,
                                            void* P2, int64_t ldp, sparch_stream_t st);
-/* C[M,N] (fp32, row stride ldc) = alpha * sum_p A[pair_a[p]] . B[pair_b[p]]^T (+ bias[n]);
- * A parts are (M, K) and B parts (N, K) bf16 row-major with row strides lda / ldb (multiples of
- * 8).  `workspace` (sparch_gemm_workspace bytes, may be NULL) enables deterministic split-K
- * when the output has fewer tiles than the GPU has SMs.                                      */
+/* C[M,N] (fp32, row stride ldc) = alpha * sum_p A[pair_a[p]] . B[pair_b[p]]^T (+ bias[n]).
+ * K-major operands (a_mn/b_mn = 0): A parts are (M, K) and B parts (N, K) bf16 row-major.
+ * MN-major operands (a_mn/b_mn = 1): the part in memory is the (K, M) resp. (K, N) row-major
+ * matrix -- the layout the contraction-over-frames GEMMs (dW, dV) find their operands in, so no
+ * transpose is materialised.  Row strides lda/ldb are multiples of 8 elements.  a_koff (MN-major
+ * A only) is added to A's K coordinate, out-of-range rows read as zero: a_koff = -1 pairs frame
+ * m of B with frame m-1 of A (S_prev in dV).  `workspace` (sparch_gemm_workspace bytes, may be
+ * NULL) enables deterministic split-K when the output has fewer tiles than the GPU has SMs.   */
 SPARCH_API size_t sparch_gemm_workspace(int M, int N, int K);
 SPARCH_API int sparch_gemm_bf16(const void* const* A_parts, int na, const void* const* B_parts,
-                                int nb, int64_t lda, int64_t ldb, const int* pair_a,
-                                const int* pair_b, int npairs, int M, int N, int K, float alpha,
-                                const float* bias, float* C, int64_t ldc, void* workspace,
-                                sparch_stream_t st);
+                                int nb, int64_t lda, int64_t ldb, int a_mn, int b_mn, int a_koff,
+                                const int* pair_a, const int* pair_b, int npairs, int M, int N,
+                                int K, float alpha, const float* bias, float* C, int64_t ldc,
+                                void* workspace, sparch_stream_t st);
 
 /* ---- recurrent kinds on the tensor pipe (snns.py:554-578, 696-727) --------------------- */
 /* Hidden size rounded up to a multiple of 32 (spike words / V0 slices are padded to it).    */

@@ -43,6 +43,8 @@ struct GemmParams {
   long long split_stride;
   float alpha;
   const float* bias;   // per column n, may be NULL (applied only when splits == 1)
+  int a_mn, b_mn;      // operand is MN-major in memory: a (K, MN) row-major matrix (weight-gradient GEMMs)
+  int a_koff;          // added to A's K coordinate (TMA zero-fills out-of-range rows): S_prev = S delayed by one frame
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -86,7 +88,21 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// kind::f16, bf16 x bf16 -> fp32, both K-major, M = 128, N = 256
+// MN-major, SWIZZLE_128B operand tile as TMA delivers it from a (K, MN) row-major matrix: per block of
+// 64 MN elements, 64 K rows of 128 bytes (8 KB); blocks of 64 MN elements follow each other.
+//   leading byte offset = distance between 64-element MN blocks, stride byte offset = distance between
+//   groups of 8 K rows (cute::UMMA canonical layout ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in elements).
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;                   // leading byte offset: next 64-wide MN block
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset: next 8 K rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// kind::f16, bf16 x bf16 -> fp32, M = 128, N = 256; bit 15 / 16 = A / B is MN-major
 constexpr uint32_t G_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
@@ -146,8 +162,20 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
           mbar_wait(bars + 8 * (GSTAGES + s), ph ^ 1);
           mbar_expect_tx(bars + 8 * s, G_STAGE_BYTES);
           const uint32_t sa = base + s * G_STAGE_BYTES;
-          tma_load_2d(sa, ma, kb * GK, m0, bars + 8 * s);
-          tma_load_2d(sa + G_A_BYTES, mb, kb * GK, n0, bars + 8 * s);
+          if (!p.a_mn) {
+            tma_load_2d(sa, ma, kb * GK, m0, bars + 8 * s);
+          } else {
+#pragma unroll
+            for (int blk = 0; blk < GM / 64; ++blk)
+              tma_load_2d(sa + blk * 8192, ma, m0 + blk * 64, kb * GK + p.a_koff, bars + 8 * s);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sa + G_A_BYTES, mb, kb * GK, n0, bars + 8 * s);
+          } else {
+#pragma unroll
+            for (int blk = 0; blk < GN / 64; ++blk)
+              tma_load_2d(sa + G_A_BYTES + blk * 8192, mb, n0 + blk * 64, kb * GK, bars + 8 * s);
+          }
         }
       }
     }
@@ -159,10 +187,15 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
         mbar_wait(bars + 8 * s, ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = base + s * G_STAGE_BYTES;
-        const uint64_t da = make_desc_k_sw128(sa), db = make_desc_k_sw128(sa + G_A_BYTES);
+        const uint64_t da = p.a_mn ? make_desc_mn_sw128(sa) : make_desc_k_sw128(sa);
+        const uint64_t db = p.b_mn ? make_desc_mn_sw128(sa + G_A_BYTES) : make_desc_k_sw128(sa + G_A_BYTES);
+        // K advance per UMMA (16 elements): K-major 32 bytes inside the swizzle atom (2 units of 16 B),
+        // MN-major 16 rows of 128 bytes (128 units)
+        const uint32_t ka = p.a_mn ? 128u : 2u, kb_ = p.b_mn ? 128u : 2u;
+        const uint32_t idesc = G_IDESC | (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);
 #pragma unroll
-        for (int k = 0; k < GK / 16; ++k)  // 16 bf16 = 32 bytes = 2 descriptor units inside the swizzle atom
-          umma_f16(tmem, da + 2 * k, db + 2 * k, G_IDESC, (it > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < GK / 16; ++k)
+          umma_f16(tmem, da + ka * k, db + kb_ * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
         umma_commit(bars + 8 * (GSTAGES + s));   // frees the smem stage when these MMAs retire
       }
       umma_commit(bars + 8 * (2 * GSTAGES));     // accumulator complete
@@ -343,6 +376,13 @@ static EncodeTiledFn get_encode() {
 }
 
 // bf16 matrix (rows, cols) row-major with row stride ld elements; box = (64 cols, box_rows rows), 128B swizzle.
+static int make_map(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows);
+
+// MN-major operand: the matrix in memory is (K rows, MN cols) row-major; one box = 64 K rows x 64 MN cols.
+static int make_map_mn(CUtensorMap* m, const void* ptr, long long krows, long long mncols, long long ld) {
+  return make_map(m, ptr, krows, mncols, ld, 64);
+}
+
 static int make_map(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
@@ -404,26 +444,31 @@ size_t sparch_gemm_workspace(int M, int N, int K) {
 }
 
 int sparch_gemm_bf16(const void* const* A_parts, int na, const void* const* B_parts, int nb, int64_t lda,
-                     int64_t ldb, const int* pair_a, const int* pair_b, int npairs, int M, int N, int K, float alpha,
-                     const float* bias, float* C, int64_t ldc, void* workspace, sparch_stream_t st_) {
+                     int64_t ldb, int a_mn, int b_mn, int a_koff, const int* pair_a, const int* pair_b, int npairs,
+                     int M, int N, int K, float alpha, const float* bias, float* C, int64_t ldc, void* workspace,
+                     sparch_stream_t st_) {
   SPARCH_REQUIRE(M > 0 && N > 0 && K > 0 && na >= 1 && na <= 3 && nb >= 1 && nb <= 3, "bad shape");
   SPARCH_REQUIRE(npairs >= 1 && npairs <= 8 && A_parts && B_parts && pair_a && pair_b && C, "bad argument");
-  SPARCH_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0 && lda >= K && ldb >= K,
-                 "operand row strides must be multiples of 8 bf16 elements (16 bytes) and >= K");
+  SPARCH_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0 && lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K),
+                 "operand row strides must be multiples of 8 bf16 elements (16 bytes) and cover a row");
+  SPARCH_REQUIRE(a_koff == 0 || a_mn, "a_koff applies to an MN-major A operand");
   cudaStream_t st = as_stream(st_);
   TmapSet maps;
   memset(&maps, 0, sizeof maps);
   for (int i = 0; i < na; ++i) {
     SPARCH_REQUIRE(A_parts[i] && (reinterpret_cast<uintptr_t>(A_parts[i]) & 15) == 0, "A part null or unaligned");
-    if (int e = make_map(&maps.a[i], A_parts[i], M, K, lda, GM)) return e;
+    if (int e = a_mn ? make_map_mn(&maps.a[i], A_parts[i], K, M, lda) : make_map(&maps.a[i], A_parts[i], M, K, lda, GM))
+      return e;
   }
   for (int i = 0; i < nb; ++i) {
     SPARCH_REQUIRE(B_parts[i] && (reinterpret_cast<uintptr_t>(B_parts[i]) & 15) == 0, "B part null or unaligned");
-    if (int e = make_map(&maps.b[i], B_parts[i], N, K, ldb, GN)) return e;
+    if (int e = b_mn ? make_map_mn(&maps.b[i], B_parts[i], K, N, ldb) : make_map(&maps.b[i], B_parts[i], N, K, ldb, GN))
+      return e;
   }
   GemmParams p;
   memset(&p, 0, sizeof p);
   p.M = M; p.N = N; p.K = K; p.npairs = npairs;
+  p.a_mn = a_mn; p.b_mn = b_mn; p.a_koff = a_koff;
   for (int i = 0; i < npairs; ++i) {
     SPARCH_REQUIRE(pair_a[i] >= 0 && pair_a[i] < na && pair_b[i] >= 0 && pair_b[i] < nb, "pair index out of range");
     p.pair_a[i] = pair_a[i];

@@ -127,32 +127,28 @@ class LinearFunction(torch.autograd.Function):
                     xa, alpha = gemm.split_rows(x2d, 1, prescale=1.0 / in_scale), float(in_scale)
                 wb = gemm.split_rows(_f32c(weight), 3)
                 Z = gemm.gemm_parts(xa, wb, K, alpha=alpha, bias=None if bias is None else _f32c(bias))
-        ctx.in_scale = in_scale
+        ctx.alpha = alpha
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(x2d, weight)
+        # the bf16 terms serve the backward GEMMs as they are (MN-major operands): no re-split
+        ctx.save_for_backward(xa, wb)
         ctx.xshape = x.shape
+        ctx.dims = (M, N, K)
         return Z.view(*x.shape[:-1], N)
 
     @staticmethod
     def backward(ctx, gZ):
-        x2d, weight = ctx.saved_tensors
-        M, K = x2d.shape
-        N = weight.shape[0]
+        xa, wb = ctx.saved_tensors
+        M, N, K = ctx.dims
         g2d = _f32c(gZ).reshape(M, N)
         dx = dw = db = None
         with _region("gemm_bwd"):
+            ga = gemm.split_rows(g2d, 3)
             if ctx.needs_input_grad[0]:
-                # dX = dZ @ W : contraction over N, B operand = W^T terms (K, N)
-                dx = gemm.gemm_parts(gemm.split_rows(g2d, 3), gemm.split_transposed(_f32c(weight), 3), N)
-                dx = dx.view(ctx.xshape)
+                # dX = dZ @ W: contraction over N; W's terms (N, K) are the MN-major B operand
+                dx = gemm.gemm_parts(ga, wb, N, b_mn=True, N=K).view(ctx.xshape)
             if ctx.needs_input_grad[1]:
-                # dW = dZ^T @ X : contraction over the Be*T frames
-                gt = gemm.split_transposed(g2d, 3)
-                if ctx.in_scale is None:
-                    xt, alpha = gemm.split_transposed(x2d, 3), 1.0
-                else:
-                    xt, alpha = gemm.split_transposed(x2d, 1, prescale=1.0 / ctx.in_scale), float(ctx.in_scale)
-                dw = gemm.gemm_parts(gt, xt, M, alpha=alpha)
+                # dW = dZ^T @ X: contraction over the Be*T frames, both operands MN-major
+                dw = gemm.gemm_parts(ga, xa, M, alpha=ctx.alpha, a_mn=True, b_mn=True, M=N, N=K)
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 db = g2d.sum(dim=0)
         return dx, dw, db, None
@@ -303,11 +299,17 @@ class SpikingCellFunction(torch.autograd.Function):
             region.__exit__()
             # dV = sum_t s_{t-1}^T dI_t, diagonal masked (clone().fill_diagonal_(0) backward)
             with _region("gemm_bwd"):
-                dV = s0.t() @ dI[:, 0, :]              # t = 0: s_{-1} is real-valued
-                if T > 1:
-                    sp = gemm.split_transposed(S.view(Be * T, H), 1, T=T, shift=1)
-                    dit = gemm.split_transposed(dI.view(Be * T, H), 3)
-                    dV += gemm.gemm_parts(sp, dit, Be * T)
+                # frame m of dI pairs with frame m-1 of S (a_koff = -1).  Inside a batch row that is
+                # s_{t-1}; across rows it pairs dI[b, 0] with S[b-1, T-1], which is replaced below by
+                # the real-valued initial state s0 (snns.py:702).
+                first = s0.clone()
+                if Be > 1:
+                    first[1:] -= S[:-1, T - 1, :]
+                dV = first.t() @ dI[:, 0, :]
+                if Be * T > 1:
+                    sp = gemm.split_rows(S.view(Be * T, H), 1)
+                    dit = gemm.split_rows(dI.view(Be * T, H), 3)
+                    dV += gemm.gemm_parts(sp, dit, Be * T, a_mn=True, b_mn=True, a_koff=-1, M=H, N=H)
                 dV.fill_diagonal_(0)
         psum = part.sum(dim=1)
         dalpha = psum[0] * _clamp_mask(alpha, ALPHA_LIM)

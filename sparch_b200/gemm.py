@@ -55,10 +55,17 @@ def split_transposed(x2d, nparts, T=0, shift=0, prescale=1.0):
     return parts
 
 
-def gemm_parts(A, B, K, alpha=1.0, bias=None, out=None, pairs=None):
-    """A: (na, M, lda) bf16 terms, B: (nb, N, ldb) bf16 terms -> (M, N) fp32."""
-    na, M, lda = A.shape
-    nb, N, ldb = B.shape
+def gemm_parts(A, B, K, alpha=1.0, bias=None, out=None, pairs=None, a_mn=False, b_mn=False, a_koff=0,
+               M=None, N=None):
+    """C (M, N) fp32 = alpha * sum_pairs A_i . B_j^T (+ bias).
+
+    K-major operand: terms of shape (n, rows, ld) with rows = M resp. N.  MN-major operand
+    (a_mn / b_mn): terms of shape (n, K, ld) holding the (K, M) resp. (K, N) matrix, M / N given
+    explicitly (ld may exceed it).  a_koff shifts A's K index (zero fill), MN-major A only."""
+    na, ra, lda = A.shape
+    nb, rb, ldb = B.shape
+    M = ra if not a_mn else M
+    N = rb if not b_mn else N
     if pairs is None:
         pairs = pairs_for(na, nb)
     dev = A.device
@@ -73,6 +80,6 @@ def gemm_parts(A, B, K, alpha=1.0, bias=None, out=None, pairs=None):
     tiles = ((M + 127) // 128) * ((N + 255) // 256)
     if tiles < 148 and K > 64:
         ws = torch.empty(_lib.lib().sparch_gemm_workspace(M, N, K), device=dev, dtype=torch.uint8)
-    call("sparch_gemm_bf16", ap, na, bp, nb, lda, ldb, pa, pb, len(pairs), M, N, K, float(alpha),
-         ptr(bias), ptr(out), out.stride(0), ptr(ws), _stream())
+    call("sparch_gemm_bf16", ap, na, bp, nb, lda, ldb, int(a_mn), int(b_mn), int(a_koff), pa, pb,
+         len(pairs), M, N, K, float(alpha), ptr(bias), ptr(out), out.stride(0), ptr(ws), _stream())
     return out

@@ -59,3 +59,33 @@ def test_transposed_gemm_with_time_shift():
     ref = torch.einsum("bti,btj->ij", S[:, :-1].double(), dI[:, 1:].double())
     err = float((dV.double() - ref).abs().max() / ref.abs().max())
     assert err < 2e-6, err
+
+
+@pytest.mark.parametrize("Kc,M,N", [(5000, 1024, 1024), (700, 96, 40), (1000, 130, 300), (64, 128, 256)])
+def test_gemm_mn_major_operands(Kc, M, N):
+    """Contraction-over-rows products C = P^T Q straight from the row-major (Kc, M) / (Kc, N) terms."""
+    from sparch_b200 import gemm
+    g = torch.Generator(device=DEV).manual_seed(Kc + M)
+    P = torch.randn(Kc, M, device=DEV, generator=g)
+    Q = torch.randn(Kc, N, device=DEV, generator=g) * 2
+    C = gemm.gemm_parts(gemm.split_rows(P, 3), gemm.split_rows(Q, 3), Kc, a_mn=True, b_mn=True, M=M, N=N)
+    ref = P.double().t() @ Q.double()
+    assert float((C.double() - ref).abs().max() / ref.abs().max()) < 2e-6
+    # mixed: K-major A with MN-major B  (dX = dZ W with W (H, Fin) row-major)
+    A = torch.randn(M, Kc, device=DEV, generator=g)
+    C = gemm.gemm_parts(gemm.split_rows(A, 3), gemm.split_rows(Q, 3), Kc, b_mn=True, N=N)
+    ref = A.double() @ Q.double()
+    assert float((C.double() - ref).abs().max() / ref.abs().max()) < 2e-6
+
+
+def test_gemm_mn_major_with_frame_delay():
+    """dV = sum_m S[m-1]^T dI[m] via a_koff = -1 (frame -1 reads as zero)."""
+    from sparch_b200 import gemm
+    Mf, H = 900, 96
+    g = torch.Generator(device=DEV).manual_seed(9)
+    S = (torch.rand(Mf, H, device=DEV, generator=g) < 0.2).float()
+    dI = torch.randn(Mf, H, device=DEV, generator=g)
+    C = gemm.gemm_parts(gemm.split_rows(S, 1), gemm.split_rows(dI, 3), Mf, a_mn=True, b_mn=True, a_koff=-1,
+                        M=H, N=H)
+    ref = S[:-1].double().t() @ dI[1:].double()
+    assert float((C.double() - ref).abs().max() / ref.abs().max()) < 2e-6
