@@ -1,7 +1,9 @@
 // Recurrent kinds (RLIF, RadLIF): the per-timestep product s_{t-1} @ V0 on the tensor pipe, fused
 // with the membrane update (snns.py:572, 718-724).
 //
-// Decomposition: CTA (slice, group) owns 32 neurons (columns of V0) and 64 batch rows.  Its slice
+// Decomposition: a CTA owns 32 neurons (columns of V0) and runs TWO independent 4-warp teams, each
+// owning 32 batch rows (its own named barrier, exchange buffers and arrival counter), so that one
+// team's exchange latency overlaps the other team's tensor work; the teams share only the V0 image.  Its slice
 // of V0 (Hp x 32) sits in shared memory as fp16 hi + fp16 lo (V0 * 2^k split in two, 22 mantissa
 // bits: products with a spike are exact, accumulation is fp32), already arranged in
 // mma.m16n8k16 B-fragment order so a warp loads its fragments with conflict-free 16-byte reads.
@@ -10,9 +12,9 @@
 // register.  A spike is encoded as 2.0 (fp16 pattern 0x4000, a single set bit), and the K order
 // inside a 32-neuron word is permuted so that the two halves of every fragment register are 16
 // bits apart in the word (the same permutation is baked into the V0 image; the factor 2 into its
-// scale).  8 warps = 4 K-quarters x 2 column halves; the K-quarters are reduced through shared
-// memory, then 256 threads apply the neuron update to the 64 x 32 block and emit the new spike
-// words, the fp32 spike/membrane/adaptation tapes.
+// scale).  The 4 warps of a team are 4 K-quarters (2 row tiles x 4 column tiles each); the K-quarters
+// are reduced through shared memory, then the team's 128 threads apply the neuron update to its 32 x 32
+// block (8 neurons per thread, state in registers) and emit the new spike words and the fp32 tapes.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -21,7 +23,9 @@
 
 namespace sparch {
 
-constexpr int RB = 64;       // batch rows per CTA
+constexpr int RB = 32;       // batch rows per team (two teams per CTA)
+constexpr int TEAMS = 2;
+constexpr int TT = 128;      // threads per team
 constexpr int RC = 32;       // neurons (V0 columns) per CTA
 constexpr int RED_RS = 40;   // row stride (floats) of the K-quarter reduction buffer: conflict-free float2 stores
 constexpr int VSCALE_EXP = 13;
@@ -156,21 +160,23 @@ struct RecBwdArgs {
   const int* meta;
   float theta;
   float *dI, *p_alpha, *p_beta, *p_a, *p_b;
-  uint32_t* panel;  // 2 x [groups][Hp/32 chunks][2048 words]
-  float* pscale;    // 2 x [groups][Hp/32][64]
+  uint32_t* panel;  // 2 x [groups][Hp/32 chunks][1024 words]   (groups of 32 rows)
+  float* pscale;    // 2 x [groups][Hp/32][32]
   int Be, T, H, Hp;
   long long* dbg;   // optional [T][8] phase clocks of CTA (0,0) (profiling aid), normally NULL
 };
 
-// ------------------------------------------------------------------ persistent variants
+// ------------------------------------------------------------------ persistent kernels
 // One cooperative launch runs all T steps.  The V0 image is loaded into shared memory once and the
 // per-neuron state (u, w, previous spike; adjoints and parameter-gradient sums in the reverse
 // kernel) stays in registers across timesteps.  The only inter-CTA traffic per step is the
-// exchange of the step's spike words (forward) or dI panels (reverse) through L2, ordered by one
-// monotonically increasing counter per batch group: every slice of the group adds 1 after its
-// stores (release); a step may start when the counter has reached slices * steps_done (acquire).
-__device__ __forceinline__ void group_wait(const int* ctr, int target) {
-  if (threadIdx.x == 0) {
+// exchange of the step's spike words (forward: tagged 8-byte words polled directly) or dI panels
+// (reverse: ordered by one monotonically increasing counter per 32-row group).
+__device__ __forceinline__ void team_sync(int team) {
+  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(TT) : "memory");
+}
+__device__ __forceinline__ void group_wait(const int* ctr, int target, int lt, int team) {
+  if (lt == 0) {
     const long long t0 = clock64();
     while (true) {
       int v;
@@ -179,42 +185,35 @@ __device__ __forceinline__ void group_wait(const int* ctr, int target) {
       if (clock64() - t0 > 4000000000LL) __trap();  // a lost arrival must not hang the GPU
     }
   }
-  __syncthreads();
+  team_sync(team);
 }
-__device__ __forceinline__ void group_arrive(int* ctr) {
+__device__ __forceinline__ void group_arrive(int* ctr, int lt, int team) {
   __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ctr) : "memory");
+  team_sync(team);
+  if (lt == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ctr) : "memory");
 }
+
+constexpr int FWD_TEAM_WORDS_FIXED = 4 * RB * RED_RS;  // reduction buffer (floats); spike tile follows
 
 template <bool ADAPT>
-__global__ void __launch_bounds__(256, 1)
-rec_fwd_persist_kernel(const RecFwdArgs p, const int group0) {
+__global__ void __launch_bounds__(TEAMS* TT, 1) rec_fwd_persist_kernel(const RecFwdArgs p, const int group0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int NW = p.Hp / 32;
-  const int RSB = NW + 1;
+  const int NW = p.Hp / 32;   // spike words per row
+  const int RSB = NW + 1;     // padded row stride of the spike-word tile
+  const int tid = threadIdx.x, lane = tid & 31, team = tid >> 7, lt = tid & (TT - 1);
+  const int kq = (tid >> 5) & 3, g = lane >> 2, q = lane & 3;
   uint32_t* simg = reinterpret_cast<uint32_t*>(smem_raw);
-  float* red = reinterpret_cast<float*>(smem_raw + (size_t)p.Hp * 128);
-  uint32_t* sbits = reinterpret_cast<uint32_t*>(red + 4 * RB * RED_RS);
+  const size_t team_words = (size_t)FWD_TEAM_WORDS_FIXED + (size_t)RB * RSB;
+  float* red = reinterpret_cast<float*>(smem_raw + (size_t)p.Hp * 128) + team * team_words;
+  uint32_t* sbits = reinterpret_cast<uint32_t*>(red + FWD_TEAM_WORDS_FIXED);
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int slice = blockIdx.x, group = group0 + blockIdx.y, row0 = group * RB;
-  const int kq = warp >> 1, nh = warp & 1, g = lane >> 2, q = lane & 3;
+  const int slice = blockIdx.x, group = group0 + TEAMS * blockIdx.y + team, row0 = group * RB;
 
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.img + (size_t)slice * p.Hp * 32);
     uint4* dst = reinterpret_cast<uint4*>(simg);
-    for (int i = tid; i < p.Hp * 8; i += 256) cp_async16(dst + i, src + i);
+    for (int i = tid; i < p.Hp * 8; i += TEAMS * TT) cp_async16(dst + i, src + i);
   }
-  const int r = tid >> 2, cg = tid & 3;
-  const int row = row0 + r;
-  const int col0 = slice * RC + cg * 8;
-  const bool live = row < p.Be && col0 < p.H;
-  const bool vec = ((p.H & 3) == 0) && (col0 + 8 <= p.H);
-  const int nv = live ? min(8, p.H - col0) : 0;
-  const int64_t idx0 = (int64_t)row * p.H + col0;
-  const float rs = ldexpf(1.0f, p.meta[0] - VSCALE_EXP);
-
   __shared__ float sprm[8][RC];  // alpha, 1-alpha, beta, a, b, 1/(1-alpha), scale, shift of the slice
   if (tid < RC) {
     const int col = min(slice * RC + tid, p.H - 1);
@@ -224,6 +223,14 @@ rec_fwd_persist_kernel(const RecFwdArgs p, const int group0) {
     sprm[6][tid] = p.scale ? p.scale[col] : 1.0f;
     sprm[7][tid] = p.scale ? p.shift[col] : 0.0f;
   }
+  const int r = lt >> 2, cg = lt & 3;
+  const int row = row0 + r;
+  const int col0 = slice * RC + cg * 8;
+  const bool live = row < p.Be && col0 < p.H;
+  const bool vec = ((p.H & 3) == 0) && (col0 + 8 <= p.H);
+  const int nv = live ? min(8, p.H - col0) : 0;
+  const int64_t idx0 = (int64_t)row * p.H + col0;
+  const float rs = ldexpf(1.0f, p.meta[0] - VSCALE_EXP);
   float u[8], w[8], s[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) u[i] = w[i] = s[i] = 0.f;
@@ -233,7 +240,11 @@ rec_fwd_persist_kernel(const RecFwdArgs p, const int group0) {
     if (ADAPT) load8(p.w0 + idx0, w, vec, nv);
   }
   cp_async_wait_all();
-  __syncthreads();
+  __syncthreads();            // V0 image and parameter table visible to both teams
+  if (row0 >= p.Be) return;   // odd number of row groups: the last CTA's second team has no rows
+  // (Starting team 1 half a step late, to run the two pipelines in anti-phase, was measured: no gain --
+  // a single warp issues one HMMA.16816 per ~18 cycles, so a team's MMA phase lasts ~4.7 k cycles with
+  // or without the other team competing for the tensor pipe.)
 
   const uint4* bimg = reinterpret_cast<const uint4*>(simg);
   bool tapes_pending = false;
@@ -247,18 +258,17 @@ rec_fwd_persist_kernel(const RecFwdArgs p, const int group0) {
     if (t > 0) {
       // Wait for and fetch the spike words of step t-1 in one go: each word travels with its step
       // tag in a single 8-byte store, so a matching tag means the data is there (no fence, no
-      // separate flag).  All of a thread's loads are issued before any tag is checked.
+      // separate flag).  All of a thread's loads are issued before any result is looked at.
       const uint2* bsrc = p.bits + (size_t)(t - 1) * p.Be * NW;
       const long long t0 = clock64();
       if (dbg_on) p.dbg[t * 8 + 4] = t0;
-      for (int base = 0; base < RB * NW; base += 256 * 8) {
-        // issue every load of the batch before looking at any result (independent L2 round trips)
+      for (int base = 0; base < RB * NW; base += TT * 8) {
         const uint2* src[8];
         int dst[8];
         bool need[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const int i = base + k * 256 + tid;
+          const int i = base + k * TT + lt;
           const int rr = i / NW, wi = i - rr * NW;
           need[k] = i < RB * NW && row0 + rr < p.Be;
           dst[k] = i < RB * NW ? rr * RSB + wi : -1;
@@ -293,64 +303,65 @@ rec_fwd_persist_kernel(const RecFwdArgs p, const int group0) {
         for (int k = 0; k < 8; ++k)
           if (dst[k] >= 0) sbits[dst[k]] = bv[k];
       }
-      __syncthreads();
+      team_sync(team);
       if (dbg_on) p.dbg[t * 8 + 0] = clock64();
-      float acc[4][2][4];
+
+      float acc[2][4][4];
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
+        for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
           for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
       for (int wi = kq; wi < NW; wi += 4) {
-        uint32_t wa[4], wb[4];
+        uint32_t wa[2], wb[2];
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
+        for (int mt = 0; mt < 2; ++mt) {
           const uint32_t x0 = sbits[(16 * mt + g) * RSB + wi], x1 = sbits[(16 * mt + g + 8) * RSB + wi];
           wa[mt] = __funnelshift_r(x0, x0, 4 * q);
           wb[mt] = __funnelshift_r(x1, x1, 4 * q);
         }
+        // both k-steps of the word: 4 passes over the 8 accumulators (hi ks0, hi ks1, lo ks0, lo ks1), so
+        // two HMMAs on the same accumulator are always 8 instructions apart
+        uint4 f[2][4];
+        uint32_t af[2][2][4];
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
           const int kk = 2 * wi + ks;
-          const uint4 f0 = bimg[((kk * 2 + nh) * 2 + 0) * 32 + lane];
-          const uint4 f1 = bimg[((kk * 2 + nh) * 2 + 1) * 32 + lane];
-          // hi terms of all 8 accumulators first, then the lo terms: consecutive HMMAs never
-          // chain on the same accumulator
-          uint32_t af[4][4];
 #pragma unroll
-          for (int mt = 0; mt < 4; ++mt) {
+          for (int nt = 0; nt < 4; ++nt) f[ks][nt] = bimg[(kk * 4 + nt) * 32 + lane];  // ((kk*2+nh)*2+blk), nt = 2nh+blk
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
             const uint32_t M = 0x40004000u;
-            af[mt][0] = __funnelshift_r(wa[mt], wa[mt], 2 * ks) & M;
-            af[mt][1] = __funnelshift_r(wb[mt], wb[mt], 2 * ks) & M;
-            af[mt][2] = __funnelshift_r(wa[mt], wa[mt], 2 * ks + 1) & M;
-            af[mt][3] = __funnelshift_r(wb[mt], wb[mt], 2 * ks + 1) & M;
-          }
-#pragma unroll
-          for (int mt = 0; mt < 4; ++mt) {
-            mma16816(acc[mt][0], af[mt][0], af[mt][1], af[mt][2], af[mt][3], f0.x, f0.y);
-            mma16816(acc[mt][1], af[mt][0], af[mt][1], af[mt][2], af[mt][3], f1.x, f1.y);
-          }
-#pragma unroll
-          for (int mt = 0; mt < 4; ++mt) {
-            mma16816(acc[mt][0], af[mt][0], af[mt][1], af[mt][2], af[mt][3], f0.z, f0.w);
-            mma16816(acc[mt][1], af[mt][0], af[mt][1], af[mt][2], af[mt][3], f1.z, f1.w);
+            af[ks][mt][0] = __funnelshift_r(wa[mt], wa[mt], 2 * ks) & M;
+            af[ks][mt][1] = __funnelshift_r(wb[mt], wb[mt], 2 * ks) & M;
+            af[ks][mt][2] = __funnelshift_r(wa[mt], wa[mt], 2 * ks + 1) & M;
+            af[ks][mt][3] = __funnelshift_r(wb[mt], wb[mt], 2 * ks + 1) & M;
           }
         }
+#pragma unroll
+        for (int part = 0; part < 2; ++part)
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+              for (int nt = 0; nt < 4; ++nt)
+                mma16816(acc[mt][nt], af[ks][mt][0], af[ks][mt][1], af[ks][mt][2], af[ks][mt][3],
+                         part ? f[ks][nt].z : f[ks][nt].x, part ? f[ks][nt].w : f[ks][nt].y);
       }
       if (dbg_on) p.dbg[t * 8 + 1] = clock64();
       float* myred = red + kq * RB * RED_RS;
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          int col = 16 * nh + 8 * nt + 2 * q;
-          *reinterpret_cast<float2*>(&myred[(16 * mt + g) * RED_RS + col]) =
-              make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+        for (int nt = 0; nt < 4; ++nt) {
+          const int col = 8 * nt + 2 * q;
+          *reinterpret_cast<float2*>(&myred[(16 * mt + g) * RED_RS + col]) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
           *reinterpret_cast<float2*>(&myred[(16 * mt + g + 8) * RED_RS + col]) =
               make_float2(acc[mt][nt][2], acc[mt][nt][3]);
         }
-      __syncthreads();
+      team_sync(team);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int c = cg * 8 + i;
@@ -393,45 +404,37 @@ rec_fwd_persist_kernel(const RecFwdArgs p, const int group0) {
       store8(p.U + o0, u, vec, nv);
       if (ADAPT) store8(p.W + o0, w, vec, nv);
     }
-    __syncthreads();             // sbits / red are rewritten by the next step
+    team_sync(team);             // sbits / red are rewritten by the next step
     if (dbg_on) p.dbg[t * 8 + 3] = clock64();
   }
 }
 
-constexpr int PB_STAGE_WORDS = 4 * 2048;  // 4 chunks of the A panel = 32 KB
+constexpr int PB_CHUNK_WORDS = 1024;                   // one 32-column chunk of a 32-row panel: 4 KB
+constexpr int PB_STAGE_WORDS = 4 * PB_CHUNK_WORDS;     // 4 chunks (one per K-quarter) = 16 KB
 constexpr int PB_STAGES = 2;
 
 template <bool ADAPT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(TEAMS* TT, 1)
 rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_total, int* __restrict__ counters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NCH = p.Hp / 32;
-  uint32_t* simg = reinterpret_cast<uint32_t*>(smem_raw);                                   // V0^T image
-  uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw + (size_t)p.Hp * 128);               // A stages
-  float* sscale = reinterpret_cast<float*>(smem_raw + (size_t)p.Hp * 128 + (size_t)PB_STAGES * PB_STAGE_WORDS * 4);
-  float* red = reinterpret_cast<float*>(ring);                                              // aliases the ring
+  const int tid = threadIdx.x, lane = tid & 31, team = tid >> 7, lt = tid & (TT - 1);
+  const int kq = (tid >> 5) & 3, g = lane >> 2, q = lane & 3;
+  uint32_t* simg = reinterpret_cast<uint32_t*>(smem_raw);                          // V0^T image (shared by both teams)
+  const size_t team_words = (size_t)PB_STAGES * PB_STAGE_WORDS + (size_t)NCH * RB;
+  uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw + (size_t)p.Hp * 128) + team * team_words;  // A stages
+  float* sscale = reinterpret_cast<float*>(ring + PB_STAGES * PB_STAGE_WORDS);
+  float* red = reinterpret_cast<float*>(ring);                                     // aliases the ring after the K loop
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int slice = blockIdx.x, group = group0 + blockIdx.y, row0 = group * RB;
+  const int slice = blockIdx.x, group = group0 + TEAMS * blockIdx.y + team, row0 = group * RB;
   const int nslices = gridDim.x;
-  const int kq = warp >> 1, nh = warp & 1, g = lane >> 2, q = lane & 3;
   int* ctr = counters + group;
 
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.img + (size_t)slice * p.Hp * 32);
     uint4* dst = reinterpret_cast<uint4*>(simg);
-    for (int i = tid; i < p.Hp * 8; i += 256) cp_async16(dst + i, src + i);
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    for (int i = tid; i < p.Hp * 8; i += TEAMS * TT) cp_async16(dst + i, src + i);
   }
-  const int r = tid >> 2, cg = tid & 3;
-  const int row = row0 + r;
-  const int col0 = slice * RC + cg * 8;
-  const bool live = row < p.Be && col0 < p.H;
-  const bool vec = ((p.H & 3) == 0) && (col0 + 8 <= p.H);
-  const int nv = live ? min(8, p.H - col0) : 0;
-  const int64_t idx0 = (int64_t)row * p.H + col0;
-  const float rs = ldexpf(1.0f, p.meta[0] - VSCALE_EXP);
-
   __shared__ float sprm[6][RC];  // alpha, 1-alpha, beta, a, b, 1/(1-alpha) of the slice
   if (tid < RC) {
     const int col = min(slice * RC + tid, p.H - 1);
@@ -439,10 +442,22 @@ rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_t
     sprm[0][tid] = q0.alpha; sprm[1][tid] = q0.oma; sprm[2][tid] = q0.beta; sprm[3][tid] = q0.a;
     sprm[4][tid] = q0.b; sprm[5][tid] = 1.0f / q0.oma;
   }
+  const int r = lt >> 2, cg = lt & 3;
+  const int row = row0 + r;
+  const int col0 = slice * RC + cg * 8;
+  const bool live = row < p.Be && col0 < p.H;
+  const bool vec = ((p.H & 3) == 0) && (col0 + 8 <= p.H);
+  const int nv = live ? min(8, p.H - col0) : 0;
+  const int64_t idx0 = (int64_t)row * p.H + col0;
+  const float rs = ldexpf(1.0f, p.meta[0] - VSCALE_EXP);
   float du[8], dw[8], pa[8], pb[8], pc[8], pd[8], ut[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) du[i] = dw[i] = pa[i] = pb[i] = pc[i] = pd[i] = ut[i] = 0.f;
   if (live && p.T > 0) load8(p.U + ((int64_t)row * p.T + (p.T - 1)) * p.H + col0, ut, vec, nv);
+  cp_async_wait_all();
+  __syncthreads();            // V0^T image and parameter table visible to both teams
+  if (row0 >= p.Be) return;   // odd number of row groups: the last CTA's second team has no rows
+
   const uint4* bimg = reinterpret_cast<const uint4*>(simg);
   const int NSC = (NCH + 3) / 4;
 
@@ -466,68 +481,67 @@ rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_t
     const bool dbg_on = p.dbg && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
     if (dbg_on) p.dbg[t * 8 + 0] = clock64();
     if (t < p.T - 1) {
-      group_wait(ctr, nslices * (p.T - 1 - t));
+      group_wait(ctr, nslices * (p.T - 1 - t), lt, team);
       if (dbg_on) p.dbg[t * 8 + 1] = clock64();
-      const uint32_t* apanel = p.panel + ((size_t)rbuf * ngroups_total + group) * NCH * 2048;
-      const float* gsc = p.pscale + ((size_t)rbuf * ngroups_total + group) * NCH * 64;
-      // (Starting each CTA's walk over the panel at a different super-chunk was measured: no gain.)
-      const int rot = 0;
+      const uint32_t* apanel = p.panel + ((size_t)rbuf * ngroups_total + group) * NCH * PB_CHUNK_WORDS;
+      const float* gsc = p.pscale + ((size_t)rbuf * ngroups_total + group) * NCH * RB;
       auto issue = [&](int sc) {
         if (sc < NSC) {
           uint32_t* dst = ring + (size_t)(sc % PB_STAGES) * PB_STAGE_WORDS;
-          const int psc = (sc + rot) % NSC;
-          const int nch = min(4, NCH - 4 * psc);
-          const uint4* sa = reinterpret_cast<const uint4*>(apanel + (size_t)4 * psc * 2048);
+          const int nch = min(4, NCH - 4 * sc);
+          const uint4* sa = reinterpret_cast<const uint4*>(apanel + (size_t)4 * sc * PB_CHUNK_WORDS);
           uint4* da = reinterpret_cast<uint4*>(dst);
-          for (int i = tid; i < nch * 512; i += 256) cp_async16(da + i, sa + i);
+          for (int i = lt; i < nch * (PB_CHUNK_WORDS / 4); i += TT) cp_async16(da + i, sa + i);
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
       };
-      for (int i = tid; i < NCH * 64; i += 256) sscale[i] = __ldcg(&gsc[i]);
+      for (int i = lt; i < NCH * RB; i += TT) sscale[i] = __ldcg(&gsc[i]);
       issue(0);
-      float acc[4][2][4];
+      float acc[2][4][4];
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
+        for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
           for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
       for (int sc = 0; sc < NSC; ++sc) {
         issue(sc + 1);
         asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-        __syncthreads();
-        const int c = 4 * ((sc + rot) % NSC) + kq;
+        team_sync(team);
+        const int c = 4 * sc + kq;
         if (c < NCH) {
-          const uint4* a4 = reinterpret_cast<const uint4*>(ring + (size_t)(sc % PB_STAGES) * PB_STAGE_WORDS) + kq * 512;
-          float tacc[4][2][4];
+          const uint4* a4 = reinterpret_cast<const uint4*>(ring + (size_t)(sc % PB_STAGES) * PB_STAGE_WORDS) +
+                            kq * (PB_CHUNK_WORDS / 4);
+          float tacc[2][4][4];
 #pragma unroll
-          for (int mt = 0; mt < 4; ++mt)
+          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt)
+            for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
               for (int i = 0; i < 4; ++i) tacc[mt][nt][i] = 0.f;
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
             const int kk = 2 * c + ks;
-            const uint4 f0 = bimg[((kk * 2 + nh) * 2 + 0) * 32 + lane];
-            const uint4 f1 = bimg[((kk * 2 + nh) * 2 + 1) * 32 + lane];
+            uint4 f[4];
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt) {
+            for (int nt = 0; nt < 4; ++nt) f[nt] = bimg[(kk * 4 + nt) * 32 + lane];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
               const uint4 ah = a4[((mt * 2 + ks) * 2 + 0) * 32 + lane];
               const uint4 al = a4[((mt * 2 + ks) * 2 + 1) * 32 + lane];
-              mma16816(tacc[mt][0], ah.x, ah.y, ah.z, ah.w, f0.x, f0.y);
-              mma16816(tacc[mt][1], ah.x, ah.y, ah.z, ah.w, f1.x, f1.y);
-              mma16816(tacc[mt][0], ah.x, ah.y, ah.z, ah.w, f0.z, f0.w);
-              mma16816(tacc[mt][1], ah.x, ah.y, ah.z, ah.w, f1.z, f1.w);
-              mma16816(tacc[mt][0], al.x, al.y, al.z, al.w, f0.x, f0.y);
-              mma16816(tacc[mt][1], al.x, al.y, al.z, al.w, f1.x, f1.y);
+#pragma unroll
+              for (int nt = 0; nt < 4; ++nt) mma16816(tacc[mt][nt], ah.x, ah.y, ah.z, ah.w, f[nt].x, f[nt].y);
+#pragma unroll
+              for (int nt = 0; nt < 4; ++nt) mma16816(tacc[mt][nt], ah.x, ah.y, ah.z, ah.w, f[nt].z, f[nt].w);
+#pragma unroll
+              for (int nt = 0; nt < 4; ++nt) mma16816(tacc[mt][nt], al.x, al.y, al.z, al.w, f[nt].x, f[nt].y);
             }
           }
 #pragma unroll
-          for (int mt = 0; mt < 4; ++mt) {
-            const float s_lo = sscale[c * 64 + 16 * mt + g], s_hi = sscale[c * 64 + 16 * mt + g + 8];
+          for (int mt = 0; mt < 2; ++mt) {
+            const float s_lo = sscale[c * RB + 16 * mt + g], s_hi = sscale[c * RB + 16 * mt + g + 8];
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
+            for (int nt = 0; nt < 4; ++nt) {
               acc[mt][nt][0] = fmaf(tacc[mt][nt][0], s_lo, acc[mt][nt][0]);
               acc[mt][nt][1] = fmaf(tacc[mt][nt][1], s_lo, acc[mt][nt][1]);
               acc[mt][nt][2] = fmaf(tacc[mt][nt][2], s_hi, acc[mt][nt][2]);
@@ -535,30 +549,26 @@ rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_t
             }
           }
         }
-        __syncthreads();
+        team_sync(team);
       }
       if (dbg_on) p.dbg[t * 8 + 2] = clock64();
       float* myred = red + kq * RB * RED_RS;
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          int col = 16 * nh + 8 * nt + 2 * q;
-          *reinterpret_cast<float2*>(&myred[(16 * mt + g) * RED_RS + col]) =
-              make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+        for (int nt = 0; nt < 4; ++nt) {
+          const int col = 8 * nt + 2 * q;
+          *reinterpret_cast<float2*>(&myred[(16 * mt + g) * RED_RS + col]) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
           *reinterpret_cast<float2*>(&myred[(16 * mt + g + 8) * RED_RS + col]) =
               make_float2(acc[mt][nt][2], acc[mt][nt][3]);
         }
-      __syncthreads();
+      team_sync(team);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int c = cg * 8 + i;
         recb[i] = ((red[(0 * RB + r) * RED_RS + c] + red[(1 * RB + r) * RED_RS + c]) +
                    (red[(2 * RB + r) * RED_RS + c] + red[(3 * RB + r) * RED_RS + c])) * rs;
       }
-    } else {
-      asm volatile("cp.async.wait_group 0;\n" ::: "memory");  // V0^T image resident before first use
-      __syncthreads();
     }
     if (live) {
       if (t > 0) {
@@ -581,6 +591,7 @@ rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_t
       }
     }
     if (t > 0) {
+      // hand dI_t to step t-1: block floating point fp16 hi/lo in mma A-fragment order
       float m = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) m = fmaxf(m, fabsf(d[i]));
@@ -590,7 +601,7 @@ rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_t
       if (m > 0.f && m <= 3.0e38f) frexpf(m, &e);
       e = max(e, -100);
       const float up_scale = ldexpf(1.0f, 4 - e), inv_scale = ldexpf(1.0f, e - 4);
-      uint32_t* wpanel = p.panel + (((size_t)wbuf * ngroups_total + group) * NCH + slice) * 2048;
+      uint32_t* wpanel = p.panel + (((size_t)wbuf * ngroups_total + group) * NCH + slice) * PB_CHUNK_WORDS;
       const int mt = r >> 4, rr = r & 15, gg = rr & 7, upper = rr >> 3, ks = cg >> 1, hs = cg & 1;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -602,9 +613,9 @@ rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_t
         wpanel[wd] = *reinterpret_cast<uint32_t*>(&hi);
         wpanel[wd + 128] = *reinterpret_cast<uint32_t*>(&lo);
       }
-      if (cg == 0) p.pscale[(((size_t)wbuf * ngroups_total + group) * NCH + slice) * 64 + r] = inv_scale;
+      if (cg == 0) p.pscale[(((size_t)wbuf * ngroups_total + group) * NCH + slice) * RB + r] = inv_scale;
       if (dbg_on) p.dbg[t * 8 + 3] = clock64();
-      group_arrive(ctr);
+      group_arrive(ctr, lt, team);
       if (dbg_on) p.dbg[t * 8 + 4] = clock64();
     }
     if (live) store8(p.dI + o0, d, vec, nv);  // tape store after the hand-over: off the critical path
@@ -620,11 +631,11 @@ rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_t
 }
 
 static size_t rec_bwd_persist_smem(int Hp) {
-  return (size_t)Hp * 128 + (size_t)PB_STAGES * PB_STAGE_WORDS * 4 + (size_t)(Hp / 32) * 64 * 4;
+  return (size_t)Hp * 128 + TEAMS * ((size_t)PB_STAGES * PB_STAGE_WORDS * 4 + (size_t)(Hp / 32) * RB * 4);
 }
 
 static size_t rec_fwd_smem(int Hp) {
-  return (size_t)Hp * 128 + (size_t)4 * RB * RED_RS * sizeof(float) + (size_t)RB * (Hp / 32 + 1) * 4;
+  return (size_t)Hp * 128 + TEAMS * ((size_t)FWD_TEAM_WORDS_FIXED * 4 + (size_t)RB * (Hp / 32 + 1) * 4);
 }
 
 }  // namespace sparch
@@ -694,16 +705,16 @@ int sparch_recur_fwd(int kind, const float* Z, const float* scale, const float* 
   }
   const int slices = Hp / RC, groups = (Be + RB - 1) / RB;
   SPARCH_REQUIRE(slices <= max_ctas, "hidden size needs more co-resident CTAs than the GPU has SMs");
-  const int gmax = max_ctas / slices;
+  const int gmax = TEAMS * (max_ctas / slices);   // row groups (of 32) per cooperative launch
   // tags are t+1 >= 1: a zeroed buffer means "nothing published yet"
   SPARCH_CUDA(cudaMemsetAsync(bits, 0, sizeof(uint2) * (size_t)T * Be * (Hp / 32), st));
   for (int g0 = 0; g0 < groups; g0 += gmax) {
     int gn = groups - g0 < gmax ? groups - g0 : gmax;
-    dim3 cgrid(slices, gn);
+    dim3 cgrid(slices, (gn + TEAMS - 1) / TEAMS);
     int group0 = g0;
     void* args[] = {(void*)&p, (void*)&group0};
     const void* fn = adapt ? (const void*)rec_fwd_persist_kernel<true> : (const void*)rec_fwd_persist_kernel<false>;
-    SPARCH_CUDA(cudaLaunchCooperativeKernel(fn, cgrid, dim3(256), args, smem + 0, st));
+    SPARCH_CUDA(cudaLaunchCooperativeKernel(fn, cgrid, dim3(TEAMS * TT), args, smem, st));
   }
   return SPARCH_OK;
 }
@@ -713,7 +724,7 @@ int sparch_recur_sync_words(int Be) { return (Be + RB - 1) / RB + 1; }
 size_t sparch_recur_bwd_workspace(int Be, int H) {
   const int Hp = sparch_recur_padded(H);
   const size_t groups = (size_t)(Be + RB - 1) / RB;
-  return 2 * groups * (Hp / 32) * 2048 * 4 + 2 * groups * (Hp / 32) * 64 * 4;
+  return 2 * groups * (Hp / 32) * PB_CHUNK_WORDS * 4 + 2 * groups * (Hp / 32) * RB * 4;
 }
 
 int sparch_recur_bwd(int kind, const float* G, const float* U, const float* W, const float* alpha,
@@ -732,7 +743,7 @@ int sparch_recur_bwd(int kind, const float* G, const float* U, const float* W, c
   const int Hp = sparch_recur_padded(H);
   const size_t groups = (size_t)(Be + RB - 1) / RB;
   uint32_t* panel = reinterpret_cast<uint32_t*>(workspace);
-  float* pscale = reinterpret_cast<float*>(panel + 2 * groups * (Hp / 32) * 2048);
+  float* pscale = reinterpret_cast<float*>(panel + 2 * groups * (Hp / 32) * PB_CHUNK_WORDS);
   RecBwdArgs p{G, U, W, alpha, beta, a, b, u0, w0, s0, img_bwd, meta, theta, dI,
                p_alpha, p_beta, p_a, p_b, panel, pscale, Be, T, H, Hp, g_dbg};
   cudaStream_t st = as_stream(st_);
@@ -746,15 +757,15 @@ int sparch_recur_bwd(int kind, const float* G, const float* U, const float* W, c
   }
   const int slices = Hp / RC;
   SPARCH_REQUIRE(slices <= max_ctas, "hidden size needs more co-resident CTAs than the GPU has SMs");
-  const int gmax = max_ctas / slices;
+  const int gmax = TEAMS * (max_ctas / slices);
   SPARCH_CUDA(cudaMemsetAsync(sync_ws, 0, sizeof(int) * groups, st));
   for (int g0 = 0; g0 < (int)groups; g0 += gmax) {
     int gn = (int)groups - g0 < gmax ? (int)groups - g0 : gmax;
-    dim3 cgrid(slices, gn);
+    dim3 cgrid(slices, (gn + TEAMS - 1) / TEAMS);
     int group0 = g0, ngt = (int)groups;
     void* args[] = {(void*)&p, (void*)&group0, (void*)&ngt, (void*)&sync_ws};
     const void* fn = adapt ? (const void*)rec_bwd_persist_kernel<true> : (const void*)rec_bwd_persist_kernel<false>;
-    SPARCH_CUDA(cudaLaunchCooperativeKernel(fn, cgrid, dim3(256), args, psmem, st));
+    SPARCH_CUDA(cudaLaunchCooperativeKernel(fn, cgrid, dim3(TEAMS * TT), args, psmem, st));
   }
   return SPARCH_OK;
 }

@@ -386,3 +386,54 @@ def test_empty_batch_and_time_are_tolerated():
                                         torch.zeros(Be, 8, device=DEV), None, torch.zeros(Be, 8, device=DEV),
                                         "LIF", 1.0, F.NormState("none"))
         assert S.shape == (Be, T, 8)
+
+
+@pytest.mark.parametrize("kind", ["LIF", "adLIF", "RLIF", "RadLIF"])
+def test_single_step_abi_against_oracle(kind):
+    """sparch_cell_step_fwd / sparch_cell_step_bwd (one timestep, caller supplies s_{t-1} @ V0):
+    drive the time loop from Python and compare tapes and gradients with the oracle."""
+    from sparch_b200._lib import call, ptr
+    from sparch_b200.functional import KINDS
+    rng = np.random.default_rng(5)
+    Be, T, H = 5, 9, 24
+    adaptive, recurrent = orc.kind_flags(kind)
+    k = KINDS[kind]
+    I = (rng.standard_normal((Be, T, H)) * 3 + 1).astype(np.float32)
+    alpha = rng.uniform(0.82, 0.96, H).astype(np.float32)
+    beta = rng.uniform(0.97, 0.99, H).astype(np.float32)
+    a = rng.uniform(0, 1, H).astype(np.float32)
+    b = rng.uniform(0, 2, H).astype(np.float32)
+    V0 = (rng.standard_normal((H, H)) / 5).astype(np.float32)
+    np.fill_diagonal(V0, 0)
+    u0, w0, s0 = (rng.uniform(0, 1, (Be, H)).astype(np.float32) for _ in range(3))
+    r = orc.cell_forward(kind, I, alpha, beta, a, b, V0 if recurrent else None, u0, w0 if adaptive else None, s0)
+    t_ = lambda z: torch.from_numpy(np.ascontiguousarray(z)).to(DEV)
+    It, al, be, aa, bb, Vt, u0t, w0t, s0t = map(t_, (I, alpha, beta, a, b, V0, u0, w0, s0))
+    S, U, W = torch.empty_like(It), torch.empty_like(It), torch.empty_like(It)
+    st = torch.cuda.current_stream().cuda_stream
+    on = lambda z, flag: ptr(z) if flag else None
+    for t in range(T):
+        rec = (s0t if t == 0 else S[:, t - 1]) @ Vt if recurrent else None
+        call("sparch_cell_step_fwd", k, t, ptr(It), None, None, ptr(al), on(be, adaptive), on(aa, adaptive),
+             on(bb, adaptive), ptr(rec), ptr(u0t), on(w0t, adaptive), ptr(s0t), 1.0, ptr(S), ptr(U),
+             on(W, adaptive), Be, T, H, st)
+    np.testing.assert_array_equal(S.cpu().numpy(), r["s"])
+    assert rel_err(U.cpu().numpy(), r["u"]) < 1e-5
+    gs = rng.standard_normal((Be, T, H)).astype(np.float32)
+    G = t_(gs)
+    dI = torch.empty_like(It)
+    carry = torch.zeros(2, Be, H, device=DEV)
+    part = torch.zeros(4, Be, H, device=DEV)
+    for t in range(T - 1, -1, -1):
+        recb = dI[:, t + 1] @ Vt.t() if (recurrent and t < T - 1) else None
+        call("sparch_cell_step_bwd", k, t, ptr(G), ptr(U), on(W, adaptive), ptr(al), on(be, adaptive),
+             on(aa, adaptive), on(bb, adaptive), ptr(recb), ptr(u0t), on(w0t, adaptive), ptr(s0t), 1.0,
+             ptr(dI), ptr(carry[0]), on(carry[1], adaptive), ptr(part[0]), on(part[1], adaptive),
+             on(part[2], adaptive), on(part[3], adaptive), Be, T, H, st)
+    bw = orc.cell_backward(kind, gs, I, alpha, beta, a, b, V0 if recurrent else None, u0,
+                           w0 if adaptive else None, s0, U=r["u"], W=r["w"], S=r["s"])
+    assert rel_err(dI.cpu().numpy(), bw["dI"]) < G_RTOL
+    assert rel_err(part[0].sum(0).cpu().numpy(), bw["dalpha"]) < G_RTOL
+    if adaptive:
+        for i, kk in enumerate(("dbeta", "da", "db")):
+            assert rel_err(part[i + 1].sum(0).cpu().numpy(), bw[kk]) < G_RTOL, kk
