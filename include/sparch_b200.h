@@ -134,13 +134,17 @@ SPARCH_API int sparch_split_bf16_transpose(const float* X, int R, int C, int npa
  * transpose is materialised.  Row strides lda/ldb are multiples of 8 elements.  a_koff (MN-major
  * A only) is added to A's K coordinate, out-of-range rows read as zero: a_koff = -1 pairs frame
  * m of B with frame m-1 of A (S_prev in dV).  `workspace` (sparch_gemm_workspace bytes, may be
- * NULL) enables deterministic split-K when the output has fewer tiles than the GPU has SMs.   */
+ * NULL) enables deterministic split-K when the output has fewer tiles than the GPU has SMs.
+ * stat_sum / stat_sumsq (N doubles each, may be NULL): the epilogue also accumulates the
+ * per-column sum and sum of squares of the finished output -- the BatchNorm1d statistics of the
+ * projection (snns.py:678-680) without another pass over Z (disables split-K).                */
 SPARCH_API size_t sparch_gemm_workspace(int M, int N, int K);
 SPARCH_API int sparch_gemm_bf16(const void* const* A_parts, int na, const void* const* B_parts,
                                 int nb, int64_t lda, int64_t ldb, int a_mn, int b_mn, int a_koff,
                                 const int* pair_a, const int* pair_b, int npairs, int M, int N,
                                 int K, float alpha, const float* bias, float* C, int64_t ldc,
-                                void* workspace, sparch_stream_t st);
+                                double* stat_sum, double* stat_sumsq, void* workspace,
+                                sparch_stream_t st);
 
 /* ---- recurrent kinds on the tensor pipe (snns.py:554-578, 696-727) --------------------- */
 /* Hidden size rounded up to a multiple of 32 (spike words / V0 slices are padded to it).    */

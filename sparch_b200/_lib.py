@@ -28,7 +28,7 @@ _PROTOS = {
     "sparch_split_bf16": "pliiifppplp",
     "sparch_split_bf16_transpose": "piiiiifppplp",
     "sparch_gemm_workspace": "iii",
-    "sparch_gemm_bf16": "pipill" + "iii" + "ppiiiifppl" + "pp",
+    "sparch_gemm_bf16": "pipill" + "iii" + "ppiiiifppl" + "pppp",
     "sparch_recur_padded": "i",
     "sparch_recur_prepare": "pipppp",
     "sparch_recur_sync_words": "i",

@@ -43,6 +43,8 @@ struct GemmParams {
   long long split_stride;
   float alpha;
   const float* bias;   // per column n, may be NULL (applied only when splits == 1)
+  double* stat_sum;    // optional per-column sum / sum of squares of the OUTPUT (BatchNorm statistics fused
+  double* stat_sumsq;  // into the epilogue, snns.py:678-680); only with splits == 1
   int a_mn, b_mn;      // operand is MN-major in memory: a (K, MN) row-major matrix (weight-gradient GEMMs)
   int a_koff;          // added to A's K coordinate (TMA zero-fills out-of-range rows): S_prev = S delayed by one frame
 };
@@ -116,14 +118,36 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// Column sums across the 32 lanes of a warp for 32 per-lane values in 31 shuffles: at each step a lane
+// keeps one half of its values and receives the partner's copy of that half; lane l ends up with the
+// total of column (bit-reversed bookkeeping folded into the index arithmetic): returns column `l`.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int step = 0; step < 5; ++step) {
+    const int half = 16 >> step;            // values kept per lane after this step
+    const int bit = 16 >> step;             // lane bit deciding which half is kept
+    const bool upper = lane & bit;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float keep = upper ? v[i + half] : v[i];
+      const float give = upper ? v[i] : v[i + half];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, give, bit);
+    }
+  }
+  return v[0];  // lane l holds the sum of column l: bit (16>>s) of l selected the upper half at step s
+}
+
+template <bool STATS>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
   extern __shared__ unsigned char gsm_raw[];
+  __shared__ float2 sstat[STATS ? 4 : 1][STATS ? GN : 1];  // per row quarter: column (sum, sum of squares) of the tile
   const uint32_t raw = smem_u32(gsm_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024-byte alignment
   unsigned char* gsm = gsm_raw + (base - raw);
-  const uint32_t bars = base + GSTAGES * G_STAGE_BYTES;         // full[4], empty[4], tmem_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gsm + GSTAGES * G_STAGE_BYTES + 128);
+  constexpr int NST = GSTAGES;
+  const uint32_t bars = base + NST * G_STAGE_BYTES;             // full[4], empty[4], tmem_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gsm + NST * G_STAGE_BYTES + 128);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
@@ -132,7 +156,7 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
   const int iters = p.npairs * (kb1 - kb0);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < GSTAGES; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(bars + 8 * s, 1);
       mbar_init(bars + 8 * (GSTAGES + s), 1);
     }
@@ -157,8 +181,8 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
         const CUtensorMap* ma = &maps.a[p.pair_a[pr]];
         const CUtensorMap* mb = &maps.b[p.pair_b[pr]];
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % GSTAGES;
-          const uint32_t ph = (it / GSTAGES) & 1;
+          const int s = it % NST;
+          const uint32_t ph = (it / NST) & 1;
           mbar_wait(bars + 8 * (GSTAGES + s), ph ^ 1);
           mbar_expect_tx(bars + 8 * s, G_STAGE_BYTES);
           const uint32_t sa = base + s * G_STAGE_BYTES;
@@ -182,8 +206,8 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
   } else if (warp == 1) {
     if (lane == 0) {
       for (int it = 0; it < iters; ++it) {
-        const int s = it % GSTAGES;
-        const uint32_t ph = (it / GSTAGES) & 1;
+        const int s = it % NST;
+        const uint32_t ph = (it / NST) & 1;
         mbar_wait(bars + 8 * s, ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = base + s * G_STAGE_BYTES;
@@ -242,6 +266,35 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (nb + i < p.N) crow[nb + i] = f[i];
+        }
+      }
+      if (STATS && nb < p.N) {  // warp-uniform: fused BatchNorm statistics of the finished output
+        float a[32], b[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = 0.f;
+          if (row < p.M && nb + i < p.N) {
+            x = __uint_as_float(v[i]) * p.alpha;
+            if (p.bias) x += p.bias[nb + i];
+          }
+          a[i] = x;
+          b[i] = x * x;
+        }
+        const float cs = warp_colsum32(a, lane), cq = warp_colsum32(b, lane);
+        sstat[quarter][c * 32 + lane] = make_float2(cs, cq);
+      }
+    }
+    if (STATS) {
+      // combine the four row quarters of the tile, then one fp64 atomic per column and quantity
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int e = threadIdx.x - 64;  // 0..127 over the epilogue warps
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int col = e + 128 * cc;
+        if (n0 + col < p.N) {
+          const float2 q0 = sstat[0][col], q1 = sstat[1][col], q2 = sstat[2][col], q3 = sstat[3][col];
+          atomicAdd(&p.stat_sum[n0 + col], (double)q0.x + (double)q1.x + (double)q2.x + (double)q3.x);
+          atomicAdd(&p.stat_sumsq[n0 + col], (double)q0.y + (double)q1.y + (double)q2.y + (double)q3.y);
         }
       }
     }
@@ -445,13 +498,14 @@ size_t sparch_gemm_workspace(int M, int N, int K) {
 
 int sparch_gemm_bf16(const void* const* A_parts, int na, const void* const* B_parts, int nb, int64_t lda,
                      int64_t ldb, int a_mn, int b_mn, int a_koff, const int* pair_a, const int* pair_b, int npairs,
-                     int M, int N, int K, float alpha, const float* bias, float* C, int64_t ldc, void* workspace,
-                     sparch_stream_t st_) {
+                     int M, int N, int K, float alpha, const float* bias, float* C, int64_t ldc, double* stat_sum,
+                     double* stat_sumsq, void* workspace, sparch_stream_t st_) {
   SPARCH_REQUIRE(M > 0 && N > 0 && K > 0 && na >= 1 && na <= 3 && nb >= 1 && nb <= 3, "bad shape");
   SPARCH_REQUIRE(npairs >= 1 && npairs <= 8 && A_parts && B_parts && pair_a && pair_b && C, "bad argument");
   SPARCH_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0 && lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K),
                  "operand row strides must be multiples of 8 bf16 elements (16 bytes) and cover a row");
   SPARCH_REQUIRE(a_koff == 0 || a_mn, "a_koff applies to an MN-major A operand");
+  SPARCH_REQUIRE((stat_sum == nullptr) == (stat_sumsq == nullptr), "stat_sum and stat_sumsq go together");
   cudaStream_t st = as_stream(st_);
   TmapSet maps;
   memset(&maps, 0, sizeof maps);
@@ -469,6 +523,11 @@ int sparch_gemm_bf16(const void* const* A_parts, int na, const void* const* B_pa
   memset(&p, 0, sizeof p);
   p.M = M; p.N = N; p.K = K; p.npairs = npairs;
   p.a_mn = a_mn; p.b_mn = b_mn; p.a_koff = a_koff;
+  p.stat_sum = stat_sum; p.stat_sumsq = stat_sumsq;
+  if (stat_sum) {
+    SPARCH_CUDA(cudaMemsetAsync(stat_sum, 0, sizeof(double) * N, st));
+    SPARCH_CUDA(cudaMemsetAsync(stat_sumsq, 0, sizeof(double) * N, st));
+  }
   for (int i = 0; i < npairs; ++i) {
     SPARCH_REQUIRE(pair_a[i] >= 0 && pair_a[i] < na && pair_b[i] >= 0 && pair_b[i] < nb, "pair index out of range");
     p.pair_a[i] = pair_a[i];
@@ -477,7 +536,7 @@ int sparch_gemm_bf16(const void* const* A_parts, int na, const void* const* B_pa
   p.kblocks = (K + GK - 1) / GK;
   const int tiles = ((M + GM - 1) / GM) * ((N + GN - 1) / GN);
   int splits = 1;
-  if (workspace && tiles < sm_count()) {
+  if (workspace && tiles < sm_count() && !stat_sum) {  // statistics need the finished tile in one epilogue
     splits = sm_count() / tiles;
     if (splits > 8) splits = 8;
     if (splits > p.kblocks) splits = p.kblocks;
@@ -497,11 +556,16 @@ int sparch_gemm_bf16(const void* const* A_parts, int na, const void* const* B_pa
   }
   static bool attr_set = false;
   if (!attr_set) {
-    SPARCH_CUDA(cudaFuncSetAttribute(gemm_tn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
+    SPARCH_CUDA(cudaFuncSetAttribute(gemm_tn_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
+    SPARCH_CUDA(cudaFuncSetAttribute(gemm_tn_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
     attr_set = true;
   }
+  // (A 2-stage ring with two CTAs per SM for short contractions was measured: no gain.)
   dim3 grid((N + GN - 1) / GN, (M + GM - 1) / GM, splits);
-  gemm_tn_bf16_kernel<<<grid, G_THREADS, G_SMEM, st>>>(maps, p);
+  if (stat_sum)
+    gemm_tn_bf16_kernel<true><<<grid, G_THREADS, G_SMEM, st>>>(maps, p);
+  else
+    gemm_tn_bf16_kernel<false><<<grid, G_THREADS, G_SMEM, st>>>(maps, p);
   SPARCH_LAUNCH_OK();
   if (splits > 1) {
     long long n = (long long)M * N;

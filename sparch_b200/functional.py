@@ -113,7 +113,9 @@ class LinearFunction(torch.autograd.Function):
     dropout) so that one exact bf16 term {0,1} suffices and c moves into the epilogue."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, in_scale):
+    def forward(ctx, x, weight, bias, in_scale, norm=None):
+        """norm: the layer's NormState; in 'bn_train' mode the GEMM epilogue also accumulates the
+        BatchNorm column statistics of the output and leaves them in ``norm.stats``."""
         _require_cuda(x, weight)
         K = x.shape[-1]
         N = weight.shape[0]
@@ -126,7 +128,17 @@ class LinearFunction(torch.autograd.Function):
                 else:
                     xa, alpha = gemm.split_rows(x2d, 1, prescale=1.0 / in_scale), float(in_scale)
                 wb = gemm.split_rows(_f32c(weight), 3)
-                Z = gemm.gemm_parts(xa, wb, K, alpha=alpha, bias=None if bias is None else _f32c(bias))
+                # BatchNorm statistics ride in the GEMM epilogue when the tile's main loop is long enough
+                # to dwarf it (measured: for the K=40 input layer the epilogue IS the kernel and a
+                # separate column-statistics pass over the L2-warm output is cheaper).
+                stats = None
+                passes = 3 if in_scale is not None else 6
+                if norm is not None and norm.mode == "bn_train" and passes * ((K + 63) // 64) >= 16:
+                    stats = torch.empty(2, N, device=x2d.device, dtype=torch.float64)
+                Z = gemm.gemm_parts(xa, wb, K, alpha=alpha, bias=None if bias is None else _f32c(bias),
+                                    stats=stats)
+                if norm is not None:
+                    norm.stats = stats
         ctx.alpha = alpha
         ctx.has_bias = bias is not None
         # the bf16 terms serve the backward GEMMs as they are (MN-major operands): no re-split
@@ -151,7 +163,7 @@ class LinearFunction(torch.autograd.Function):
                 dw = gemm.gemm_parts(ga, xa, M, alpha=ctx.alpha, a_mn=True, b_mn=True, M=N, N=K)
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 db = g2d.sum(dim=0)
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
 class NormState:
@@ -167,6 +179,7 @@ class NormState:
         self.running_var = running_var
         self.eps = eps
         self.momentum = momentum
+        self.stats = None   # (2, H) float64 column sum / sum of squares when the projection GEMM fused them
 
 
 def _fold_norm(Z2d, gamma, bn_beta, norm):
@@ -186,8 +199,10 @@ def _fold_norm(Z2d, gamma, bn_beta, norm):
         raise ValueError(f"unknown normalisation mode {norm.mode}")
     if M <= 1:
         raise ValueError("Expected more than 1 value per channel when training")
-    sums = torch.empty(2, H, dtype=torch.float64, device=dev)
-    call("sparch_col_stats", ptr(Z2d), M, H, ptr(sums[0]), ptr(sums[1]), _stream())
+    sums = norm.stats
+    if sums is None:        # projection not done by LinearFunction (direct use of the cell Function)
+        sums = torch.empty(2, H, dtype=torch.float64, device=dev)
+        call("sparch_col_stats", ptr(Z2d), M, H, ptr(sums[0]), ptr(sums[1]), _stream())
     out = torch.empty(4, H, dtype=torch.float32, device=dev)
     call("sparch_bn_fold_train", ptr(sums[0]), ptr(sums[1]), M, ptr(gamma), ptr(bn_beta),
          float(norm.eps), float(norm.momentum), ptr(norm.running_mean), ptr(norm.running_var),

@@ -56,12 +56,13 @@ def split_transposed(x2d, nparts, T=0, shift=0, prescale=1.0):
 
 
 def gemm_parts(A, B, K, alpha=1.0, bias=None, out=None, pairs=None, a_mn=False, b_mn=False, a_koff=0,
-               M=None, N=None):
+               M=None, N=None, stats=None):
     """C (M, N) fp32 = alpha * sum_pairs A_i . B_j^T (+ bias).
 
     K-major operand: terms of shape (n, rows, ld) with rows = M resp. N.  MN-major operand
     (a_mn / b_mn): terms of shape (n, K, ld) holding the (K, M) resp. (K, N) matrix, M / N given
-    explicitly (ld may exceed it).  a_koff shifts A's K index (zero fill), MN-major A only."""
+    explicitly (ld may exceed it).  a_koff shifts A's K index (zero fill), MN-major A only.
+    stats: optional (2, N) float64 tensor receiving the per-column sum / sum of squares of C."""
     na, ra, lda = A.shape
     nb, rb, ldb = B.shape
     M = ra if not a_mn else M
@@ -78,8 +79,9 @@ def gemm_parts(A, B, K, alpha=1.0, bias=None, out=None, pairs=None, a_mn=False, 
     pb = (ctypes.c_int * len(pairs))(*[p[1] for p in pairs])
     ws = None
     tiles = ((M + 127) // 128) * ((N + 255) // 256)
-    if tiles < 148 and K > 64:
+    if tiles < 148 and K > 64 and stats is None:
         ws = torch.empty(_lib.lib().sparch_gemm_workspace(M, N, K), device=dev, dtype=torch.uint8)
     call("sparch_gemm_bf16", ap, na, bp, nb, lda, ldb, int(a_mn), int(b_mn), int(a_koff), pa, pb,
-         len(pairs), M, N, K, float(alpha), ptr(bias), ptr(out), out.stride(0), ptr(ws), _stream())
+         len(pairs), M, N, K, float(alpha), ptr(bias), ptr(out), out.stride(0),
+         None if stats is None else ptr(stats[0]), None if stats is None else ptr(stats[1]), ptr(ws), _stream())
     return out

@@ -128,8 +128,8 @@ class _SpikingLayerBase(nn.Module):
             x = torch.cat([x, x.flip(1)], dim=0)
         if self.batch_size != x.shape[0]:                        # snns.py:671-672
             self.batch_size = x.shape[0]
-        Wx = LinearFunction.apply(x, self.W.weight, self.W.bias, in_scale)   # snns.py:675
         gamma, bn_beta, norm = _norm_args(self)
+        Wx = LinearFunction.apply(x, self.W.weight, self.W.bias, in_scale, norm)   # snns.py:675
         if norm is None:                                         # layernorm, snns.py:678-680
             Wx = self.norm(Wx)
             norm = NormState("none")
@@ -218,8 +218,8 @@ class ReadoutLayer(nn.Module):
     def forward(self, x, in_scale=None):
         if not x.is_cuda:
             raise RuntimeError("sparch_b200 layers run on CUDA only (no CPU fallback)")
-        Wx = LinearFunction.apply(x, self.W.weight, self.W.bias, in_scale)   # snns.py:796
         gamma, bn_beta, norm = _norm_args(self)
+        Wx = LinearFunction.apply(x, self.W.weight, self.W.bias, in_scale, norm)   # snns.py:796
         if norm is None:
             Wx = self.norm(Wx)
             norm = NormState("none")

@@ -89,3 +89,18 @@ def test_gemm_mn_major_with_frame_delay():
                         M=H, N=H)
     ref = S[:-1].double().t() @ dI[1:].double()
     assert float((C.double() - ref).abs().max() / ref.abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 520, 72), (25600, 1024, 40), (130, 35, 256)])
+def test_gemm_fused_column_statistics(M, N, K):
+    """BatchNorm statistics of the projection output accumulated in the GEMM epilogue."""
+    from sparch_b200 import gemm
+    g = torch.Generator(device=DEV).manual_seed(M + N)
+    A = torch.randn(M, K, device=DEV, generator=g)
+    B = torch.randn(N, K, device=DEV, generator=g)
+    bias = torch.randn(N, device=DEV, generator=g)
+    stats = torch.empty(2, N, dtype=torch.float64, device=DEV)
+    C = gemm.gemm_parts(gemm.split_rows(A, 3), gemm.split_rows(B, 3), K, alpha=1.5, bias=bias, stats=stats)
+    ref = C.double()
+    assert float((stats[0] - ref.sum(0)).abs().max() / ref.sum(0).abs().max()) < 1e-6
+    assert float((stats[1] - (ref * ref).sum(0)).abs().max() / (ref * ref).sum(0).abs().max()) < 1e-6
