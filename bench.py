@@ -299,14 +299,23 @@ def run_ours(args, cfg, rank, local_rank, world):
     alg_bytes = 16.5 * elts
     rec_total_ms = (rec_ms.get("recurrence_fwd", 0.0) + rec_ms.get("recurrence_bwd", 0.0)) / args.steps
     achieved = alg_bytes / (rec_total_ms * 1e-3) / 1e9 if rec_total_ms > 0 else None
+    traffic = None
+    try:                                                      # from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_recur_traffic.json")))
+        if tj.get("config") == args.config:
+            traffic = tj["traffic_bytes_per_step"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "kernel": "membrane recurrence fwd+bwd (all launches of one train step)",
                 "ms_per_step": rec_total_ms,
                 "ms_fwd": rec_ms.get("recurrence_fwd", 0.0) / args.steps,
                 "ms_bwd": rec_ms.get("recurrence_bwd", 0.0) / args.steps, "algorithmic_bytes_per_step": alg_bytes,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                "share_of_step": rec_total_ms / (ms / args.steps) if rec_total_ms else None}
+                "share_of_step": rec_total_ms / (ms / args.steps) if rec_total_ms else None,
+                "note": "the recurrence is bounded by its 2*T dependent steps per layer (latency + legacy-HMMA "
+                        "issue), not by HBM: see DESIGN.md section 5 for the latency floor"}
 
     # ---- CPU baseline beside it (bounded sample: the full config batch, 2 timed steps) --------
     cpu = None
