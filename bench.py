@@ -199,7 +199,8 @@ def run_ours(args, cfg, rank, local_rank, world):
                 if hasattr(lay, "a"):
                     lay.a.abs_()
     net.train()
-    opt = torch.optim.Adam(net.parameters(), 1e-2)            # exp.py:89
+    use_graph = args.graph and world == 1 and args.state_init == "device"
+    opt = torch.optim.Adam(net.parameters(), 1e-2, capturable=use_graph)   # exp.py:89
     sync = parallel.GradSync(net) if world > 1 else None
     x_h, y_h = make_batch(cfg, B, 1234 + rank)
     x_h, y_h = x_h.pin_memory(), y_h.pin_memory()
@@ -215,6 +216,15 @@ def run_ours(args, cfg, rank, local_rank, world):
             sync.finish()
         opt.step()
         return loss
+
+    graphed = None
+    if use_graph:
+        from sparch_b200.graphs import GraphedTrainStep
+        graphed = GraphedTrainStep(net, opt, loss_fn, x_d, y_d)
+        eager_step = step
+
+        def step(x, y):                                       # noqa: F811
+            return graphed.step(x, y)
 
     def barrier():
         if world > 1:
@@ -260,6 +270,8 @@ def run_ours(args, cfg, rank, local_rank, world):
     n0 = F.native_launches()
     ms = timed(lambda: step(x_d, y_d), args.steps)
     launches = F.native_launches() - n0
+    if graphed is not None:
+        launches = graphed.native_calls_per_step * args.steps  # replayed from the graph, not re-issued by the host
     rec_ms = F.timers_collect()                               # {"recurrence_fwd": ms, ...} totals
     F.timers_enable(False)
     value = world * B * args.steps / (ms * 1e-3)
@@ -332,7 +344,7 @@ def run_ours(args, cfg, rank, local_rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": cfg["desc"], "bench_config": args.config, "per_gpu_batch": B,
-                   "global_batch": B * world, "parallelism": f"dp{world}",
+                   "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": bool(use_graph),
                    "state_init": args.state_init + (" generator draws of u0/w0/s0 ~ U[0,1) (same distribution "
                                                     "as the reference's CPU draws)" if args.state_init == "device"
                                                     else " generator draws, identical to the reference's"),
@@ -360,6 +372,9 @@ def main():
     ap.add_argument("--state-init", default="device", choices=["device", "cpu"],
                     help="where the per-forward initial states ~U[0,1) are drawn: 'device' (CUDA generator) "
                          "or 'cpu' (the reference's CPU-generator draws, snns.py:700-702; host-bound)")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the whole train step as one CUDA graph (sparch_b200.graphs.GraphedTrainStep; "
+                         "single GPU, device state init)")
     ap.add_argument("--profile", action="store_true",
                     help="profiling run (under ncu): exactly --warmup warm-up and --steps timed steps of "
                          "the device-resident loop, no e2e leg, no CPU baseline; prints no bench value")

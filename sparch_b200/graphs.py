@@ -1,0 +1,58 @@
+"""Whole-train-step CUDA graph (the glue of sparch/exp.py:352-382).
+
+The reference's step is ``net(x)`` -> ``CrossEntropyLoss`` -> ``backward`` -> ``Adam.step`` with two
+host syncs per step (exp.py:363, 381).  Small configurations (3x128 LIF/adLIF) launch a few hundred
+short kernels per step and are bound by launch overhead, not by the GPU.  ``GraphedTrainStep``
+captures forward + loss + backward + optimizer update ONCE into a CUDA graph -- every library
+call made by ``sparch_b200`` (including the cooperative persistent kernels, the TMA-fed GEMMs and
+the memsets inside the C ABI) is a plain stream operation -- and replays it per batch.
+
+Requirements: ``set_state_init("device")`` (the CPU-generator draws of the default mode are host
+work and cannot be captured), an optimizer built with ``capturable=True``, fixed batch shape.
+"""
+import torch
+
+from . import functional as F
+from . import snns
+
+
+class GraphedTrainStep:
+    def __init__(self, net, optimizer, loss_fn, x_example, y_example, warmup=3):
+        if snns._STATE_INIT != "device":
+            raise RuntimeError('GraphedTrainStep needs sparch_b200.set_state_init("device")')
+        if not x_example.is_cuda:
+            raise RuntimeError("GraphedTrainStep runs on CUDA tensors only")
+        self.net, self.opt, self.loss_fn = net, optimizer, loss_fn
+        self.x = torch.empty_like(x_example)
+        self.y = torch.empty_like(y_example)
+        self.x.copy_(x_example)
+        self.y.copy_(y_example)
+        F.timers_enable(False)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):          # warm-up: one-time attribute calls, allocator pools, Adam state
+            for _ in range(warmup):
+                self._eager_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        self.opt.zero_grad(set_to_none=True)
+        n0 = F.native_launches()
+        with torch.cuda.graph(self.graph):
+            self.out, self.rates, self.loss = self._eager_step()
+        self.native_calls_per_step = F.native_launches() - n0
+
+    def _eager_step(self):
+        out, rates = self.net(self.x)
+        loss = self.loss_fn(out, self.y)
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        self.opt.step()
+        return out, rates, loss
+
+    def step(self, x, y):
+        """Copy the batch into the static buffers and replay; returns the (device) loss tensor."""
+        self.x.copy_(x, non_blocking=True)
+        self.y.copy_(y, non_blocking=True)
+        self.graph.replay()
+        return self.loss

@@ -437,3 +437,34 @@ def test_single_step_abi_against_oracle(kind):
     if adaptive:
         for i, kk in enumerate(("dbeta", "da", "db")):
             assert rel_err(part[i + 1].sum(0).cpu().numpy(), bw[kk]) < G_RTOL, kk
+
+
+def test_graphed_train_step_matches_eager_statistics():
+    """GraphedTrainStep (forward + loss + backward + Adam in one CUDA graph, cooperative kernels
+    included) trains like the eager step: same first loss up to the random initial states, finite
+    and decreasing afterwards, parameters updated on replay."""
+    import sparch_b200
+    from sparch_b200.graphs import GraphedTrainStep
+    sparch_b200.set_state_init("device")
+    try:
+        torch.manual_seed(0)
+        kw = dict(layer_sizes=[64, 64, 5], neuron_type="RadLIF", dropout=0.1)
+        net = sparch_b200.SNN((16, None, 12), **kw).to(DEV)
+        ref = sparch_b200.SNN((16, None, 12), **kw).to(DEV)
+        ref.load_state_dict(net.state_dict())
+        x = torch.randn(16, 20, 12, device=DEV)
+        y = torch.randint(0, 5, (16,), device=DEV)
+        loss_fn = torch.nn.CrossEntropyLoss()
+        out, _ = ref(x)
+        eager_first = float(loss_fn(out, y))
+        opt = torch.optim.Adam(net.parameters(), 1e-2, capturable=True)
+        g = GraphedTrainStep(net, opt, loss_fn, x, y, warmup=0 + 1)
+        w_before = net.snn[0].W.weight.detach().clone()
+        losses = [float(g.step(x, y)) for _ in range(40)]
+        assert all(np.isfinite(losses))
+        assert abs(losses[0] - eager_first) < 0.5 * eager_first      # same model, different random states
+        assert np.mean(losses[-5:]) < np.mean(losses[:5])            # it trains
+        assert not torch.equal(w_before, net.snn[0].W.weight)        # replays update the parameters
+        assert g.native_calls_per_step > 10
+    finally:
+        sparch_b200.set_state_init("cpu")
