@@ -41,20 +41,26 @@ cell_fwd_stream_kernel(const float* __restrict__ Z, const float* __restrict__ sc
   const bool affine = scale != nullptr;
   float u = u0[idx], s = s0[idx], w = ADAPT ? w0[idx] : 0.0f;
   int64_t base = bi * (int64_t)T * H + h;
+  // Software pipeline: the loads of chunk c+1 are in flight while chunk c's dependent chain runs.
+  float zn[TU];
+#pragma unroll
+  for (int k = 0; k < TU; ++k) zn[k] = (k < T) ? __ldcs(&Z[base + (int64_t)k * H]) : 0.0f;
   for (int t0 = 0; t0 < T; t0 += TU) {
     float z[TU];
 #pragma unroll
+    for (int k = 0; k < TU; ++k) z[k] = zn[k];
+#pragma unroll
     for (int k = 0; k < TU; ++k)
-      z[k] = (t0 + k < T) ? __ldcs(&Z[base + (int64_t)(t0 + k) * H]) : 0.0f;
+      zn[k] = (t0 + TU + k < T) ? __ldcs(&Z[base + (int64_t)(t0 + TU + k) * H]) : 0.0f;
 #pragma unroll
     for (int k = 0; k < TU; ++k) {
       if (t0 + k < T) {
         float cur = affine ? __fmaf_rn(z[k], sc, sf) : z[k];
         step_fwd<ADAPT>(p, cur, theta, u, w, s);
         int64_t o = base + (int64_t)(t0 + k) * H;
-        S[o] = s;
-        U[o] = u;
-        if (ADAPT) W[o] = w;
+        __stcs(&S[o], s);
+        __stcs(&U[o], u);
+        if (ADAPT) __stcs(&W[o], w);
       }
     }
   }
@@ -115,8 +121,9 @@ cell_bwd_stream_kernel(const float* __restrict__ G, const float* __restrict__ U,
   int64_t base = bi * (int64_t)T * H + h;
   float du = 0.f, dw = 0.f, pa = 0.f, pb = 0.f, pc = 0.f, pd = 0.f;
   float u_t = T > 0 ? U[base + (int64_t)(T - 1) * H] : 0.f;
-  for (int t1 = T - 1; t1 >= 0; t1 -= TU) {
-    float g[TU], up[TU], wp[TU];
+  // Software pipeline: the tape reads of the next (earlier) chunk are in flight while this chunk's
+  // dependent chain runs.
+  auto fetch = [&](int t1, float (&g)[TU], float (&up)[TU], float (&wp)[TU]) {
 #pragma unroll
     for (int k = 0; k < TU; ++k) {
       int t = t1 - k;
@@ -132,6 +139,18 @@ cell_bwd_stream_kernel(const float* __restrict__ G, const float* __restrict__ U,
         }
       }
     }
+  };
+  float gn[TU], upn[TU], wpn[TU];
+  fetch(T - 1, gn, upn, wpn);
+  for (int t1 = T - 1; t1 >= 0; t1 -= TU) {
+    float g[TU], up[TU], wp[TU];
+#pragma unroll
+    for (int k = 0; k < TU; ++k) {
+      g[k] = gn[k];
+      up[k] = upn[k];
+      wp[k] = wpn[k];
+    }
+    if (t1 - TU >= 0) fetch(t1 - TU, gn, upn, wpn);
 #pragma unroll
     for (int k = 0; k < TU; ++k) {
       int t = t1 - k;
@@ -139,7 +158,7 @@ cell_bwd_stream_kernel(const float* __restrict__ G, const float* __restrict__ U,
         float s_prev = t > 0 ? spike_of(__fsub_rn(up[k], theta)) : s0[idx];
         float d = step_bwd<ADAPT>(p, inv_oma, theta, g[k], 0.0f, u_t, up[k], s_prev, wp[k], du, dw,
                                   pa, pb, pc, pd);
-        dI[base + (int64_t)t * H] = d;
+        __stcs(&dI[base + (int64_t)t * H], d);
         u_t = up[k];
       }
     }
