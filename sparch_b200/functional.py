@@ -228,6 +228,11 @@ def _norm_backward(dI2d, Z2d, gamma, bn_beta, norm, scale, mean, rstd):
     return dgamma, dbeta
 
 
+# Largest hidden size whose 32-column V0 slice (fp16 hi/lo, Hp*128 bytes) fits next to the exchange
+# buffers in the persistent kernels' shared memory; beyond it the recurrent kinds take the stepwise path.
+RECUR_MAX_H = 1376
+
+
 class SpikingCellFunction(torch.autograd.Function):
     """Normalisation fold + membrane recurrence of one spiking layer.
 
@@ -263,8 +268,18 @@ class SpikingCellFunction(torch.autograd.Function):
                 call("sparch_cell_fwd", k, ptr(Z), ptr(scale), ptr(shift), ptr(al), ptr(be), ptr(aa),
                      ptr(bb), ptr(u0), ptr(w0), ptr(s0), float(theta), ptr(S), ptr(U), ptr(Wt), Be, T,
                      H, st)
+            elif H > RECUR_MAX_H:
+                # V0 slice too large for shared memory: general stepwise path, one launch per timestep
+                # with s_{t-1} @ V0 as a library GEMM (sparch_cell_step_fwd)
+                rec = torch.empty(Be, H, device=dev, dtype=torch.float32)
+                for t in range(T):
+                    torch.matmul(s0 if t == 0 else S[:, t - 1, :], V0, out=rec)  # snns.py:720
+                    call("sparch_cell_step_fwd", k, t, ptr(Z), ptr(scale), ptr(shift), ptr(al),
+                         ptr(be), ptr(aa), ptr(bb), ptr(rec), ptr(u0), ptr(w0), ptr(s0), float(theta),
+                         ptr(S), ptr(U), ptr(Wt), Be, T, H, st)
+                ctx.rec = None
             else:
-                # tensor-core step kernels: s_{t-1} @ V0 from packed spike planes (csrc/recur.cu)
+                # persistent tensor-core kernels: s_{t-1} @ V0 from packed spike planes (csrc/recur.cu)
                 Hp = _lib.lib().sparch_recur_padded(H)
                 img_f = torch.empty(Hp * Hp, device=dev, dtype=torch.int32)
                 img_b = torch.empty(Hp * Hp, device=dev, dtype=torch.int32)
@@ -304,6 +319,17 @@ class SpikingCellFunction(torch.autograd.Function):
                  ptr(u0), ptr(w0), ptr(s0), theta, ptr(dI), pp[0], pp[1], pp[2], pp[3], Be, T, H, st)
             region.__exit__()
             dV = None
+        elif ctx.rec is None:
+            carry = torch.zeros(2, Be, H, device=dev, dtype=torch.float32)
+            recb = torch.empty(Be, H, device=dev, dtype=torch.float32)
+            V0t = V0.t()
+            for t in range(T - 1, -1, -1):
+                if t < T - 1:
+                    torch.matmul(dI[:, t + 1, :], V0t, out=recb)
+                call("sparch_cell_step_bwd", k, t, ptr(G), ptr(U), ptr(Wt), ptr(al), ptr(be), ptr(aa),
+                     ptr(bb), ptr(recb) if t < T - 1 else None, ptr(u0), ptr(w0), ptr(s0), theta,
+                     ptr(dI), ptr(carry[0]), ptr(carry[1]) if adaptive else None, pp[0], pp[1], pp[2],
+                     pp[3], Be, T, H, st)
         else:
             img_b, meta = ctx.rec
             ws = torch.empty(_lib.lib().sparch_recur_bwd_workspace(Be, H), device=dev, dtype=torch.uint8)
@@ -311,6 +337,7 @@ class SpikingCellFunction(torch.autograd.Function):
             call("sparch_recur_bwd", k, ptr(G), ptr(U), ptr(Wt), ptr(al), ptr(be), ptr(aa), ptr(bb),
                  ptr(img_b), ptr(meta), ptr(u0), ptr(w0), ptr(s0), theta, ptr(dI), pp[0], pp[1], pp[2],
                  pp[3], ptr(ws), ptr(sync), Be, T, H, st)
+        if recurrent:
             region.__exit__()
             # dV = sum_t s_{t-1}^T dI_t, diagonal masked (clone().fill_diagonal_(0) backward)
             with _region("gemm_bwd"):
