@@ -191,6 +191,7 @@ def run_ours(args, cfg, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
     B = cfg["B"]
     sparch_b200.set_state_init(args.state_init)
+    sparch_b200.set_precision(args.precision)
     torch.manual_seed(0)
     net = sparch_b200.SNN((B, None, cfg["F"]), **model_kwargs(cfg)).to(dev)
     if cfg.get("stable_a"):
@@ -341,7 +342,8 @@ def run_ours(args, cfg, rank, local_rank, world):
     line = {
         "metric": "train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.precision == "fp32" else "bf16 products, f32 state/accumulation",
         "data": "synthetic",
         "config": {"workload": cfg["desc"], "bench_config": args.config, "per_gpu_batch": B,
                    "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": bool(use_graph),
@@ -372,6 +374,8 @@ def main():
     ap.add_argument("--state-init", default="device", choices=["device", "cpu"],
                     help="where the per-forward initial states ~U[0,1) are drawn: 'device' (CUDA generator) "
                          "or 'cpu' (the reference's CPU-generator draws, snns.py:700-702; host-bound)")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"],
+                    help="fp32 (default, the reference's arithmetic to ~1e-6) or the reduced-precision mode")
     ap.add_argument("--graph", action="store_true",
                     help="replay the whole train step as one CUDA graph (sparch_b200.graphs.GraphedTrainStep; "
                          "single GPU, device state init)")

@@ -158,13 +158,16 @@ SPARCH_API int sparch_recur_prepare(const float* V, int H, uint32_t* img_fwd, ui
  * chunk: V0 slices stay in shared memory, neuron state in registers; each step's spike words
  * cross CTAs through L2 as tagged 64-bit words.  rec0 (Be,H) = s0 @ V0 (s0 is real-valued,
  * snns.py:702).  Writes the fp32 tapes S, U (and W for RadLIF) and `bits`, the packed spike
- * planes [T][Be][Hp/32] of 8-byte words {32 spikes, t+1} (2 * T*Be*Hp/32 uint32).               */
+ * planes [T][Be][Hp/32] of 8-byte words {32 spikes, t+1} (2 * T*Be*Hp/32 uint32).
+ * reduced = 0: fp32-equivalent products (V0 as fp16 hi + lo); reduced = 1: the reduced-precision
+ * mode, hi terms only (11 mantissa bits), for sparch_recur_bwd also hi x hi only.               */
 SPARCH_API int sparch_recur_fwd(int kind, const float* Z, const float* scale, const float* shift,
                                 const float* alpha, const float* beta, const float* a,
                                 const float* b, const float* rec0, const uint32_t* img_fwd,
                                 const int* meta, const float* u0, const float* w0,
                                 const float* s0, float theta, float* S, float* U, float* W,
-                                uint32_t* bits, int Be, int T, int H, sparch_stream_t st);
+                                uint32_t* bits, int reduced, int Be, int T, int H,
+                                sparch_stream_t st);
 /* Profiling aid: device buffer of T*4 int64 that receives, per timestep, the SM clock of CTA (0,0)
  * after the spike-word wait, after the MMA loop, after the reduction and at the end of the step
  * for the following sparch_recur_fwd launches (NULL switches it off).                          */
@@ -181,8 +184,8 @@ SPARCH_API int sparch_recur_bwd(int kind, const float* G, const float* U, const 
                                 const float* b, const uint32_t* img_bwd, const int* meta,
                                 const float* u0, const float* w0, const float* s0, float theta,
                                 float* dI, float* p_alpha, float* p_beta, float* p_a,
-                                float* p_b, void* workspace, int* sync_ws, int Be, int T, int H,
-                                sparch_stream_t st);
+                                float* p_b, void* workspace, int* sync_ws, int reduced, int Be,
+                                int T, int H, sparch_stream_t st);
 
 /* ---- ReadoutLayer cell (snns.py:807-825) ---------------------------------------------- */
 /* u_t = alpha*u_{t-1} + (1-alpha)*I_t ; out = sum_t softmax(u_t, dim=1).  U (B,T,C) tape.  */

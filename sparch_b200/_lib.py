@@ -33,9 +33,9 @@ _PROTOS = {
     "sparch_recur_prepare": "pipppp",
     "sparch_recur_sync_words": "i",
     "sparch_recur_debug_clocks": "p",
-    "sparch_recur_fwd": "i" + "p" * 13 + "f" + "pppp" + "iii" + "p",
+    "sparch_recur_fwd": "i" + "p" * 13 + "f" + "pppp" + "iiii" + "p",
     "sparch_recur_bwd_workspace": "ii",
-    "sparch_recur_bwd": "i" + "p" * 12 + "f" + "p" * 7 + "iii" + "p",
+    "sparch_recur_bwd": "i" + "p" * 12 + "f" + "p" * 7 + "iiii" + "p",
     "sparch_readout_fwd": "p" * 7 + "iii" + "p",
     "sparch_readout_bwd": "p" * 6 + "iii" + "p",
 }

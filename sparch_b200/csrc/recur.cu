@@ -104,6 +104,7 @@ struct RecFwdArgs {
   int Be, T, H, Hp;
   long long* dbg;  // optional [T][8] phase clocks of CTA (0,0) (profiling aid), normally NULL
   int dbg_flags;   // profiling experiments (results invalid): 1 no tag wait, 2 no tape stores, 4 no Z loads
+  int reduced;     // 1: reduced-precision mode, hi term of V0 only (11 mantissa bits)
 };
 
 __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
@@ -164,6 +165,7 @@ struct RecBwdArgs {
   float* pscale;    // 2 x [groups][Hp/32][32]
   int Be, T, H, Hp;
   long long* dbg;   // optional [T][8] phase clocks of CTA (0,0) (profiling aid), normally NULL
+  int reduced;      // 1: reduced-precision mode, hi x hi product only, lo halves of the panel not moved
 };
 
 // ------------------------------------------------------------------ persistent kernels
@@ -339,8 +341,10 @@ __global__ void __launch_bounds__(TEAMS* TT, 1) rec_fwd_persist_kernel(const Rec
             af[ks][mt][3] = __funnelshift_r(wb[mt], wb[mt], 2 * ks + 1) & M;
           }
         }
+        const int nparts = p.reduced ? 1 : 2;
 #pragma unroll
-        for (int part = 0; part < 2; ++part)
+        for (int part = 0; part < 2; ++part) {
+          if (part >= nparts) break;
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
@@ -349,6 +353,7 @@ __global__ void __launch_bounds__(TEAMS* TT, 1) rec_fwd_persist_kernel(const Rec
               for (int nt = 0; nt < 4; ++nt)
                 mma16816(acc[mt][nt], af[ks][mt][0], af[ks][mt][1], af[ks][mt][2], af[ks][mt][3],
                          part ? f[ks][nt].z : f[ks][nt].x, part ? f[ks][nt].w : f[ks][nt].y);
+        }
       }
       if (dbg_on) p.dbg[t * 8 + 1] = clock64();
       float* myred = red + kq * RB * RED_RS;
@@ -491,7 +496,10 @@ rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_t
           const int nch = min(4, NCH - 4 * sc);
           const uint4* sa = reinterpret_cast<const uint4*>(apanel + (size_t)4 * sc * PB_CHUNK_WORDS);
           uint4* da = reinterpret_cast<uint4*>(dst);
-          for (int i = lt; i < nch * (PB_CHUNK_WORDS / 4); i += TT) cp_async16(da + i, sa + i);
+          // 16-byte unit i: bit 5 selects the hi (0) / lo (1) block of a (row tile, k-step); the reduced
+          // mode never touches the lo blocks
+          for (int i = lt; i < nch * (PB_CHUNK_WORDS / 4); i += TT)
+            if (!(p.reduced && (i & 32))) cp_async16(da + i, sa + i);
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
       };
@@ -531,10 +539,12 @@ rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_t
               const uint4 al = a4[((mt * 2 + ks) * 2 + 1) * 32 + lane];
 #pragma unroll
               for (int nt = 0; nt < 4; ++nt) mma16816(tacc[mt][nt], ah.x, ah.y, ah.z, ah.w, f[nt].x, f[nt].y);
+              if (!p.reduced) {
 #pragma unroll
-              for (int nt = 0; nt < 4; ++nt) mma16816(tacc[mt][nt], ah.x, ah.y, ah.z, ah.w, f[nt].z, f[nt].w);
+                for (int nt = 0; nt < 4; ++nt) mma16816(tacc[mt][nt], ah.x, ah.y, ah.z, ah.w, f[nt].z, f[nt].w);
 #pragma unroll
-              for (int nt = 0; nt < 4; ++nt) mma16816(tacc[mt][nt], al.x, al.y, al.z, al.w, f[nt].x, f[nt].y);
+                for (int nt = 0; nt < 4; ++nt) mma16816(tacc[mt][nt], al.x, al.y, al.z, al.w, f[nt].x, f[nt].y);
+              }
             }
           }
 #pragma unroll
@@ -683,7 +693,7 @@ int sparch_recur_fwd(int kind, const float* Z, const float* scale, const float* 
                      const float* alpha, const float* beta, const float* a, const float* b,
                      const float* rec0, const uint32_t* img_fwd, const int* meta, const float* u0,
                      const float* w0, const float* s0, float theta, float* S, float* U, float* W,
-                     uint32_t* bits, int Be, int T, int H, sparch_stream_t st_) {
+                     uint32_t* bits, int reduced, int Be, int T, int H, sparch_stream_t st_) {
   SPARCH_REQUIRE(kind == SPARCH_RLIF || kind == SPARCH_RADLIF, "recurrent kinds only");
   SPARCH_REQUIRE(Be >= 0 && T >= 0 && H > 0, "bad shape");
   SPARCH_REQUIRE((scale == nullptr) == (shift == nullptr), "scale and shift go together");
@@ -695,7 +705,7 @@ int sparch_recur_fwd(int kind, const float* Z, const float* scale, const float* 
   const size_t smem = rec_fwd_smem(Hp);
   SPARCH_REQUIRE(smem <= 225 * 1024, "hidden size too large for the resident V0 slice (H <= 1376)");
   RecFwdArgs p{Z, scale, shift, alpha, beta, a, b, rec0, u0, w0, s0, img_fwd, meta, theta, S, U, W,
-               reinterpret_cast<uint2*>(bits), Be, T, H, Hp, g_dbg, g_dbg_flags};
+               reinterpret_cast<uint2*>(bits), Be, T, H, Hp, g_dbg, g_dbg_flags, reduced ? 1 : 0};
   cudaStream_t st = as_stream(st_);
   static int max_ctas = 0;
   if (max_ctas == 0) {
@@ -731,7 +741,7 @@ int sparch_recur_bwd(int kind, const float* G, const float* U, const float* W, c
                      const float* beta, const float* a, const float* b, const uint32_t* img_bwd,
                      const int* meta, const float* u0, const float* w0, const float* s0, float theta,
                      float* dI, float* p_alpha, float* p_beta, float* p_a, float* p_b, void* workspace,
-                     int* sync_ws, int Be, int T, int H, sparch_stream_t st_) {
+                     int* sync_ws, int reduced, int Be, int T, int H, sparch_stream_t st_) {
   SPARCH_REQUIRE(kind == SPARCH_RLIF || kind == SPARCH_RADLIF, "recurrent kinds only");
   SPARCH_REQUIRE(Be >= 0 && T >= 0 && H > 0, "bad shape");
   if (Be == 0 || T == 0) return SPARCH_OK;
@@ -745,7 +755,7 @@ int sparch_recur_bwd(int kind, const float* G, const float* U, const float* W, c
   uint32_t* panel = reinterpret_cast<uint32_t*>(workspace);
   float* pscale = reinterpret_cast<float*>(panel + 2 * groups * (Hp / 32) * PB_CHUNK_WORDS);
   RecBwdArgs p{G, U, W, alpha, beta, a, b, u0, w0, s0, img_bwd, meta, theta, dI,
-               p_alpha, p_beta, p_a, p_b, panel, pscale, Be, T, H, Hp, g_dbg};
+               p_alpha, p_beta, p_a, p_b, panel, pscale, Be, T, H, Hp, g_dbg, reduced ? 1 : 0};
   cudaStream_t st = as_stream(st_);
   const size_t psmem = rec_bwd_persist_smem(Hp);
   SPARCH_REQUIRE(psmem <= 225 * 1024, "hidden size too large for the resident V0^T slice");

@@ -469,3 +469,51 @@ def test_graphed_train_step_matches_eager_statistics():
         assert g.native_calls_per_step > 10
     finally:
         sparch_b200.set_state_init("cpu")
+
+
+def test_reduced_precision_mode():
+    """set_precision("bf16"): one bf16 term per GEMM operand, hi terms only in the recurrence.
+    Stated tolerance: teacher-forced single steps flip <= 2e-3 of the spikes; free-running short
+    trains flip <= 2e-2; where the trains coincide the gradients agree to 3e-2 relative L2; a whole
+    model's loss stays within 5 % of the fp32 mode."""
+    import sparch_b200
+    from tests.helpers import rel_l2
+    g = Golden("radlif_bn_h64")
+    net = _net(g)
+    try:
+        sparch_b200.set_precision("bf16")
+        for i, lay, I, u0, w0, s0 in _hidden_layer_inputs(g, net):
+            p, V0 = _layer_params(lay)
+            r = orc.cell_forward(lay._kind, I, p["alpha"], p.get("beta"), p.get("a"), p.get("b"), V0, u0, w0, s0,
+                                 theta=lay.threshold)
+            Be, T, H = I.shape
+            prev = lambda X, x0: np.concatenate([x0[:, None, :], X[:, :-1, :]], axis=1).reshape(Be * T, H)
+            _, S1 = _run_cell(lay, I.reshape(Be * T, 1, H), prev(r["u"], u0), prev(r["w"], w0), prev(r["s"], s0))
+            flips1 = float((S1.detach().cpu().numpy().reshape(Be * T, H) != r["s"].reshape(Be * T, H)).mean())
+            assert flips1 <= 2e-3, (i, flips1)
+            for q in (lay.alpha, lay.beta, lay.a, lay.b, lay.V.weight):
+                q.grad = None
+            It, S = _run_cell(lay, I, u0, w0, s0, need_grad=True)
+            flips = float((S.detach().cpu().numpy() != r["s"]).mean())
+            assert flips <= 2e-2, (i, flips)
+            if flips == 0:
+                gs = np.random.default_rng(1).standard_normal(r["s"].shape).astype(np.float32)
+                S.backward(torch.from_numpy(gs).to(DEV))
+                bw = orc.cell_backward(lay._kind, gs, I, p["alpha"], p["beta"], p["a"], p["b"], V0, u0, w0, s0,
+                                       theta=lay.threshold, U=r["u"], W=r["w"], S=r["s"])
+                assert rel_l2(It.grad.cpu().numpy(), bw["dI"]) < 3e-2
+                assert rel_l2(lay.V.weight.grad.cpu().numpy(), bw["dV"]) < 3e-2
+        # whole model: same weights and seeds in both modes
+        losses = {}
+        for mode in ("fp32", "bf16"):
+            sparch_b200.set_precision(mode)
+            m = _net(g)
+            torch.manual_seed(42)
+            out, _ = m(g.t("x", DEV))
+            loss = g.loss_fn(out, g.t("y", DEV))
+            loss.backward()
+            assert all(torch.isfinite(q.grad).all() for q in m.parameters())
+            losses[mode] = float(loss)
+        assert abs(losses["bf16"] - losses["fp32"]) <= 0.05 * abs(losses["fp32"]), losses
+    finally:
+        sparch_b200.set_precision("fp32")
