@@ -365,7 +365,7 @@ def run_ours(args, cfg, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="cfg4", choices=sorted(CONFIGS),
                     help="cfg4 (default) is the configuration BASELINE.json's metric is quoted on")

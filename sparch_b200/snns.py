@@ -294,5 +294,7 @@ class SNN(nn.Module):
                 # a spiking layer emits exactly {0, 1/(1-p)} in training and {0, 1} otherwise
                 p = snn_lay.drop.p
                 in_scale = 1.0 / (1.0 - p) if (snn_lay.drop.training and 0.0 < p < 1.0) else 1.0
-        firing_rates = torch.cat(all_spikes, dim=2).mean(dim=(0, 1))   # snns.py:174
+        # snns.py:174 takes cat(all_spikes, dim=2).mean(dim=(0, 1)); the per-neuron means are the same
+        # without materialising the concatenated (B, T, sum H) tensor
+        firing_rates = torch.cat([s.mean(dim=(0, 1)) for s in all_spikes], dim=0)
         return x, firing_rates
