@@ -177,6 +177,15 @@ struct RecBwdArgs {
 __device__ __forceinline__ void team_sync(int team) {
   asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(TT) : "memory");
 }
+// Ping-pong of the two teams' tensor phases (named barriers 3 and 4, all 256 threads counted): a team
+// enters its MMA loop only after the other team has left its own, so each finds the tensor pipe free.
+__device__ __forceinline__ void pingpong_wait(int team) {
+  asm volatile("bar.sync %0, %1;" ::"r"(3 + team), "n"(TEAMS * TT) : "memory");
+}
+__device__ __forceinline__ void pingpong_pass(int team) {  // lets the OTHER team go
+  asm volatile("bar.arrive %0, %1;" ::"r"(3 + (team ^ 1)), "n"(TEAMS * TT) : "memory");
+}
+
 __device__ __forceinline__ void group_wait(const int* ctr, int target, int lt, int team) {
   if (lt == 0) {
     const long long t0 = clock64();
@@ -244,12 +253,20 @@ __global__ void __launch_bounds__(TEAMS* TT, 1) rec_fwd_persist_kernel(const Rec
   cp_async_wait_all();
   __syncthreads();            // V0 image and parameter table visible to both teams
   if (row0 >= p.Be) return;   // odd number of row groups: the last CTA's second team has no rows
+  if (team == 1 && (p.dbg_flags & 8)) return;  // experiment: team 0 alone on the SM (team 1's rows are not computed)
+  if (team == 1 && p.dbg_flags >= 16) {  // experiment: start team 1 (dbg_flags / 16) * 256 cycles late
+    const long long t0 = clock64();
+    while (clock64() - t0 < (long long)(p.dbg_flags / 16) * 256) {}
+  }
   // (Starting team 1 half a step late, to run the two pipelines in anti-phase, was measured: no gain --
   // a single warp issues one HMMA.16816 per ~18 cycles, so a team's MMA phase lasts ~4.7 k cycles with
   // or without the other team competing for the tensor pipe.)
 
   const uint4* bimg = reinterpret_cast<const uint4*>(simg);
   bool tapes_pending = false;
+  // both teams of this CTA have rows (and the experiment flags leave both running): alternate MMA phases
+  const bool pingpong = (group0 + TEAMS * blockIdx.y + 1) * RB < p.Be && !(p.dbg_flags & (8 | 32));
+  if (pingpong && team == 1) pingpong_pass(1);  // team 0 goes first
   for (int t = 0; t < p.T; ++t) {
     const int64_t o0 = ((int64_t)row * p.T + t) * p.H + col0;
     float z[8], rec[8];
@@ -306,7 +323,10 @@ __global__ void __launch_bounds__(TEAMS* TT, 1) rec_fwd_persist_kernel(const Rec
           if (dst[k] >= 0) sbits[dst[k]] = bv[k];
       }
       team_sync(team);
+      if (pingpong) pingpong_wait(team);
       if (dbg_on) p.dbg[t * 8 + 0] = clock64();
+      const bool dbg_on1 = p.dbg && tid == TT && blockIdx.x == 0 && blockIdx.y == 0;  // team 1's view
+      if (dbg_on1) p.dbg[t * 8 + 5] = clock64();
 
       float acc[2][4][4];
 #pragma unroll
@@ -355,7 +375,9 @@ __global__ void __launch_bounds__(TEAMS* TT, 1) rec_fwd_persist_kernel(const Rec
                          part ? f[ks][nt].z : f[ks][nt].x, part ? f[ks][nt].w : f[ks][nt].y);
         }
       }
+      if (pingpong) pingpong_pass(team);
       if (dbg_on) p.dbg[t * 8 + 1] = clock64();
+      if (dbg_on1) p.dbg[t * 8 + 6] = clock64();
       float* myred = red + kq * RB * RED_RS;
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)

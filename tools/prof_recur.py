@@ -53,6 +53,9 @@ if os.environ.get("SPARCH_PHASES"):
           "update+publish %.0f | total %.0f"
           % (m(d[:, 0] - prev_end), m(d[:, 1] - d[:, 0]), m(d[:, 2] - d[:, 1]), m(d[:, 3] - d[:, 2]),
              m(d[:, 3] - prev_end)))
+    ov = torch.minimum(c[2:, 1], c[2:, 6]) - torch.maximum(c[2:, 0], c[2:, 5])
+    print("team overlap (same SM clock): team1 mma start - team0 mma start %.0f cycles, team1 mma %.0f, overlap of the two MMA "
+          "phases %.0f cycles/step" % (m(c[2:, 5] - c[2:, 0]), m(c[2:, 6] - c[2:, 5]), float(ov.clamp(min=0).mean())))
     dbg.zero_()
     call("sparch_recur_debug_clocks", ptr(dbg))
     I2 = I.detach().clone().requires_grad_(True)
