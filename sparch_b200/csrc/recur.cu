@@ -166,6 +166,7 @@ struct RecBwdArgs {
   int Be, T, H, Hp;
   long long* dbg;   // optional [T][8] phase clocks of CTA (0,0) (profiling aid), normally NULL
   int reduced;      // 1: reduced-precision mode, hi x hi product only, lo halves of the panel not moved
+  int dbg_flags;    // profiling experiments (results invalid): 8 team 0 alone, 32 no ping-pong
 };
 
 // ------------------------------------------------------------------ persistent kernels
@@ -204,15 +205,48 @@ __device__ __forceinline__ void group_arrive(int* ctr, int lt, int team) {
   if (lt == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ctr) : "memory");
 }
 
-constexpr int FWD_TEAM_WORDS_FIXED = 4 * RB * RED_RS;  // reduction buffer (floats); spike tile follows
+// Forward teams are 8 warps (K-eighths, 512 threads per CTA): a warp's HMMA issue rate bounds a team's
+// MMA phase, so the forward kernel -- whose register budget allows it -- halves each warp's share; the
+// neuron update then has 4 neurons per thread.
+constexpr int FW = 8;                 // warps per forward team
+constexpr int FT = FW * 32;           // threads per forward team
+constexpr int FWD_TEAM_WORDS_FIXED = FW * RB * RED_RS;  // reduction buffer (floats); spike tile follows
+
+__device__ __forceinline__ void fteam_sync(int team) {
+  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(FT) : "memory");
+}
+__device__ __forceinline__ void fpingpong_wait(int team) {
+  asm volatile("bar.sync %0, %1;" ::"r"(3 + team), "n"(TEAMS * FT) : "memory");
+}
+__device__ __forceinline__ void fpingpong_pass(int team) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(3 + (team ^ 1)), "n"(TEAMS * FT) : "memory");
+}
+__device__ __forceinline__ void load4(const float* __restrict__ p, float (&v)[4], bool vec, int nv) {
+  if (vec) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = i < nv ? p[i] : 0.f;
+  }
+}
+__device__ __forceinline__ void store4(float* __restrict__ p, const float (&v)[4], bool vec, int nv) {
+  if (vec) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < nv) p[i] = v[i];
+  }
+}
 
 template <bool ADAPT>
-__global__ void __launch_bounds__(TEAMS* TT, 1) rec_fwd_persist_kernel(const RecFwdArgs p, const int group0) {
+__global__ void __launch_bounds__(TEAMS* FT, 1) rec_fwd_persist_kernel(const RecFwdArgs p, const int group0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NW = p.Hp / 32;   // spike words per row
   const int RSB = NW + 1;     // padded row stride of the spike-word tile
-  const int tid = threadIdx.x, lane = tid & 31, team = tid >> 7, lt = tid & (TT - 1);
-  const int kq = (tid >> 5) & 3, g = lane >> 2, q = lane & 3;
+  const int tid = threadIdx.x, lane = tid & 31, team = tid / FT, lt = tid % FT;
+  const int kq = (tid >> 5) % FW, g = lane >> 2, q = lane & 3;
   uint32_t* simg = reinterpret_cast<uint32_t*>(smem_raw);
   const size_t team_words = (size_t)FWD_TEAM_WORDS_FIXED + (size_t)RB * RSB;
   float* red = reinterpret_cast<float*>(smem_raw + (size_t)p.Hp * 128) + team * team_words;
@@ -223,7 +257,7 @@ __global__ void __launch_bounds__(TEAMS* TT, 1) rec_fwd_persist_kernel(const Rec
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.img + (size_t)slice * p.Hp * 32);
     uint4* dst = reinterpret_cast<uint4*>(simg);
-    for (int i = tid; i < p.Hp * 8; i += TEAMS * TT) cp_async16(dst + i, src + i);
+    for (int i = tid; i < p.Hp * 8; i += TEAMS * FT) cp_async16(dst + i, src + i);
   }
   __shared__ float sprm[8][RC];  // alpha, 1-alpha, beta, a, b, 1/(1-alpha), scale, shift of the slice
   if (tid < RC) {
@@ -234,21 +268,21 @@ __global__ void __launch_bounds__(TEAMS* TT, 1) rec_fwd_persist_kernel(const Rec
     sprm[6][tid] = p.scale ? p.scale[col] : 1.0f;
     sprm[7][tid] = p.scale ? p.shift[col] : 0.0f;
   }
-  const int r = lt >> 2, cg = lt & 3;
+  const int r = lt >> 3, cg = lt & 7;   // 256 threads on the team's 32 x 32 block: 4 neurons of one row each
   const int row = row0 + r;
-  const int col0 = slice * RC + cg * 8;
+  const int col0 = slice * RC + cg * 4;
   const bool live = row < p.Be && col0 < p.H;
-  const bool vec = ((p.H & 3) == 0) && (col0 + 8 <= p.H);
-  const int nv = live ? min(8, p.H - col0) : 0;
+  const bool vec = ((p.H & 3) == 0) && (col0 + 4 <= p.H);
+  const int nv = live ? min(4, p.H - col0) : 0;
   const int64_t idx0 = (int64_t)row * p.H + col0;
   const float rs = ldexpf(1.0f, p.meta[0] - VSCALE_EXP);
-  float u[8], w[8], s[8];
+  float u[4], w[4], s[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) u[i] = w[i] = s[i] = 0.f;
+  for (int i = 0; i < 4; ++i) u[i] = w[i] = s[i] = 0.f;
   if (live) {
-    load8(p.u0 + idx0, u, vec, nv);
-    load8(p.s0 + idx0, s, vec, nv);
-    if (ADAPT) load8(p.w0 + idx0, w, vec, nv);
+    load4(p.u0 + idx0, u, vec, nv);
+    load4(p.s0 + idx0, s, vec, nv);
+    if (ADAPT) load4(p.w0 + idx0, w, vec, nv);
   }
   cp_async_wait_all();
   __syncthreads();            // V0 image and parameter table visible to both teams
@@ -266,14 +300,14 @@ __global__ void __launch_bounds__(TEAMS* TT, 1) rec_fwd_persist_kernel(const Rec
   bool tapes_pending = false;
   // both teams of this CTA have rows (and the experiment flags leave both running): alternate MMA phases
   const bool pingpong = (group0 + TEAMS * blockIdx.y + 1) * RB < p.Be && !(p.dbg_flags & (8 | 32));
-  if (pingpong && team == 1) pingpong_pass(1);  // team 0 goes first
+  if (pingpong && team == 1) fpingpong_pass(1);  // team 0 goes first
   for (int t = 0; t < p.T; ++t) {
     const int64_t o0 = ((int64_t)row * p.T + t) * p.H + col0;
-    float z[8], rec[8];
+    float z[4], rec[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) z[i] = rec[i] = 0.f;
+    for (int i = 0; i < 4; ++i) z[i] = rec[i] = 0.f;
     const bool dbg_on = p.dbg && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
-    if (live && !(p.dbg_flags & 4)) load8(p.Z + o0, z, vec, nv);  // independent of the exchange: issued before the wait
+    if (live && !(p.dbg_flags & 4)) load4(p.Z + o0, z, vec, nv);  // independent of the exchange: issued before the wait
     if (t > 0) {
       // Wait for and fetch the spike words of step t-1 in one go: each word travels with its step
       // tag in a single 8-byte store, so a matching tag means the data is there (no fence, no
@@ -281,23 +315,23 @@ __global__ void __launch_bounds__(TEAMS* TT, 1) rec_fwd_persist_kernel(const Rec
       const uint2* bsrc = p.bits + (size_t)(t - 1) * p.Be * NW;
       const long long t0 = clock64();
       if (dbg_on) p.dbg[t * 8 + 4] = t0;
-      for (int base = 0; base < RB * NW; base += TT * 8) {
-        const uint2* src[8];
-        int dst[8];
-        bool need[8];
+      for (int base = 0; base < RB * NW; base += FT * 4) {
+        const uint2* src[4];
+        int dst[4];
+        bool need[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int i = base + k * TT + lt;
+        for (int k = 0; k < 4; ++k) {
+          const int i = base + k * FT + lt;
           const int rr = i / NW, wi = i - rr * NW;
           need[k] = i < RB * NW && row0 + rr < p.Be;
           dst[k] = i < RB * NW ? rr * RSB + wi : -1;
           src[k] = bsrc + (size_t)(row0 + rr) * NW + wi;
         }
-        uint32_t bv[8], tg[8];
+        uint32_t bv[4], tg[4];
         bool ok;
         do {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
+          for (int k = 0; k < 4; ++k) {
             bv[k] = 0;
             tg[k] = (uint32_t)t;
             if (need[k])
@@ -309,23 +343,23 @@ __global__ void __launch_bounds__(TEAMS* TT, 1) rec_fwd_persist_kernel(const Rec
           if (tapes_pending) {  // step t-1's tape stores ride in the shadow of the L2 round trip
             tapes_pending = false;
             const int64_t op = o0 - p.H;
-            store8(p.S + op, s, vec, nv);
-            store8(p.U + op, u, vec, nv);
-            if (ADAPT) store8(p.W + op, w, vec, nv);
+            store4(p.S + op, s, vec, nv);
+            store4(p.U + op, u, vec, nv);
+            if (ADAPT) store4(p.W + op, w, vec, nv);
           }
           ok = true;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) ok = ok && (tg[k] == (uint32_t)t || (p.dbg_flags & 1));
+          for (int k = 0; k < 4; ++k) ok = ok && (tg[k] == (uint32_t)t || (p.dbg_flags & 1));
           if (!ok && clock64() - t0 > 4000000000LL) __trap();  // a lost store must not hang the GPU
         } while (!ok);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
+        for (int k = 0; k < 4; ++k)
           if (dst[k] >= 0) sbits[dst[k]] = bv[k];
       }
-      team_sync(team);
-      if (pingpong) pingpong_wait(team);
+      fteam_sync(team);
+      if (pingpong) fpingpong_wait(team);
       if (dbg_on) p.dbg[t * 8 + 0] = clock64();
-      const bool dbg_on1 = p.dbg && tid == TT && blockIdx.x == 0 && blockIdx.y == 0;  // team 1's view
+      const bool dbg_on1 = p.dbg && tid == FT && blockIdx.x == 0 && blockIdx.y == 0;  // team 1's view
       if (dbg_on1) p.dbg[t * 8 + 5] = clock64();
 
       float acc[2][4][4];
@@ -335,7 +369,7 @@ __global__ void __launch_bounds__(TEAMS* TT, 1) rec_fwd_persist_kernel(const Rec
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
           for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
-      for (int wi = kq; wi < NW; wi += 4) {
+      for (int wi = kq; wi < NW; wi += FW) {
         uint32_t wa[2], wb[2];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
@@ -375,7 +409,7 @@ __global__ void __launch_bounds__(TEAMS* TT, 1) rec_fwd_persist_kernel(const Rec
                          part ? f[ks][nt].z : f[ks][nt].x, part ? f[ks][nt].w : f[ks][nt].y);
         }
       }
-      if (pingpong) pingpong_pass(team);
+      if (pingpong) fpingpong_pass(team);
       if (dbg_on) p.dbg[t * 8 + 1] = clock64();
       if (dbg_on1) p.dbg[t * 8 + 6] = clock64();
       float* myred = red + kq * RB * RED_RS;
@@ -388,23 +422,26 @@ __global__ void __launch_bounds__(TEAMS* TT, 1) rec_fwd_persist_kernel(const Rec
           *reinterpret_cast<float2*>(&myred[(16 * mt + g + 8) * RED_RS + col]) =
               make_float2(acc[mt][nt][2], acc[mt][nt][3]);
         }
-      team_sync(team);
+      fteam_sync(team);
+      {
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = cg * 8 + i;
-        rec[i] = ((red[(0 * RB + r) * RED_RS + c] + red[(1 * RB + r) * RED_RS + c]) +
-                  (red[(2 * RB + r) * RED_RS + c] + red[(3 * RB + r) * RED_RS + c])) * rs;
+        for (int k = 0; k < FW; ++k) {
+          const float4 v = *reinterpret_cast<const float4*>(&red[(k * RB + r) * RED_RS + cg * 4]);
+          sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        }
+        rec[0] = sum.x * rs; rec[1] = sum.y * rs; rec[2] = sum.z * rs; rec[3] = sum.w * rs;
       }
       if (dbg_on) p.dbg[t * 8 + 2] = clock64();
     } else if (live) {
-      load8(p.rec0 + idx0, rec, vec, nv);
+      load4(p.rec0 + idx0, rec, vec, nv);
     }
     uint32_t my = 0;
     if (live) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         if (i < nv) {
-          const int lc = cg * 8 + i;
+          const int lc = cg * 4 + i;
           NeuronParams npi;
           npi.alpha = sprm[0][lc]; npi.oma = sprm[1][lc]; npi.beta = sprm[2][lc]; npi.a = sprm[3][lc];
           npi.b = sprm[4][lc];
@@ -413,12 +450,13 @@ __global__ void __launch_bounds__(TEAMS* TT, 1) rec_fwd_persist_kernel(const Rec
           float wi_ = ADAPT ? w[i] : 0.f;
           step_fwd<ADAPT>(npi, cur, p.theta, u[i], wi_, s[i]);
           w[i] = wi_;
-          my |= (s[i] > 0.f ? 1u : 0u) << (cg * 8 + i);
+          my |= (s[i] > 0.f ? 1u : 0u) << (cg * 4 + i);
         }
       }
     }
     my |= __shfl_xor_sync(0xffffffffu, my, 1);
     my |= __shfl_xor_sync(0xffffffffu, my, 2);
+    my |= __shfl_xor_sync(0xffffffffu, my, 4);
     if (cg == 0 && row < p.Be)   // publish first: this store is what the other slices wait for
       asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p.bits + ((size_t)t * p.Be + row) * NW + slice),
                    "r"(my), "r"((uint32_t)(t + 1))
@@ -427,11 +465,11 @@ __global__ void __launch_bounds__(TEAMS* TT, 1) rec_fwd_persist_kernel(const Rec
     // spike-word loads are in flight (u, w, s stay unchanged in registers until then).
     tapes_pending = live && !(p.dbg_flags & 2);
     if (tapes_pending && t == p.T - 1) {
-      store8(p.S + o0, s, vec, nv);
-      store8(p.U + o0, u, vec, nv);
-      if (ADAPT) store8(p.W + o0, w, vec, nv);
+      store4(p.S + o0, s, vec, nv);
+      store4(p.U + o0, u, vec, nv);
+      if (ADAPT) store4(p.W + o0, w, vec, nv);
     }
-    team_sync(team);             // sbits / red are rewritten by the next step
+    fteam_sync(team);            // sbits / red are rewritten by the next step
     if (dbg_on) p.dbg[t * 8 + 3] = clock64();
   }
 }
@@ -484,6 +522,12 @@ rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_t
   cp_async_wait_all();
   __syncthreads();            // V0^T image and parameter table visible to both teams
   if (row0 >= p.Be) return;   // odd number of row groups: the last CTA's second team has no rows
+  if (team == 1 && (p.dbg_flags & 8)) return;  // experiment: team 0 alone on the SM
+  // (Alternating the two teams' panel-stream + MMA phases like the forward kernel does was measured:
+  // a team alone needs 10.5 k cycles for that phase, 13.7 k when both overlap -- serialising them
+  // (2 x 10.5 k) is slower than overlapping, 22.5 k vs 21.1 k per step.  The switch is kept for experiments.)
+  const bool pingpong = (p.dbg_flags & 64) && (group0 + TEAMS * blockIdx.y + 1) * RB < p.Be;
+  if (pingpong && team == 1) pingpong_pass(1);
 
   const uint4* bimg = reinterpret_cast<const uint4*>(simg);
   const int NSC = (NCH + 3) / 4;
@@ -509,6 +553,7 @@ rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_t
     if (dbg_on) p.dbg[t * 8 + 0] = clock64();
     if (t < p.T - 1) {
       group_wait(ctr, nslices * (p.T - 1 - t), lt, team);
+      if (pingpong) pingpong_wait(team);
       if (dbg_on) p.dbg[t * 8 + 1] = clock64();
       const uint32_t* apanel = p.panel + ((size_t)rbuf * ngroups_total + group) * NCH * PB_CHUNK_WORDS;
       const float* gsc = p.pscale + ((size_t)rbuf * ngroups_total + group) * NCH * RB;
@@ -583,6 +628,7 @@ rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_t
         }
         team_sync(team);
       }
+      if (pingpong) pingpong_pass(team);
       if (dbg_on) p.dbg[t * 8 + 2] = clock64();
       float* myred = red + kq * RB * RED_RS;
 #pragma unroll
@@ -725,7 +771,7 @@ int sparch_recur_fwd(int kind, const float* Z, const float* scale, const float* 
   SPARCH_REQUIRE(!adapt || (beta && a && b && w0 && W), "adaptive kind needs beta, a, b, w0, W");
   const int Hp = sparch_recur_padded(H);
   const size_t smem = rec_fwd_smem(Hp);
-  SPARCH_REQUIRE(smem <= 225 * 1024, "hidden size too large for the resident V0 slice (H <= 1376)");
+  SPARCH_REQUIRE(smem <= 225 * 1024, "hidden size too large for the resident V0 slice (H <= 1088)");
   RecFwdArgs p{Z, scale, shift, alpha, beta, a, b, rec0, u0, w0, s0, img_fwd, meta, theta, S, U, W,
                reinterpret_cast<uint2*>(bits), Be, T, H, Hp, g_dbg, g_dbg_flags, reduced ? 1 : 0};
   cudaStream_t st = as_stream(st_);
@@ -746,7 +792,7 @@ int sparch_recur_fwd(int kind, const float* Z, const float* scale, const float* 
     int group0 = g0;
     void* args[] = {(void*)&p, (void*)&group0};
     const void* fn = adapt ? (const void*)rec_fwd_persist_kernel<true> : (const void*)rec_fwd_persist_kernel<false>;
-    SPARCH_CUDA(cudaLaunchCooperativeKernel(fn, cgrid, dim3(TEAMS * TT), args, smem, st));
+    SPARCH_CUDA(cudaLaunchCooperativeKernel(fn, cgrid, dim3(TEAMS * FT), args, smem, st));
   }
   return SPARCH_OK;
 }
@@ -777,7 +823,7 @@ int sparch_recur_bwd(int kind, const float* G, const float* U, const float* W, c
   uint32_t* panel = reinterpret_cast<uint32_t*>(workspace);
   float* pscale = reinterpret_cast<float*>(panel + 2 * groups * (Hp / 32) * PB_CHUNK_WORDS);
   RecBwdArgs p{G, U, W, alpha, beta, a, b, u0, w0, s0, img_bwd, meta, theta, dI,
-               p_alpha, p_beta, p_a, p_b, panel, pscale, Be, T, H, Hp, g_dbg, reduced ? 1 : 0};
+               p_alpha, p_beta, p_a, p_b, panel, pscale, Be, T, H, Hp, g_dbg, reduced ? 1 : 0, g_dbg_flags};
   cudaStream_t st = as_stream(st_);
   const size_t psmem = rec_bwd_persist_smem(Hp);
   SPARCH_REQUIRE(psmem <= 225 * 1024, "hidden size too large for the resident V0^T slice");
