@@ -557,21 +557,24 @@ rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_t
       if (dbg_on) p.dbg[t * 8 + 1] = clock64();
       const uint32_t* apanel = p.panel + ((size_t)rbuf * ngroups_total + group) * NCH * PB_CHUNK_WORDS;
       const float* gsc = p.pscale + ((size_t)rbuf * ngroups_total + group) * NCH * RB;
-      auto issue = [&](int sc) {
-        if (sc < NSC) {
-          uint32_t* dst = ring + (size_t)(sc % PB_STAGES) * PB_STAGE_WORDS;
-          const int nch = min(4, NCH - 4 * sc);
-          const uint4* sa = reinterpret_cast<const uint4*>(apanel + (size_t)4 * sc * PB_CHUNK_WORDS);
-          uint4* da = reinterpret_cast<uint4*>(dst);
+      // Each warp streams ITS chunks (c = 4j + kq) through a private 2-slot ring: no team barrier inside
+      // the K loop, so the four warps drift apart and one warp's L2 wait is covered by the others' MMAs.
+      uint32_t* wring = ring + (size_t)kq * (2 * PB_CHUNK_WORDS);
+      auto issue = [&](int j) {
+        const int c = 4 * j + kq;
+        if (c < NCH) {
+          const uint4* sa = reinterpret_cast<const uint4*>(apanel + (size_t)c * PB_CHUNK_WORDS);
+          uint4* da = reinterpret_cast<uint4*>(wring + (size_t)(j & 1) * PB_CHUNK_WORDS);
           // 16-byte unit i: bit 5 selects the hi (0) / lo (1) block of a (row tile, k-step); the reduced
           // mode never touches the lo blocks
-          for (int i = lt; i < nch * (PB_CHUNK_WORDS / 4); i += TT)
+          for (int i = lane; i < PB_CHUNK_WORDS / 4; i += 32)
             if (!(p.reduced && (i & 32))) cp_async16(da + i, sa + i);
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
       };
-      for (int i = lt; i < NCH * RB; i += TT) sscale[i] = __ldcg(&gsc[i]);
       issue(0);
+      for (int i = lt; i < NCH * RB; i += TT) sscale[i] = __ldcg(&gsc[i]);
+      team_sync(team);   // scales visible (the ring itself is warp-private)
       float acc[2][4][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
@@ -579,14 +582,13 @@ rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_t
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
           for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
-      for (int sc = 0; sc < NSC; ++sc) {
-        issue(sc + 1);
+      for (int j = 0; j < NSC; ++j) {
+        issue(j + 1);
         asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-        team_sync(team);
-        const int c = 4 * sc + kq;
+        __syncwarp();
+        const int c = 4 * j + kq;
         if (c < NCH) {
-          const uint4* a4 = reinterpret_cast<const uint4*>(ring + (size_t)(sc % PB_STAGES) * PB_STAGE_WORDS) +
-                            kq * (PB_CHUNK_WORDS / 4);
+          const uint4* a4 = reinterpret_cast<const uint4*>(wring + (size_t)(j & 1) * PB_CHUNK_WORDS);
           float tacc[2][4][4];
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt)
@@ -626,8 +628,9 @@ rec_bwd_persist_kernel(const RecBwdArgs p, const int group0, const int ngroups_t
             }
           }
         }
-        team_sync(team);
+        __syncwarp();    // every lane is done with the slot before the next iteration refills it
       }
+      team_sync(team);   // all warps are done with the ring: the reduction buffer aliases it
       if (pingpong) pingpong_pass(team);
       if (dbg_on) p.dbg[t * 8 + 2] = clock64();
       float* myred = red + kq * RB * RED_RS;
