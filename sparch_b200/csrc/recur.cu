@@ -205,12 +205,13 @@ __device__ __forceinline__ void group_arrive(int* ctr, int lt, int team) {
   if (lt == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ctr) : "memory");
 }
 
-// Forward teams are 8 warps (K-eighths, 512 threads per CTA): a warp's HMMA issue rate bounds a team's
-// MMA phase, so the forward kernel -- whose register budget allows it -- halves each warp's share; the
-// neuron update then has 4 neurons per thread.
+// Forward teams are 8 warps (4 K-quarters x 2 column halves, 512 threads per CTA): a warp's HMMA issue
+// rate bounds a team's MMA phase, so the forward kernel -- whose register budget allows it -- halves
+// each warp's share; the neuron update then has 4 neurons per thread.
 constexpr int FW = 8;                 // warps per forward team
 constexpr int FT = FW * 32;           // threads per forward team
-constexpr int FWD_TEAM_WORDS_FIXED = FW * RB * RED_RS;  // reduction buffer (floats); spike tile follows
+constexpr int FKQ = 4;                // K-quarters; the 8 warps are 4 K-quarters x 2 column halves
+constexpr int FWD_TEAM_WORDS_FIXED = FKQ * RB * RED_RS;  // reduction buffer (floats); spike tile follows
 
 __device__ __forceinline__ void fteam_sync(int team) {
   asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(FT) : "memory");
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(TEAMS* FT, 1) rec_fwd_persist_kernel(const Rec
   const int NW = p.Hp / 32;   // spike words per row
   const int RSB = NW + 1;     // padded row stride of the spike-word tile
   const int tid = threadIdx.x, lane = tid & 31, team = tid / FT, lt = tid % FT;
-  const int kq = (tid >> 5) % FW, g = lane >> 2, q = lane & 3;
+  const int kq = ((tid >> 5) % FW) >> 1, nh = (tid >> 5) & 1, g = lane >> 2, q = lane & 3;
   uint32_t* simg = reinterpret_cast<uint32_t*>(smem_raw);
   const size_t team_words = (size_t)FWD_TEAM_WORDS_FIXED + (size_t)RB * RSB;
   float* red = reinterpret_cast<float*>(smem_raw + (size_t)p.Hp * 128) + team * team_words;
@@ -362,14 +363,14 @@ __global__ void __launch_bounds__(TEAMS* FT, 1) rec_fwd_persist_kernel(const Rec
       const bool dbg_on1 = p.dbg && tid == FT && blockIdx.x == 0 && blockIdx.y == 0;  // team 1's view
       if (dbg_on1) p.dbg[t * 8 + 5] = clock64();
 
-      float acc[2][4][4];
+      float acc[2][2][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
+        for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
           for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
-      for (int wi = kq; wi < NW; wi += FW) {
+      for (int wi = kq; wi < NW; wi += FKQ) {
         uint32_t wa[2], wb[2];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
@@ -379,13 +380,13 @@ __global__ void __launch_bounds__(TEAMS* FT, 1) rec_fwd_persist_kernel(const Rec
         }
         // both k-steps of the word: 4 passes over the 8 accumulators (hi ks0, hi ks1, lo ks0, lo ks1), so
         // two HMMAs on the same accumulator are always 8 instructions apart
-        uint4 f[2][4];
+        uint4 f[2][2];
         uint32_t af[2][2][4];
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
           const int kk = 2 * wi + ks;
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) f[ks][nt] = bimg[(kk * 4 + nt) * 32 + lane];  // ((kk*2+nh)*2+blk), nt = 2nh+blk
+          for (int nt = 0; nt < 2; ++nt) f[ks][nt] = bimg[((kk * 2 + nh) * 2 + nt) * 32 + lane];
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt) {
             const uint32_t M = 0x40004000u;
@@ -404,7 +405,7 @@ __global__ void __launch_bounds__(TEAMS* FT, 1) rec_fwd_persist_kernel(const Rec
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-              for (int nt = 0; nt < 4; ++nt)
+              for (int nt = 0; nt < 2; ++nt)
                 mma16816(acc[mt][nt], af[ks][mt][0], af[ks][mt][1], af[ks][mt][2], af[ks][mt][3],
                          part ? f[ks][nt].z : f[ks][nt].x, part ? f[ks][nt].w : f[ks][nt].y);
         }
@@ -416,8 +417,8 @@ __global__ void __launch_bounds__(TEAMS* FT, 1) rec_fwd_persist_kernel(const Rec
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          const int col = 8 * nt + 2 * q;
+        for (int nt = 0; nt < 2; ++nt) {
+          const int col = 16 * nh + 8 * nt + 2 * q;
           *reinterpret_cast<float2*>(&myred[(16 * mt + g) * RED_RS + col]) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
           *reinterpret_cast<float2*>(&myred[(16 * mt + g + 8) * RED_RS + col]) =
               make_float2(acc[mt][nt][2], acc[mt][nt][3]);
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(TEAMS* FT, 1) rec_fwd_persist_kernel(const Rec
       {
         float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < FW; ++k) {
+        for (int k = 0; k < FKQ; ++k) {
           const float4 v = *reinterpret_cast<const float4*>(&red[(k * RB + r) * RED_RS + cg * 4]);
           sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
         }
@@ -774,7 +775,7 @@ int sparch_recur_fwd(int kind, const float* Z, const float* scale, const float* 
   SPARCH_REQUIRE(!adapt || (beta && a && b && w0 && W), "adaptive kind needs beta, a, b, w0, W");
   const int Hp = sparch_recur_padded(H);
   const size_t smem = rec_fwd_smem(Hp);
-  SPARCH_REQUIRE(smem <= 225 * 1024, "hidden size too large for the resident V0 slice (H <= 1088)");
+  SPARCH_REQUIRE(smem <= 225 * 1024, "hidden size too large for the resident V0 slice");
   RecFwdArgs p{Z, scale, shift, alpha, beta, a, b, rec0, u0, w0, s0, img_fwd, meta, theta, S, U, W,
                reinterpret_cast<uint2*>(bits), Be, T, H, Hp, g_dbg, g_dbg_flags, reduced ? 1 : 0};
   cudaStream_t st = as_stream(st_);

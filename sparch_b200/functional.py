@@ -252,7 +252,7 @@ def _norm_backward(dI2d, Z2d, gamma, bn_beta, norm, scale, mean, rstd):
 
 # Largest hidden size whose 32-column V0 slice (fp16 hi/lo, Hp*128 bytes) fits next to the exchange
 # buffers in the persistent kernels' shared memory; beyond it the recurrent kinds take the stepwise path.
-RECUR_MAX_H = 1088
+RECUR_MAX_H = 1184
 
 
 class SpikingCellFunction(torch.autograd.Function):

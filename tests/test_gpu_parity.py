@@ -373,6 +373,7 @@ def _oracle_cell_check(kind, Be, T, H, seed, drive=(3.0, 1.2), stable=True):
     ("adLIF", 65, 33, 77),      # streaming kernels, odd sizes, T not a multiple of the prefetch depth
     ("LIF", 1, 1, 1),
     ("RadLIF", 6, 4, 1440),     # beyond the resident-V0 limit: stepwise general path
+    ("RLIF", 40, 3, 1184),      # the largest hidden size the persistent kernels hold
 ])
 def test_cell_edge_shapes_against_oracle(kind, Be, T, H):
     _oracle_cell_check(kind, Be, T, H, seed=Be + T + H)
