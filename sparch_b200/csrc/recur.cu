@@ -200,7 +200,8 @@ __device__ __forceinline__ void group_wait(const int* ctr, int target, int lt, i
   team_sync(team);
 }
 __device__ __forceinline__ void group_arrive(int* ctr, int lt, int team) {
-  __threadfence();
+  // The team barrier orders every thread's panel stores before thread 0's release at gpu scope
+  // (release is cumulative over what the barrier made visible to thread 0): one fence, not 128.
   team_sync(team);
   if (lt == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ctr) : "memory");
 }
