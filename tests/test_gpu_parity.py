@@ -518,3 +518,48 @@ def test_reduced_precision_mode():
         assert abs(losses["bf16"] - losses["fp32"]) <= 0.05 * abs(losses["fp32"]), losses
     finally:
         sparch_b200.set_precision("fp32")
+
+
+def test_full_size_cfg4_layer_against_oracle_on_gpu():
+    """BASELINE.json's headline shape (RadLIF, B=256, T=100, H=1024, F=40): the first layer's spike
+    train against the oracle's torch restatement run on the same device (stable draw a <- |a|), the
+    forward is bit-reproducible run to run, and the loss of the whole model agrees with the oracle."""
+    sp, _ = _mods()
+    kw = dict(layer_sizes=[1024, 1024, 35], neuron_type="RadLIF", normalization="batchnorm")
+    torch.manual_seed(0)
+    net = sp.SNN((256, None, 40), **kw)
+    ref = orc.build_oracle_snn((256, None, 40), **kw)
+    ref.load_state_dict(net.state_dict())
+    for m in (net, ref):
+        with torch.no_grad():
+            for lay in m.snn:
+                if hasattr(lay, "a"):
+                    lay.a.abs_()
+                if isinstance(getattr(lay, "norm", None), torch.nn.BatchNorm1d):
+                    lay.norm.weight.fill_(3.0)   # default gamma=1, beta=0 leaves the net almost silent
+                    lay.norm.bias.fill_(0.8)
+    net, ref = net.to(DEV), ref.to(DEV)
+    ref.snn[0].capture = {}
+    torch.manual_seed(1234)
+    x = torch.randn(256, 100, 40, device=DEV)
+    y = torch.randint(0, 35, (256,), device=DEV)
+    got = {}
+    h = net.snn[0].register_forward_hook(lambda m, i, o: got.__setitem__(0, o.detach()))
+    torch.manual_seed(42)
+    out, rates = net(x)
+    first = got[0].clone()
+    torch.manual_seed(42)
+    out2, _ = net(x)
+    h.remove()
+    assert torch.equal(first, got[0]) and torch.equal(out, out2), "forward is not reproducible"
+    torch.manual_seed(42)
+    out_r, rates_r = ref(x)
+    s_ref = ref.snn[0].capture["s"]
+    flips = float((first != s_ref).float().mean())
+    assert 0.005 < float(s_ref.mean()) < 0.9
+    assert flips <= FLIP_TOL, flips
+    loss = torch.nn.functional.cross_entropy(out, y)
+    loss_r = torch.nn.functional.cross_entropy(out_r, y)
+    # a handful of threshold straddlers reshuffle later spikes (SURVEY.md 7 #1): compare at 2 %
+    assert abs(float(loss) - float(loss_r)) <= 0.02 * abs(float(loss_r)), (float(loss), float(loss_r))
+    assert float((rates - rates_r).abs().max()) < 0.02
