@@ -563,3 +563,15 @@ def test_full_size_cfg4_layer_against_oracle_on_gpu():
     # a handful of threshold straddlers reshuffle later spikes: compare at 2 %
     assert abs(float(loss) - float(loss_r)) <= 0.02 * abs(float(loss_r)), (float(loss), float(loss_r))
     assert float((rates - rates_r).abs().max()) < 0.02
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_recurrent_cells_random_shape_sweep(seed):
+    """Seeded random shapes (batch not a multiple of the 32-row teams, hidden size not a multiple of the
+    32-neuron slices / 128-neuron K-quarters, 1..7 steps) for the persistent recurrent kernels."""
+    rng = np.random.default_rng(1000 + seed)
+    kind = ("RLIF", "RadLIF")[seed % 2]
+    Be = int(rng.choice([1, 2, 31, 32, 33, 63, 64, 65, 100, 257]))
+    H = int(rng.choice([1, 8, 31, 32, 33, 48, 96, 100, 130, 260, 512]))
+    T = int(rng.integers(1, 8))
+    _oracle_cell_check(kind, Be, T, H, seed=seed, drive=(3.0, 1.5))
