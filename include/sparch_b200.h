@@ -187,6 +187,24 @@ SPARCH_API int sparch_recur_bwd(int kind, const float* G, const float* U, const 
                                 float* p_b, void* workspace, int* sync_ws, int reduced, int Be,
                                 int T, int H, sparch_stream_t st);
 
+/* Reverse pass of an RLIF/RadLIF layer with dI_{t+1} @ V0^T on tcgen05 (A panels as K-major fp16
+ * hi/lo matrices fetched by TMA, D in TMEM, one per-row scale derived one step late).  Same
+ * results contract as sparch_recur_bwd.  img from sparch_recur_prepare_tc
+ * (sparch_recur_bwd_tc_image_bytes bytes), meta from sparch_recur_prepare, workspace of
+ * sparch_recur_bwd_tc_workspace bytes.                                                        */
+SPARCH_API int sparch_recur_tc_padded(int H);
+SPARCH_API size_t sparch_recur_bwd_tc_image_bytes(int H);
+SPARCH_API size_t sparch_recur_bwd_tc_workspace(int Be, int T, int H);
+SPARCH_API int sparch_recur_prepare_tc(const float* V, int H, void* img, const int* meta,
+                                       sparch_stream_t st);
+SPARCH_API int sparch_recur_bwd_tc(int kind, const float* G, const float* U, const float* W,
+                                   const float* alpha, const float* beta, const float* a,
+                                   const float* b, const void* img, const int* meta,
+                                   const float* u0, const float* w0, const float* s0, float theta,
+                                   float* dI, float* p_alpha, float* p_beta, float* p_a,
+                                   float* p_b, void* workspace, int Be, int T, int H,
+                                   sparch_stream_t st);
+
 /* ---- ReadoutLayer cell (snns.py:807-825) ---------------------------------------------- */
 /* u_t = alpha*u_{t-1} + (1-alpha)*I_t ; out = sum_t softmax(u_t, dim=1).  U (B,T,C) tape.  */
 SPARCH_API int sparch_readout_fwd(const float* Z, const float* scale, const float* shift,

@@ -36,6 +36,11 @@ _PROTOS = {
     "sparch_recur_fwd": "i" + "p" * 13 + "f" + "pppp" + "iiii" + "p",
     "sparch_recur_bwd_workspace": "ii",
     "sparch_recur_bwd": "i" + "p" * 12 + "f" + "p" * 7 + "iiii" + "p",
+    "sparch_recur_tc_padded": "i",
+    "sparch_recur_bwd_tc_image_bytes": "i",
+    "sparch_recur_bwd_tc_workspace": "iii",
+    "sparch_recur_prepare_tc": "pippp",
+    "sparch_recur_bwd_tc": "i" + "p" * 12 + "f" + "p" * 6 + "iii" + "p",
     "sparch_readout_fwd": "p" * 7 + "iii" + "p",
     "sparch_readout_bwd": "p" * 6 + "iii" + "p",
 }
@@ -63,7 +68,7 @@ def lib():
         h.sparch_last_error.argtypes = []
         for name, sig in _PROTOS.items():
             fn = getattr(h, name)
-            fn.restype = ctypes.c_size_t if name.endswith("_workspace") else _I
+            fn.restype = ctypes.c_size_t if name.endswith(("_workspace", "_bytes")) else _I
             fn.argtypes = [_CT[c] for c in sig]
         _lib = h
     return _lib

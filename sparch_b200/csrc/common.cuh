@@ -34,6 +34,8 @@ int cuda_fail(const char* what, cudaError_t e);
 inline cudaStream_t as_stream(sparch_stream_t st) { return reinterpret_cast<cudaStream_t>(st); }
 
 int sm_count();
+long long* recur_debug_buffer();  // profiling aid set by sparch_recur_debug_clocks (recur.cu), normally NULL
+int recur_debug_flags();
 
 // Surrogate window and threshold tests on v = u - theta, exactly as the reference evaluates them
 // in fp32 (snns.py:29, 33-35): spike iff v > 0; gradient passes iff -0.5 < v <= 0.5.

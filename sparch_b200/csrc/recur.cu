@@ -93,6 +93,8 @@ __global__ void vprep_kernel(const float* __restrict__ V, int H, int Hp, int tra
 
 static long long* g_dbg = nullptr;  // see sparch_recur_debug_clocks
 static int g_dbg_flags = 0;
+long long* recur_debug_buffer() { return g_dbg; }
+int recur_debug_flags() { return g_dbg_flags; }
 
 struct RecFwdArgs {
   const float *Z, *scale, *shift, *alpha, *beta, *a, *b, *rec0, *u0, *w0, *s0;

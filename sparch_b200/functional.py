@@ -255,6 +255,12 @@ def _norm_backward(dI2d, Z2d, gamma, bn_beta, norm, scale, mean, rstd):
 RECUR_MAX_H = 1184
 
 
+# Reverse recurrence kernel: "mma" = mma.sync kernel (block-floating-point panels, per-chunk scales),
+# "tc" = tcgen05 kernel (TMA-fed fp16 hi/lo panels, per-row lagged scale, D in TMEM).
+RECUR_BWD = os.environ.get("SPARCH_B200_BWD", "mma")
+RECUR_TC_MAX_H = 1280
+
+
 class SpikingCellFunction(torch.autograd.Function):
     """Normalisation fold + membrane recurrence of one spiking layer.
 
@@ -308,6 +314,12 @@ class SpikingCellFunction(torch.autograd.Function):
                 meta = torch.empty(2, device=dev, dtype=torch.int32)
                 call("sparch_recur_prepare", ptr(V.detach().contiguous()), H, ptr(img_f), ptr(img_b),
                      ptr(meta), st)
+                if RECUR_BWD == "tc" and H <= RECUR_TC_MAX_H:
+                    img_b = torch.empty(_lib.lib().sparch_recur_bwd_tc_image_bytes(H), device=dev, dtype=torch.uint8)
+                    call("sparch_recur_prepare_tc", ptr(V.detach().contiguous()), H, ptr(img_b), ptr(meta), st)
+                    ctx.tc = True
+                else:
+                    ctx.tc = False
                 ctx.rec = (img_b, meta)
                 ctx.reduced = int(_PRECISION == "bf16")
                 rec0 = torch.matmul(s0, V0)        # t = 0: s_{-1} is real-valued (snns.py:702)
@@ -354,6 +366,12 @@ class SpikingCellFunction(torch.autograd.Function):
                      ptr(bb), ptr(recb) if t < T - 1 else None, ptr(u0), ptr(w0), ptr(s0), theta,
                      ptr(dI), ptr(carry[0]), ptr(carry[1]) if adaptive else None, pp[0], pp[1], pp[2],
                      pp[3], Be, T, H, st)
+        elif ctx.tc:
+            img_b, meta = ctx.rec
+            ws = torch.empty(_lib.lib().sparch_recur_bwd_tc_workspace(Be, T, H), device=dev, dtype=torch.uint8)
+            call("sparch_recur_bwd_tc", k, ptr(G), ptr(U), ptr(Wt), ptr(al), ptr(be), ptr(aa), ptr(bb),
+                 ptr(img_b), ptr(meta), ptr(u0), ptr(w0), ptr(s0), theta, ptr(dI), pp[0], pp[1], pp[2],
+                 pp[3], ptr(ws), Be, T, H, st)
         else:
             img_b, meta = ctx.rec
             ws = torch.empty(_lib.lib().sparch_recur_bwd_workspace(Be, H), device=dev, dtype=torch.uint8)

@@ -379,6 +379,28 @@ def test_cell_edge_shapes_against_oracle(kind, Be, T, H):
     _oracle_cell_check(kind, Be, T, H, seed=Be + T + H)
 
 
+@pytest.mark.parametrize("kind,Be,T,H", [
+    ("RadLIF", 300, 7, 96),     # ragged last 64-row group, hidden size padded to the 64-wide K blocks
+    ("RadLIF", 70, 5, 1000),    # H not a multiple of 32
+    ("RLIF", 3, 1, 40),         # single timestep: no UMMA at all
+    ("RLIF", 33, 60, 130),      # longer chain, odd sizes
+    ("RadLIF", 640, 4, 512),    # 10 groups x 16 slices: two cooperative launches
+    ("RadLIF", 256, 12, 1024),  # the cfg4 layer width
+])
+def test_tcgen05_reverse_recurrence_against_oracle(kind, Be, T, H):
+    """The opt-in tcgen05 reverse-recurrence kernel (sparch_recur_bwd_tc) meets the same bar as the
+    default kernel."""
+    _, F = _mods()
+    old = F.RECUR_BWD
+    F.RECUR_BWD = "tc"
+    try:
+        n0 = F.native_launches()
+        _oracle_cell_check(kind, Be, T, H, seed=Be + T + H)
+        assert F.native_launches() > n0
+    finally:
+        F.RECUR_BWD = old
+
+
 def test_empty_batch_and_time_are_tolerated():
     _, F = _mods()
     for Be, T in ((0, 5), (4, 0)):
