@@ -187,9 +187,10 @@ SPARCH_API int sparch_recur_bwd(int kind, const float* G, const float* U, const 
                                 float* p_b, void* workspace, int* sync_ws, int reduced, int Be,
                                 int T, int H, sparch_stream_t st);
 
-/* Reverse pass of an RLIF/RadLIF layer with dI_{t+1} @ V0^T on tcgen05 (A panels as K-major fp16
- * hi/lo matrices fetched by TMA, D in TMEM, one per-row scale derived one step late).  Same
- * results contract as sparch_recur_bwd.  img from sparch_recur_prepare_tc
+/* Reverse pass of an RLIF/RadLIF layer with dI_{t+1} @ V0^T on tcgen05: clusters of 4 CTAs split K,
+ * A panels as K-major fp16 hi/lo matrices fetched by TMA, D in TMEM, partial products reduce-scattered
+ * through distributed shared memory, one per-row scale derived one step late.  H <= 1024.  Same
+ * results contract as sparch_recur_bwd (reduced != 0: hi terms only).  img from sparch_recur_prepare_tc
  * (sparch_recur_bwd_tc_image_bytes bytes), meta from sparch_recur_prepare, workspace of
  * sparch_recur_bwd_tc_workspace bytes.                                                        */
 SPARCH_API int sparch_recur_tc_padded(int H);
@@ -202,7 +203,7 @@ SPARCH_API int sparch_recur_bwd_tc(int kind, const float* G, const float* U, con
                                    const float* b, const void* img, const int* meta,
                                    const float* u0, const float* w0, const float* s0, float theta,
                                    float* dI, float* p_alpha, float* p_beta, float* p_a,
-                                   float* p_b, void* workspace, int Be, int T, int H,
+                                   float* p_b, void* workspace, int reduced, int Be, int T, int H,
                                    sparch_stream_t st);
 
 /* ---- ReadoutLayer cell (snns.py:807-825) ---------------------------------------------- */

@@ -1,22 +1,24 @@
 // Reverse-time recurrence of the recurrent kinds with dI_{t+1} @ V0^T on tcgen05 (alternative to
-// rec_bwd_persist_kernel in recur.cu; same decomposition, same BPTT update, same hand-over idea).
+// rec_bwd_persist_kernel in recur.cu; same BPTT update, same hand-over idea), split-K over a cluster.
 //
-//   CTA (slice, group) = 32 presynaptic neurons j x 64 batch rows, persistent over all T steps.
-//   B operand: the slice of V0 (rows j, K = all neurons c) as fp16 hi + lo, K-major SWIZZLE_128B tiles,
-//              resident in shared memory (KB x 2 x 4 KB).
+//   Cluster of 4 CTAs = 64 batch rows x 128 presynaptic neurons j, persistent over all T steps.  CTA
+//   rank r of the cluster multiplies over its QUARTER of K (neurons c in [r Hp/4, (r+1) Hp/4)) for all
+//   128 columns, then the four 64 x 128 partial products are reduce-scattered through distributed
+//   shared memory: rank r sums and owns columns 32 r .. 32 r + 31 (so CTA bx updates neurons 32 bx ..).
+//   B operand: V0[128 j][Hp/4 c] as fp16 hi + lo, K-major SWIZZLE_128B tiles resident in shared memory
+//              (Hp/256 x 2 x 16 KB = 128 KB at H = 1024).
 //   A operand: dI_{t+1} of the 64 rows, handed over through L2 as two plain row-major fp16 matrices
-//              (hi, lo), fetched by TMA (64 rows x 64 K boxes, SWIZZLE_128B) into a 4-stage ring.
-//   D: 64 x 32 fp32 in 32 TMEM columns; per K16 three UMMAs (hi*hi, hi*lo, lo*hi), 192 per step, issued
+//              (hi, lo); each CTA fetches only its K quarter by TMA (64 x 64 boxes, SWIZZLE_128B).
+//   D: 64 x 128 fp32 in 128 TMEM columns; per K16 three UMMAs (hi*hi, hi*lo, lo*hi) with N = 128, issued
 //      by one thread; the update warps read D with tcgen05.ld (M = 64 layout: rows 16q..16q+15 live in
-//      TMEM lanes 32q..32q+15).
+//      TMEM lanes 32q..32q+15) and scatter the column quarters to their owners (st.shared::cluster +
+//      remote mbarrier arrive).
 //
-// STATUS (measured on B200, cfg4 layer shape Be 256, T 100, H 1024): results agree with the mma.sync
-// kernel to 4e-7 of the gradient maximum, but a step takes 22k cycles against 17.6k: the issuing thread
-// spends ~58 cycles per tcgen05.mma at M = 64, N = 32 (704 cycles per 64-wide K block whether 4 or 12 of
-// the 12 UMMA slots execute, with or without TMA traffic, one or six TMEM accumulators), i.e. 11k
-// cycles per step for the 192 UMMAs the three fp16 terms need -- the per-instruction cost, not the
-// tensor pipe (16-cycle floor) or L2, is the bound, and V0's fp16 hi+lo residency (128 KB for 32
-// neurons) rules out a wider N.  Kept as an opt-in alternative (SPARCH_B200_BWD=tc), not the default.
+// Why split K instead of N (measured on B200 with the first version of this kernel, one CTA = 64 rows x
+// 32 neurons over the whole K range): a tcgen05.mma at M = 64 costs ~58 cycles whether N is 32 or 128,
+// so the 192 UMMAs a whole-K CTA needs per step took 11.3 k cycles, more than the mma.sync kernel.  With
+// N = 128 and a quarter of K a CTA issues 48 per step, and the panel traffic out of L2 drops from 256 KB
+// to 64 KB per CTA per step.
 //
 // Scaling.  fp16 needs a scale, and the tensor core accumulates over the whole K range without
 // intervention, so the scale must be per ROW (not per 32-column chunk as in the mma.sync kernel).  The
@@ -35,8 +37,12 @@
 namespace sparch {
 
 constexpr int TC_ROWS = 64;            // batch rows per CTA
-constexpr int TC_COLS = 32;            // neurons per CTA
-constexpr int TC_STAGES = 4;           // A ring depth
+constexpr int TC_COLS = 32;            // neurons updated per CTA
+constexpr int TC_CL = 4;               // CTAs per cluster = K quarters
+constexpr int TC_N = TC_COLS * TC_CL;  // UMMA N: neurons per cluster
+constexpr int TC_STAGES = 3;           // A ring depth (a fourth stage leaves too little L1: measured slower)
+constexpr int TC_RS = 65;              // receive buffer: float4 row stride (64 rows + 1: conflict-free reads)
+constexpr int TC_RECV_BYTES = TC_CL * 8 * TC_RS * 16;
 constexpr int TC_STAGE_BYTES = 16384;  // 64 rows x 64 K x (hi, lo) fp16
 constexpr int TC_THREADS = 320;        // warp 0 TMA, warp 1 MMA, warps 2..9 update
 constexpr int TC_VSCALE_EXP = 13;
@@ -47,30 +53,33 @@ struct TcMaps {
 
 struct RecBwdTcArgs {
   const float *G, *U, *W, *alpha, *beta, *a, *b, *u0, *w0, *s0;
-  const uint32_t* img;   // [slice][kb][part][32 rows x 128 B] swizzled fp16 tiles of V0 (vprep_umma_kernel)
+  const uint32_t* img;   // [CTA][kb][part][128 rows x 128 B] swizzled fp16 tiles of V0 (vprep_umma_kernel)
   const int* meta;
   const float* gmax;     // [Be][T] row maxima of |G|
   float theta;
   float *dI, *p_alpha, *p_beta, *p_a, *p_b;
   __half *panel_hi, *panel_lo;  // [2][groups*64][Hp]
   float* cmax;                  // [2][groups][Hp/32][64] chunk maxima of |dI_t|
-  int Be, T, H, Hp, KB;
+  int Be, T, H, Hp, KB;  // Hp: H padded to 256; KB = Hp / 256 k-blocks of 64 per CTA
+  int reduced;
   long long* dbg;  // optional [T][8] phase clocks of CTA (0,0) (profiling aid), normally NULL
-  int dbg_flags;   // profiling experiments (results invalid): 1 hi*hi UMMA only, 4 no TMA traffic, 16 no UMMA
+  int dbg_flags;   // profiling experiments (results invalid): 4 no TMA traffic, 16 no UMMA
 };
 
-// V0 slice as UMMA B tiles: element (n, k) of k-block kb: halves offset n*64 + ((k/8) ^ (n&7))*8 + k%8.
+// V0 as UMMA B tiles.  CTA bx = (cluster bx / 4, rank bx % 4) holds rows j = 128 (bx / 4) + n, n < 128, and
+// K = (bx % 4) Hp / 4 + 64 kb + k; element (n, k) of a tile: halves offset n*64 + ((k/8) ^ (n&7))*8 + k%8.
 __global__ void vprep_umma_kernel(const float* __restrict__ V, int H, int Hp, int KB, const int* __restrict__ meta,
                                   __half* __restrict__ img) {
-  const int64_t per_slice = (int64_t)KB * 2 * 2048;
-  const int64_t total = per_slice * (Hp / TC_COLS);
+  const int64_t per_cta = (int64_t)KB * 2 * (TC_N * 64);
+  const int64_t total = per_cta * (Hp / TC_COLS);
   const float sc = ldexpf(1.0f, TC_VSCALE_EXP - meta[0]);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int slice = (int)(i / per_slice);
-    int r = (int)(i % per_slice);
-    const int e = r & 7, chunk_sw = (r >> 3) & 7, n = (r >> 6) & 31, part = (r >> 11) & 1, kb = r >> 12;
+    const int bx = (int)(i / per_cta);
+    int r = (int)(i % per_cta);
+    const int e = r & 7, chunk_sw = (r >> 3) & 7, n = (r >> 6) & (TC_N - 1), part = (r >> 13) & 1, kb = r >> 14;
     const int k = ((chunk_sw ^ (n & 7)) << 3) + e;
-    const int row = slice * TC_COLS + n, col = kb * 64 + k;  // V[row = presynaptic j][col = neuron c]
+    const int row = (bx / TC_CL) * TC_N + n;                      // V[row = presynaptic j][col = neuron c]
+    const int col = (bx % TC_CL) * (Hp / TC_CL) + kb * 64 + k;
     float x = 0.f;
     if (row < H && col < H && row != col) x = V[(int64_t)row * H + col] * sc;
     const __half hi = __float2half_rn(x);
@@ -108,25 +117,30 @@ rec_bwd_tc_kernel(const __grid_constant__ TcMaps maps, const RecBwdTcArgs p, con
   const uint32_t raw = smem_u32(tsm_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   unsigned char* tsm = tsm_raw + (base - raw);
-  const uint32_t vimg = base;                                   // KB * 8 KB
-  const uint32_t ring = base + (uint32_t)p.KB * 8192;           // TC_STAGES * 16 KB
-  const uint32_t bars = ring + TC_STAGES * TC_STAGE_BYTES;      // full[4], empty[4], acc_full, acc_empty
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tsm + (size_t)p.KB * 8192 + TC_STAGES * TC_STAGE_BYTES + 128);
-  float* spart = reinterpret_cast<float*>(tsm + (size_t)p.KB * 8192 + TC_STAGES * TC_STAGE_BYTES + 256);  // [64][4]
+  const size_t v_bytes = (size_t)p.KB * 2 * (TC_N * 128);       // KB x (hi, lo) x 16 KB
+  const uint32_t vimg = base;
+  const uint32_t ring = base + (uint32_t)v_bytes;               // TC_STAGES * 16 KB
+  const uint32_t recv = ring + TC_STAGES * TC_STAGE_BYTES;      // [4 source ranks][8 column groups][65] float4
+  const uint32_t bars = recv + TC_RECV_BYTES;                   // full[4], empty[4], acc_full, acc_empty, recv_full
+  unsigned char* tail = tsm + v_bytes + TC_STAGES * TC_STAGE_BYTES + TC_RECV_BYTES;
+  const float4* recv_f4 = reinterpret_cast<const float4*>(tail - TC_RECV_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 128);
   __shared__ float sprm[6][TC_COLS];
+  constexpr int B_ACC_FULL = 2 * TC_STAGES, B_ACC_EMPTY = 2 * TC_STAGES + 1, B_RECV = 2 * TC_STAGES + 2;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slice = blockIdx.x, group = group0 + blockIdx.y, row0 = group * TC_ROWS;
+  const int rank = blockIdx.x % TC_CL;  // == %cluster_ctarank for cluster dims (4, 1, 1)
   const int nslices = gridDim.x, NCH = p.Hp / 32;
   int* ctr = counters + group;
   const bool dbg_cta = p.dbg && blockIdx.x == 0 && blockIdx.y == 0;
 
   {  // resident V0 tiles
-    const uint4* src = reinterpret_cast<const uint4*>(p.img + (size_t)slice * p.KB * 2048);
+    const uint4* src = reinterpret_cast<const uint4*>(p.img) + (size_t)slice * (v_bytes / 16);
     uint4* dst = reinterpret_cast<uint4*>(tsm);
-    for (int i = tid; i < p.KB * 512; i += TC_THREADS) {
-      uint32_t s = smem_u32(dst + i);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(src + i));
+    for (int i = tid; i < (int)(v_bytes / 16); i += TC_THREADS) {
+      uint32_t sa = smem_u32(dst + i);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + i));
     }
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
   }
@@ -137,23 +151,26 @@ rec_bwd_tc_kernel(const __grid_constant__ TcMaps maps, const RecBwdTcArgs p, con
     sprm[4][tid] = q0.b; sprm[5][tid] = 1.0f / q0.oma;
   }
   if (tid == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(bars + 8 * s, 1);
-      mbar_init(bars + 8 * (TC_STAGES + s), 1);
+    for (int st = 0; st < TC_STAGES; ++st) {
+      mbar_init(bars + 8 * st, 1);
+      mbar_init(bars + 8 * (TC_STAGES + st), 1);
     }
-    mbar_init(bars + 8 * (2 * TC_STAGES), 1);      // acc_full: one tcgen05.commit
-    mbar_init(bars + 8 * (2 * TC_STAGES + 1), 8);  // acc_empty: one arrival per update warp
+    mbar_init(bars + 8 * B_ACC_FULL, 1);    // one tcgen05.commit
+    mbar_init(bars + 8 * B_ACC_EMPTY, 8);   // one arrival per update warp
+    mbar_init(bars + 8 * B_RECV, 1);  // armed per step with the 32 KB the four ranks deliver (st.async complete_tx)
+    mbar_expect_tx(bars + 8 * B_RECV, TC_CL * TC_ROWS * TC_COLS * 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32u)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // make the cp.async-written tiles visible to the tensor core's (async proxy) reads
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  // cluster-wide: nobody may arrive on a peer's recv barrier before it is initialised
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
   const float rs = ldexpf(1.0f, p.meta[0] - TC_VSCALE_EXP);
@@ -189,8 +206,9 @@ rec_bwd_tc_kernel(const __grid_constant__ TcMaps maps, const RecBwdTcArgs p, con
           }
           mbar_expect_tx(bars + 8 * s, TC_STAGE_BYTES);
           const uint32_t sa = ring + s * TC_STAGE_BYTES;
-          tma_load_2d(sa, &maps.hi, kb * 64, y, bars + 8 * s);
-          tma_load_2d(sa + 8192, &maps.lo, kb * 64, y, bars + 8 * s);
+          const int x = rank * (p.Hp / TC_CL) + kb * 64;  // this rank's K quarter
+          tma_load_2d(sa, &maps.hi, x, y, bars + 8 * s);
+          tma_load_2d(sa + 8192, &maps.lo, x, y, bars + 8 * s);
         }
       }
       __syncwarp();
@@ -198,11 +216,11 @@ rec_bwd_tc_kernel(const __grid_constant__ TcMaps maps, const RecBwdTcArgs p, con
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      // kind::f16, fp16 x fp16 -> fp32, both K-major, M = 64, N = 32
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_COLS >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+      // kind::f16, fp16 x fp16 -> fp32, both K-major, M = 64, N = 128
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
       int it = 0, step = 0;
       for (int t = p.T - 2; t >= 0; --t, ++step) {
-        mbar_wait(bars + 8 * (2 * TC_STAGES + 1), (step & 1) ^ 1);  // D drained by the update warps
+        mbar_wait(bars + 8 * B_ACC_EMPTY, (step & 1) ^ 1);  // D drained by the update warps
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int kb = 0; kb < p.KB; ++kb, ++it) {
           const int s = it % TC_STAGES;
@@ -210,31 +228,29 @@ rec_bwd_tc_kernel(const __grid_constant__ TcMaps maps, const RecBwdTcArgs p, con
           mbar_wait(bars + 8 * s, ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (dbg_cta && kb == 0) p.dbg[t * 8 + 1] = clock64();
-          if (dbg_cta && t == p.T / 2) p.dbg[p.T * 8 + kb * 4] = clock64();
           const uint32_t sa = ring + s * TC_STAGE_BYTES;
           const uint64_t a_hi = make_desc_k_sw128(sa), a_lo = make_desc_k_sw128(sa + 8192);
-          const uint64_t b_hi = make_desc_k_sw128(vimg + (uint32_t)(kb * 2 + 0) * 4096);
-          const uint64_t b_lo = make_desc_k_sw128(vimg + (uint32_t)(kb * 2 + 1) * 4096);
+          const uint64_t b_hi = make_desc_k_sw128(vimg + (uint32_t)(kb * 2 + 0) * (TC_N * 128));
+          const uint64_t b_lo = make_desc_k_sw128(vimg + (uint32_t)(kb * 2 + 1) * (TC_N * 128));
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             if (p.dbg_flags & 16) continue;
             umma_f16(tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            if (p.dbg_flags & 1) continue;
+            if (p.reduced) continue;  // reduced-precision mode: hi * hi only
             umma_f16(tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
             umma_f16(tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
           }
-          if (dbg_cta && t == p.T / 2) p.dbg[p.T * 8 + kb * 4 + 1] = clock64();
           umma_commit(bars + 8 * (TC_STAGES + s));
-          if (dbg_cta && t == p.T / 2) p.dbg[p.T * 8 + kb * 4 + 2] = clock64();
         }
-        umma_commit(bars + 8 * (2 * TC_STAGES));
+        umma_commit(bars + 8 * B_ACC_FULL);
         if (dbg_cta) p.dbg[t * 8 + 2] = clock64();
       }
     }
   } else {
     // ===== update warps: BPTT for the 64 x 32 block, 8 neurons of one row per thread =====
     const int uw = warp - 2, q = warp & 3, half = uw >> 2;  // TMEM lane quarter of this warp, column half
-    const int r = 16 * q + (lane & 15), cq = 2 * half + (lane >> 4);  // row of the block, quarter of its 32 columns
+    // (q, half) only address TMEM; the update itself maps 4 consecutive lanes to the 4 column quarters of a row
+    const int r = 8 * uw + (lane >> 2), cq = lane & 3;
     const int row = row0 + r;
     const int col0 = slice * TC_COLS + cq * 8;
     const bool live = row < p.Be && col0 < p.H;
@@ -294,34 +310,79 @@ rec_bwd_tc_kernel(const __grid_constant__ TcMaps maps, const RecBwdTcArgs p, con
         const float* cm = p.cmax + ((size_t)rbuf * ngroups_total + group) * NCH * TC_ROWS;
         for (int c = cq; c < NCH; c += 4) m_next = fmaxf(m_next, __ldcg(&cm[c * TC_ROWS + r]));
       }
-      spart[r * 4 + cq] = m_next;
-      upd_sync();
-      m_next = fmaxf(fmaxf(spart[r * 4 + 0], spart[r * 4 + 1]), fmaxf(spart[r * 4 + 2], spart[r * 4 + 3]));
+      m_next = fmaxf(m_next, __shfl_xor_sync(0xffffffffu, m_next, 1));
+      m_next = fmaxf(m_next, __shfl_xor_sync(0xffffffffu, m_next, 2));
       const float g_row = row < p.Be ? p.gmax[(size_t)row * p.T + t] : 0.f;
       const float s_t = scale_from_max(fmaxf(m_next, 0.25f * g_row));
       if (t < p.T - 1) {
-        // ---- D = dI_{t+1} (scaled) @ V0^T (scaled): read this thread's 8 values
-        mbar_wait(bars + 8 * (2 * TC_STAGES), step & 1);
+        // ---- partial D = dI_{t+1}[:, K quarter] (scaled) @ V0^T (scaled): this warp holds rows 16q..16q+15
+        // (lanes 0..15) x columns 64 half .. 64 half + 63 = the column quarters of ranks 2 half, 2 half + 1
+        mbar_wait(bars + 8 * B_ACC_FULL, step & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (dbg_on) p.dbg[t * 8 + 3] = clock64();
-        uint32_t v[16];
-        const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * half);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int dq = 0; dq < 2; ++dq) {
+          const int dest = 2 * half + dq;
+          uint32_t v[32];
+          const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * dest);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (lane < 16) {
+            // row 16q + lane, 32 columns -> slot [this rank] of the owner's receive buffer, laid out
+            // [rank][4-column group j][row] so that one store instruction covers contiguous bytes.
+            // (Spreading the stores over all 32 lanes by shuffles was measured: no faster, more registers.)
+            const uint32_t la = recv + (uint32_t)((rank * 8 * TC_RS) + 16 * q + lane) * 16;
+            uint32_t ra, rb;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(dest));
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(bars + 8 * B_RECV), "r"(dest));
+#pragma unroll
+            for (int j = 0; j < 8; ++j)  // each store reports its 16 bytes to the owner's barrier: no fence, no arrival
+              asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                               ra + 16 * TC_RS * j),
+                           "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]), "r"(rb)
+                           : "memory");
+          }
+        }
+        if (dbg_on) p.dbg[(p.T + t) * 8 + 4] = clock64();
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8 * (2 * TC_STAGES + 1)) : "memory");
-        // lanes 0..15 hold row r's 16 columns; lanes 16..31 take columns 8..15 from lane-16
-        const float k = inv_s_next * rs;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t hi8 = __shfl_sync(0xffffffffu, v[8 + j], lane & 15);
-          recb[j] = __uint_as_float(lane < 16 ? v[j] : hi8) * k;
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8 * B_ACC_EMPTY) : "memory");
+        if (dbg_on) p.dbg[(p.T + t) * 8 + 5] = clock64();
+        // ---- this CTA's column quarter from the four ranks, summed in rank order
+        {
+          uint32_t done = 0;
+          const long long t0 = clock64();
+          while (!done) {
+            asm volatile(
+                "{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+                "selp.u32 %0, 1, 0, p;\n}"
+                : "=r"(done)
+                : "r"(bars + 8 * B_RECV), "r"((uint32_t)(step & 1))
+                : "memory");
+            if (!done && clock64() - t0 > 4000000000LL) __trap();
+          }
         }
+        if (tid == 64 && t > 0) mbar_expect_tx(bars + 8 * B_RECV, TC_CL * TC_ROWS * TC_COLS * 4);  // arm the next phase
+        if (dbg_on) p.dbg[t * 8 + 6] = clock64();
+        const float k = inv_s_next * rs;
+        float acc[8];
+#pragma unroll
+        for (int src = 0; src < TC_CL; ++src) {
+          const float4* rp = recv_f4 + (src * 8 + 2 * cq) * TC_RS + r;
+          const float4 x0 = rp[0], x1 = rp[TC_RS];
+          const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) acc[jj] = src == 0 ? xs[jj] : acc[jj] + xs[jj];
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) recb[jj] = acc[jj] * k;
         ++step;
       }
       if (live) {
@@ -344,17 +405,17 @@ rec_bwd_tc_kernel(const __grid_constant__ TcMaps maps, const RecBwdTcArgs p, con
           }
         }
       }
+      if (dbg_on) p.dbg[(p.T + t) * 8 + 0] = clock64();
       if (t > 0) {
         // ---- hand dI_t over: chunk maximum (for the next scale) and fp16 hi/lo rows scaled by s_t
         float m = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) m = fmaxf(m, fabsf(d[i]));
-        upd_sync();                       // spart was read above by everyone
-        spart[r * 4 + cq] = m;
-        upd_sync();
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        if (dbg_on) p.dbg[(p.T + t) * 8 + 1] = clock64();
         if (cq == 0) {
-          const float cmx = fmaxf(fmaxf(spart[r * 4 + 0], spart[r * 4 + 1]), fmaxf(spart[r * 4 + 2], spart[r * 4 + 3]));
-          p.cmax[(((size_t)wbuf * ngroups_total + group) * NCH + slice) * TC_ROWS + r] = cmx;
+          p.cmax[(((size_t)wbuf * ngroups_total + group) * NCH + slice) * TC_ROWS + r] = m;
         }
         __align__(16) __half hh[8], hl[8];
 #pragma unroll
@@ -366,7 +427,9 @@ rec_bwd_tc_kernel(const __grid_constant__ TcMaps maps, const RecBwdTcArgs p, con
         const size_t po = ((size_t)(wbuf * ngroups_total + group) * TC_ROWS + r) * p.Hp + slice * TC_COLS + cq * 8;
         *reinterpret_cast<uint4*>(p.panel_hi + po) = *reinterpret_cast<const uint4*>(hh);
         *reinterpret_cast<uint4*>(p.panel_lo + po) = *reinterpret_cast<const uint4*>(hl);
+        if (dbg_on) p.dbg[(p.T + t) * 8 + 2] = clock64();
         upd_sync();                       // every update thread's panel stores are issued
+        if (dbg_on) p.dbg[(p.T + t) * 8 + 3] = clock64();
         if (tid == 64) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ctr) : "memory");
         if (dbg_on) p.dbg[t * 8 + 4] = clock64();
       }
@@ -397,13 +460,17 @@ rec_bwd_tc_kernel(const __grid_constant__ TcMaps maps, const RecBwdTcArgs p, con
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  // cluster-wide: no CTA leaves while a peer may still store into its receive buffer
+  __syncwarp();
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
   }
 }
 
-static size_t rec_bwd_tc_smem(int KB) { return (size_t)KB * 8192 + TC_STAGES * TC_STAGE_BYTES + 256 + 1024 + 1024; }
+static size_t rec_bwd_tc_smem(int KB) {
+  return (size_t)KB * 2 * (TC_N * 128) + TC_STAGES * TC_STAGE_BYTES + TC_RECV_BYTES + 256 + 1024;
+}
 
 }  // namespace sparch
 
@@ -411,12 +478,12 @@ using namespace sparch;
 
 extern "C" {
 
-// Hidden size padded to the 64-neuron K blocks of the tcgen05 reverse kernel.
-int sparch_recur_tc_padded(int H) { return ((H + 63) / 64) * 64; }
+// Hidden size padded so that each of the cluster's four K quarters is a whole number of 64-neuron K blocks.
+int sparch_recur_tc_padded(int H) { return ((H + 255) / 256) * 256; }
 
 size_t sparch_recur_bwd_tc_image_bytes(int H) {
   const int Hp = sparch_recur_tc_padded(H);
-  return (size_t)(Hp / TC_COLS) * (Hp / 64) * 2 * 2048 * sizeof(__half);
+  return (size_t)Hp * Hp * 2 * sizeof(__half);  // hi + lo
 }
 
 size_t sparch_recur_bwd_tc_workspace(int Be, int T, int H) {
@@ -432,8 +499,8 @@ size_t sparch_recur_bwd_tc_workspace(int Be, int T, int H) {
 // sparch_recur_prepare (meta[0] = E, max|V0| < 2^E).
 int sparch_recur_prepare_tc(const float* V, int H, void* img, const int* meta, sparch_stream_t st_) {
   SPARCH_REQUIRE(V && H > 0 && img && meta, "null pointer");
-  const int Hp = sparch_recur_tc_padded(H), KB = Hp / 64;
-  int64_t total = (int64_t)(Hp / TC_COLS) * KB * 2 * 2048;
+  const int Hp = sparch_recur_tc_padded(H), KB = Hp / (64 * TC_CL);
+  int64_t total = (int64_t)Hp * Hp * 2;
   int nb = (int)((total + 255) / 256);
   if (nb > sm_count() * 16) nb = sm_count() * 16;
   vprep_umma_kernel<<<nb, 256, 0, as_stream(st_)>>>(V, H, Hp, KB, meta, reinterpret_cast<__half*>(img));
@@ -444,7 +511,7 @@ int sparch_recur_prepare_tc(const float* V, int H, void* img, const int* meta, s
 int sparch_recur_bwd_tc(int kind, const float* G, const float* U, const float* W, const float* alpha,
                         const float* beta, const float* a, const float* b, const void* img, const int* meta,
                         const float* u0, const float* w0, const float* s0, float theta, float* dI, float* p_alpha,
-                        float* p_beta, float* p_a, float* p_b, void* workspace, int Be, int T, int H,
+                        float* p_beta, float* p_a, float* p_b, void* workspace, int reduced, int Be, int T, int H,
                         sparch_stream_t st_) {
   SPARCH_REQUIRE(kind == SPARCH_RLIF || kind == SPARCH_RADLIF, "recurrent kinds only");
   SPARCH_REQUIRE(Be >= 0 && T >= 0 && H > 0, "bad shape");
@@ -453,18 +520,17 @@ int sparch_recur_bwd_tc(int kind, const float* G, const float* U, const float* W
   const bool adapt = kind & 1;
   SPARCH_REQUIRE(!adapt || (W && beta && a && b && w0 && p_beta && p_a && p_b),
                  "adaptive kind needs W, beta, a, b, w0 and the partial buffers");
-  const int Hp = sparch_recur_tc_padded(H), KB = Hp / 64;
+  const int Hp = sparch_recur_tc_padded(H), KB = Hp / (64 * TC_CL);
   const size_t smem = rec_bwd_tc_smem(KB);
-  SPARCH_REQUIRE(smem <= 225 * 1024, "hidden size too large for the resident V0 tiles");
+  SPARCH_REQUIRE(smem + 768 <= 227 * 1024, "hidden size too large for the resident V0 tiles");
   cudaStream_t st = as_stream(st_);
   static bool attr_set = false;
   if (!attr_set) {
-    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 768));
+    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 768));
     attr_set = true;
   }
   const int groups = (Be + TC_ROWS - 1) / TC_ROWS, slices = Hp / TC_COLS;
-  SPARCH_REQUIRE(slices <= sm_count(), "hidden size needs more co-resident CTAs than the GPU has SMs");
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   const size_t panel_bytes = (size_t)2 * groups * TC_ROWS * Hp * sizeof(__half);
   __half* panel_hi = reinterpret_cast<__half*>(ws);
@@ -486,15 +552,33 @@ int sparch_recur_bwd_tc(int kind, const float* G, const float* U, const float* W
   if (int e = make_map(&maps.lo, panel_lo, (long long)2 * groups * TC_ROWS, Hp, Hp, TC_ROWS, CU_TENSOR_MAP_DATA_TYPE_FLOAT16))
     return e;
   RecBwdTcArgs p{G, U, W, alpha, beta, a, b, u0, w0, s0, reinterpret_cast<const uint32_t*>(img), meta, gmax, theta,
-                 dI, p_alpha, p_beta, p_a, p_b, panel_hi, panel_lo, cmax, Be, T, H, Hp, KB, recur_debug_buffer(), recur_debug_flags()};
-  const int gmaxl = sm_count() / slices;
+                 dI, p_alpha, p_beta, p_a, p_b, panel_hi, panel_lo, cmax, Be, T, H, Hp, KB, reduced ? 1 : 0, recur_debug_buffer(), recur_debug_flags()};
+  const void* fn = adapt ? (const void*)rec_bwd_tc_kernel<true> : (const void*)rec_bwd_tc_kernel<false>;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = TC_CL;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeCooperative;  // every CTA of a launch must be resident: they wait on each other
+  attrs[1].val.cooperative = 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 2;
+  cfg.gridDim = dim3(slices, 1);
+  int max_clusters = 0;
+  SPARCH_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg));
+  const int gmaxl = max_clusters * TC_CL / slices;
+  SPARCH_REQUIRE(gmaxl >= 1, "hidden size needs more co-resident 4-CTA clusters than the GPU can hold");
   for (int g0 = 0; g0 < groups; g0 += gmaxl) {
     int gn = groups - g0 < gmaxl ? groups - g0 : gmaxl;
-    dim3 cgrid(slices, gn);
+    cfg.gridDim = dim3(slices, gn);
     int group0 = g0, ngt = groups;
     void* args[] = {(void*)&maps, (void*)&p, (void*)&group0, (void*)&ngt, (void*)&counters};
-    const void* fn = adapt ? (const void*)rec_bwd_tc_kernel<true> : (const void*)rec_bwd_tc_kernel<false>;
-    SPARCH_CUDA(cudaLaunchCooperativeKernel(fn, cgrid, dim3(TC_THREADS), args, smem, st));
+    SPARCH_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
   }
   return SPARCH_OK;
 }

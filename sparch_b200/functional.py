@@ -255,10 +255,11 @@ def _norm_backward(dI2d, Z2d, gamma, bn_beta, norm, scale, mean, rstd):
 RECUR_MAX_H = 1184
 
 
-# Reverse recurrence kernel: "mma" = mma.sync kernel (block-floating-point panels, per-chunk scales),
-# "tc" = tcgen05 kernel (TMA-fed fp16 hi/lo panels, per-row lagged scale, D in TMEM).
-RECUR_BWD = os.environ.get("SPARCH_B200_BWD", "mma")
-RECUR_TC_MAX_H = 1280
+# Reverse recurrence kernel: "tc" = tcgen05 kernel (clusters of 4 CTAs split K, TMA-fed fp16 hi/lo panels,
+# per-row lagged scale, D in TMEM; H <= RECUR_TC_MAX_H), "mma" = mma.sync kernel (block-floating-point
+# panels, per-chunk scales; also serves RECUR_TC_MAX_H < H <= RECUR_MAX_H).
+RECUR_BWD = os.environ.get("SPARCH_B200_BWD", "tc")
+RECUR_TC_MAX_H = 1024
 
 
 class SpikingCellFunction(torch.autograd.Function):
@@ -309,17 +310,16 @@ class SpikingCellFunction(torch.autograd.Function):
             else:
                 # persistent tensor-core kernels: s_{t-1} @ V0 from packed spike planes (csrc/recur.cu)
                 Hp = _lib.lib().sparch_recur_padded(H)
+                use_tc = RECUR_BWD == "tc" and H <= RECUR_TC_MAX_H
                 img_f = torch.empty(Hp * Hp, device=dev, dtype=torch.int32)
-                img_b = torch.empty(Hp * Hp, device=dev, dtype=torch.int32)
+                img_b = None if use_tc else torch.empty(Hp * Hp, device=dev, dtype=torch.int32)
                 meta = torch.empty(2, device=dev, dtype=torch.int32)
                 call("sparch_recur_prepare", ptr(V.detach().contiguous()), H, ptr(img_f), ptr(img_b),
                      ptr(meta), st)
-                if RECUR_BWD == "tc" and H <= RECUR_TC_MAX_H:
+                if use_tc:  # V0 as swizzled UMMA tiles for the tcgen05 reverse kernel (csrc/recur_tc.cu)
                     img_b = torch.empty(_lib.lib().sparch_recur_bwd_tc_image_bytes(H), device=dev, dtype=torch.uint8)
                     call("sparch_recur_prepare_tc", ptr(V.detach().contiguous()), H, ptr(img_b), ptr(meta), st)
-                    ctx.tc = True
-                else:
-                    ctx.tc = False
+                ctx.tc = use_tc
                 ctx.rec = (img_b, meta)
                 ctx.reduced = int(_PRECISION == "bf16")
                 rec0 = torch.matmul(s0, V0)        # t = 0: s_{-1} is real-valued (snns.py:702)
@@ -371,7 +371,7 @@ class SpikingCellFunction(torch.autograd.Function):
             ws = torch.empty(_lib.lib().sparch_recur_bwd_tc_workspace(Be, T, H), device=dev, dtype=torch.uint8)
             call("sparch_recur_bwd_tc", k, ptr(G), ptr(U), ptr(Wt), ptr(al), ptr(be), ptr(aa), ptr(bb),
                  ptr(img_b), ptr(meta), ptr(u0), ptr(w0), ptr(s0), theta, ptr(dI), pp[0], pp[1], pp[2],
-                 pp[3], ptr(ws), Be, T, H, st)
+                 pp[3], ptr(ws), ctx.reduced, Be, T, H, st)
         else:
             img_b, meta = ctx.rec
             ws = torch.empty(_lib.lib().sparch_recur_bwd_workspace(Be, H), device=dev, dtype=torch.uint8)

@@ -379,20 +379,21 @@ def test_cell_edge_shapes_against_oracle(kind, Be, T, H):
     _oracle_cell_check(kind, Be, T, H, seed=Be + T + H)
 
 
+@pytest.mark.parametrize("mode", ["tc", "mma"])
 @pytest.mark.parametrize("kind,Be,T,H", [
-    ("RadLIF", 300, 7, 96),     # ragged last 64-row group, hidden size padded to the 64-wide K blocks
+    ("RadLIF", 300, 7, 96),     # ragged last 64-row group, hidden size padded to the K quarters
     ("RadLIF", 70, 5, 1000),    # H not a multiple of 32
     ("RLIF", 3, 1, 40),         # single timestep: no UMMA at all
     ("RLIF", 33, 60, 130),      # longer chain, odd sizes
     ("RadLIF", 640, 4, 512),    # 10 groups x 16 slices: two cooperative launches
     ("RadLIF", 256, 12, 1024),  # the cfg4 layer width
 ])
-def test_tcgen05_reverse_recurrence_against_oracle(kind, Be, T, H):
-    """The opt-in tcgen05 reverse-recurrence kernel (sparch_recur_bwd_tc) meets the same bar as the
-    default kernel."""
+def test_both_reverse_recurrence_kernels_against_oracle(kind, Be, T, H, mode):
+    """The tcgen05 reverse-recurrence kernel (sparch_recur_bwd_tc, the default up to H = 1024) and the
+    mma.sync one (sparch_recur_bwd) meet the same bar."""
     _, F = _mods()
     old = F.RECUR_BWD
-    F.RECUR_BWD = "tc"
+    F.RECUR_BWD = mode
     try:
         n0 = F.native_launches()
         _oracle_cell_check(kind, Be, T, H, seed=Be + T + H)

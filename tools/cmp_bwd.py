@@ -41,7 +41,7 @@ for mode in ("mma", "tc"):
     out[mode] = [x.grad.clone() for x in ((I, alpha, beta, a, b, V) if adaptive else (I, alpha, V))]
     if mode == "tc" and os.environ.get("SPARCH_PHASES"):
         from sparch_b200._lib import call, ptr
-        dbg = torch.zeros(T + 8, 8, dtype=torch.int64, device=dev)
+        dbg = torch.zeros(2 * T + 8, 8, dtype=torch.int64, device=dev)
         S = F.SpikingCellFunction.apply(I, None, None, alpha, beta if adaptive else None,
                                         a if adaptive else None, b if adaptive else None, V, u0,
                                         w0 if adaptive else None, s0, kind, 1.0, F.NormState("none"))
@@ -50,14 +50,17 @@ for mode in ("mma", "tc"):
         S.backward(g)
         torch.cuda.synchronize()
         call("sparch_recur_debug_clocks", None)
-        kb = dbg.cpu()[T:T + 8].reshape(16, 4)
-        print('per-k-block clocks at t=T/2 (after full-wait, UMMAs issued, after commit), relative:', [[int(x - kb[0, 0]) for x in r[:3]] for r in kb[:6]])
+        e = dbg.cpu().double()[T + 2:2 * T - 3]
         c = dbg.cpu().double()[2:T - 3]   # rows t = 2 .. T-4; step t-1 follows step t in time
         m = lambda x: float(x.mean())
         print("tc phases, cycles/step (CTA 0,0): step start -> counter seen %.0f | -> first k-block landed %.0f | "
-              "-> last UMMA issued %.0f | -> D complete %.0f | -> released %.0f | total %.0f"
+              "-> last UMMA issued %.0f | -> D complete %.0f | -> quarters received %.0f | -> released %.0f | total %.0f"
               % (m(c[:, 0] - c[:, 5]), m(c[:, 1] - c[:, 0]), m(c[:, 2] - c[:, 1]), m(c[:, 3] - c[:, 2]),
-                 m(c[:, 4] - c[:, 3]), m(c[:-1, 5] - c[1:, 5])))
+                 m(c[:, 6] - c[:, 3]), m(c[:, 4] - c[:, 6]), m(c[:-1, 5] - c[1:, 5])))
+        print("  D complete -> TMEM read + scatter stores issued %.0f | -> arrivals sent %.0f | -> quarters received %.0f | "
+              "-> BPTT update done %.0f | -> chunk max exchanged %.0f | -> panel stores issued %.0f | -> all warps' stores issued %.0f "
+              "| -> released %.0f" % (m(e[:, 4] - c[:, 3]), m(e[:, 5] - e[:, 4]), m(c[:, 6] - e[:, 5]), m(e[:, 0] - c[:, 6]),
+                                     m(e[:, 1] - e[:, 0]), m(e[:, 2] - e[:, 1]), m(e[:, 3] - e[:, 2]), m(c[:, 4] - e[:, 3])))
 names = ("dI", "dalpha", "dbeta", "da", "db", "dV") if adaptive else ("dI", "dalpha", "dV")
 for n, x, y in zip(names, out["mma"], out["tc"]):
     den = float(x.abs().max())
