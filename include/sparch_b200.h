@@ -72,10 +72,11 @@ SPARCH_API int sparch_bn_fold_train(const double* sum, const double* sumsq, int6
                          const float* beta, float eps, float momentum, float* running_mean,
                          float* running_var, float* mean, float* rstd, float* scale,
                          float* shift, int H, sparch_stream_t st);
-/* dZ[m,h] = scale[h]*(dI[m,h] - sum1[h]/M - xhat[m,h]*sum2[h]/M), in place on dI.        */
+/* dZ[m,h] = scale[h]*(dI[m,h] - sum1[h]/M - xhat[m,h]*sum2[h]/M), in place on dI.  amax (may be
+ * NULL): receives the bit pattern of max|dZ| (zeroed here) for the fp16 split of the gradient GEMMs. */
 SPARCH_API int sparch_bn_bwd_apply(float* dI, const float* Z, const float* mean, const float* rstd,
                         const float* scale, const double* sum1, const double* sum2, int64_t M,
-                        int H, sparch_stream_t st);
+                        int H, uint32_t* amax, sparch_stream_t st);
 
 /* ---- membrane recurrence, forward (snns.py:282-303, 419-445, 554-578, 696-727) ------- */
 /* Non-recurrent kinds (LIF, adLIF): whole time loop in one streaming kernel, state in
@@ -145,6 +146,29 @@ SPARCH_API int sparch_gemm_bf16(const void* const* A_parts, int na, const void* 
                                 int K, float alpha, const float* bias, float* C, int64_t ldc,
                                 double* stat_sum, double* stat_sumsq, void* workspace,
                                 sparch_stream_t st);
+
+/* fp16 two-term operands (the default of the fp32-equivalent mode): x * 2^k = hi + lo with hi, lo fp16
+ * (22 mantissa bits) and ONE power-of-two scale per tensor, chosen from max|x| so that the largest
+ * value lands in [2^12, 2^13).  general x general needs 3 tensor-pipe passes (hi.hi, hi.lo, lo.hi) instead
+ * of the 6 of three bf16 terms, spikes x general 2 instead of 3.
+ * sparch_absmax: *amax = bit pattern of max|X| (uint32; zeroed here).  sparch_split_f16: nparts 1 or 2
+ * fp16 terms of prescale * 2^k * X, k derived from *amax (amax NULL: k = 0, e.g. spikes with
+ * prescale = 1-p); compute_amax != 0 runs sparch_absmax into *amax first (one call, no host round trip),
+ * 0 takes the value a producer kernel left there.  sparch_gemm_terms: sparch_gemm_bf16 with fp16 != 0 selecting fp16 terms; amax_a /
+ * amax_b (NULL = unscaled operand) are the same device words the splits used, the epilogue undoes both
+ * scales.  No host synchronisation anywhere: the scale travels through device memory.            */
+SPARCH_API int sparch_absmax(const float* X, int64_t ldx, int64_t M, int K, uint32_t* amax,
+                             sparch_stream_t st);
+SPARCH_API int sparch_split_f16(const float* X, int64_t ldx, int M, int K, int nparts, float prescale,
+                                uint32_t* amax, int compute_amax, void* P0, void* P1, int64_t ldp,
+                                sparch_stream_t st);
+SPARCH_API int sparch_gemm_terms(int fp16, const void* const* A_parts, int na, const uint32_t* amax_a,
+                                 const void* const* B_parts, int nb, const uint32_t* amax_b,
+                                 int64_t lda, int64_t ldb, int a_mn, int b_mn, int a_koff,
+                                 const int* pair_a, const int* pair_b, int npairs, int M, int N,
+                                 int K, float alpha, const float* bias, float* C, int64_t ldc,
+                                 double* stat_sum, double* stat_sumsq, void* workspace,
+                                 sparch_stream_t st);
 
 /* ---- recurrent kinds on the tensor pipe (snns.py:554-578, 696-727) --------------------- */
 /* Hidden size rounded up to a multiple of 32 (spike words / V0 slices are padded to it).    */

@@ -20,7 +20,7 @@ _PROTOS = {
     "sparch_col_stats": "plippp",
     "sparch_col_dot": "pppplippp",
     "sparch_bn_fold_train": "pplppffppppppip",
-    "sparch_bn_bwd_apply": "pppppppli" "p",
+    "sparch_bn_bwd_apply": "pppppppli" "pp",
     "sparch_cell_fwd": "i" + "p" * 10 + "f" + "ppp" + "iii" + "p",
     "sparch_cell_step_fwd": "ii" + "p" * 11 + "f" + "ppp" + "iii" + "p",
     "sparch_cell_bwd": "i" + "p" * 10 + "f" + "p" * 5 + "iii" + "p",
@@ -29,6 +29,9 @@ _PROTOS = {
     "sparch_split_bf16_transpose": "piiiiifppplp",
     "sparch_gemm_workspace": "iii",
     "sparch_gemm_bf16": "pipill" + "iii" + "ppiiiifppl" + "pppp",
+    "sparch_absmax": "pllipp",
+    "sparch_split_f16": "pliiifpipplp",
+    "sparch_gemm_terms": "ipippipll" + "iii" + "ppiiiifppl" + "pppp",
     "sparch_recur_padded": "i",
     "sparch_recur_prepare": "pipppp",
     "sparch_recur_sync_words": "i",

@@ -16,6 +16,7 @@
 // fixed order (deterministic).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "tcgen05_utils.cuh"
@@ -48,7 +49,21 @@ struct GemmParams {
   double* stat_sumsq;  // into the epilogue, snns.py:678-680); only with splits == 1
   int a_mn, b_mn;      // operand is MN-major in memory: a (K, MN) row-major matrix (weight-gradient GEMMs)
   int a_koff;          // added to A's K coordinate (TMA zero-fills out-of-range rows): S_prev = S delayed by one frame
+  int fp16;            // operand terms are fp16 (scaled hi/lo pairs, sparch_split_f16) instead of bf16
+  const uint32_t* amax_a;  // fp16 terms: bit pattern of max|x| of the split tensor (its power-of-two scale is
+  const uint32_t* amax_b;  // undone in the epilogue); NULL = unscaled
 };
+
+// Power-of-two scale of an fp16 hi/lo split: brings max|x| into [2^12, 2^13) (fp16 keeps 11 bits from
+// there down to 2^-14, the lo term another 11 below the hi term's last bit).  The same function gives the
+// split kernel its scale and the GEMM epilogue the inverse, from the bit pattern of max|x|.
+__device__ __forceinline__ int f16_scale_exp(uint32_t amax_bits) {
+  const int E = (int)((amax_bits >> 23) & 0xffu);          // biased exponent of max|x|
+  if (amax_bits == 0u || E == 0xff) return 0;               // all zero / inf / nan: leave unscaled
+  int e = E - 126;                                          // max|x| = f * 2^e, f in [0.5, 1)
+  if (e < -60) e = -60;
+  return 13 - e;
+}
 
 // MN-major, SWIZZLE_128B operand tile as TMA delivers it from a (K, MN) row-major matrix: per block of
 // 64 MN elements, 64 K rows of 128 bytes (8 KB); blocks of 64 MN elements follow each other.
@@ -64,8 +79,10 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// kind::f16, bf16 x bf16 -> fp32, M = 128, N = 256; bit 15 / 16 = A / B is MN-major
-constexpr uint32_t G_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
+// kind::f16 -> fp32 accumulator, M = 128, N = 256; bits 7 / 10 = A / B format (0 fp16, 1 bf16), bit 15 / 16 = A / B
+// is MN-major
+constexpr uint32_t G_IDESC = (1u << 4) | ((uint32_t)(GN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
+constexpr uint32_t G_IDESC_BF16 = (1u << 7) | (1u << 10);
 
 // Column sums across the 32 lanes of a warp for 32 per-lane values in 31 shuffles: at each step a lane
 // keeps one half of its values and receives the partner's copy of that half; lane l ends up with the
@@ -165,7 +182,7 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
         // K advance per UMMA (16 elements): K-major 32 bytes inside the swizzle atom (2 units of 16 B),
         // MN-major 16 rows of 128 bytes (128 units)
         const uint32_t ka = p.a_mn ? 128u : 2u, kb_ = p.b_mn ? 128u : 2u;
-        const uint32_t idesc = G_IDESC | (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);
+        const uint32_t idesc = G_IDESC | (p.fp16 ? 0u : G_IDESC_BF16) | (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);
 #pragma unroll
         for (int k = 0; k < GK / 16; ++k)
           umma_f16(tmem, da + ka * k, db + kb_ * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
@@ -181,6 +198,10 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float* crow = p.C + (size_t)blockIdx.z * p.split_stride + (size_t)row * p.ldc;
     const bool final_out = gridDim.z == 1;
+    // alpha and the inverse scales of fp16 operands (powers of two: exact), applied one after the other so that
+    // no intermediate product leaves the fp32 range
+    const float inv_a = p.amax_a ? ldexpf(1.0f, -f16_scale_exp(*p.amax_a)) : 1.0f;
+    const float inv_b = p.amax_b ? ldexpf(1.0f, -f16_scale_exp(*p.amax_b)) : 1.0f;
     const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
     for (int c = 0; c < GN / 32; ++c) {
       uint32_t v[32];
@@ -203,7 +224,7 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
         for (int i = 0; i < 32; ++i) {
           f[i] = __uint_as_float(v[i]);
           if (final_out) {
-            f[i] *= p.alpha;
+            f[i] = f[i] * inv_a * inv_b * p.alpha;
             if (p.bias && nb + i < p.N) f[i] += p.bias[nb + i];
           }
         }
@@ -223,7 +244,7 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
         for (int i = 0; i < 32; ++i) {
           float x = 0.f;
           if (row < p.M && nb + i < p.N) {
-            x = __uint_as_float(v[i]) * p.alpha;
+            x = __uint_as_float(v[i]) * inv_a * inv_b * p.alpha;
             if (p.bias) x += p.bias[nb + i];
           }
           a[i] = x;
@@ -257,13 +278,16 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, long long split_stride, int M,
                                      int N, long long ldc_part, float* __restrict__ C, long long ldc, float alpha,
-                                     const float* __restrict__ bias) {
+                                     const float* __restrict__ bias, const uint32_t* __restrict__ amax_a,
+                                     const uint32_t* __restrict__ amax_b) {
   long long n = (long long)M * N;
+  const float inv_a = amax_a ? ldexpf(1.0f, -f16_scale_exp(*amax_a)) : 1.0f;
+  const float inv_b = amax_b ? ldexpf(1.0f, -f16_scale_exp(*amax_b)) : 1.0f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     int r = (int)(i / N), c = (int)(i % N);
     float s = 0.f;
     for (int z = 0; z < splits; ++z) s += part[z * split_stride + (long long)r * ldc_part + c];
-    s *= alpha;
+    s = s * inv_a * inv_b * alpha;
     if (bias) s += bias[c];
     C[(long long)r * ldc + c] = s;
   }
@@ -361,6 +385,64 @@ split_transpose_kernel(const float* __restrict__ X, int R, int C, int nparts, in
   }
 }
 
+
+// ------------------------------------------------------------------ fp32 -> scaled fp16 hi/lo terms
+// max|X| as a float bit pattern (non-negative floats order like unsigned integers); *amax zeroed by the caller.
+__global__ void absmax_kernel(const float* __restrict__ X, long long ldx, long long M, int K, uint32_t* __restrict__ amax) {
+  const bool vec = ((ldx & 3) == 0) && ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  float m = 0.f;
+  if (vec) {
+    const long long k4 = K / 4, n = M * k4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      const long long r = i / k4;
+      const float4 v = *reinterpret_cast<const float4*>(X + r * ldx + (i - r * k4) * 4);
+      m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+  } else {
+    const long long n = M * K;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      const long long r = i / K;
+      m = fmaxf(m, fabsf(X[r * ldx + (i - r * K)]));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax, __float_as_uint(m));
+}
+
+// parts[i][r][c] = i-th fp16 term of prescale * 2^k * X[r][c], k = f16_scale_exp(*amax) (0 without amax).
+__global__ void split_rows_f16_kernel(const float* __restrict__ X, long long ldx, int M, int K, int nparts, float prescale,
+                                      const uint32_t* __restrict__ amax, __half* __restrict__ P0, __half* __restrict__ P1,
+                                      long long ldp) {
+  const long long segs_per_row = ldp / 8;
+  const long long n = (long long)M * segs_per_row;
+  const bool vec_in = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  const float sc = amax ? ldexpf(1.0f, f16_scale_exp(*amax)) : 1.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / segs_per_row;
+    const int c = (int)(i - r * segs_per_row) * 8;
+    float x[8];
+    const float* src = X + r * ldx + c;
+    if (vec_in && c + 8 <= K) {
+      float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = c + j < K ? src[j] : 0.f;
+    }
+    __align__(16) __half h0[8], h1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = x[j] * prescale * sc;   // powers of two / exact spike prescale: no rounding
+      h0[j] = __float2half_rn(v);
+      h1[j] = __float2half_rn(v - __half2float(h0[j]));
+    }
+    const long long o = r * ldp + c;
+    *reinterpret_cast<uint4*>(P0 + o) = *reinterpret_cast<const uint4*>(h0);
+    if (nparts > 1) *reinterpret_cast<uint4*>(P1 + o) = *reinterpret_cast<const uint4*>(h1);
+  }
+}
+
 }  // namespace sparch
 
 using namespace sparch;
@@ -401,10 +483,50 @@ size_t sparch_gemm_workspace(int M, int N, int K) {
   return (size_t)8 * M * (((size_t)N + 3) / 4 * 4) * sizeof(float);
 }
 
+int sparch_absmax(const float* X, int64_t ldx, int64_t M, int K, uint32_t* amax, sparch_stream_t st) {
+  SPARCH_REQUIRE(M >= 0 && K > 0 && ldx >= K && amax, "bad argument");
+  SPARCH_CUDA(cudaMemsetAsync(amax, 0, sizeof(uint32_t), as_stream(st)));
+  if (M == 0) return SPARCH_OK;
+  SPARCH_REQUIRE(X, "null pointer");
+  int64_t n = M * (int64_t)K / 4, g = (n + 255) / 256, cap = (int64_t)sm_count() * 8;
+  if (g < 1) g = 1;
+  absmax_kernel<<<(unsigned)(g < cap ? g : cap), 256, 0, as_stream(st)>>>(X, ldx, M, K, amax);
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+int sparch_split_f16(const float* X, int64_t ldx, int M, int K, int nparts, float prescale, uint32_t* amax,
+                     int compute_amax, void* P0, void* P1, int64_t ldp, sparch_stream_t st) {
+  SPARCH_REQUIRE(M >= 0 && K > 0 && nparts >= 1 && nparts <= 2 && ldp >= K && ldx >= K, "bad shape");
+  SPARCH_REQUIRE(P0 && (nparts < 2 || P1), "null part pointer");
+  SPARCH_REQUIRE(!compute_amax || amax, "compute_amax needs the amax word");
+  if (compute_amax)
+    if (int e = sparch_absmax(X, ldx, M, K, amax, st)) return e;
+  if (M == 0) return SPARCH_OK;
+  SPARCH_REQUIRE(X, "null pointer");
+  SPARCH_REQUIRE((ldp % 8) == 0, "ldp must be a multiple of 8");
+  int64_t n = (int64_t)M * (ldp / 8);
+  int64_t g = (n + 255) / 256, cap = (int64_t)sm_count() * 16;
+  split_rows_f16_kernel<<<(unsigned)(g < cap ? g : cap), 256, 0, as_stream(st)>>>(X, ldx, M, K, nparts, prescale, amax,
+                                                                                  (__half*)P0, (__half*)P1, ldp);
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
 int sparch_gemm_bf16(const void* const* A_parts, int na, const void* const* B_parts, int nb, int64_t lda,
                      int64_t ldb, int a_mn, int b_mn, int a_koff, const int* pair_a, const int* pair_b, int npairs,
                      int M, int N, int K, float alpha, const float* bias, float* C, int64_t ldc, double* stat_sum,
                      double* stat_sumsq, void* workspace, sparch_stream_t st_) {
+  return sparch_gemm_terms(0, A_parts, na, nullptr, B_parts, nb, nullptr, lda, ldb, a_mn, b_mn, a_koff, pair_a, pair_b,
+                           npairs, M, N, K, alpha, bias, C, ldc, stat_sum, stat_sumsq, workspace, st_);
+}
+
+int sparch_gemm_terms(int fp16, const void* const* A_parts, int na, const uint32_t* amax_a, const void* const* B_parts,
+                      int nb, const uint32_t* amax_b, int64_t lda, int64_t ldb, int a_mn, int b_mn, int a_koff,
+                      const int* pair_a, const int* pair_b, int npairs, int M, int N, int K, float alpha,
+                      const float* bias, float* C, int64_t ldc, double* stat_sum, double* stat_sumsq, void* workspace,
+                      sparch_stream_t st_) {
+  SPARCH_REQUIRE(fp16 || (!amax_a && !amax_b), "scaled operands are fp16 terms");
   SPARCH_REQUIRE(M > 0 && N > 0 && K > 0 && na >= 1 && na <= 3 && nb >= 1 && nb <= 3, "bad shape");
   SPARCH_REQUIRE(npairs >= 1 && npairs <= 8 && A_parts && B_parts && pair_a && pair_b && C, "bad argument");
   SPARCH_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0 && lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K),
@@ -428,6 +550,7 @@ int sparch_gemm_bf16(const void* const* A_parts, int na, const void* const* B_pa
   memset(&p, 0, sizeof p);
   p.M = M; p.N = N; p.K = K; p.npairs = npairs;
   p.a_mn = a_mn; p.b_mn = b_mn; p.a_koff = a_koff;
+  p.fp16 = fp16 ? 1 : 0; p.amax_a = amax_a; p.amax_b = amax_b;
   p.stat_sum = stat_sum; p.stat_sumsq = stat_sumsq;
   if (stat_sum) {
     SPARCH_CUDA(cudaMemsetAsync(stat_sum, 0, sizeof(double) * N, st));
@@ -476,7 +599,8 @@ int sparch_gemm_bf16(const void* const* A_parts, int na, const void* const* B_pa
     long long n = (long long)M * N;
     long long g = (n + 255) / 256, cap = (long long)sm_count() * 8;
     splitk_reduce_kernel<<<(unsigned)(g < cap ? g : cap), 256, 0, st>>>(reinterpret_cast<float*>(workspace), splits,
-                                                                        p.split_stride, M, N, ldw, C, ldc, alpha, bias);
+                                                                        p.split_stride, M, N, ldw, C, ldc, alpha, bias, amax_a,
+                                                                        amax_b);
     SPARCH_LAUNCH_OK();
   }
   return SPARCH_OK;

@@ -150,16 +150,43 @@ __global__ void bn_fold_train_kernel(const double* __restrict__ sum, const doubl
 __global__ void bn_bwd_apply_kernel(float* __restrict__ dI, const float* __restrict__ Z,
                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                     const float* __restrict__ scale, const double* __restrict__ s1,
-                                    const double* __restrict__ s2, int64_t M, int H) {
+                                    const double* __restrict__ s2, int64_t M, int H, uint32_t* __restrict__ amax) {
   const double invM = 1.0 / (double)M;
-  int64_t n = M * (int64_t)H;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {
-    int h = (int)(i % H);
-    float c1 = (float)(s1[h] * invM), c2 = (float)(s2[h] * invM);
-    float xh = (Z[i] - mean[h]) * rstd[h];
-    dI[i] = scale[h] * (dI[i] - c1 - xh * c2);
+  float mx = 0.f;
+  if ((H & 3) == 0) {
+    // a thread keeps its 4 columns for the whole grid-stride walk when the stride is a multiple of H/4
+    const int64_t h4 = H / 4, n4 = M * h4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const int h = (int)(i % h4) * 4;
+      const float4 mu = *reinterpret_cast<const float4*>(mean + h), rs = *reinterpret_cast<const float4*>(rstd + h);
+      const float4 sc = *reinterpret_cast<const float4*>(scale + h);
+      const float4 z = reinterpret_cast<const float4*>(Z)[i];
+      float4 d = reinterpret_cast<float4*>(dI)[i];
+      d.x = sc.x * (d.x - (float)(s1[h] * invM) - (z.x - mu.x) * rs.x * (float)(s2[h] * invM));
+      d.y = sc.y * (d.y - (float)(s1[h + 1] * invM) - (z.y - mu.y) * rs.y * (float)(s2[h + 1] * invM));
+      d.z = sc.z * (d.z - (float)(s1[h + 2] * invM) - (z.z - mu.z) * rs.z * (float)(s2[h + 2] * invM));
+      d.w = sc.w * (d.w - (float)(s1[h + 3] * invM) - (z.w - mu.w) * rs.w * (float)(s2[h + 3] * invM));
+      reinterpret_cast<float4*>(dI)[i] = d;
+      mx = fmaxf(fmaxf(mx, fmaxf(fabsf(d.x), fabsf(d.y))), fmaxf(fabsf(d.z), fabsf(d.w)));
+    }
+  } else {
+    int64_t n = M * (int64_t)H;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+      int h = (int)(i % H);
+      float c1 = (float)(s1[h] * invM), c2 = (float)(s2[h] * invM);
+      float xh = (Z[i] - mean[h]) * rstd[h];
+      const float d = scale[h] * (dI[i] - c1 - xh * c2);
+      dI[i] = d;
+      mx = fmaxf(mx, fabsf(d));
+    }
+  }
+  if (amax) {  // max|dZ| for the fp16 split of the weight- and data-gradient GEMMs (sparch_split_f16)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(amax, __float_as_uint(mx));
   }
 }
 
@@ -221,10 +248,11 @@ int sparch_bn_fold_train(const double* sum, const double* sumsq, int64_t M, cons
 
 int sparch_bn_bwd_apply(float* dI, const float* Z, const float* mean, const float* rstd,
                         const float* scale, const double* sum1, const double* sum2, int64_t M, int H,
-                        sparch_stream_t st) {
+                        uint32_t* amax, sparch_stream_t st) {
   SPARCH_REQUIRE(M > 0 && H > 0 && dI && Z && mean && rstd && scale && sum1 && sum2, "bad argument");
-  bn_bwd_apply_kernel<<<ew_grid(M * (int64_t)H, 256), 256, 0, as_stream(st)>>>(dI, Z, mean, rstd, scale,
-                                                                              sum1, sum2, M, H);
+  if (amax) SPARCH_CUDA(cudaMemsetAsync(amax, 0, sizeof(uint32_t), as_stream(st)));
+  bn_bwd_apply_kernel<<<ew_grid(M * (int64_t)H / 4, 256), 256, 0, as_stream(st)>>>(dI, Z, mean, rstd, scale,
+                                                                                  sum1, sum2, M, H, amax);
   SPARCH_LAUNCH_OK();
   return SPARCH_OK;
 }

@@ -1,6 +1,6 @@
 // ReadoutLayer cell (snns.py:807-825): non-spiking leaky integrator whose output is the sum over
 // time of softmax(u_t) across the class dimension, and its reverse pass.
-// One block per batch row, one thread per class; the softmax reductions are block-wide.
+// One block per batch row; see the kernels for the decomposition.
 #include "common.cuh"
 
 namespace sparch {
@@ -16,78 +16,110 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// Block-wide reduction for blockDim.x <= 1024.  `sh` holds 32 floats; every thread gets the result.
-template <bool IS_MAX>
-__device__ __forceinline__ float block_reduce(float v, float* sh) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  v = IS_MAX ? warp_max(v) : warp_sum(v);
-  if (nw == 1) return v;
-  __syncthreads();  // previous use of sh is finished
-  if (lane == 0) sh[wid] = v;
-  __syncthreads();
-  float r = lane < nw ? sh[lane] : (IS_MAX ? -INFINITY : 0.0f);
-  return IS_MAX ? warp_max(r) : warp_sum(r);
-}
-
+// The membrane u_t is a per-(b, c) linear scan (no coupling across classes), only the softmax couples
+// the classes of one step.  So a block (one batch row) works on chunks of TCH timesteps held in shared
+// memory: (1) coalesced load of the chunk's inputs, (2) the dependent chain u_t per class thread --
+// T fused multiply-adds, no reduction inside the chain, (3) one warp per timestep for the softmax
+// (shuffle reductions), (4) per class the sum over the chunk's steps in time order (snns.py:823 adds
+// them in that order).  The first version did two block-wide reductions inside every dependent step.
 __global__ void readout_fwd_kernel(const float* __restrict__ Z, const float* __restrict__ scale,
                                    const float* __restrict__ shift, const float* __restrict__ alpha,
                                    const float* __restrict__ u0, float* __restrict__ out,
-                                   float* __restrict__ U, int T, int C) {
-  __shared__ float sh[32];
-  const int c = threadIdx.x;
-  const bool live = c < C;
+                                   float* __restrict__ U, int T, int C, int TCH) {
+  extern __shared__ float su[];  // [TCH][C]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const bool live = tid < C;
   const int64_t b = blockIdx.x;
-  const float al = live ? alpha[c] : 0.f, oma = __fsub_rn(1.0f, al);
-  const float sc = (live && scale) ? scale[c] : 1.0f, sf = (live && shift) ? shift[c] : 0.0f;
+  const float al = live ? alpha[tid] : 0.f, oma = __fsub_rn(1.0f, al);
+  const float sc = (live && scale) ? scale[tid] : 1.0f, sf = (live && shift) ? shift[tid] : 0.0f;
   const bool affine = scale != nullptr;
-  float u = live ? u0[b * C + c] : 0.f, acc = 0.f;
-  const int64_t base = b * (int64_t)T * C + c;
-  float znext = (live && T > 0) ? Z[base] : 0.f;
-  for (int t = 0; t < T; ++t) {
-    float z = znext;
-    if (live && t + 1 < T) znext = Z[base + (int64_t)(t + 1) * C];
-    float cur = affine ? __fmaf_rn(z, sc, sf) : z;
-    u = __fadd_rn(__fmul_rn(al, u), __fmul_rn(oma, cur));  // snns.py:822
-    float m = block_reduce<true>(live ? u : -INFINITY, sh);
-    float e = live ? expf(u - m) : 0.f;
-    float den = block_reduce<false>(e, sh);
-    if (live) {
-      acc += e / den;  // snns.py:823
-      U[base + (int64_t)t * C] = u;
+  float u = live ? u0[b * C + tid] : 0.f, acc = 0.f;
+  for (int t0 = 0; t0 < T; t0 += TCH) {
+    const int nt = min(TCH, T - t0), n = nt * C;
+    const int64_t base = (b * (int64_t)T + t0) * C;
+    for (int i = tid; i < n; i += blockDim.x) su[i] = Z[base + i];
+    __syncthreads();
+    if (live)
+      for (int t = 0; t < nt; ++t) {
+        const float z = su[t * C + tid];
+        const float cur = affine ? __fmaf_rn(z, sc, sf) : z;
+        u = __fadd_rn(__fmul_rn(al, u), __fmul_rn(oma, cur));  // snns.py:822
+        su[t * C + tid] = u;
+      }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) U[base + i] = su[i];
+    for (int t = warp; t < nt; t += nw) {
+      float* row = su + t * C;
+      float m = -INFINITY;
+      for (int c = lane; c < C; c += 32) m = fmaxf(m, row[c]);
+      m = warp_max(m);
+      float den = 0.f;
+      for (int c = lane; c < C; c += 32) den += expf(row[c] - m);
+      den = warp_sum(den);
+      for (int c = lane; c < C; c += 32) row[c] = expf(row[c] - m) / den;
     }
+    __syncthreads();
+    if (live)
+      for (int t = 0; t < nt; ++t) acc += su[t * C + tid];  // snns.py:823
+    __syncthreads();
   }
-  if (live) out[b * C + c] = acc;
+  if (live) out[b * C + tid] = acc;
 }
 
+// Reverse pass, same chunking (chunks walked backwards): the softmax Jacobian term x_t = p_t (g - <p_t, g>)
+// depends only on the taped u_t, so one warp per timestep computes it for the whole chunk; the dependent
+// chain du_t = x_t + alpha du_{t+1} then runs per class thread without reductions.
 __global__ void readout_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ U,
                                    const float* __restrict__ alpha, const float* __restrict__ u0,
-                                   float* __restrict__ dI, float* __restrict__ p_alpha, int T, int C) {
-  __shared__ float sh[32];
-  const int c = threadIdx.x;
-  const bool live = c < C;
+                                   float* __restrict__ dI, float* __restrict__ p_alpha, int T, int C, int TCH) {
+  extern __shared__ float sm[];
+  float* su = sm;                 // [TCH + 1][C]: row 0 = u of the step before the chunk
+  float* sx = sm + (TCH + 1) * C; // [TCH][C]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const bool live = tid < C;
   const int64_t b = blockIdx.x;
-  const float al = live ? alpha[c] : 0.f, oma = __fsub_rn(1.0f, al), inv_oma = 1.0f / oma;
-  const float go = live ? gout[b * C + c] : 0.f;
-  const int64_t base = b * (int64_t)T * C + c;
+  const float al = live ? alpha[tid] : 0.f, oma = __fsub_rn(1.0f, al), inv_oma = 1.0f / oma;
+  const float* go = gout + b * C;
   float du = 0.f, pa = 0.f;
-  float u_t = (live && T > 0) ? U[base + (int64_t)(T - 1) * C] : 0.f;
-  for (int t = T - 1; t >= 0; --t) {
-    float u_prev = 0.f;
-    if (live) u_prev = t > 0 ? U[base + (int64_t)(t - 1) * C] : u0[b * C + c];
-    float m = block_reduce<true>(live ? u_t : -INFINITY, sh);
-    float e = live ? expf(u_t - m) : 0.f;
-    float den = block_reduce<false>(e, sh);
-    float pr = e / den;
-    float dot = block_reduce<false>(pr * go, sh);
-    float du_t = pr * (go - dot) + al * du;
-    if (live) {
-      dI[base + (int64_t)t * C] = oma * du_t;
-      pa += du_t * ((u_prev - u_t) * inv_oma);  // d u_t / d alpha = u_{t-1} - I_t
+  const int nchunks = (T + TCH - 1) / TCH;
+  for (int ch = nchunks - 1; ch >= 0; --ch) {
+    const int t0 = ch * TCH, nt = min(TCH, T - t0), n = nt * C;
+    const int64_t base = (b * (int64_t)T + t0) * C;
+    for (int i = tid; i < n; i += blockDim.x) su[C + i] = U[base + i];
+    for (int i = tid; i < C; i += blockDim.x) su[i] = t0 > 0 ? U[base - C + i] : u0[b * C + i];
+    __syncthreads();
+    for (int t = warp; t < nt; t += nw) {
+      const float* row = su + (t + 1) * C;
+      float m = -INFINITY;
+      for (int c = lane; c < C; c += 32) m = fmaxf(m, row[c]);
+      m = warp_max(m);
+      float den = 0.f;
+      for (int c = lane; c < C; c += 32) den += expf(row[c] - m);
+      den = warp_sum(den);
+      float dot = 0.f;
+      for (int c = lane; c < C; c += 32) dot += expf(row[c] - m) / den * go[c];
+      dot = warp_sum(dot);
+      for (int c = lane; c < C; c += 32) sx[t * C + c] = expf(row[c] - m) / den * (go[c] - dot);
     }
-    du = du_t;
-    u_t = u_prev;
+    __syncthreads();
+    if (live)
+      for (int t = nt - 1; t >= 0; --t) {
+        const float du_t = sx[t * C + tid] + al * du;
+        sx[t * C + tid] = oma * du_t;
+        pa += du_t * ((su[t * C + tid] - su[(t + 1) * C + tid]) * inv_oma);  // d u_t / d alpha = u_{t-1} - I_t
+        du = du_t;
+      }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) dI[base + i] = sx[i];
+    __syncthreads();
   }
-  if (live) p_alpha[b * C + c] = pa;
+  if (live) p_alpha[b * C + tid] = pa;
+}
+
+static int readout_chunk(int T, int C, int arrays) {
+  int tch = (40 * 1024) / (arrays * C * (int)sizeof(float)) - 1;
+  if (tch > T) tch = T;
+  return tch < 1 ? 1 : tch;
 }
 
 }  // namespace sparch
@@ -103,7 +135,10 @@ int sparch_readout_fwd(const float* Z, const float* scale, const float* shift, c
   if (B == 0) return SPARCH_OK;
   SPARCH_REQUIRE(alpha && u0 && out && (T == 0 || (Z && U)), "null pointer");
   int threads = ((C + 31) / 32) * 32;
-  readout_fwd_kernel<<<B, threads, 0, as_stream(st)>>>(Z, scale, shift, alpha, u0, out, U, T, C);
+  if (threads < 128) threads = 128;
+  const int tch = readout_chunk(T, C, 1);
+  readout_fwd_kernel<<<B, threads, (size_t)tch * C * sizeof(float), as_stream(st)>>>(Z, scale, shift, alpha, u0, out, U,
+                                                                                      T, C, tch);
   SPARCH_LAUNCH_OK();
   return SPARCH_OK;
 }
@@ -114,7 +149,10 @@ int sparch_readout_bwd(const float* gout, const float* U, const float* alpha, co
   if (B == 0) return SPARCH_OK;
   SPARCH_REQUIRE(gout && alpha && u0 && p_alpha && (T == 0 || (U && dI)), "null pointer");
   int threads = ((C + 31) / 32) * 32;
-  readout_bwd_kernel<<<B, threads, 0, as_stream(st)>>>(gout, U, alpha, u0, dI, p_alpha, T, C);
+  if (threads < 128) threads = 128;
+  const int tch = readout_chunk(T, C, 2);
+  readout_bwd_kernel<<<B, threads, (size_t)(2 * tch + 1) * C * sizeof(float), as_stream(st)>>>(gout, U, alpha, u0, dI,
+                                                                                                p_alpha, T, C, tch);
   SPARCH_LAUNCH_OK();
   return SPARCH_OK;
 }

@@ -38,14 +38,12 @@ _PRECISION = "fp32"
 
 def set_precision(mode):
     global _PRECISION
-    if mode not in ("fp32", "bf16"):
-        raise ValueError("precision must be 'fp32' or 'bf16'")
-    _PRECISION = mode
-
-
-def _terms(full):
-    """Number of bf16 terms for a general fp32 operand."""
-    return 1 if _PRECISION == "bf16" else full
+    if mode not in ("fp32", "fp32-bf16x3", "bf16"):
+        raise ValueError("precision must be 'fp32', 'fp32-bf16x3' or 'bf16'")
+    # "fp32-bf16x3": the fp32-equivalent mode with three bf16 terms per GEMM operand instead of two scaled
+    # fp16 terms (6 / 3 tensor-pipe passes instead of 3 / 2): kept for comparison measurements
+    gemm.MODE = {"fp32": "f16x2", "fp32-bf16x3": "bf16x3", "bf16": "bf16x1"}[mode]
+    _PRECISION = "bf16" if mode == "bf16" else "fp32"
 
 
 # Optional CUDA-event timers around named regions (bench.py's roofline leg).  Events are recorded
@@ -146,37 +144,39 @@ class LinearFunction(torch.autograd.Function):
         with torch.no_grad():
             with _region("gemm_fwd"):
                 if in_scale is None:
-                    xa, alpha = gemm.split_rows(x2d, _terms(3)), 1.0
+                    xa, alpha = gemm.split_general(x2d), 1.0
                 else:
-                    xa, alpha = gemm.split_rows(x2d, 1, prescale=1.0 / in_scale), float(in_scale)
-                wb = gemm.split_rows(_f32c(weight), _terms(3))
+                    xa, alpha = gemm.split_binary(x2d, prescale=1.0 / in_scale), float(in_scale)
+                wb = gemm.split_general(_f32c(weight))
                 # BatchNorm statistics ride in the GEMM epilogue when the tile's main loop is long enough
                 # to dwarf it (measured: for the K=40 input layer the epilogue IS the kernel and a
                 # separate column-statistics pass over the L2-warm output is cheaper).
                 stats = None
-                passes = xa.shape[0] * wb.shape[0]
-                if norm is not None and norm.mode == "bn_train" and passes * ((K + 63) // 64) >= 16:
+                passes = len(gemm.pairs_for(xa.n, wb.n))
+                if norm is not None and norm.mode == "bn_train" and passes * ((K + 63) // 64) >= 8:
                     stats = torch.empty(2, N, device=x2d.device, dtype=torch.float64)
                 Z = gemm.gemm_parts(xa, wb, K, alpha=alpha, bias=None if bias is None else _f32c(bias),
                                     stats=stats)
                 if norm is not None:
                     norm.stats = stats
         ctx.alpha = alpha
+        ctx.norm = norm      # the cell's backward leaves max|dZ| there (NormState.dz_amax)
         ctx.has_bias = bias is not None
-        # the bf16 terms serve the backward GEMMs as they are (MN-major operands): no re-split
-        ctx.save_for_backward(xa, wb)
+        # the terms serve the backward GEMMs as they are (MN-major operands): no re-split
+        ctx.save_for_backward(xa.parts, xa.amax, wb.parts, wb.amax)
         ctx.xshape = x.shape
         ctx.dims = (M, N, K)
         return Z.view(*x.shape[:-1], N)
 
     @staticmethod
     def backward(ctx, gZ):
-        xa, wb = ctx.saved_tensors
+        xa, wb = gemm.Terms(*ctx.saved_tensors[:2]), gemm.Terms(*ctx.saved_tensors[2:])
         M, N, K = ctx.dims
         g2d = _f32c(gZ).reshape(M, N)
         dx = dw = db = None
         with _region("gemm_bwd"):
-            ga = gemm.split_rows(g2d, xa.shape[0] if xa.shape[0] > 1 else wb.shape[0])
+            # max|dZ| left by the producer of this gradient (BatchNorm backward), if any
+            ga = gemm.split_general(g2d, amax=None if ctx.norm is None else ctx.norm.dz_amax)
             if ctx.needs_input_grad[0]:
                 # dX = dZ @ W: contraction over N; W's terms (N, K) are the MN-major B operand
                 dx = gemm.gemm_parts(ga, wb, N, b_mn=True, N=K).view(ctx.xshape)
@@ -202,6 +202,7 @@ class NormState:
         self.eps = eps
         self.momentum = momentum
         self.stats = None   # (2, H) float64 column sum / sum of squares when the projection GEMM fused them
+        self.dz_amax = None  # (1,) int32 bit pattern of max|dZ| left by the BatchNorm backward for the fp16 split
 
 
 def _fold_norm(Z2d, gamma, bn_beta, norm):
@@ -243,8 +244,10 @@ def _norm_backward(dI2d, Z2d, gamma, bn_beta, norm, scale, mean, rstd):
     dgamma = sums[1].float() if gamma is not None else None
     dbeta = sums[0].float() if bn_beta is not None else None
     if norm.mode == "bn_train":
+        amax = torch.empty(1, device=dI2d.device, dtype=torch.int32) if gemm.MODE == "f16x2" else None
         call("sparch_bn_bwd_apply", ptr(dI2d), ptr(Z2d), ptr(mean), ptr(rstd), ptr(scale),
-             ptr(sums[0]), ptr(sums[1]), M, H, _stream())
+             ptr(sums[0]), ptr(sums[1]), M, H, ptr(amax), _stream())
+        norm.dz_amax = amax
     else:
         dI2d.mul_(scale)
     return dgamma, dbeta
@@ -391,8 +394,8 @@ class SpikingCellFunction(torch.autograd.Function):
                     first[1:] -= S[:-1, T - 1, :]
                 dV = first.t() @ dI[:, 0, :]
                 if Be * T > 1:
-                    sp = gemm.split_rows(S.view(Be * T, H), 1)
-                    dit = gemm.split_rows(dI.view(Be * T, H), _terms(3))
+                    sp = gemm.split_binary(S.view(Be * T, H))
+                    dit = gemm.split_general(dI.view(Be * T, H))
                     dV += gemm.gemm_parts(sp, dit, Be * T, a_mn=True, b_mn=True, a_koff=-1, M=H, N=H)
                 dV.fill_diagonal_(0)
         psum = part.sum(dim=1)

@@ -17,10 +17,74 @@ PAIRS_33 = [(2, 0), (1, 1), (0, 2), (1, 0), (0, 1), (0, 0)]
 PAIRS_13 = [(0, 2), (0, 1), (0, 0)]
 PAIRS_31 = [(2, 0), (1, 0), (0, 0)]
 PAIRS_11 = [(0, 0)]
+# fp16 hi/lo terms: hi.lo + lo.hi + hi.hi (lo.lo is below 2^-22 of the product)
+PAIRS_22 = [(1, 0), (0, 1), (0, 0)]
+PAIRS_12 = [(0, 1), (0, 0)]
+PAIRS_21 = [(1, 0), (0, 0)]
 
 
 def pairs_for(na, nb):
-    return {(3, 3): PAIRS_33, (1, 3): PAIRS_13, (3, 1): PAIRS_31, (1, 1): PAIRS_11}[(na, nb)]
+    return {(3, 3): PAIRS_33, (1, 3): PAIRS_13, (3, 1): PAIRS_31, (1, 1): PAIRS_11,
+            (2, 2): PAIRS_22, (1, 2): PAIRS_12, (2, 1): PAIRS_21}[(na, nb)]
+
+
+# How a general fp32 operand travels to the tensor pipe.
+#   "f16x2" (default): two fp16 terms of x * 2^k, one power-of-two scale per tensor taken from max|x| on the
+#            device (22 mantissa bits; general x general = 3 passes, spikes x general = 2)
+#   "bf16x3": three bf16 terms (24 bits, no scale; 6 resp. 3 passes) -- the first round-1 scheme, kept for comparison
+#   "bf16x1": one bf16 term (the reduced-precision mode of sparch_b200.set_precision("bf16"))
+MODE = "f16x2"
+
+
+class Terms:
+    """The terms of one split operand: ``parts`` (n, rows, ld) fp16/bf16 and, for scaled fp16 terms,
+    ``amax`` (1,) int32 holding the bit pattern of max|x| (the GEMM epilogue undoes the scale)."""
+    __slots__ = ("parts", "amax")
+
+    def __init__(self, parts, amax=None):
+        self.parts = parts
+        self.amax = amax
+
+    @property
+    def n(self):
+        return self.parts.shape[0]
+
+
+def absmax(x2d):
+    """(1,) int32 device tensor: bit pattern of max|x| (no host synchronisation)."""
+    x2d = x2d.contiguous() if x2d.stride(-1) != 1 else x2d
+    out = torch.empty(1, device=x2d.device, dtype=torch.int32)
+    call("sparch_absmax", ptr(x2d), x2d.stride(0), x2d.shape[0], x2d.shape[1], ptr(out), _stream())
+    return out
+
+
+def split_f16(x2d, nparts, prescale=1.0, amax=None, scaled=True):
+    """(M, K) fp32 -> Terms of nparts fp16 tensors (M, ld).  scaled: one power-of-two scale from max|x|
+    (computed here unless the producer of x already left it in ``amax``)."""
+    x2d = x2d.contiguous() if x2d.stride(-1) != 1 else x2d
+    M, K = x2d.shape
+    ld = _pad8(K)
+    compute = scaled and amax is None
+    if compute:
+        amax = torch.empty(1, device=x2d.device, dtype=torch.int32)
+    parts = torch.empty(nparts, M, ld, device=x2d.device, dtype=torch.float16)
+    call("sparch_split_f16", ptr(x2d), x2d.stride(0), M, K, nparts, float(prescale), ptr(amax) if scaled else None,
+         int(compute), ptr(parts[0]), ptr(parts[1]) if nparts > 1 else None, ld, _stream())
+    return Terms(parts, amax if scaled else None)
+
+
+def split_general(x2d, amax=None):
+    """Terms of a general fp32 operand in the current MODE."""
+    if MODE == "f16x2":
+        return split_f16(x2d, 2, amax=amax)
+    return Terms(split_rows(x2d, 3 if MODE == "bf16x3" else 1))
+
+
+def split_binary(x2d, prescale=1.0):
+    """One exact term of an operand whose values are all 0 or 1/prescale (spikes, dropped spikes)."""
+    if MODE == "f16x2":
+        return split_f16(x2d, 1, prescale=prescale, scaled=False)
+    return Terms(split_rows(x2d, 1, prescale=prescale))
 
 
 def _stream():
@@ -62,7 +126,15 @@ def gemm_parts(A, B, K, alpha=1.0, bias=None, out=None, pairs=None, a_mn=False, 
     K-major operand: terms of shape (n, rows, ld) with rows = M resp. N.  MN-major operand
     (a_mn / b_mn): terms of shape (n, K, ld) holding the (K, M) resp. (K, N) matrix, M / N given
     explicitly (ld may exceed it).  a_koff shifts A's K index (zero fill), MN-major A only.
-    stats: optional (2, N) float64 tensor receiving the per-column sum / sum of squares of C."""
+    stats: optional (2, N) float64 tensor receiving the per-column sum / sum of squares of C.
+    A, B: ``Terms`` or plain (n, rows, ld) bf16 tensors of unscaled terms."""
+    amax_a = amax_b = None
+    if isinstance(A, Terms):
+        A, amax_a = A.parts, A.amax
+    if isinstance(B, Terms):
+        B, amax_b = B.parts, B.amax
+    fp16 = A.dtype == torch.float16
+    assert (B.dtype == torch.float16) == fp16, "both operands must use the same 16-bit format"
     na, ra, lda = A.shape
     nb, rb, ldb = B.shape
     M = ra if not a_mn else M
@@ -81,7 +153,8 @@ def gemm_parts(A, B, K, alpha=1.0, bias=None, out=None, pairs=None, a_mn=False, 
     tiles = ((M + 127) // 128) * ((N + 255) // 256)
     if tiles < 148 and K > 64 and stats is None:
         ws = torch.empty(_lib.lib().sparch_gemm_workspace(M, N, K), device=dev, dtype=torch.uint8)
-    call("sparch_gemm_bf16", ap, na, bp, nb, lda, ldb, int(a_mn), int(b_mn), int(a_koff), pa, pb,
+    call("sparch_gemm_terms", int(fp16), ap, na, ptr(amax_a), bp, nb, ptr(amax_b), lda, ldb, int(a_mn), int(b_mn),
+         int(a_koff), pa, pb,
          len(pairs), M, N, K, float(alpha), ptr(bias), ptr(out), out.stride(0),
          None if stats is None else ptr(stats[0]), None if stats is None else ptr(stats[1]), ptr(ws), _stream())
     return out

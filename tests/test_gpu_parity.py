@@ -598,3 +598,24 @@ def test_recurrent_cells_random_shape_sweep(seed):
     H = int(rng.choice([1, 8, 31, 32, 33, 48, 96, 100, 130, 260, 512]))
     T = int(rng.integers(1, 8))
     _oracle_cell_check(kind, Be, T, H, seed=seed, drive=(3.0, 1.5))
+
+
+@pytest.mark.parametrize("B,T,C", [(5, 100, 35), (3, 700, 20), (2, 23, 300), (4, 1, 7), (2, 40, 1024)])
+def test_readout_cell_against_oracle(B, T, C):
+    """ReadoutLayer cell (snns.py:807-825) through the C ABI: chunked scan + warp-per-step softmax,
+    including shapes whose T exceeds one shared-memory chunk and class counts above one warp."""
+    _, F = _mods()
+    rng = np.random.default_rng(B * 1000 + T + C)
+    I = rng.standard_normal((B, T, C)).astype(np.float32) * 2
+    alpha = rng.uniform(0.82, 0.96, C).astype(np.float32)
+    u0 = rng.uniform(0, 1, (B, C)).astype(np.float32)
+    gout = rng.standard_normal((B, C)).astype(np.float32)
+    It = torch.from_numpy(I).to(DEV).requires_grad_(True)
+    al = torch.from_numpy(alpha).to(DEV).requires_grad_(True)
+    out = F.ReadoutCellFunction.apply(It, None, None, al, torch.from_numpy(u0).to(DEV), F.NormState("none"))
+    out.backward(torch.from_numpy(gout).to(DEV))
+    f = orc.readout_forward(I, alpha, u0)
+    bw = orc.readout_backward(gout, I, alpha, u0, f["u"])
+    assert rel_err(out.detach().cpu().numpy(), f["out"]) < 1e-5
+    assert rel_err(It.grad.cpu().numpy(), bw["dI"]) < G_RTOL
+    assert rel_err(al.grad.cpu().numpy(), bw["dalpha"]) < 5e-5
