@@ -26,7 +26,7 @@ namespace sparch {
 constexpr int GM = 128, GN = 256, GK = 64, GSTAGES = 4;
 constexpr int G_A_BYTES = GM * GK * 2, G_B_BYTES = GN * GK * 2, G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
 constexpr int G_THREADS = 192;
-constexpr uint32_t G_TMEM_COLS = 256;
+constexpr uint32_t G_TMEM_COLS = 512;   // two fp32 accumulators of 256 columns
 constexpr size_t G_SMEM = (size_t)GSTAGES * G_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct TmapSet {
@@ -39,7 +39,8 @@ struct GemmParams {
   int npairs;
   int pair_a[8], pair_b[8];
   int kblocks;         // ceil(K / 64)
-  int kb_per_split;    // k-blocks handled by one blockIdx.z
+  int kb_per_split;    // k-blocks handled by one split
+  int splits;          // split-K factor (work items = splits x tiles)
   float* C;            // final output (splits == 1) or partial buffer [splits][M][ldc]
   long long ldc;
   long long split_stride;
@@ -103,6 +104,11 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];  // lane l holds the sum of column l: bit (16>>s) of l selected the upper half at step s
 }
 
+// Persistent kernel: gridDim.x = min(#work items, #SMs) CTAs walk the (split, m-tile, n-tile) items with a stride
+// of gridDim.x.  The fp32 accumulator is double-buffered in TMEM (2 x 256 columns): while the epilogue warps
+// drain tile j (tcgen05.ld -> alpha / bias / statistics -> global), the MMA warp already accumulates tile j + 1,
+// and the TMA ring keeps its phase across tiles, so only the first tile's prologue and the last tile's epilogue
+// are exposed.
 template <bool STATS>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
@@ -112,21 +118,23 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
   const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024-byte alignment
   unsigned char* gsm = gsm_raw + (base - raw);
   constexpr int NST = GSTAGES;
-  const uint32_t bars = base + NST * G_STAGE_BYTES;             // full[4], empty[4], tmem_full
+  const uint32_t bars = base + NST * G_STAGE_BYTES;             // full[4], empty[4], tmem_full[2], tmem_empty[2]
+  constexpr int B_TFULL = 2 * GSTAGES, B_TEMPTY = 2 * GSTAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gsm + NST * G_STAGE_BYTES + 128);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
-  const int kb0 = blockIdx.z * p.kb_per_split;
-  const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
-  const int iters = p.npairs * (kb1 - kb0);
+  const int tiles_n = (p.N + GN - 1) / GN, tiles = tiles_n * ((p.M + GM - 1) / GM);
+  const int items = tiles * p.splits;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) {
       mbar_init(bars + 8 * s, 1);
       mbar_init(bars + 8 * (GSTAGES + s), 1);
     }
-    mbar_init(bars + 8 * (2 * GSTAGES), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bars + 8 * (B_TFULL + b), 1);    // one tcgen05.commit
+      mbar_init(bars + 8 * (B_TEMPTY + b), 4);   // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -143,129 +151,158 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
-      for (int pr = 0; pr < p.npairs; ++pr) {
-        const CUtensorMap* ma = &maps.a[p.pair_a[pr]];
-        const CUtensorMap* mb = &maps.b[p.pair_b[pr]];
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % NST;
-          const uint32_t ph = (it / NST) & 1;
-          mbar_wait(bars + 8 * (GSTAGES + s), ph ^ 1);
-          mbar_expect_tx(bars + 8 * s, G_STAGE_BYTES);
-          const uint32_t sa = base + s * G_STAGE_BYTES;
-          if (!p.a_mn) {
-            tma_load_2d(sa, ma, kb * GK, m0, bars + 8 * s);
-          } else {
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int z = item / tiles, tile = item - z * tiles;
+        const int m0 = (tile / tiles_n) * GM, n0 = (tile % tiles_n) * GN;
+        const int kb0 = z * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+        for (int pr = 0; pr < p.npairs; ++pr) {
+          const CUtensorMap* ma = &maps.a[p.pair_a[pr]];
+          const CUtensorMap* mb = &maps.b[p.pair_b[pr]];
+          for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            const int s = it % NST;
+            const uint32_t ph = (it / NST) & 1;
+            mbar_wait(bars + 8 * (GSTAGES + s), ph ^ 1);
+            mbar_expect_tx(bars + 8 * s, G_STAGE_BYTES);
+            const uint32_t sa = base + s * G_STAGE_BYTES;
+            if (!p.a_mn) {
+              tma_load_2d(sa, ma, kb * GK, m0, bars + 8 * s);
+            } else {
 #pragma unroll
-            for (int blk = 0; blk < GM / 64; ++blk)
-              tma_load_2d(sa + blk * 8192, ma, m0 + blk * 64, kb * GK + p.a_koff, bars + 8 * s);
-          }
-          if (!p.b_mn) {
-            tma_load_2d(sa + G_A_BYTES, mb, kb * GK, n0, bars + 8 * s);
-          } else {
+              for (int blk = 0; blk < GM / 64; ++blk)
+                tma_load_2d(sa + blk * 8192, ma, m0 + blk * 64, kb * GK + p.a_koff, bars + 8 * s);
+            }
+            if (!p.b_mn) {
+              tma_load_2d(sa + G_A_BYTES, mb, kb * GK, n0, bars + 8 * s);
+            } else {
 #pragma unroll
-            for (int blk = 0; blk < GN / 64; ++blk)
-              tma_load_2d(sa + G_A_BYTES + blk * 8192, mb, n0 + blk * 64, kb * GK, bars + 8 * s);
+              for (int blk = 0; blk < GN / 64; ++blk)
+                tma_load_2d(sa + G_A_BYTES + blk * 8192, mb, n0 + blk * 64, kb * GK, bars + 8 * s);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % NST;
-        const uint32_t ph = (it / NST) & 1;
-        mbar_wait(bars + 8 * s, ph);
+      // K advance per UMMA (16 elements): K-major 32 bytes inside the swizzle atom (2 units of 16 B),
+      // MN-major 16 rows of 128 bytes (128 units)
+      const uint32_t ka = p.a_mn ? 128u : 2u, kb_ = p.b_mn ? 128u : 2u;
+      const uint32_t idesc = G_IDESC | (p.fp16 ? 0u : G_IDESC_BF16) | (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);
+      int it = 0, j = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++j) {
+        const int z = item / tiles;
+        const int kb0 = z * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+        const int iters = p.npairs * (kb1 - kb0);
+        const int buf = j & 1;
+        mbar_wait(bars + 8 * (B_TEMPTY + buf), ((j >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = base + s * G_STAGE_BYTES;
-        const uint64_t da = p.a_mn ? make_desc_mn_sw128(sa) : make_desc_k_sw128(sa);
-        const uint64_t db = p.b_mn ? make_desc_mn_sw128(sa + G_A_BYTES) : make_desc_k_sw128(sa + G_A_BYTES);
-        // K advance per UMMA (16 elements): K-major 32 bytes inside the swizzle atom (2 units of 16 B),
-        // MN-major 16 rows of 128 bytes (128 units)
-        const uint32_t ka = p.a_mn ? 128u : 2u, kb_ = p.b_mn ? 128u : 2u;
-        const uint32_t idesc = G_IDESC | (p.fp16 ? 0u : G_IDESC_BF16) | (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);
+        const uint32_t dacc = tmem + (uint32_t)(buf * GN);
+        for (int li = 0; li < iters; ++li, ++it) {
+          const int s = it % NST;
+          const uint32_t ph = (it / NST) & 1;
+          mbar_wait(bars + 8 * s, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = base + s * G_STAGE_BYTES;
+          const uint64_t da = p.a_mn ? make_desc_mn_sw128(sa) : make_desc_k_sw128(sa);
+          const uint64_t db = p.b_mn ? make_desc_mn_sw128(sa + G_A_BYTES) : make_desc_k_sw128(sa + G_A_BYTES);
 #pragma unroll
-        for (int k = 0; k < GK / 16; ++k)
-          umma_f16(tmem, da + ka * k, db + kb_ * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-        umma_commit(bars + 8 * (GSTAGES + s));   // frees the smem stage when these MMAs retire
+          for (int k = 0; k < GK / 16; ++k)
+            umma_f16(dacc, da + ka * k, db + kb_ * k, idesc, (li > 0 || k > 0) ? 1u : 0u);
+          umma_commit(bars + 8 * (GSTAGES + s));   // frees the smem stage when these MMAs retire
+        }
+        umma_commit(bars + 8 * (B_TFULL + buf));   // accumulator complete
       }
-      umma_commit(bars + 8 * (2 * GSTAGES));     // accumulator complete
     }
   } else {
     // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
     const int quarter = warp & 3;
-    const int row = m0 + quarter * 32 + lane;
-    mbar_wait(bars + 8 * (2 * GSTAGES), 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float* crow = p.C + (size_t)blockIdx.z * p.split_stride + (size_t)row * p.ldc;
-    const bool final_out = gridDim.z == 1;
+    const bool final_out = p.splits == 1;
     // alpha and the inverse scales of fp16 operands (powers of two: exact), applied one after the other so that
     // no intermediate product leaves the fp32 range
     const float inv_a = p.amax_a ? ldexpf(1.0f, -f16_scale_exp(*p.amax_a)) : 1.0f;
     const float inv_b = p.amax_b ? ldexpf(1.0f, -f16_scale_exp(*p.amax_b)) : 1.0f;
     const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-    for (int c = 0; c < GN / 32; ++c) {
-      uint32_t v[32];
-      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32);
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-            "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-            "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-            "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const int nb = n0 + c * 32;
-      if (row < p.M && nb < p.N) {
-        float f[32];
+    int j = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++j) {
+      const int z = item / tiles, tile = item - z * tiles;
+      const int m0 = (tile / tiles_n) * GM, n0 = (tile % tiles_n) * GN;
+      const int buf = j & 1;
+      const int row = m0 + quarter * 32 + lane;
+      mbar_wait(bars + 8 * (B_TFULL + buf), (j >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float* crow = p.C + (size_t)z * p.split_stride + (size_t)row * p.ldc;
+      for (int c = 0; c < GN / 32; ++c) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * GN + c * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+              "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+              "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+              "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c == GN / 32 - 1) {
+          // the whole accumulator is in registers: hand the TMEM buffer back before the stores
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0)
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8 * (B_TEMPTY + buf)) : "memory");
+        }
+        const int nb = n0 + c * 32;
+        if (row < p.M && nb < p.N) {
+          float f[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          f[i] = __uint_as_float(v[i]);
-          if (final_out) {
-            f[i] = f[i] * inv_a * inv_b * p.alpha;
-            if (p.bias && nb + i < p.N) f[i] += p.bias[nb + i];
+          for (int i = 0; i < 32; ++i) {
+            f[i] = __uint_as_float(v[i]);
+            if (final_out) {
+              f[i] = f[i] * inv_a * inv_b * p.alpha;
+              if (p.bias && nb + i < p.N) f[i] += p.bias[nb + i];
+            }
+          }
+          if (vec && nb + 32 <= p.N) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<float4*>(crow + nb + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (nb + i < p.N) crow[nb + i] = f[i];
           }
         }
-        if (vec && nb + 32 <= p.N) {
+        if (STATS && nb < p.N) {  // warp-uniform: fused BatchNorm statistics of the finished output
+          float a[32], b[32];
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(crow + nb + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (nb + i < p.N) crow[nb + i] = f[i];
-        }
-      }
-      if (STATS && nb < p.N) {  // warp-uniform: fused BatchNorm statistics of the finished output
-        float a[32], b[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = 0.f;
-          if (row < p.M && nb + i < p.N) {
-            x = __uint_as_float(v[i]) * inv_a * inv_b * p.alpha;
-            if (p.bias) x += p.bias[nb + i];
+          for (int i = 0; i < 32; ++i) {
+            float x = 0.f;
+            if (row < p.M && nb + i < p.N) {
+              x = __uint_as_float(v[i]) * inv_a * inv_b * p.alpha;
+              if (p.bias) x += p.bias[nb + i];
+            }
+            a[i] = x;
+            b[i] = x * x;
           }
-          a[i] = x;
-          b[i] = x * x;
+          const float cs = warp_colsum32(a, lane), cq = warp_colsum32(b, lane);
+          sstat[quarter][c * 32 + lane] = make_float2(cs, cq);
         }
-        const float cs = warp_colsum32(a, lane), cq = warp_colsum32(b, lane);
-        sstat[quarter][c * 32 + lane] = make_float2(cs, cq);
       }
-    }
-    if (STATS) {
-      // combine the four row quarters of the tile, then one fp64 atomic per column and quantity
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int e = threadIdx.x - 64;  // 0..127 over the epilogue warps
+      if (STATS) {
+        // combine the four row quarters of the tile, then one fp64 atomic per column and quantity
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int e = threadIdx.x - 64;  // 0..127 over the epilogue warps
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int col = e + 128 * cc;
-        if (n0 + col < p.N) {
-          const float2 q0 = sstat[0][col], q1 = sstat[1][col], q2 = sstat[2][col], q3 = sstat[3][col];
-          atomicAdd(&p.stat_sum[n0 + col], (double)q0.x + (double)q1.x + (double)q2.x + (double)q3.x);
-          atomicAdd(&p.stat_sumsq[n0 + col], (double)q0.y + (double)q1.y + (double)q2.y + (double)q3.y);
+        for (int cc = 0; cc < 2; ++cc) {
+          const int col = e + 128 * cc;
+          if (n0 + col < p.N) {
+            const float2 q0 = sstat[0][col], q1 = sstat[1][col], q2 = sstat[2][col], q3 = sstat[3][col];
+            atomicAdd(&p.stat_sum[n0 + col], (double)q0.x + (double)q1.x + (double)q2.x + (double)q3.x);
+            atomicAdd(&p.stat_sumsq[n0 + col], (double)q0.y + (double)q1.y + (double)q2.y + (double)q3.y);
+          }
         }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // sstat is rewritten by the next tile
       }
     }
   }
@@ -589,7 +626,9 @@ int sparch_gemm_terms(int fp16, const void* const* A_parts, int na, const uint32
     attr_set = true;
   }
   // (A 2-stage ring with two CTAs per SM for short contractions was measured: no gain.)
-  dim3 grid((N + GN - 1) / GN, (M + GM - 1) / GM, splits);
+  p.splits = splits;
+  const int items = tiles * splits;
+  dim3 grid(items < sm_count() ? items : sm_count());
   if (stat_sum)
     gemm_tn_bf16_kernel<true><<<grid, G_THREADS, G_SMEM, st>>>(maps, p);
   else

@@ -29,6 +29,7 @@
 // i.e. <= 2^-29 of the row maximum -- below fp32 rounding of the dominant terms.  Every slice computes
 // the same s_t from the same published chunk maxima, so producer and consumers agree.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "cell_math.cuh"
 #include "common.cuh"
@@ -567,7 +568,10 @@ int sparch_recur_bwd_tc(int kind, const float* G, const float* U, const float* W
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cfg.attrs = attrs;
-  cfg.numAttrs = 2;
+  // Nsight Compute (2025.2) cannot replay a launch that is both clustered and cooperative; SPARCH_B200_TC_COOP=0
+  // drops the cooperative attribute for profiling runs (co-residency then rests on the occupancy query below alone).
+  static const bool coop = !(getenv("SPARCH_B200_TC_COOP") && getenv("SPARCH_B200_TC_COOP")[0] == '0');
+  cfg.numAttrs = coop ? 2 : 1;
   cfg.gridDim = dim3(slices, 1);
   int max_clusters = 0;
   SPARCH_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg));

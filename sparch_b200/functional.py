@@ -126,6 +126,13 @@ class SpikeFunctionBoxcar(torch.autograd.Function):
         return gx
 
 
+# BatchNorm statistics can ride in the projection GEMM's epilogue (gemm_tn_bf16_kernel<true>) when a tile's main
+# loop has at least this many (pass, k-block) iterations.  Measured at cfg 4 with the persistent two-pass fp16
+# GEMM: the fused epilogue costs more than a separate sparch_col_stats pass over the L2-warm output (5.01 vs
+# 4.95 ms per graphed train step), so it is off by default; SPARCH_B200_FUSED_STATS_MIN_ITERS=8 switches it on.
+FUSED_STATS_MIN_ITERS = int(os.environ.get("SPARCH_B200_FUSED_STATS_MIN_ITERS", "1000000"))
+
+
 class LinearFunction(torch.autograd.Function):
     """Time-parallel projection ``x @ W^T + b`` over all Be*T frames (snns.py:675) and its
     autograd, on the tcgen05 GEMM.  ``in_scale``: None for a general fp32 input (three bf16
@@ -153,7 +160,7 @@ class LinearFunction(torch.autograd.Function):
                 # separate column-statistics pass over the L2-warm output is cheaper).
                 stats = None
                 passes = len(gemm.pairs_for(xa.n, wb.n))
-                if norm is not None and norm.mode == "bn_train" and passes * ((K + 63) // 64) >= 8:
+                if (norm is not None and norm.mode == "bn_train" and passes * ((K + 63) // 64) >= FUSED_STATS_MIN_ITERS):
                     stats = torch.empty(2, N, device=x2d.device, dtype=torch.float64)
                 Z = gemm.gemm_parts(xa, wb, K, alpha=alpha, bias=None if bias is None else _f32c(bias),
                                     stats=stats)
