@@ -216,7 +216,8 @@ SPARCH_API int sparch_recur_bwd(int kind, const float* G, const float* U, const 
  * through distributed shared memory, one per-row scale derived one step late.  H <= 1024.  Same
  * results contract as sparch_recur_bwd (reduced != 0: hi terms only).  img from sparch_recur_prepare_tc
  * (sparch_recur_bwd_tc_image_bytes bytes), meta from sparch_recur_prepare, workspace of
- * sparch_recur_bwd_tc_workspace bytes.                                                        */
+ * sparch_recur_bwd_tc_workspace bytes.  gmax_in (Be*T floats, may be NULL): row maxima of |G| when the
+ * producer of G already computed them (sparch_spike_post_bwd); NULL = computed here.              */
 SPARCH_API int sparch_recur_tc_padded(int H);
 SPARCH_API size_t sparch_recur_bwd_tc_image_bytes(int H);
 SPARCH_API size_t sparch_recur_bwd_tc_workspace(int Be, int T, int H);
@@ -228,7 +229,35 @@ SPARCH_API int sparch_recur_bwd_tc(int kind, const float* G, const float* U, con
                                    const float* u0, const float* w0, const float* s0, float theta,
                                    float* dI, float* p_alpha, float* p_beta, float* p_a,
                                    float* p_b, void* workspace, int reduced, int Be, int T, int H,
-                                   sparch_stream_t st);
+                                   const float* gmax_in, sparch_stream_t st);
+
+/* ---- around the recurrence: dropout, firing-rate counts, operand terms, parameter clamps ------- */
+/* One pass over the spike tensor S (M = Be*T rows, H columns, values exactly 0/1):
+ *   out   (M,H) fp32 = dropout(S) with keep probability 1-p_drop, kept values scaled by 1/(1-p_drop)
+ *         (snns.py:692; NULL allowed when p_drop == 0: the output is S itself);
+ *   term  (M, ld = H rounded up to 8) 16-bit {0,1}: 1 where out != 0 -- the exact one-term operand of the
+ *         next layer's projection GEMM (fp16 if fp16_terms else bf16; the factor 1/(1-p) goes in alpha);
+ *   sterm same for S itself -- the S_prev operand of this layer's dV GEMM; term/sterm may be NULL;
+ *   counts (H) int32: number of non-zero outputs per neuron (zeroed here) -- firing rate = counts *
+ *         1/(1-p) / M (snns.py:174), exact and order-independent.
+ * The mask comes from Philox4x32-10 keyed by *seed (device uint64) and the element's position, so
+ * sparch_spike_post_bwd regenerates it instead of reading a stored mask.                         */
+SPARCH_API int sparch_spike_post_fwd(const float* S, int64_t M, int H, float p_drop, const void* seed,
+                                     float* out, void* term, void* sterm, int fp16_terms, int* counts,
+                                     sparch_stream_t st);
+/* GS = G * mask / (1-p_drop) with the same mask; gmax (M floats, may be NULL; zeroed here) receives the
+ * row maxima of |GS| (input of sparch_recur_bwd_tc).                                              */
+SPARCH_API int sparch_spike_post_bwd(const float* G, int64_t M, int H, float p_drop, const void* seed,
+                                     float* GS, float* gmax, sparch_stream_t st);
+/* out[k][h] = clamp(p_k[h], lims[2k], lims[2k+1]) for k < nk (nk = 1: alpha only; 4: alpha, beta, a, b;
+ * snns.py:706-709).  lims is a HOST array of 8 floats.                                           */
+SPARCH_API int sparch_neuron_params(const float* alpha, const float* beta, const float* a, const float* b,
+                                    const float* lims, int nk, int H, float* out, sparch_stream_t st);
+/* grads[k][h] = (sum_b part[k][b][h]) * [lims[2k] <= p_k[h] <= lims[2k+1]]: batch reduction of the
+ * per-(b,h) partial parameter gradients and the clamp's backward.  lims is a HOST array.          */
+SPARCH_API int sparch_param_grads(const float* part, const float* alpha, const float* beta, const float* a,
+                                  const float* b, const float* lims, int nk, int Be, int H, float* grads,
+                                  sparch_stream_t st);
 
 /* ---- ReadoutLayer cell (snns.py:807-825) ---------------------------------------------- */
 /* u_t = alpha*u_{t-1} + (1-alpha)*I_t ; out = sum_t softmax(u_t, dim=1).  U (B,T,C) tape.  */

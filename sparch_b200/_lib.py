@@ -43,7 +43,11 @@ _PROTOS = {
     "sparch_recur_bwd_tc_image_bytes": "i",
     "sparch_recur_bwd_tc_workspace": "iii",
     "sparch_recur_prepare_tc": "pippp",
-    "sparch_recur_bwd_tc": "i" + "p" * 12 + "f" + "p" * 6 + "iiii" + "p",
+    "sparch_recur_bwd_tc": "i" + "p" * 12 + "f" + "p" * 6 + "iiii" + "pp",
+    "sparch_spike_post_fwd": "plifppppipp",
+    "sparch_spike_post_bwd": "plifpppp",
+    "sparch_neuron_params": "pppppiipp",
+    "sparch_param_grads": "ppppppiiipp",
     "sparch_readout_fwd": "p" * 7 + "iii" + "p",
     "sparch_readout_bwd": "p" * 6 + "iii" + "p",
 }

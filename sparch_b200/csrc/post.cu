@@ -1,0 +1,267 @@
+// What surrounds the membrane recurrence of a spiking layer, fused into single passes:
+//   * spike_post_fwd: dropout of the spike tensor (snns.py:692) + the per-neuron spike counts behind
+//     SNN.forward's firing rates (snns.py:174) + the 16-bit {0,1} operand terms the next layer's projection
+//     GEMM and this layer's dV GEMM read -- one read of S instead of four passes (dropout, mean, two splits);
+//   * spike_post_bwd: dropout backward with the mask REGENERATED from the counter-based generator (no mask
+//     tensor is stored) + the row maxima of the gradient that the tcgen05 reverse recurrence scales with;
+//   * neuron_params / param_grads: the clamp of alpha, beta, a, b (snns.py:706-709) and its backward (batch
+//     reduction of the per-(b,h) partial gradients + clamp mask) as one launch each instead of ~25 ATen ops.
+#include "common.cuh"
+
+namespace sparch {
+
+// Philox4x32-10 (Salmon et al. 2011): counter-based, so forward and backward draw the same mask from
+// (seed, item) without storing it.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// keep[j] for the 8 elements of work item `item` (8 consecutive columns of one row): element kept iff its
+// 32-bit draw >= thresh = p * 2^32.
+__device__ __forceinline__ void keep8(const unsigned long long* __restrict__ seed, long long item, uint32_t thresh,
+                                      bool (&keep)[8]) {
+  const unsigned long long sd = *seed;
+  const uint2 key = make_uint2((uint32_t)sd, (uint32_t)(sd >> 32));
+  const uint4 a = philox4x32_10(make_uint4((uint32_t)item, (uint32_t)((unsigned long long)item >> 32), 0u, 0u), key);
+  const uint4 b = philox4x32_10(make_uint4((uint32_t)item, (uint32_t)((unsigned long long)item >> 32), 1u, 0u), key);
+  keep[0] = a.x >= thresh; keep[1] = a.y >= thresh; keep[2] = a.z >= thresh; keep[3] = a.w >= thresh;
+  keep[4] = b.x >= thresh; keep[5] = b.y >= thresh; keep[6] = b.z >= thresh; keep[7] = b.w >= thresh;
+}
+
+__global__ void __launch_bounds__(256)
+spike_post_fwd_kernel(const float* __restrict__ S, long long M, int H, long long ld, float scale, uint32_t thresh,
+                      const unsigned long long* __restrict__ seed, float* __restrict__ out,
+                      uint16_t* __restrict__ term, uint16_t* __restrict__ sterm, uint16_t one_bits,
+                      int* __restrict__ counts, int use_hist) {
+  extern __shared__ int hist[];
+  if (counts && use_hist) {
+    for (int h = threadIdx.x; h < H; h += blockDim.x) hist[h] = 0;
+    __syncthreads();
+  }
+  const long long segs = ld / 8, n = M * segs;
+  const bool vec = ((H & 3) == 0) && ((reinterpret_cast<uintptr_t>(S) & 15) == 0) &&
+                   (!out || (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / segs;
+    const int c = (int)(i - r * segs) * 8;
+    const float* src = S + r * H + c;
+    float x[8];
+    if (vec && c + 8 <= H) {
+      const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = c + j < H ? src[j] : 0.f;
+    }
+    bool keep[8];
+    if (thresh) {
+      keep8(seed, i, thresh, keep);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) keep[j] = true;
+    }
+    float y[8];
+    __align__(16) uint16_t tb[8], sb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      y[j] = keep[j] ? x[j] * scale : 0.f;
+      tb[j] = y[j] != 0.f ? one_bits : (uint16_t)0;
+      sb[j] = x[j] != 0.f ? one_bits : (uint16_t)0;
+    }
+    if (out) {
+      float* dst = out + r * H + c;
+      if (vec && c + 8 <= H) {
+        *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c + j < H) dst[j] = y[j];
+      }
+    }
+    if (term) *reinterpret_cast<uint4*>(term + r * ld + c) = *reinterpret_cast<const uint4*>(tb);
+    if (sterm) *reinterpret_cast<uint4*>(sterm + r * ld + c) = *reinterpret_cast<const uint4*>(sb);
+    if (counts) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (y[j] != 0.f) atomicAdd(use_hist ? &hist[c + j] : &counts[c + j], 1);
+    }
+  }
+  if (counts && use_hist) {
+    __syncthreads();
+    for (int h = threadIdx.x; h < H; h += blockDim.x)
+      if (hist[h]) atomicAdd(&counts[h], hist[h]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+spike_post_bwd_kernel(const float* __restrict__ G, long long M, int H, float scale, uint32_t thresh,
+                      const unsigned long long* __restrict__ seed, float* __restrict__ GS, uint32_t* __restrict__ gmax) {
+  const long long segs = (H + 7) / 8, n = M * segs;
+  const bool vec = ((H & 3) == 0) && ((reinterpret_cast<uintptr_t>(G) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(GS) & 15) == 0);
+  const long long total = (n + 31) / 32 * 32;  // whole warps walk the loop (shuffles below)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const bool on = i < n;
+    const long long r = on ? i / segs : -1;
+    const int c = on ? (int)(i - r * segs) * 8 : 0;
+    float m = 0.f;
+    if (on) {
+      const float* src = G + r * H + c;
+      float x[8];
+      if (vec && c + 8 <= H) {
+        const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = c + j < H ? src[j] : 0.f;
+      }
+      bool keep[8];
+      keep8(seed, i, thresh, keep);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        x[j] = keep[j] ? x[j] * scale : 0.f;
+        m = fmaxf(m, fabsf(x[j]));
+      }
+      float* dst = GS + r * H + c;
+      if (vec && c + 8 <= H) {
+        *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c + j < H) dst[j] = x[j];
+      }
+    }
+    if (gmax) {
+      // one atomic per warp when all its items sit in the same row (H a multiple of 256), else per thread
+      const long long r0 = __shfl_sync(0xffffffffu, r, 0);
+      if (__all_sync(0xffffffffu, r == r0)) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0 && on && m > 0.f) atomicMax(&gmax[r], __float_as_uint(m));
+      } else if (on && m > 0.f) {
+        atomicMax(&gmax[r], __float_as_uint(m));
+      }
+    }
+  }
+}
+
+// out[k][h] = clamp(p_k[h], lo_k, hi_k) for the given parameter vectors (NULL = skipped), torch.clamp semantics.
+struct ParamSet {
+  const float* p[4];
+  float lo[4], hi[4];
+};
+
+__global__ void neuron_params_kernel(const ParamSet ps, int nk, int H, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nk * H) return;
+  const int k = i / H, h = i - k * H;
+  const float x = ps.p[k][h];
+  out[i] = x != x ? x : fminf(fmaxf(x, ps.lo[k]), ps.hi[k]);
+}
+
+// grads[k][h] = (sum_b part[k][b][h]) * [lo_k <= p_k[h] <= hi_k]   (clamp backward passes on the closed interval)
+__global__ void __launch_bounds__(256) param_grads_kernel(const float* __restrict__ part, const ParamSet ps, int nk, int Be,
+                                                          int H, float* __restrict__ grads) {
+  __shared__ float red[8][33];
+  const int k = blockIdx.y, h = blockIdx.x * 32 + threadIdx.x, ry = threadIdx.y;
+  float s = 0.f;
+  if (h < H)
+    for (int b = ry; b < Be; b += 8) s += part[((size_t)k * Be + b) * H + h];
+  red[ry][threadIdx.x] = s;
+  __syncthreads();
+  if (ry == 0 && h < H) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
+    const float x = ps.p[k][h];
+    grads[(size_t)k * H + h] = (x >= ps.lo[k] && x <= ps.hi[k]) ? t : 0.f;
+  }
+}
+
+}  // namespace sparch
+
+using namespace sparch;
+
+extern "C" {
+
+int sparch_spike_post_fwd(const float* S, int64_t M, int H, float p_drop, const void* seed, float* out, void* term,
+                          void* sterm, int fp16_terms, int* counts, sparch_stream_t st_) {
+  SPARCH_REQUIRE(M >= 0 && H > 0 && p_drop >= 0.f && p_drop < 1.f, "bad argument");
+  SPARCH_REQUIRE(p_drop == 0.f || (seed && out), "dropout needs the seed word and an output tensor");
+  cudaStream_t st = as_stream(st_);
+  if (counts) SPARCH_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * H, st));
+  if (M == 0) return SPARCH_OK;
+  SPARCH_REQUIRE(S, "null pointer");
+  const int64_t ld = ((int64_t)H + 7) / 8 * 8;
+  const int64_t n = M * (ld / 8);
+  int64_t g = (n + 255) / 256, cap = (int64_t)sm_count() * 8;
+  const int use_hist = counts && H <= 8192;
+  const uint32_t thresh = p_drop > 0.f ? (uint32_t)fmin((double)p_drop * 4294967296.0, 4294967295.0) : 0u;
+  spike_post_fwd_kernel<<<(unsigned)(g < cap ? g : cap), 256, use_hist ? sizeof(int) * H : 0, st>>>(
+      S, M, H, ld, 1.0f / (1.0f - p_drop), thresh, reinterpret_cast<const unsigned long long*>(seed), out,
+      reinterpret_cast<uint16_t*>(term), reinterpret_cast<uint16_t*>(sterm), fp16_terms ? (uint16_t)0x3C00 : (uint16_t)0x3F80,
+      counts, use_hist);
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+int sparch_spike_post_bwd(const float* G, int64_t M, int H, float p_drop, const void* seed, float* GS, float* gmax,
+                          sparch_stream_t st_) {
+  SPARCH_REQUIRE(M >= 0 && H > 0 && p_drop > 0.f && p_drop < 1.f && seed, "bad argument");
+  cudaStream_t st = as_stream(st_);
+  if (gmax && M > 0) SPARCH_CUDA(cudaMemsetAsync(gmax, 0, sizeof(float) * M, st));
+  if (M == 0) return SPARCH_OK;
+  SPARCH_REQUIRE(G && GS, "null pointer");
+  const int64_t n = M * (((int64_t)H + 7) / 8);
+  int64_t g = (n + 255) / 256, cap = (int64_t)sm_count() * 8;
+  const uint32_t thresh = (uint32_t)fmin((double)p_drop * 4294967296.0, 4294967295.0);
+  spike_post_bwd_kernel<<<(unsigned)(g < cap ? g : cap), 256, 0, st>>>(G, M, H, 1.0f / (1.0f - p_drop), thresh,
+                                                                        reinterpret_cast<const unsigned long long*>(seed),
+                                                                        GS, reinterpret_cast<uint32_t*>(gmax));
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+static ParamSet make_param_set(const float* alpha, const float* beta, const float* a, const float* b, const float* lims,
+                               int nk) {
+  ParamSet ps;
+  const float* p[4] = {alpha, beta, a, b};
+  for (int k = 0; k < 4; ++k) {
+    ps.p[k] = k < nk ? p[k] : nullptr;
+    ps.lo[k] = lims[2 * k];
+    ps.hi[k] = lims[2 * k + 1];
+  }
+  return ps;
+}
+
+int sparch_neuron_params(const float* alpha, const float* beta, const float* a, const float* b, const float* lims,
+                         int nk, int H, float* out, sparch_stream_t st) {
+  SPARCH_REQUIRE((nk == 1 || nk == 4) && H > 0 && alpha && lims && out && (nk == 1 || (beta && a && b)), "bad argument");
+  const ParamSet ps = make_param_set(alpha, beta, a, b, lims, nk);
+  neuron_params_kernel<<<(nk * H + 255) / 256, 256, 0, as_stream(st)>>>(ps, nk, H, out);
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+int sparch_param_grads(const float* part, const float* alpha, const float* beta, const float* a, const float* b,
+                       const float* lims, int nk, int Be, int H, float* grads, sparch_stream_t st) {
+  SPARCH_REQUIRE((nk == 1 || nk == 4) && H > 0 && Be >= 0 && alpha && lims && grads && (Be == 0 || part) &&
+                     (nk == 1 || (beta && a && b)),
+                 "bad argument");
+  const ParamSet ps = make_param_set(alpha, beta, a, b, lims, nk);
+  param_grads_kernel<<<dim3((H + 31) / 32, nk), dim3(32, 8), 0, as_stream(st)>>>(part, ps, nk, Be, H, grads);
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+}  // extern "C"

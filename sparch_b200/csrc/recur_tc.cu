@@ -513,7 +513,7 @@ int sparch_recur_bwd_tc(int kind, const float* G, const float* U, const float* W
                         const float* beta, const float* a, const float* b, const void* img, const int* meta,
                         const float* u0, const float* w0, const float* s0, float theta, float* dI, float* p_alpha,
                         float* p_beta, float* p_a, float* p_b, void* workspace, int reduced, int Be, int T, int H,
-                        sparch_stream_t st_) {
+                        const float* gmax_in, sparch_stream_t st_) {
   SPARCH_REQUIRE(kind == SPARCH_RLIF || kind == SPARCH_RADLIF, "recurrent kinds only");
   SPARCH_REQUIRE(Be >= 0 && T >= 0 && H > 0, "bad shape");
   if (Be == 0 || T == 0) return SPARCH_OK;
@@ -541,7 +541,9 @@ int sparch_recur_bwd_tc(int kind, const float* G, const float* U, const float* W
   int* counters = reinterpret_cast<int*>(gmax + (size_t)Be * T);
   SPARCH_CUDA(cudaMemsetAsync(ws, 0, 2 * panel_bytes, st));  // rows beyond Be / columns beyond H read as zero
   SPARCH_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * groups, st));
-  {
+  if (gmax_in) {  // the producer of G already left the row maxima (sparch_spike_post_bwd)
+    gmax = const_cast<float*>(gmax_in);
+  } else {
     const int64_t warps = (int64_t)Be * T;
     gmax_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(G, Be, T, H, gmax);
     SPARCH_LAUNCH_OK();

@@ -5,6 +5,7 @@ loops (sparch/models/snns.py:282-303, 419-445, 554-578, 696-727, 807-825) and it
 ``SpikeFunctionBoxcar`` (snns.py:20-36).  Inputs must be CUDA fp32 tensors: there is no
 CPU path (``RuntimeError`` otherwise).
 """
+import ctypes
 import math
 import os
 
@@ -20,6 +21,7 @@ ALPHA_LIM = (math.exp(-1 / 5), math.exp(-1 / 25))
 BETA_LIM = (math.exp(-1 / 30), math.exp(-1 / 120))
 A_LIM = (-1.0, 1.0)
 B_LIM = (0.0, 2.0)
+_LIMS = (ctypes.c_float * 8)(*ALPHA_LIM, *BETA_LIM, *A_LIM, *B_LIM)   # host array for the C ABI
 
 
 def _stream():
@@ -140,9 +142,11 @@ class LinearFunction(torch.autograd.Function):
     dropout) so that one exact bf16 term {0,1} suffices and c moves into the epilogue."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, in_scale, norm=None):
-        """norm: the layer's NormState; in 'bn_train' mode the GEMM epilogue also accumulates the
-        BatchNorm column statistics of the output and leaves them in ``norm.stats``."""
+    def forward(ctx, x, weight, bias, in_scale, norm=None, x_terms=None):
+        """norm: the layer's NormState; in 'bn_train' mode the GEMM epilogue can also accumulate the
+        BatchNorm column statistics of the output and leave them in ``norm.stats``.
+        x_terms: the one-term {0,1} image of x (x = in_scale * x_terms) when the producing layer's
+        post pass already wrote it (SpikePost): no split pass over x."""
         _require_cuda(x, weight)
         K = x.shape[-1]
         N = weight.shape[0]
@@ -150,7 +154,9 @@ class LinearFunction(torch.autograd.Function):
         M = x2d.shape[0]
         with torch.no_grad():
             with _region("gemm_fwd"):
-                if in_scale is None:
+                if x_terms is not None and in_scale is not None:
+                    xa, alpha = x_terms, float(in_scale)
+                elif in_scale is None:
                     xa, alpha = gemm.split_general(x2d), 1.0
                 else:
                     xa, alpha = gemm.split_binary(x2d, prescale=1.0 / in_scale), float(in_scale)
@@ -192,7 +198,7 @@ class LinearFunction(torch.autograd.Function):
                 dw = gemm.gemm_parts(ga, xa, M, alpha=ctx.alpha, a_mn=True, b_mn=True, M=N, N=K)
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 db = g2d.sum(dim=0)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
 class NormState:
@@ -210,6 +216,10 @@ class NormState:
         self.momentum = momentum
         self.stats = None   # (2, H) float64 column sum / sum of squares when the projection GEMM fused them
         self.dz_amax = None  # (1,) int32 bit pattern of max|dZ| left by the BatchNorm backward for the fp16 split
+        # per-call hand-overs between the cell Function and SpikePostFunction (which runs after it in the
+        # forward and before it in the backward):
+        self.sterm = None    # gemm.Terms: the {0,1} 16-bit image of S, the S_prev operand of dV
+        self.gmax = None     # (Be*T,) row maxima of |dL/dS| for the tcgen05 reverse recurrence
 
 
 def _fold_norm(Z2d, gamma, bn_beta, norm):
@@ -290,11 +300,12 @@ class SpikingCellFunction(torch.autograd.Function):
         Be, T, H = Z.shape
         dev = Z.device
         st = _stream()
+        alpha, beta, a, b = _f32c(alpha), _f32c(beta), _f32c(a), _f32c(b)
         with torch.no_grad():
-            al = alpha.clamp(*ALPHA_LIM)
-            be = beta.clamp(*BETA_LIM) if adaptive else None
-            aa = a.clamp(*A_LIM) if adaptive else None
-            bb = b.clamp(*B_LIM) if adaptive else None
+            cl = torch.empty(4 if adaptive else 1, H, device=dev, dtype=torch.float32)   # snns.py:706-709
+            call("sparch_neuron_params", ptr(alpha), ptr(beta), ptr(a), ptr(b), _LIMS, cl.shape[0], H, ptr(cl), st)
+            al, be, aa, bb = cl[0], (cl[1] if adaptive else None), (cl[2] if adaptive else None), \
+                (cl[3] if adaptive else None)
             V0 = V.detach().clone().fill_diagonal_(0) if recurrent else None  # snns.py:712
             u0, w0, s0 = _f32c(u0), _f32c(w0) if adaptive else None, _f32c(s0)
             Z2d = Z.view(Be * T, H)
@@ -381,7 +392,7 @@ class SpikingCellFunction(torch.autograd.Function):
             ws = torch.empty(_lib.lib().sparch_recur_bwd_tc_workspace(Be, T, H), device=dev, dtype=torch.uint8)
             call("sparch_recur_bwd_tc", k, ptr(G), ptr(U), ptr(Wt), ptr(al), ptr(be), ptr(aa), ptr(bb),
                  ptr(img_b), ptr(meta), ptr(u0), ptr(w0), ptr(s0), theta, ptr(dI), pp[0], pp[1], pp[2],
-                 pp[3], ptr(ws), ctx.reduced, Be, T, H, st)
+                 pp[3], ptr(ws), ctx.reduced, Be, T, H, ptr(norm.gmax), st)
         else:
             img_b, meta = ctx.rec
             ws = torch.empty(_lib.lib().sparch_recur_bwd_workspace(Be, H), device=dev, dtype=torch.uint8)
@@ -401,20 +412,100 @@ class SpikingCellFunction(torch.autograd.Function):
                     first[1:] -= S[:-1, T - 1, :]
                 dV = first.t() @ dI[:, 0, :]
                 if Be * T > 1:
-                    sp = gemm.split_binary(S.view(Be * T, H))
+                    sp = norm.sterm if norm.sterm is not None else gemm.split_binary(S.view(Be * T, H))
                     dit = gemm.split_general(dI.view(Be * T, H))
                     dV += gemm.gemm_parts(sp, dit, Be * T, a_mn=True, b_mn=True, a_koff=-1, M=H, N=H)
                 dV.fill_diagonal_(0)
-        psum = part.sum(dim=1)
-        dalpha = psum[0] * _clamp_mask(alpha, ALPHA_LIM)
-        dbeta = da = db = None
-        if adaptive:
-            dbeta = psum[1] * _clamp_mask(beta, BETA_LIM)
-            da = psum[2] * _clamp_mask(a, A_LIM)
-            db = psum[3] * _clamp_mask(b, B_LIM)
+        norm.gmax = None     # consumed: belongs to this backward pass only
+        pg = torch.empty(npart, H, device=dev, dtype=torch.float32)
+        call("sparch_param_grads", ptr(part), ptr(alpha), ptr(beta), ptr(a), ptr(b), _LIMS, npart, Be, H, ptr(pg), st)
+        dalpha = pg[0]
+        dbeta, da, db = (pg[1], pg[2], pg[3]) if adaptive else (None, None, None)
         dgamma, dbnb = _norm_backward(dI.view(Be * T, H), Z.view(Be * T, H), gamma, bn_beta, norm,
                                       scale, mean, rstd)
         return (dI, dgamma, dbnb, dalpha, dbeta, da, db, dV, None, None, None, None, None, None)
+
+
+class SpikePost:
+    """What the post pass of a spiking layer leaves for its consumers: the next projection's operand
+    (``terms``, x = scale * terms) and the per-neuron counts of non-zero outputs."""
+    __slots__ = ("terms", "counts", "scale", "rows")
+
+    def __init__(self, terms, counts, scale, rows):
+        self.terms, self.counts, self.scale, self.rows = terms, counts, scale, rows
+
+    def rates(self, out):
+        """Per-neuron mean of the layer output over (batch, time) (snns.py:174), differentiable in ``out``."""
+        return FiringRateFunction.apply(out, self.counts, self.scale / self.rows)
+
+
+class FiringRateFunction(torch.autograd.Function):
+    """mean over (B, T) of a spike tensor whose non-zero values all equal ``scale * rows``, from integer counts."""
+
+    @staticmethod
+    def forward(ctx, out, counts, factor):
+        ctx.shape = out.shape
+        return counts.to(torch.float32) * factor
+
+    @staticmethod
+    def backward(ctx, g):
+        B, T, H = ctx.shape
+        return (g / (B * T)).expand(B, T, H), None, None
+
+
+class _DropoutPostFunction(torch.autograd.Function):
+    """Dropout of the spike tensor (snns.py:692) fused with the counts / operand terms (csrc/post.cu).  The
+    backward regenerates the mask from the seed and also leaves the row maxima of the result for the tcgen05
+    reverse recurrence in ``cell_state.gmax``."""
+
+    @staticmethod
+    def forward(ctx, S, p, seed, out_bufs, cell_state, want_gmax):
+        Be, T, H = S.shape
+        out, term, sterm, counts = out_bufs
+        call("sparch_spike_post_fwd", ptr(S), Be * T, H, float(p), ptr(seed), ptr(out), ptr(term), ptr(sterm),
+             int(term.dtype == torch.float16), ptr(counts), _stream())
+        ctx.p, ctx.seed, ctx.cell_state, ctx.want_gmax = float(p), seed, cell_state, want_gmax
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _f32c(g)
+        Be, T, H = g.shape
+        gS = torch.empty_like(g)
+        gmax = torch.empty(Be * T, device=g.device, dtype=torch.float32) if ctx.want_gmax else None
+        call("sparch_spike_post_bwd", ptr(g), Be * T, H, ctx.p, ptr(ctx.seed), ptr(gS), ptr(gmax), _stream())
+        ctx.cell_state.gmax = gmax
+        return gS, None, None, None, None, None
+
+
+def spike_post(S, p, cell_state, recurrent):
+    """Post pass of a spiking layer: returns (out, SpikePost).  p: dropout probability in effect (0 in eval
+    mode).  cell_state: the NormState the layer's cell Function was called with."""
+    _require_cuda(S)
+    S = _f32c(S)
+    Be, T, H = S.shape
+    M, ld, dev = Be * T, (H + 7) // 8 * 8, S.device
+    dt = torch.float16 if gemm.MODE == "f16x2" else torch.bfloat16
+    term = torch.empty(1, M, ld, device=dev, dtype=dt)
+    counts = torch.empty(H, device=dev, dtype=torch.int32)
+    need_grad = torch.is_grad_enabled() and S.requires_grad
+    if p > 0.0:
+        sterm = torch.empty(1, M, ld, device=dev, dtype=dt) if (recurrent and need_grad) else None
+        seed = torch.empty(1, device=dev, dtype=torch.int64).random_()     # device generator, as nn.Dropout
+        out = torch.empty_like(S)
+        want_gmax = recurrent and RECUR_BWD == "tc" and H <= RECUR_TC_MAX_H
+        out = _DropoutPostFunction.apply(S, p, seed, (out, term, sterm, counts), cell_state, want_gmax)
+        if sterm is not None:
+            cell_state.sterm = gemm.Terms(sterm)
+        scale = 1.0 / (1.0 - p)
+    else:
+        with torch.no_grad():
+            call("sparch_spike_post_fwd", ptr(S), M, H, 0.0, None, None, ptr(term), None,
+                 int(dt == torch.float16), ptr(counts), _stream())
+        if recurrent and need_grad:
+            cell_state.sterm = gemm.Terms(term)
+        out, scale = S, 1.0
+    return out, SpikePost(gemm.Terms(term), counts, scale, M)
 
 
 class ReadoutCellFunction(torch.autograd.Function):
@@ -426,8 +517,10 @@ class ReadoutCellFunction(torch.autograd.Function):
         Z = _f32c(Z)
         B, T, C = Z.shape
         st = _stream()
+        alpha = _f32c(alpha)
         with torch.no_grad():
-            al = alpha.clamp(*ALPHA_LIM)
+            al = torch.empty(C, device=Z.device, dtype=torch.float32)
+            call("sparch_neuron_params", ptr(alpha), None, None, None, _LIMS, 1, C, ptr(al), st)
             u0 = _f32c(u0)
             scale, shift, mean, rstd = _fold_norm(Z.view(B * T, C), gamma, bn_beta, norm)
             out = torch.empty(B, C, device=Z.device, dtype=torch.float32)
@@ -447,7 +540,8 @@ class ReadoutCellFunction(torch.autograd.Function):
         dI = torch.empty_like(Z)
         part = torch.empty(B, C, device=Z.device, dtype=torch.float32)
         call("sparch_readout_bwd", ptr(g), ptr(U), ptr(al), ptr(u0), ptr(dI), ptr(part), B, T, C, st)
-        dalpha = part.sum(dim=0) * _clamp_mask(alpha, ALPHA_LIM)
+        dalpha = torch.empty(C, device=Z.device, dtype=torch.float32)
+        call("sparch_param_grads", ptr(part), ptr(alpha), None, None, None, _LIMS, 1, B, C, ptr(dalpha), st)
         dgamma, dbnb = _norm_backward(dI.view(B * T, C), Z.view(B * T, C), gamma, bn_beta, ctx.norm,
                                       scale, mean, rstd)
         return dI, dgamma, dbnb, dalpha, None, None

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from .functional import (LinearFunction, NormState, ReadoutCellFunction, SpikeFunctionBoxcar,
-                         SpikingCellFunction)
+                         SpikingCellFunction, spike_post)
 
 # Where the per-forward initial states u_{-1}, w_{-1}, s_{-1} ~ U[0,1) are drawn.
 #   "cpu"    (default): torch.rand on the CPU default generator, then copied to the device --
@@ -119,25 +119,40 @@ class _SpikingLayerBase(nn.Module):
             self.normalize = True
         self.drop = nn.Dropout(p=dropout)
 
-    def forward(self, x, in_scale=None):
+    def forward(self, x, in_scale=None, x_terms=None, post_out=None):
         """``in_scale``: None for a general input; c when every input value is exactly 0 or c
-        (the previous spiking layer's output), which lets the projection use one exact bf16 term."""
+        (the previous spiking layer's output), which lets the projection use one exact 16-bit term.
+        ``x_terms`` / ``post_out`` (used by SNN.forward): the previous layer's ``SpikePost.terms``, and a list
+        that receives this layer's ``SpikePost`` (or None)."""
+        out, post = self._forward_post(x, in_scale, x_terms)
+        if post_out is not None:
+            post_out.append(post)
+        return out
+
+    def _forward_post(self, x, in_scale=None, x_terms=None):
+        """forward() plus what the layer's post pass leaves for the next layer and for the firing rates
+        (``functional.SpikePost`` or None); ``x_terms``: the previous layer's ``SpikePost.terms``."""
         if not x.is_cuda:
             raise RuntimeError("sparch_b200 layers run on CUDA only (no CPU fallback)")
         if self.bidirectional:                                   # snns.py:666-668
             x = torch.cat([x, x.flip(1)], dim=0)
+            x_terms = None
         if self.batch_size != x.shape[0]:                        # snns.py:671-672
             self.batch_size = x.shape[0]
         gamma, bn_beta, norm = _norm_args(self)
-        Wx = LinearFunction.apply(x, self.W.weight, self.W.bias, in_scale, norm)   # snns.py:675
+        Wx = LinearFunction.apply(x, self.W.weight, self.W.bias, in_scale, norm, x_terms)   # snns.py:675
         if norm is None:                                         # layernorm, snns.py:678-680
             Wx = self.norm(Wx)
             norm = NormState("none")
         s = self._cell(Wx, gamma, bn_beta, norm)
-        if self.bidirectional:                                   # snns.py:686-689
-            s_f, s_b = s.chunk(2, dim=0)
-            s = torch.cat([s_f, s_b.flip(1)], dim=2)
-        return self.drop(s)                                      # snns.py:692
+        p = self.drop.p if self.drop.training else 0.0
+        if self.bidirectional or p >= 1.0:
+            if self.bidirectional:                               # snns.py:686-689
+                s_f, s_b = s.chunk(2, dim=0)
+                s = torch.cat([s_f, s_b.flip(1)], dim=2)
+            return self.drop(s), None                            # snns.py:692
+        # dropout (snns.py:692) + spike counts + the next projection's operand in one pass over s
+        return spike_post(s, p, norm, self._recurrent)
 
     def _cell(self, Wx, gamma, bn_beta, norm):
         device = Wx.device
@@ -215,11 +230,11 @@ class ReadoutLayer(nn.Module):
             self.normalize = True
         self.drop = nn.Dropout(p=dropout)  # constructed but never applied, as in the reference
 
-    def forward(self, x, in_scale=None):
+    def forward(self, x, in_scale=None, x_terms=None):
         if not x.is_cuda:
             raise RuntimeError("sparch_b200 layers run on CUDA only (no CPU fallback)")
         gamma, bn_beta, norm = _norm_args(self)
-        Wx = LinearFunction.apply(x, self.W.weight, self.W.bias, in_scale, norm)   # snns.py:796
+        Wx = LinearFunction.apply(x, self.W.weight, self.W.bias, in_scale, norm, x_terms)   # snns.py:796
         if norm is None:
             Wx = self.norm(Wx)
             norm = NormState("none")
@@ -285,16 +300,23 @@ class SNN(nn.Module):
                 x = x.reshape(x.shape[0], x.shape[1], x.shape[2] * x.shape[3])
             else:
                 raise NotImplementedError
-        all_spikes = []
+        rates = []
         in_scale = None          # the network input is a general fp32 tensor
+        post = None              # the previous spiking layer's post pass (operand terms, spike counts)
         for i, snn_lay in enumerate(self.snn):
-            x = snn_lay(x, in_scale=in_scale)
+            x_terms = post.terms if post is not None else None
             if not (self.use_readout_layer and i == self.num_layers - 1):
-                all_spikes.append(x)
+                holder = []
+                x = snn_lay(x, in_scale=in_scale, x_terms=x_terms, post_out=holder)   # __call__: hooks fire
+                post = holder[0]
+                # snns.py:174 takes cat(all_spikes, dim=2).mean(dim=(0, 1)); the per-neuron means are the same
+                # without materialising the concatenated (B, T, sum H) tensor -- from the post pass's integer
+                # counts when there is one
+                rates.append(post.rates(x) if post is not None else x.mean(dim=(0, 1)))
                 # a spiking layer emits exactly {0, 1/(1-p)} in training and {0, 1} otherwise
                 p = snn_lay.drop.p
                 in_scale = 1.0 / (1.0 - p) if (snn_lay.drop.training and 0.0 < p < 1.0) else 1.0
-        # snns.py:174 takes cat(all_spikes, dim=2).mean(dim=(0, 1)); the per-neuron means are the same
-        # without materialising the concatenated (B, T, sum H) tensor
-        firing_rates = torch.cat([s.mean(dim=(0, 1)) for s in all_spikes], dim=0)
+            else:
+                x = snn_lay(x, in_scale=in_scale, x_terms=x_terms)
+        firing_rates = torch.cat(rates, dim=0)
         return x, firing_rates

@@ -619,3 +619,72 @@ def test_readout_cell_against_oracle(B, T, C):
     assert rel_err(out.detach().cpu().numpy(), f["out"]) < 1e-5
     assert rel_err(It.grad.cpu().numpy(), bw["dI"]) < G_RTOL
     assert rel_err(al.grad.cpu().numpy(), bw["dalpha"]) < 5e-5
+
+
+@pytest.mark.parametrize("Be,T,H,p", [(4, 25, 1024, 0.25), (3, 7, 37, 0.5), (2, 5, 256, 0.1), (5, 9, 40, 0.0)])
+def test_spike_post_pass(Be, T, H, p):
+    """Fused dropout + counts + operand terms (csrc/post.cu): values, mask statistics, the mask the backward
+    regenerates, the row maxima it leaves, and the differentiable firing rates (snns.py:174, 692)."""
+    _, F = _mods()
+    from sparch_b200 import gemm
+    g = torch.Generator(device=DEV).manual_seed(Be * H)
+    S = (torch.rand(Be, T, H, device=DEV, generator=g) < 0.3).float().requires_grad_(True)
+    st = F.NormState("none")
+    torch.manual_seed(7)
+    out, post = F.spike_post(S, p, st, recurrent=True)
+    scale = 1.0 / (1.0 - p)
+    o = out.detach()
+    assert torch.all((o == 0) | ((o - scale).abs() < 1e-6))
+    assert torch.all(o[S.detach() == 0] == 0)
+    nspk = float(S.detach().sum())
+    kept = float((o != 0).sum()) / nspk
+    assert abs(kept - (1 - p)) < 4 * (p * (1 - p) / nspk) ** 0.5 + 1e-9, kept
+    ld = (H + 7) // 8 * 8
+    one = post.terms.parts.dtype
+    assert post.terms.parts.shape == (1, Be * T, ld) and one == (torch.float16 if gemm.MODE == "f16x2" else torch.bfloat16)
+    assert torch.equal(post.terms.parts[0, :, :H].float().view(Be, T, H), (o != 0).float())
+    assert float(post.terms.parts[0, :, H:].abs().sum()) == 0
+    assert torch.equal(st.sterm.parts[0, :, :H].float().view(Be, T, H), S.detach())
+    assert torch.equal(post.counts.long(), (o != 0).sum(dim=(0, 1)))
+    rates = post.rates(out)
+    assert rel_err(rates.detach().cpu().numpy(), o.mean(dim=(0, 1)).cpu().numpy()) < 1e-6
+    gup = torch.randn(Be, T, H, device=DEV, generator=g)
+    grate = torch.randn(H, device=DEV, generator=g)
+    ((out * gup).sum() + (rates * grate).sum()).backward()
+    gin = gup + grate / (Be * T)
+    mask = (o != 0).float() if p > 0 else torch.ones_like(o)
+    # positions where S == 0 carry no information about the mask in the forward output: compare where S == 1
+    sel = S.detach() == 1
+    want = gin * mask * scale
+    assert rel_err(S.grad[sel].cpu().numpy(), want[sel].cpu().numpy()) < 1e-6
+    if p > 0:
+        zero_frac = float((S.grad[~sel] == 0).float().mean())
+        assert abs(zero_frac - p) < 4 * (p * (1 - p) / float((~sel).sum())) ** 0.5, zero_frac
+        assert st.gmax is not None
+        np.testing.assert_allclose(st.gmax.view(Be, T).cpu().numpy(), S.grad.abs().amax(dim=2).cpu().numpy(), rtol=0, atol=0)
+        # a second draw uses a new seed
+        out2, _ = F.spike_post(S, p, F.NormState("none"), recurrent=False)
+        assert not torch.equal(out2, out)
+
+
+def test_param_clamp_and_grad_kernels():
+    _, F = _mods()
+    from sparch_b200._lib import call, ptr
+    H, Be = 77, 19
+    g = torch.Generator(device=DEV).manual_seed(4)
+    ps = [torch.rand(H, device=DEV, generator=g) * 1.4 - 0.2 for _ in range(4)]
+    ps[2] = ps[2] * 3 - 1.5
+    ps[0][3] = F.ALPHA_LIM[0]        # exactly on the boundary: gradient passes (closed interval)
+    out = torch.empty(4, H, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    call("sparch_neuron_params", ptr(ps[0]), ptr(ps[1]), ptr(ps[2]), ptr(ps[3]), F._LIMS, 4, H, ptr(out), st)
+    lims = (F.ALPHA_LIM, F.BETA_LIM, F.A_LIM, F.B_LIM)
+    for k in range(4):
+        assert torch.equal(out[k], ps[k].clamp(*lims[k]))
+    part = torch.randn(4, Be, H, device=DEV, generator=g)
+    grads = torch.empty(4, H, device=DEV)
+    call("sparch_param_grads", ptr(part), ptr(ps[0]), ptr(ps[1]), ptr(ps[2]), ptr(ps[3]), F._LIMS, 4, Be, H, ptr(grads), st)
+    for k in range(4):
+        ref = orc.clamp_grad_mask(ps[k].cpu().numpy(), lims[k]) * part[k].double().sum(0).cpu().numpy()
+        assert rel_err(grads[k].cpu().numpy(), ref) < 1e-6
+    assert float(grads[0][3]) != 0.0
