@@ -200,7 +200,7 @@ def run_ours(args, cfg, rank, local_rank, world):
                 if hasattr(lay, "a"):
                     lay.a.abs_()
     net.train()
-    use_graph = args.graph and world == 1 and args.state_init == "device"
+    use_graph = (not args.no_graph) and args.state_init == "device"
     # exp.py:89's Adam; fused=True is the same update in one multi-tensor kernel
     opt = torch.optim.Adam(net.parameters(), 1e-2, capturable=use_graph, fused=True)
     sync = parallel.GradSync(net) if world > 1 else None
@@ -222,7 +222,7 @@ def run_ours(args, cfg, rank, local_rank, world):
     graphed = None
     if use_graph:
         from sparch_b200.graphs import GraphedTrainStep
-        graphed = GraphedTrainStep(net, opt, loss_fn, x_d, y_d)
+        graphed = GraphedTrainStep(net, opt, loss_fn, x_d, y_d, sync=sync)
         eager_step = step
 
         def step(x, y):                                       # noqa: F811
@@ -277,6 +277,14 @@ def run_ours(args, cfg, rank, local_rank, world):
     rec_ms = F.timers_collect()                               # {"recurrence_fwd": ms, ...} totals
     F.timers_enable(False)
     value = world * B * args.steps / (ms * 1e-3)
+    if graphed is not None:
+        # CUDA events cannot be placed inside a replayed graph: the per-kernel durations behind the roofline come
+        # from the same steps issued eagerly (same kernels, same buffers) right after the timed region
+        F.timers_enable(True)
+        for _ in range(args.steps):
+            eager_step(x_d, y_d)
+        rec_ms = F.timers_collect()
+        F.timers_enable(False)
 
     # ---- end to end: pinned host batch -> device, loss read back every step ------------------
     def e2e_step():
@@ -299,7 +307,11 @@ def run_ours(args, cfg, rank, local_rank, world):
     clocks = sampler.stop() if rank == 0 else None            # samples cover the timed + e2e (+ filler) load
 
     if rank != 0:
-        return
+        # Hard exit: tearing down a process group whose collectives live inside a captured CUDA graph was seen to
+        # hang at interpreter exit; this rank's measured work is complete and synchronised.
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
     # ---- roofline of the recurrence kernels (16.5 B per (b,t,h) per spiking layer)
     peaks = {}
     try:
@@ -328,7 +340,10 @@ def run_ours(args, cfg, rank, local_rank, world):
                 "ms_bwd": rec_ms.get("recurrence_bwd", 0.0) / args.steps, "algorithmic_bytes_per_step": alg_bytes,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "share_of_step": rec_total_ms / (ms / args.steps) if rec_total_ms else None,
-                "note": "the recurrence is bounded by its 2*T dependent steps per layer (latency + legacy-HMMA "
+                "timed": ("CUDA events around the recurrence launches of the same steps issued eagerly right after "
+                          "the graphed timed region") if graphed is not None else
+                         "CUDA events around the recurrence launches inside the timed region",
+                "note": "the recurrence is bounded by its 2*T dependent steps per layer (exchange latency + tensor "
                         "issue), not by HBM: see DESIGN.md section 5 for the latency floor"}
 
     # ---- CPU baseline beside it (bounded sample: the full config batch, 2 timed steps) --------
@@ -360,7 +375,8 @@ def run_ours(args, cfg, rank, local_rank, world):
     }
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        sys.stderr.flush()
+        os._exit(0)                                           # see the note at the other ranks' exit
 
 
 def main():
@@ -378,8 +394,9 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"],
                     help="fp32 (default, the reference's arithmetic to ~1e-6) or the reduced-precision mode")
     ap.add_argument("--graph", action="store_true",
-                    help="replay the whole train step as one CUDA graph (sparch_b200.graphs.GraphedTrainStep; "
-                         "single GPU, device state init)")
+                    help="(default) replay the whole train step -- forward, loss, backward, gradient all-reduce, "
+                         "Adam -- as one CUDA graph (sparch_b200.graphs.GraphedTrainStep; needs device state init)")
+    ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly, launch by launch")
     ap.add_argument("--profile", action="store_true",
                     help="profiling run (under ncu): exactly --warmup warm-up and --steps timed steps of "
                          "the device-resident loop, no e2e leg, no CPU baseline; prints no bench value")

@@ -17,12 +17,15 @@ from . import snns
 
 
 class GraphedTrainStep:
-    def __init__(self, net, optimizer, loss_fn, x_example, y_example, warmup=3):
+    def __init__(self, net, optimizer, loss_fn, x_example, y_example, warmup=3, sync=None):
+        """sync: a ``parallel.GradSync`` (data-parallel runs): its bucketed all-reduces are issued by the
+        gradient hooks during the captured backward and become part of the graph (NCCL kernels on the
+        process group's stream, joined back before the optimizer step)."""
         if snns._STATE_INIT != "device":
             raise RuntimeError('GraphedTrainStep needs sparch_b200.set_state_init("device")')
         if not x_example.is_cuda:
             raise RuntimeError("GraphedTrainStep runs on CUDA tensors only")
-        self.net, self.opt, self.loss_fn = net, optimizer, loss_fn
+        self.net, self.opt, self.loss_fn, self.sync = net, optimizer, loss_fn, sync
         self.x = torch.empty_like(x_example)
         self.y = torch.empty_like(y_example)
         self.x.copy_(x_example)
@@ -38,7 +41,8 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         self.opt.zero_grad(set_to_none=True)
         n0 = F.native_launches()
-        with torch.cuda.graph(self.graph):
+        # thread_local: the NCCL watchdog thread polls its events while this thread captures
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local" if sync is not None else "global"):
             self.out, self.rates, self.loss = self._eager_step()
         self.native_calls_per_step = F.native_launches() - n0
 
@@ -47,6 +51,8 @@ class GraphedTrainStep:
         loss = self.loss_fn(out, self.y)
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
+        if self.sync is not None:
+            self.sync.finish()
         self.opt.step()
         return out, rates, loss
 
