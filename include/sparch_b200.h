@@ -62,9 +62,10 @@ SPARCH_API int sparch_boxcar_bwd(const float* x, const float* gs, float* gx, int
 SPARCH_API int sparch_col_stats(const float* Z, int64_t M, int H, double* sum, double* sumsq,
                      sparch_stream_t st);
 /* sum1[h] = sum_m A[m,h]; sum2[h] = sum_m A[m,h]*(Zn[m,h]-mean[h])*rstd[h]  (BN backward
- * reductions, autograd of snns.py:679).  mean/rstd may be NULL => sum2 = sum A*Zn.       */
+ * reductions, autograd of snns.py:679).  mean/rstd may be NULL => sum2 = sum A*Zn.  amax_a (may be
+ * NULL): also leaves the bit pattern of max|A| (for the fp16 split of A = dI in the dV GEMM).  */
 SPARCH_API int sparch_col_dot(const float* A, const float* Zn, const float* mean, const float* rstd,
-                   int64_t M, int H, double* sum1, double* sum2, sparch_stream_t st);
+                   int64_t M, int H, double* sum1, double* sum2, uint32_t* amax_a, sparch_stream_t st);
 /* train-mode fold: mean, biased var -> rstd; scale = gamma*rstd; shift = beta-mean*scale;
  * running stats updated with the unbiased variance (momentum form of ATen). gamma/beta or
  * running_* may be NULL.                                                                 */
@@ -77,6 +78,16 @@ SPARCH_API int sparch_bn_fold_train(const double* sum, const double* sumsq, int6
 SPARCH_API int sparch_bn_bwd_apply(float* dI, const float* Z, const float* mean, const float* rstd,
                         const float* scale, const double* sum1, const double* sum2, int64_t M,
                         int H, uint32_t* amax, sparch_stream_t st);
+
+/* Same dZ written directly as the two scaled fp16 terms (sparch_split_f16 layout, row stride ldp) that the
+ * weight- and data-gradient GEMMs read, without the fp32 tensor in between (dZ32 may be NULL; it may
+ * alias dI).  amax_dI: max|dI| bits from sparch_col_dot; bound (out): bit pattern of the upper bound of
+ * max|dZ| that fixed the terms' scale -- pass it to sparch_gemm_terms as the operand's amax word;
+ * coef: scratch of 2*H floats (the per-column constants sum1/M, sum2/M converted once).            */
+SPARCH_API int sparch_bn_bwd_apply_f16(const float* dI, const float* Z, const float* mean, const float* rstd,
+                        const float* scale, const double* sum1, const double* sum2, int64_t M, int H,
+                        const uint32_t* amax_dI, uint32_t* bound, float* coef, void* P0, void* P1,
+                        int64_t ldp, float* dZ32, sparch_stream_t st);
 
 /* ---- membrane recurrence, forward (snns.py:282-303, 419-445, 554-578, 696-727) ------- */
 /* Non-recurrent kinds (LIF, adLIF): whole time loop in one streaming kernel, state in

@@ -18,7 +18,8 @@ _PROTOS = {
     "sparch_boxcar_fwd": "pplp",
     "sparch_boxcar_bwd": "ppplp",
     "sparch_col_stats": "plippp",
-    "sparch_col_dot": "pppplippp",
+    "sparch_col_dot": "pppplipppp",
+    "sparch_bn_bwd_apply_f16": "pppppppli" "ppppplpp",
     "sparch_bn_fold_train": "pplppffppppppip",
     "sparch_bn_bwd_apply": "pppppppli" "pp",
     "sparch_cell_fwd": "i" + "p" * 10 + "f" + "ppp" + "iii" + "p",

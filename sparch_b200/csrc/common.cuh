@@ -42,4 +42,16 @@ int recur_debug_flags();
 __device__ __forceinline__ float spike_of(float v) { return v > 0.0f ? 1.0f : 0.0f; }
 __device__ __forceinline__ bool window_of(float v) { return v > -0.5f && v <= 0.5f; }
 
+
+// Power-of-two scale of an fp16 hi/lo split: brings max|x| into [2^12, 2^13) (fp16 keeps 11 bits from
+// there down to 2^-14, the lo term another 11 below the hi term's last bit).  The same function gives the
+// split kernel its scale and the GEMM epilogue the inverse, from the bit pattern of max|x|.
+__device__ __forceinline__ int f16_scale_exp(uint32_t amax_bits) {
+  const int E = (int)((amax_bits >> 23) & 0xffu);          // biased exponent of max|x|
+  if (amax_bits == 0u || E == 0xff) return 0;               // all zero / inf / nan: leave unscaled
+  int e = E - 126;                                          // max|x| = f * 2^e, f in [0.5, 1)
+  if (e < -60) e = -60;
+  return 13 - e;
+}
+
 }  // namespace sparch

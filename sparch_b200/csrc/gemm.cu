@@ -55,17 +55,6 @@ struct GemmParams {
   const uint32_t* amax_b;  // undone in the epilogue); NULL = unscaled
 };
 
-// Power-of-two scale of an fp16 hi/lo split: brings max|x| into [2^12, 2^13) (fp16 keeps 11 bits from
-// there down to 2^-14, the lo term another 11 below the hi term's last bit).  The same function gives the
-// split kernel its scale and the GEMM epilogue the inverse, from the bit pattern of max|x|.
-__device__ __forceinline__ int f16_scale_exp(uint32_t amax_bits) {
-  const int E = (int)((amax_bits >> 23) & 0xffu);          // biased exponent of max|x|
-  if (amax_bits == 0u || E == 0xff) return 0;               // all zero / inf / nan: leave unscaled
-  int e = E - 126;                                          // max|x| = f * 2^e, f in [0.5, 1)
-  if (e < -60) e = -60;
-  return 13 - e;
-}
-
 // MN-major, SWIZZLE_128B operand tile as TMA delivers it from a (K, MN) row-major matrix: per block of
 // 64 MN elements, 64 K rows of 128 bytes (8 KB); blocks of 64 MN elements follow each other.
 //   leading byte offset = distance between 64-element MN blocks, stride byte offset = distance between

@@ -6,6 +6,8 @@
 
 #include <string>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace sparch {
@@ -98,12 +100,115 @@ __global__ void col_reduce_kernel(const float* __restrict__ A, const float* __re
   }
 }
 
+// Same reductions with 16-byte loads: a thread owns 4 consecutive columns, a block 128 columns x 8 row lanes,
+// four rows in flight per thread.  A row's partial products are summed in fp32 over 4 rows before they enter the
+// fp64 accumulators (the fp64 pipe is narrow; 4-term fp32 sums of same-sign-agnostic values cost <1 ulp each).
+// amax (may be NULL): bit pattern of max|A|, for the fp16 split of A that follows (dV's dI operand).
+template <bool DOT>
+__global__ void __launch_bounds__(256)
+col_reduce4_kernel(const float* __restrict__ A, const float* __restrict__ Zn, const float* __restrict__ mean,
+                   const float* __restrict__ rstd, int64_t M, int H, int64_t rows_per_block, double* __restrict__ o1,
+                   double* __restrict__ o2, uint32_t* __restrict__ amax) {
+  __shared__ double sh[2][CS_ROWS][32][4];
+  const int h = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > M) r1 = M;
+  double a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+  float mx = 0.f;
+  if (h < H) {
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rs = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (DOT && mean) {
+      mu = *reinterpret_cast<const float4*>(mean + h);
+      rs = *reinterpret_cast<const float4*>(rstd + h);
+    }
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 4 * CS_ROWS) {
+      float4 v[4], z[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int64_t rr = r + k * CS_ROWS;
+        v[k] = rr < r1 ? *reinterpret_cast<const float4*>(A + rr * H + h) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (DOT) z[k] = rr < r1 ? *reinterpret_cast<const float4*>(Zn + rr * H + h) : mu;
+      }
+      float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float vv[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+        const float zz[4] = {DOT ? (z[k].x - mu.x) * rs.x : v[k].x, DOT ? (z[k].y - mu.y) * rs.y : v[k].y,
+                             DOT ? (z[k].z - mu.z) * rs.z : v[k].z, DOT ? (z[k].w - mu.w) * rs.w : v[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          s1[j] += vv[j];
+          s2[j] += vv[j] * zz[j];
+          mx = fmaxf(mx, fabsf(vv[j]));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a1[j] += (double)s1[j];
+        a2[j] += (double)s2[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sh[0][threadIdx.y][threadIdx.x][j] = a1[j];
+    sh[1][threadIdx.y][threadIdx.x][j] = a2[j];
+  }
+  __syncthreads();
+  if (threadIdx.y < 2 && h < H) {      // row lane 0 finishes the sums, lane 1 the dot products
+    double* o = threadIdx.y ? o2 : o1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < CS_ROWS; ++k) t += sh[threadIdx.y][k][threadIdx.x][j];
+      atomicAdd(&o[h + j], t);
+    }
+  }
+  if (amax) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (threadIdx.x == 0 && mx > 0.f) atomicMax(amax, __float_as_uint(mx));
+  }
+}
+
+__global__ void absmax_scalar_kernel(const float* __restrict__ A, int64_t n, uint32_t* __restrict__ amax) {
+  float mx = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    mx = fmaxf(mx, fabsf(A[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(amax, __float_as_uint(mx));
+}
+
 static int col_reduce_launch(bool dot, const float* A, const float* Zn, const float* mean,
                              const float* rstd, int64_t M, int H, double* o1, double* o2,
-                             cudaStream_t st) {
+                             cudaStream_t st, uint32_t* amax = nullptr) {
   SPARCH_CUDA(cudaMemsetAsync(o1, 0, sizeof(double) * H, st));
   SPARCH_CUDA(cudaMemsetAsync(o2, 0, sizeof(double) * H, st));
+  if (amax) SPARCH_CUDA(cudaMemsetAsync(amax, 0, sizeof(uint32_t), st));
   if (M == 0) return SPARCH_OK;
+  const bool al16 = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Zn) | reinterpret_cast<uintptr_t>(mean) |
+                      reinterpret_cast<uintptr_t>(rstd)) & 15) == 0;
+  if ((H & 3) == 0 && al16) {
+    const int cb4 = (H / 4 + 31) / 32;
+    int64_t want4 = (int64_t)sm_count() * 8 / cb4;
+    if (want4 < 1) want4 = 1;
+    int64_t rpb4 = (M + want4 - 1) / want4;
+    if (rpb4 < 64) rpb4 = 64;
+    dim3 grid4(cb4, (unsigned)((M + rpb4 - 1) / rpb4)), block4(32, CS_ROWS);
+    if (dot)
+      col_reduce4_kernel<true><<<grid4, block4, 0, st>>>(A, Zn, mean, rstd, M, H, rpb4, o1, o2, amax);
+    else
+      col_reduce4_kernel<false><<<grid4, block4, 0, st>>>(A, nullptr, nullptr, nullptr, M, H, rpb4, o1, o2, amax);
+    SPARCH_LAUNCH_OK();
+    return SPARCH_OK;
+  }
+  if (amax) {
+    absmax_scalar_kernel<<<sm_count() * 4, 256, 0, st>>>(A, M * (int64_t)H, amax);
+    SPARCH_LAUNCH_OK();
+  }
   int cb = (H + 31) / 32;
   // enough row-slabs to fill the machine a few times over, at least 64 rows each
   int64_t want = (int64_t)sm_count() * 8 / cb;
@@ -190,6 +295,118 @@ __global__ void bn_bwd_apply_kernel(float* __restrict__ dI, const float* __restr
   }
 }
 
+// bound[0] = bit pattern of an upper bound of max|dZ|: max_h |scale_h| * (max|dI| + max_h |c1_h| + sqrt(M) max_h |c2_h|)
+// (|xhat| <= sqrt(M - 1) for batch statistics).  The bound only positions the fp16 scale; an fp16 hi/lo pair keeps
+// its 22 bits over 2^-20 of the scaled range, so a bound that is loose by two orders of magnitude costs nothing.
+__global__ void __launch_bounds__(1024)
+bn_bwd_bound_kernel(const float* __restrict__ scale, const double* __restrict__ s1, const double* __restrict__ s2,
+                    int64_t M, int H, const uint32_t* __restrict__ amax_dI, uint32_t* __restrict__ bound,
+                    float* __restrict__ coef) {
+  __shared__ float sh[3][32];
+  float ms = 0.f, m1 = 0.f, m2 = 0.f;
+  const double invM = 1.0 / (double)M;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    const float c1 = (float)(s1[h] * invM), c2 = (float)(s2[h] * invM);
+    coef[h] = c1;          // the per-column constants of the apply pass, converted once
+    coef[H + h] = c2;
+    ms = fmaxf(ms, fabsf(scale[h]));
+    m1 = fmaxf(m1, fabsf(c1));
+    m2 = fmaxf(m2, fabsf(c2));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ms = fmaxf(ms, __shfl_xor_sync(0xffffffffu, ms, o));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+    m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = ms; sh[1][threadIdx.x >> 5] = m1; sh[2][threadIdx.x >> 5] = m2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      ms = fmaxf(ms, sh[0][w]); m1 = fmaxf(m1, sh[1][w]); m2 = fmaxf(m2, sh[2][w]);
+    }
+    const float b = ms * (__uint_as_float(*amax_dI) + m1 + sqrtf((float)M) * m2);
+    *bound = __float_as_uint(b);
+  }
+}
+
+// dZ = scale (dI - c1 - xhat c2) written straight as the two scaled fp16 terms the gradient GEMMs read (and as
+// fp32 only if dZ32 is given): the fp32 dZ tensor and the split pass over it disappear.
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_f16_kernel(const float* __restrict__ dI, const float* __restrict__ Z, const float* __restrict__ mean,
+                        const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ coef,
+                        int64_t M, int H, const uint32_t* __restrict__ bound,
+                        __half* __restrict__ P0, __half* __restrict__ P1, int64_t ldp, float* __restrict__ dZ32) {
+  const float sc2 = ldexpf(1.0f, f16_scale_exp(*bound));
+  const int64_t segs = ldp / 8, n = M * segs;
+  const bool vec = (H & 3) == 0;
+  const float* c1 = coef;
+  const float* c2 = coef + H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / segs;
+    const int c = (int)(i - r * segs) * 8;
+    float d[8], z[8];
+    const float* dp = dI + r * H + c;
+    const float* zp = Z + r * H + c;
+    if (vec && c + 8 <= H) {
+      const float4 a = *reinterpret_cast<const float4*>(dp), b = *reinterpret_cast<const float4*>(dp + 4);
+      const float4 e = *reinterpret_cast<const float4*>(zp), f = *reinterpret_cast<const float4*>(zp + 4);
+      d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+      z[0] = e.x; z[1] = e.y; z[2] = e.z; z[3] = e.w; z[4] = f.x; z[5] = f.y; z[6] = f.z; z[7] = f.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        d[j] = c + j < H ? dp[j] : 0.f;
+        z[j] = c + j < H ? zp[j] : 0.f;
+      }
+    }
+    float pm[8], pr[8], ps[8], p1[8], p2[8];
+    if (vec && c + 8 <= H) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float4 a = *reinterpret_cast<const float4*>(mean + c + 4 * q), b = *reinterpret_cast<const float4*>(rstd + c + 4 * q);
+        const float4 e = *reinterpret_cast<const float4*>(scale + c + 4 * q), f = *reinterpret_cast<const float4*>(c1 + c + 4 * q);
+        const float4 g = *reinterpret_cast<const float4*>(c2 + c + 4 * q);
+        pm[4 * q] = a.x; pm[4 * q + 1] = a.y; pm[4 * q + 2] = a.z; pm[4 * q + 3] = a.w;
+        pr[4 * q] = b.x; pr[4 * q + 1] = b.y; pr[4 * q + 2] = b.z; pr[4 * q + 3] = b.w;
+        ps[4 * q] = e.x; ps[4 * q + 1] = e.y; ps[4 * q + 2] = e.z; ps[4 * q + 3] = e.w;
+        p1[4 * q] = f.x; p1[4 * q + 1] = f.y; p1[4 * q + 2] = f.z; p1[4 * q + 3] = f.w;
+        p2[4 * q] = g.x; p2[4 * q + 1] = g.y; p2[4 * q + 2] = g.z; p2[4 * q + 3] = g.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int h = min(c + j, H - 1);
+        pm[j] = mean[h]; pr[j] = rstd[h]; ps[j] = scale[h]; p1[j] = c1[h]; p2[j] = c2[h];
+      }
+    }
+    __align__(16) __half h0[8], h1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x = c + j < H ? ps[j] * (d[j] - p1[j] - (z[j] - pm[j]) * pr[j] * p2[j]) : 0.f;
+      d[j] = x;
+      const float v = x * sc2;
+      h0[j] = __float2half_rn(v);
+      h1[j] = __float2half_rn(v - __half2float(h0[j]));
+    }
+    *reinterpret_cast<uint4*>(P0 + r * ldp + c) = *reinterpret_cast<const uint4*>(h0);
+    *reinterpret_cast<uint4*>(P1 + r * ldp + c) = *reinterpret_cast<const uint4*>(h1);
+    if (dZ32) {
+      float* op = dZ32 + r * H + c;
+      if (vec && c + 8 <= H) {
+        *reinterpret_cast<float4*>(op) = make_float4(d[0], d[1], d[2], d[3]);
+        *reinterpret_cast<float4*>(op + 4) = make_float4(d[4], d[5], d[6], d[7]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c + j < H) op[j] = d[j];
+      }
+    }
+  }
+}
+
 static int ew_grid(int64_t n, int block) {
   int64_t g = (n + block - 1) / block;
   int64_t cap = (int64_t)sm_count() * 16;
@@ -228,10 +445,10 @@ int sparch_col_stats(const float* Z, int64_t M, int H, double* sum, double* sums
 }
 
 int sparch_col_dot(const float* A, const float* Zn, const float* mean, const float* rstd, int64_t M,
-                   int H, double* sum1, double* sum2, sparch_stream_t st) {
+                   int H, double* sum1, double* sum2, uint32_t* amax_a, sparch_stream_t st) {
   SPARCH_REQUIRE(M >= 0 && H > 0 && sum1 && sum2 && (M == 0 || (A && Zn)), "bad shape or null pointer");
   SPARCH_REQUIRE((mean == nullptr) == (rstd == nullptr), "mean and rstd go together");
-  return col_reduce_launch(true, A, Zn, mean, rstd, M, H, sum1, sum2, as_stream(st));
+  return col_reduce_launch(true, A, Zn, mean, rstd, M, H, sum1, sum2, as_stream(st), amax_a);
 }
 
 int sparch_bn_fold_train(const double* sum, const double* sumsq, int64_t M, const float* gamma,
@@ -253,6 +470,22 @@ int sparch_bn_bwd_apply(float* dI, const float* Z, const float* mean, const floa
   if (amax) SPARCH_CUDA(cudaMemsetAsync(amax, 0, sizeof(uint32_t), as_stream(st)));
   bn_bwd_apply_kernel<<<ew_grid(M * (int64_t)H / 4, 256), 256, 0, as_stream(st)>>>(dI, Z, mean, rstd, scale,
                                                                                   sum1, sum2, M, H, amax);
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+int sparch_bn_bwd_apply_f16(const float* dI, const float* Z, const float* mean, const float* rstd, const float* scale,
+                            const double* sum1, const double* sum2, int64_t M, int H, const uint32_t* amax_dI,
+                            uint32_t* bound, float* coef, void* P0, void* P1, int64_t ldp, float* dZ32,
+                            sparch_stream_t st) {
+  SPARCH_REQUIRE(M > 0 && H > 0 && dI && Z && mean && rstd && scale && sum1 && sum2 && amax_dI && bound && coef &&
+                     P0 && P1,
+                 "bad argument");
+  SPARCH_REQUIRE((ldp % 8) == 0 && ldp >= H, "ldp must be a multiple of 8 covering a row");
+  bn_bwd_bound_kernel<<<1, 1024, 0, as_stream(st)>>>(scale, sum1, sum2, M, H, amax_dI, bound, coef);
+  SPARCH_LAUNCH_OK();
+  bn_bwd_apply_f16_kernel<<<ew_grid(M * (ldp / 8), 256), 256, 0, as_stream(st)>>>(
+      dI, Z, mean, rstd, scale, coef, M, H, bound, (__half*)P0, (__half*)P1, ldp, dZ32);
   SPARCH_LAUNCH_OK();
   return SPARCH_OK;
 }
