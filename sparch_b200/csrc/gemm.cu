@@ -27,7 +27,9 @@ constexpr int GM = 128, GN = 256, GK = 64, GSTAGES = 4;
 constexpr int G_A_BYTES = GM * GK * 2, G_B_BYTES = GN * GK * 2, G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
 constexpr int G_THREADS = 192;
 constexpr uint32_t G_TMEM_COLS = 512;   // two fp32 accumulators of 256 columns
-constexpr size_t G_SMEM = (size_t)GSTAGES * G_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int G_EP_PITCH = 36;           // floats per staged row: 16-byte accesses stay conflict-free
+constexpr int G_EP_BYTES = 4 * 32 * G_EP_PITCH * 4;  // one 32 x 32 staging tile per epilogue warp
+constexpr size_t G_SMEM = (size_t)GSTAGES * G_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + G_EP_BYTES;
 
 struct TmapSet {
   CUtensorMap a[3];
@@ -110,6 +112,7 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
   const uint32_t bars = base + NST * G_STAGE_BYTES;             // full[4], empty[4], tmem_full[2], tmem_empty[2]
   constexpr int B_TFULL = 2 * GSTAGES, B_TEMPTY = 2 * GSTAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gsm + NST * G_STAGE_BYTES + 128);
+  float* ep_stage = reinterpret_cast<float*>(gsm + NST * G_STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = (p.N + GN - 1) / GN, tiles = tiles_n * ((p.M + GM - 1) / GM);
@@ -252,15 +255,28 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
               if (p.bias && nb + i < p.N) f[i] += p.bias[nb + i];
             }
           }
-          if (vec && nb + 32 <= p.N) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(crow + nb + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-          } else {
+          if (!(vec && nb + 32 <= p.N)) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (nb + i < p.N) crow[nb + i] = f[i];
+          } else {
+            // stage the warp's 32 x 32 block: a thread holds one ROW, but a coalesced store wants 8 lanes per row
+            float* my = ep_stage + (size_t)(quarter * 32 + lane) * G_EP_PITCH;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(my + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
           }
+        }
+        if (vec && nb + 32 <= p.N) {  // warp-uniform
+          __syncwarp();
+          const int rl = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rl, grow = m0 + quarter * 32 + rr;
+            const float4 v4 = *reinterpret_cast<const float4*>(ep_stage + (size_t)(quarter * 32 + rr) * G_EP_PITCH + c4);
+            if (grow < p.M)
+              *reinterpret_cast<float4*>(p.C + (size_t)z * p.split_stride + (size_t)grow * p.ldc + nb + c4) = v4;
+          }
+          __syncwarp();
         }
         if (STATS && nb < p.N) {  // warp-uniform: fused BatchNorm statistics of the finished output
           float a[32], b[32];
