@@ -135,8 +135,11 @@ class _SpikingLayerBase(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("sparch_b200 layers run on CUDA only (no CPU fallback)")
         if self.bidirectional:                                   # snns.py:666-668
+            if x_terms is not None:   # the same batch-wise flip/cat on the 16-bit operand image instead of a re-split
+                n, _, ld = x_terms.parts.shape
+                p3 = x_terms.parts.view(n, x.shape[0], x.shape[1], ld)
+                x_terms = type(x_terms)(torch.cat([p3, p3.flip(2)], dim=1).view(n, -1, ld), x_terms.amax)
             x = torch.cat([x, x.flip(1)], dim=0)
-            x_terms = None
         if self.batch_size != x.shape[0]:                        # snns.py:671-672
             self.batch_size = x.shape[0]
         gamma, bn_beta, norm = _norm_args(self)
@@ -146,13 +149,14 @@ class _SpikingLayerBase(nn.Module):
             norm = NormState("none")
         s = self._cell(Wx, gamma, bn_beta, norm)
         p = self.drop.p if self.drop.training else 0.0
-        if self.bidirectional or p >= 1.0:
-            if self.bidirectional:                               # snns.py:686-689
-                s_f, s_b = s.chunk(2, dim=0)
-                s = torch.cat([s_f, s_b.flip(1)], dim=2)
+        if self.bidirectional:                                   # snns.py:686-689
+            s_f, s_b = s.chunk(2, dim=0)
+            s = torch.cat([s_f, s_b.flip(1)], dim=2)
+        if p >= 1.0:
             return self.drop(s), None                            # snns.py:692
-        # dropout (snns.py:692) + spike counts + the next projection's operand in one pass over s
-        return spike_post(s, p, norm, self._recurrent)
+        # dropout (snns.py:692) + spike counts + the next projection's operand in one pass over s; the merged
+        # bidirectional tensor is not the cell's own output, so it cannot serve the cell's dV product
+        return spike_post(s, p, norm, self._recurrent and not self.bidirectional)
 
     def _cell(self, Wx, gamma, bn_beta, norm):
         device = Wx.device
