@@ -201,8 +201,13 @@ def run_ours(args, cfg, rank, local_rank, world):
                     lay.a.abs_()
     net.train()
     use_graph = (not args.no_graph) and args.state_init == "device"
-    # exp.py:89's Adam; fused=True is the same update in one multi-tensor kernel
-    opt = torch.optim.Adam(net.parameters(), 1e-2, capturable=use_graph, fused=True)
+    # exp.py:89's Adam: the same update as one launch over all parameter tensors with the step count on the device
+    # (sparch_b200/optim.py); --adam torch uses torch.optim.Adam(fused=True)
+    if args.adam == "sparch":
+        from sparch_b200.optim import Adam
+        opt = Adam(net.parameters(), 1e-2)
+    else:
+        opt = torch.optim.Adam(net.parameters(), 1e-2, capturable=use_graph, fused=True)
     sync = parallel.GradSync(net) if world > 1 else None
     x_h, y_h = make_batch(cfg, B, 1234 + rank)
     x_h, y_h = x_h.pin_memory(), y_h.pin_memory()
@@ -397,6 +402,8 @@ def main():
                     help="(default) replay the whole train step -- forward, loss, backward, gradient all-reduce, "
                          "Adam -- as one CUDA graph (sparch_b200.graphs.GraphedTrainStep; needs device state init)")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly, launch by launch")
+    ap.add_argument("--adam", default="sparch", choices=["sparch", "torch"],
+                    help="optimizer of the train step: sparch_b200.optim.Adam (one launch) or torch.optim.Adam(fused=True)")
     ap.add_argument("--profile", action="store_true",
                     help="profiling run (under ncu): exactly --warmup warm-up and --steps timed steps of "
                          "the device-resident loop, no e2e leg, no CPU baseline; prints no bench value")

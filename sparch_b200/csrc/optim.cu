@@ -1,0 +1,84 @@
+// Train-step glue: the Adam update of exp.py:89 (torch.optim.Adam defaults: no weight decay, no
+// amsgrad) for ALL parameter tensors in one launch.  torch's fused multi-tensor Adam walks 64 K-element chunks with
+// one block each (~50 blocks for the 3.2 M parameters of cfg 4); here the tensors form one virtual index space cut
+// into 1024-element blocks, so the update runs at memory speed.  The step count lives on the device (graph replay).
+#include "common.cuh"
+
+namespace sparch {
+
+constexpr int ADAM_MAX_TENSORS = 48;
+constexpr int ADAM_BLOCK_ELEMS = 1024;
+
+struct AdamTable {
+  float* p[ADAM_MAX_TENSORS];
+  const float* g[ADAM_MAX_TENSORS];
+  float* m[ADAM_MAX_TENSORS];
+  float* v[ADAM_MAX_TENSORS];
+  long long n[ADAM_MAX_TENSORS];
+  int first_block[ADAM_MAX_TENSORS + 1];   // block index where tensor i starts
+  int count;
+};
+
+__global__ void __launch_bounds__(256)
+adam_kernel(const AdamTable tb, const long long* __restrict__ step, float lr, float beta1, float beta2, float eps) {
+  // tensor of this block: binary search over first_block
+  int lo = 0, hi = tb.count;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (tb.first_block[mid] <= (int)blockIdx.x) lo = mid; else hi = mid;
+  }
+  const long long base = (long long)(blockIdx.x - tb.first_block[lo]) * ADAM_BLOCK_ELEMS;
+  const long long n = tb.n[lo];
+  float* __restrict__ p = tb.p[lo];
+  const float* __restrict__ g = tb.g[lo];
+  float* __restrict__ m = tb.m[lo];
+  float* __restrict__ v = tb.v[lo];
+  const float t = (float)(*step);
+  const float bc1 = 1.0f - powf(beta1, t), bc2s = sqrtf(1.0f - powf(beta2, t));
+  const float step_size = lr / bc1;
+#pragma unroll
+  for (int k = 0; k < ADAM_BLOCK_ELEMS / 256; ++k) {
+    const long long i = base + k * 256 + threadIdx.x;
+    if (i < n) {
+      const float gi = g[i];
+      const float mi = m[i] + (1.0f - beta1) * (gi - m[i]);           // lerp, as ATen's fused kernel
+      const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+      m[i] = mi;
+      v[i] = vi;
+      p[i] -= step_size * mi / (sqrtf(vi) / bc2s + eps);
+    }
+  }
+}
+
+}  // namespace sparch
+
+using namespace sparch;
+
+extern "C" {
+
+int sparch_adam_step(int count, float* const* params, const float* const* grads, float* const* exp_avg,
+                     float* const* exp_avg_sq, const int64_t* numel, const int64_t* step, float lr, float beta1,
+                     float beta2, float eps, sparch_stream_t st) {
+  SPARCH_REQUIRE(count >= 0 && count <= ADAM_MAX_TENSORS, "at most 48 tensors per call");
+  if (count == 0) return SPARCH_OK;
+  SPARCH_REQUIRE(params && grads && exp_avg && exp_avg_sq && numel && step, "null pointer");
+  AdamTable tb;
+  int blocks = 0, used = 0;
+  for (int i = 0; i < count; ++i) {
+    if (numel[i] <= 0) continue;
+    SPARCH_REQUIRE(params[i] && grads[i] && exp_avg[i] && exp_avg_sq[i], "null tensor pointer");
+    tb.p[used] = params[i]; tb.g[used] = grads[i]; tb.m[used] = exp_avg[i]; tb.v[used] = exp_avg_sq[i];
+    tb.n[used] = numel[i];
+    tb.first_block[used] = blocks;
+    blocks += (int)((numel[i] + ADAM_BLOCK_ELEMS - 1) / ADAM_BLOCK_ELEMS);
+    ++used;
+  }
+  tb.first_block[used] = blocks;
+  tb.count = used;
+  if (blocks == 0) return SPARCH_OK;
+  adam_kernel<<<blocks, 256, 0, as_stream(st)>>>(tb, reinterpret_cast<const long long*>(step), lr, beta1, beta2, eps);
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+}  // extern "C"

@@ -161,10 +161,15 @@ class _SpikingLayerBase(nn.Module):
     def _cell(self, Wx, gamma, bn_beta, norm):
         device = Wx.device
         Be, H = Wx.shape[0], Wx.shape[2]
-        # initial states from the CPU generator in the reference's order (snns.py:700-702)
-        ut = _rand_state(Be, H, device)
-        wt = _rand_state(Be, H, device) if self._adaptive else None
-        st = _rand_state(Be, H, device)
+        # initial states in the reference's order ut, [wt,] st (snns.py:700-702): from the CPU generator (identical
+        # draws), or in "device" mode as one draw of the 2-3 states on the CUDA generator
+        if _STATE_INIT == "device":
+            r = torch.rand(3 if self._adaptive else 2, Be, H, device=device)
+            ut, wt, st = r[0], (r[1] if self._adaptive else None), r[-1]
+        else:
+            ut = _rand_state(Be, H, device)
+            wt = _rand_state(Be, H, device) if self._adaptive else None
+            st = _rand_state(Be, H, device)
         return SpikingCellFunction.apply(
             Wx, gamma, bn_beta, self.alpha, getattr(self, "beta", None), getattr(self, "a", None),
             getattr(self, "b", None), self.V.weight if self._recurrent else None, ut, wt, st,

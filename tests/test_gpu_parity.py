@@ -688,3 +688,25 @@ def test_param_clamp_and_grad_kernels():
         ref = orc.clamp_grad_mask(ps[k].cpu().numpy(), lims[k]) * part[k].double().sum(0).cpu().numpy()
         assert rel_err(grads[k].cpu().numpy(), ref) < 1e-6
     assert float(grads[0][3]) != 0.0
+
+
+def test_single_launch_adam_matches_torch():
+    """sparch_b200.optim.Adam (one launch for all tensors, device step count) against torch.optim.Adam."""
+    from sparch_b200.optim import Adam
+    g = torch.Generator(device=DEV).manual_seed(11)
+    shapes = [(1024, 40), (1024,), (35, 1024), (7,), (1, 1), (300, 257)]
+    pa = [torch.randn(*s, device=DEV, generator=g).requires_grad_(True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    oa, ob = Adam(pa, 1e-2), torch.optim.Adam(pb, 1e-2)
+    for it in range(5):
+        for x, y in zip(pa, pb):
+            gr = torch.randn(*x.shape, device=DEV, generator=g) * (10.0 ** (it - 2))
+            x.grad, y.grad = gr.clone(), gr.clone()
+        oa.step()
+        ob.step()
+    for x, y in zip(pa, pb):
+        assert rel_err(x.detach().cpu().numpy(), y.detach().cpu().numpy()) < 2e-6
+    cpu_p = torch.zeros(3, requires_grad=True)
+    cpu_p.grad = torch.ones(3)
+    with pytest.raises(RuntimeError):
+        Adam([cpu_p], 1e-2).step()
