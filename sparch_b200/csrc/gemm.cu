@@ -248,11 +248,14 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
         if (row < p.M && nb < p.N) {
           float f[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            f[i] = __uint_as_float(v[i]);
-            if (final_out) {
-              f[i] = f[i] * inv_a * inv_b * p.alpha;
-              if (p.bias && nb + i < p.N) f[i] += p.bias[nb + i];
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (final_out) {   // uniform branches: predicated-off bias loads would still cost ~10 issue slots per element
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = f[i] * inv_a * inv_b * p.alpha;
+            if (p.bias) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (nb + i < p.N) f[i] += p.bias[nb + i];
             }
           }
           if (!(vec && nb + 32 <= p.N)) {
