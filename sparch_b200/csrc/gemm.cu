@@ -43,6 +43,8 @@ struct GemmParams {
   int kblocks;         // ceil(K / 64)
   int kb_per_split;    // k-blocks handled by one split
   int splits;          // split-K factor (work items = splits x tiles)
+  int tile_n;          // output tile width = UMMA N: 256, or N rounded up to 16 when the whole output is narrower
+                       // (readout projection N = 35, input-layer dW N = 40: a 256-wide tile would be 80 % padding)
   float* C;            // final output (splits == 1) or partial buffer [splits][M][ldc]
   long long ldc;
   long long split_stride;
@@ -73,7 +75,7 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {
 
 // kind::f16 -> fp32 accumulator, M = 128, N = 256; bits 7 / 10 = A / B format (0 fp16, 1 bf16), bit 15 / 16 = A / B
 // is MN-major
-constexpr uint32_t G_IDESC = (1u << 4) | ((uint32_t)(GN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
+constexpr uint32_t G_IDESC = (1u << 4) | ((uint32_t)(GM >> 4) << 24);   // N field (bits 17..22) = tile_n >> 3, set per launch
 constexpr uint32_t G_IDESC_BF16 = (1u << 7) | (1u << 10);
 
 // Column sums across the 32 lanes of a warp for 32 per-lane values in 31 shuffles: at each step a lane
@@ -115,7 +117,9 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
   float* ep_stage = reinterpret_cast<float*>(gsm + NST * G_STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_n = (p.N + GN - 1) / GN, tiles = tiles_n * ((p.M + GM - 1) / GM);
+  const int TN = p.tile_n;
+  const int tiles_n = (p.N + TN - 1) / TN, tiles = tiles_n * ((p.M + GM - 1) / GM);
+  const uint32_t b_bytes = p.b_mn ? (uint32_t)((TN + 63) / 64) * 8192u : (uint32_t)TN * 128u;
   const int items = tiles * p.splits;
 
   if (threadIdx.x == 0) {
@@ -145,7 +149,7 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
       int it = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int z = item / tiles, tile = item - z * tiles;
-        const int m0 = (tile / tiles_n) * GM, n0 = (tile % tiles_n) * GN;
+        const int m0 = (tile / tiles_n) * GM, n0 = (tile % tiles_n) * TN;
         const int kb0 = z * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
         for (int pr = 0; pr < p.npairs; ++pr) {
           const CUtensorMap* ma = &maps.a[p.pair_a[pr]];
@@ -154,7 +158,7 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
             const int s = it % NST;
             const uint32_t ph = (it / NST) & 1;
             mbar_wait(bars + 8 * (GSTAGES + s), ph ^ 1);
-            mbar_expect_tx(bars + 8 * s, G_STAGE_BYTES);
+            mbar_expect_tx(bars + 8 * s, G_A_BYTES + b_bytes);
             const uint32_t sa = base + s * G_STAGE_BYTES;
             if (!p.a_mn) {
               tma_load_2d(sa, ma, kb * GK, m0, bars + 8 * s);
@@ -167,7 +171,7 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
               tma_load_2d(sa + G_A_BYTES, mb, kb * GK, n0, bars + 8 * s);
             } else {
 #pragma unroll
-              for (int blk = 0; blk < GN / 64; ++blk)
+              for (int blk = 0; blk < (TN + 63) / 64; ++blk)
                 tma_load_2d(sa + G_A_BYTES + blk * 8192, mb, n0 + blk * 64, kb * GK, bars + 8 * s);
             }
           }
@@ -179,7 +183,8 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
       // K advance per UMMA (16 elements): K-major 32 bytes inside the swizzle atom (2 units of 16 B),
       // MN-major 16 rows of 128 bytes (128 units)
       const uint32_t ka = p.a_mn ? 128u : 2u, kb_ = p.b_mn ? 128u : 2u;
-      const uint32_t idesc = G_IDESC | (p.fp16 ? 0u : G_IDESC_BF16) | (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);
+      const uint32_t idesc = G_IDESC | ((uint32_t)(TN >> 3) << 17) | (p.fp16 ? 0u : G_IDESC_BF16) | (p.a_mn ? (1u << 15) : 0u) |
+                             (p.b_mn ? (1u << 16) : 0u);
       int it = 0, j = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++j) {
         const int z = item / tiles;
@@ -217,13 +222,14 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
     int j = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++j) {
       const int z = item / tiles, tile = item - z * tiles;
-      const int m0 = (tile / tiles_n) * GM, n0 = (tile % tiles_n) * GN;
+      const int m0 = (tile / tiles_n) * GM, n0 = (tile % tiles_n) * TN;
       const int buf = j & 1;
       const int row = m0 + quarter * 32 + lane;
       mbar_wait(bars + 8 * (B_TFULL + buf), (j >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float* crow = p.C + (size_t)z * p.split_stride + (size_t)row * p.ldc;
-      for (int c = 0; c < GN / 32; ++c) {
+      const int nchunks = (TN + 31) / 32;
+      for (int c = 0; c < nchunks; ++c) {
         uint32_t v[32];
         const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * GN + c * 32);
         asm volatile(
@@ -237,7 +243,7 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
               "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c == GN / 32 - 1) {
+        if (c == nchunks - 1) {
           // the whole accumulator is in registers: hand the TMEM buffer back before the stores
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
@@ -579,6 +585,7 @@ int sparch_gemm_terms(int fp16, const void* const* A_parts, int na, const uint32
   SPARCH_REQUIRE(a_koff == 0 || a_mn, "a_koff applies to an MN-major A operand");
   SPARCH_REQUIRE((stat_sum == nullptr) == (stat_sumsq == nullptr), "stat_sum and stat_sumsq go together");
   cudaStream_t st = as_stream(st_);
+  const int tile_n = N >= GN ? GN : (N + 15) / 16 * 16;
   TmapSet maps;
   memset(&maps, 0, sizeof maps);
   for (int i = 0; i < na; ++i) {
@@ -588,7 +595,7 @@ int sparch_gemm_terms(int fp16, const void* const* A_parts, int na, const uint32
   }
   for (int i = 0; i < nb; ++i) {
     SPARCH_REQUIRE(B_parts[i] && (reinterpret_cast<uintptr_t>(B_parts[i]) & 15) == 0, "B part null or unaligned");
-    if (int e = b_mn ? make_map_mn(&maps.b[i], B_parts[i], K, N, ldb) : make_map(&maps.b[i], B_parts[i], N, K, ldb, GN))
+    if (int e = b_mn ? make_map_mn(&maps.b[i], B_parts[i], K, N, ldb) : make_map(&maps.b[i], B_parts[i], N, K, ldb, tile_n))
       return e;
   }
   GemmParams p;
@@ -607,7 +614,7 @@ int sparch_gemm_terms(int fp16, const void* const* A_parts, int na, const uint32
     p.pair_b[i] = pair_b[i];
   }
   p.kblocks = (K + GK - 1) / GK;
-  const int tiles = ((M + GM - 1) / GM) * ((N + GN - 1) / GN);
+  const int tiles = ((M + GM - 1) / GM) * ((N + tile_n - 1) / tile_n);
   int splits = 1;
   if (workspace && tiles < sm_count() && !stat_sum) {  // statistics need the finished tile in one epilogue
     splits = sm_count() / tiles;
@@ -635,6 +642,7 @@ int sparch_gemm_terms(int fp16, const void* const* A_parts, int na, const uint32
   }
   // (A 2-stage ring with two CTAs per SM for short contractions was measured: no gain.)
   p.splits = splits;
+  p.tile_n = tile_n;
   const int items = tiles * splits;
   dim3 grid(items < sm_count() ? items : sm_count());
   if (stat_sum)

@@ -200,8 +200,13 @@ class LinearFunction(torch.autograd.Function):
                 # dX = dZ @ W: contraction over N; W's terms (N, K) are the MN-major B operand
                 dx = gemm.gemm_parts(ga, wb, N, b_mn=True, N=K).view(ctx.xshape)
             if ctx.needs_input_grad[1]:
-                # dW = dZ^T @ X: contraction over the Be*T frames, both operands MN-major
-                dw = gemm.gemm_parts(ga, xa, M, alpha=ctx.alpha, a_mn=True, b_mn=True, M=N, N=K)
+                # dW = dZ^T @ X: contraction over the Be*T frames, both operands MN-major.  A layer with few
+                # outputs (readout: N = 35) computes dW^T = X^T @ dZ instead, so that the small dimension is the
+                # narrow UMMA N (tile width 48) and not a 128-row tile that is 73 % padding.
+                if N <= 64 and K >= 2 * N:
+                    dw = gemm.gemm_parts(xa, ga, M, alpha=ctx.alpha, a_mn=True, b_mn=True, M=K, N=N).t()
+                else:
+                    dw = gemm.gemm_parts(ga, xa, M, alpha=ctx.alpha, a_mn=True, b_mn=True, M=N, N=K)
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 db = g2d.sum(dim=0)
         return dx, dw, db, None, None, None
