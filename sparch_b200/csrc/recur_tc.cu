@@ -133,7 +133,12 @@ rec_bwd_tc_kernel(const __grid_constant__ TcMaps maps, const RecBwdTcArgs p, con
   const int slice = blockIdx.x, group = group0 + blockIdx.y, row0 = group * TC_ROWS;
   const int rank = blockIdx.x % TC_CL;  // == %cluster_ctarank for cluster dims (4, 1, 1)
   const int nslices = gridDim.x, NCH = p.Hp / 32;
-  int* ctr = counters + group;
+  // Hand-over flags: one arrival counter per (row group, 64-neuron K block); the two slices that produce a K block
+  // add 1 each per step.  A consumer waits per K block of its own K quarter (and not for all 32 slices of the group):
+  // less skew to wait out, and two instead of 32 CTAs contend for an address.
+  const int NKB = p.Hp / 64;                           // K blocks per row = flags per group (<= 16 for H <= 1024)
+  int* flags = counters + (size_t)group * NKB;
+  int* my_flag = flags + slice / 2;
   const bool dbg_cta = p.dbg && blockIdx.x == 0 && blockIdx.y == 0;
 
   {  // resident V0 tiles
@@ -181,30 +186,31 @@ rec_bwd_tc_kernel(const __grid_constant__ TcMaps maps, const RecBwdTcArgs p, con
     int it = 0;
     for (int t = p.T - 2; t >= 0; --t) {
       const int rbuf = (t + 1) & 1;
-      if (lane == 0) {  // panel(t+1) published by every slice of the group
-        const int target = nslices * (p.T - 1 - t);
+      const int target = 2 * (p.T - 1 - t);            // both producer slices of a K block have published panel(t+1)
+      const int y = (rbuf * ngroups_total + group) * TC_ROWS;
+      // lanes 0..KB-1: wait for K block `lane` of this rank's quarter, then fetch it (each lane drives its own ring
+      // slot).  Rounds of TC_STAGES lanes: two fills of the same slot must reach its empty barrier one after the other,
+      // a parity wait cannot tell "one phase behind" from "three behind".
+      for (int base_kb = 0; base_kb < p.KB; base_kb += TC_STAGES) {
+      if (lane >= base_kb && lane < min(base_kb + TC_STAGES, p.KB)) {
+        const int kb = lane;
+        const int* f = flags + rank * p.KB + kb;
         const long long t0 = clock64();
         while (true) {
           int v;
-          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
           if (v >= target) break;
           if (clock64() - t0 > 4000000000LL) __trap();
         }
         asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of other SMs -> TMA reads
-        if (dbg_cta) p.dbg[t * 8 + 0] = clock64();
-      }
-      __syncwarp();
-      asm volatile("bar.arrive 2, 288;" ::: "memory");    // the update warps may read the chunk maxima now
-      if (lane == 0) {
-        const int y = (rbuf * ngroups_total + group) * TC_ROWS;
-        for (int kb = 0; kb < p.KB; ++kb, ++it) {
-          const int s = it % TC_STAGES;
-          const uint32_t ph = (it / TC_STAGES) & 1;
-          mbar_wait(bars + 8 * (TC_STAGES + s), ph ^ 1);
-          if (p.dbg_flags & 4) {
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8 * s) : "memory");
-            continue;
-          }
+        if (dbg_cta && kb == 0) p.dbg[t * 8 + 0] = clock64();
+        const int it_kb = it + kb;
+        const int s = it_kb % TC_STAGES;
+        const uint32_t ph = (it_kb / TC_STAGES) & 1;
+        mbar_wait(bars + 8 * (TC_STAGES + s), ph ^ 1);
+        if (p.dbg_flags & 4) {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8 * s) : "memory");
+        } else {
           mbar_expect_tx(bars + 8 * s, TC_STAGE_BYTES);
           const uint32_t sa = ring + s * TC_STAGE_BYTES;
           const int x = rank * (p.Hp / TC_CL) + kb * 64;  // this rank's K quarter
@@ -213,6 +219,21 @@ rec_bwd_tc_kernel(const __grid_constant__ TcMaps maps, const RecBwdTcArgs p, con
         }
       }
       __syncwarp();
+      }
+      it += p.KB;
+      // the chunk maxima of ALL slices feed the row scale: wait for the rest of the group's flags (off the MMA's path)
+      if (lane < NKB) {
+        const int* f = flags + lane;
+        const long long t0 = clock64();
+        while (true) {
+          int v;
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+          if (v >= target) break;
+          if (clock64() - t0 > 4000000000LL) __trap();
+        }
+      }
+      __syncwarp();
+      asm volatile("bar.arrive 2, 288;" ::: "memory");    // the update warps may read the chunk maxima now
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -431,7 +452,7 @@ rec_bwd_tc_kernel(const __grid_constant__ TcMaps maps, const RecBwdTcArgs p, con
         if (dbg_on) p.dbg[(p.T + t) * 8 + 2] = clock64();
         upd_sync();                       // every update thread's panel stores are issued
         if (dbg_on) p.dbg[(p.T + t) * 8 + 3] = clock64();
-        if (tid == 64) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ctr) : "memory");
+        if (tid == 64) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(my_flag) : "memory");
         if (dbg_on) p.dbg[t * 8 + 4] = clock64();
       }
       if (live) {
@@ -493,7 +514,7 @@ size_t sparch_recur_bwd_tc_workspace(int Be, int T, int H) {
   return 2 * (2 * groups * TC_ROWS * Hp * sizeof(__half))  // panels hi, lo
          + 2 * groups * (Hp / 32) * TC_ROWS * sizeof(float)  // chunk maxima
          + (size_t)Be * T * sizeof(float)                    // gmax
-         + groups * sizeof(int) + 256;
+         + groups * (Hp / 64) * sizeof(int) + 256;
 }
 
 // V (H,H) raw recurrent weight -> swizzled fp16 hi/lo UMMA tiles of V0 (zero diagonal); meta from
@@ -540,7 +561,7 @@ int sparch_recur_bwd_tc(int kind, const float* G, const float* U, const float* W
   float* gmax = cmax + (size_t)2 * groups * (Hp / 32) * TC_ROWS;
   int* counters = reinterpret_cast<int*>(gmax + (size_t)Be * T);
   SPARCH_CUDA(cudaMemsetAsync(ws, 0, 2 * panel_bytes, st));  // rows beyond Be / columns beyond H read as zero
-  SPARCH_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * groups, st));
+  SPARCH_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * groups * (Hp / 64), st));
   if (gmax_in) {  // the producer of G already left the row maxima (sparch_spike_post_bwd)
     gmax = const_cast<float*>(gmax_in);
   } else {
