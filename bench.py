@@ -292,10 +292,20 @@ def run_ours(args, cfg, rank, local_rank, world):
         F.timers_enable(False)
 
     # ---- end to end: pinned host batch -> device, loss read back every step ------------------
-    def e2e_step():
-        x_d.copy_(x_h, non_blocking=True)
-        y_d.copy_(y_h, non_blocking=True)
-        return float(step(x_d, y_d).item())                   # exp.py:363 loss.item()
+    if graphed is not None:
+        # every step: its batch pinned-host -> device (on a copy stream, under the previous step: input double
+        # buffering), the step, the loss read back by the host (exp.py:363 loss.item())
+        graphed.stage(x_h, y_h)
+
+        def e2e_step():
+            loss = graphed.step_staged()
+            graphed.stage(x_h, y_h)                           # the NEXT step's batch
+            return float(loss.item())
+    else:
+        def e2e_step():
+            x_d.copy_(x_h, non_blocking=True)
+            y_d.copy_(y_h, non_blocking=True)
+            return float(step(x_d, y_d).item())               # exp.py:363 loss.item()
 
     for _ in range(2):
         e2e_step()

@@ -26,6 +26,7 @@ class GraphedTrainStep:
         if not x_example.is_cuda:
             raise RuntimeError("GraphedTrainStep runs on CUDA tensors only")
         self.net, self.opt, self.loss_fn, self.sync = net, optimizer, loss_fn, sync
+        self._copy_stream = None
         self.x = torch.empty_like(x_example)
         self.y = torch.empty_like(y_example)
         self.x.copy_(x_example)
@@ -60,5 +61,29 @@ class GraphedTrainStep:
         """Copy the batch into the static buffers and replay; returns the (device) loss tensor."""
         self.x.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
+        self.graph.replay()
+        return self.loss
+
+    # ---- input double-buffering: the next batch's host->device copy runs on a copy stream under the current step
+    def stage(self, x_host, y_host):
+        """Start copying the NEXT batch (pinned host tensors) into staging buffers on a side stream."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._sx, self._sy = torch.empty_like(self.x), torch.empty_like(self.y)
+            self._staged, self._consumed = torch.cuda.Event(), torch.cuda.Event()
+            self._consumed.record()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._consumed)      # the previous staged batch has been taken over
+            self._sx.copy_(x_host, non_blocking=True)
+            self._sy.copy_(y_host, non_blocking=True)
+            self._staged.record()
+
+    def step_staged(self):
+        """Run one step on the batch handed to stage(); returns the (device) loss tensor."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged)
+        self.x.copy_(self._sx, non_blocking=True)             # device-to-device, a few microseconds
+        self.y.copy_(self._sy, non_blocking=True)
+        self._consumed.record()
         self.graph.replay()
         return self.loss
