@@ -16,13 +16,51 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Block-wide copy of n floats with several independent 16-byte accesses in flight per thread (a one-load-per-
+// iteration loop leaves a 128-thread block waiting a full memory latency per 512 bytes).
+__device__ __forceinline__ void block_copy(float* __restrict__ dst, const float* __restrict__ src, int n) {
+  const bool vec = ((n & 3) == 0) && (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0);
+  if (vec) {
+    const int n4 = n >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * blockDim.x) {
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * blockDim.x;
+        if (i < n4) v[k] = s4[i];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * blockDim.x;
+        if (i < n4) d4[i] = v[k];
+      }
+    }
+  } else {
+    for (int i0 = threadIdx.x; i0 < n; i0 += 4 * blockDim.x) {
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * blockDim.x;
+        if (i < n) v[k] = src[i];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * blockDim.x;
+        if (i < n) dst[i] = v[k];
+      }
+    }
+  }
+}
+
 // The membrane u_t is a per-(b, c) linear scan (no coupling across classes), only the softmax couples
 // the classes of one step.  So a block (one batch row) works on chunks of TCH timesteps held in shared
 // memory: (1) coalesced load of the chunk's inputs, (2) the dependent chain u_t per class thread --
 // T fused multiply-adds, no reduction inside the chain, (3) one warp per timestep for the softmax
 // (shuffle reductions), (4) per class the sum over the chunk's steps in time order (snns.py:823 adds
 // them in that order).  The first version did two block-wide reductions inside every dependent step.
-__global__ void readout_fwd_kernel(const float* __restrict__ Z, const float* __restrict__ scale,
+__global__ void __launch_bounds__(1024) readout_fwd_kernel(const float* __restrict__ Z, const float* __restrict__ scale,
                                    const float* __restrict__ shift, const float* __restrict__ alpha,
                                    const float* __restrict__ u0, float* __restrict__ out,
                                    float* __restrict__ U, int T, int C, int TCH) {
@@ -37,7 +75,7 @@ __global__ void readout_fwd_kernel(const float* __restrict__ Z, const float* __r
   for (int t0 = 0; t0 < T; t0 += TCH) {
     const int nt = min(TCH, T - t0), n = nt * C;
     const int64_t base = (b * (int64_t)T + t0) * C;
-    for (int i = tid; i < n; i += blockDim.x) su[i] = Z[base + i];
+    block_copy(su, Z + base, n);
     __syncthreads();
     if (live)
       for (int t = 0; t < nt; ++t) {
@@ -47,7 +85,7 @@ __global__ void readout_fwd_kernel(const float* __restrict__ Z, const float* __r
         su[t * C + tid] = u;
       }
     __syncthreads();
-    for (int i = tid; i < n; i += blockDim.x) U[base + i] = su[i];
+    block_copy(U + base, su, n);
     for (int t = warp; t < nt; t += nw) {
       float* row = su + t * C;
       float m = -INFINITY;
@@ -69,12 +107,13 @@ __global__ void readout_fwd_kernel(const float* __restrict__ Z, const float* __r
 // Reverse pass, same chunking (chunks walked backwards): the softmax Jacobian term x_t = p_t (g - <p_t, g>)
 // depends only on the taped u_t, so one warp per timestep computes it for the whole chunk; the dependent
 // chain du_t = x_t + alpha du_{t+1} then runs per class thread without reductions.
-__global__ void readout_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ U,
+__global__ void __launch_bounds__(1024) readout_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ U,
                                    const float* __restrict__ alpha, const float* __restrict__ u0,
                                    float* __restrict__ dI, float* __restrict__ p_alpha, int T, int C, int TCH) {
   extern __shared__ float sm[];
-  float* su = sm;                 // [TCH + 1][C]: row 0 = u of the step before the chunk
-  float* sx = sm + (TCH + 1) * C; // [TCH][C]
+  const int pad = (4 - (C & 3)) & 3;                            // so that su + C (the chunk itself) is 16-byte aligned
+  float* su = sm + pad;                                          // [TCH + 1][C]: row 0 = u of the step before the chunk
+  float* sx = sm + (pad + (TCH + 1) * C + 3) / 4 * 4;            // [TCH][C], 16-byte aligned
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const bool live = tid < C;
   const int64_t b = blockIdx.x;
@@ -85,7 +124,7 @@ __global__ void readout_bwd_kernel(const float* __restrict__ gout, const float* 
   for (int ch = nchunks - 1; ch >= 0; --ch) {
     const int t0 = ch * TCH, nt = min(TCH, T - t0), n = nt * C;
     const int64_t base = (b * (int64_t)T + t0) * C;
-    for (int i = tid; i < n; i += blockDim.x) su[C + i] = U[base + i];
+    block_copy(su + C, U + base, n);
     for (int i = tid; i < C; i += blockDim.x) su[i] = t0 > 0 ? U[base - C + i] : u0[b * C + i];
     __syncthreads();
     for (int t = warp; t < nt; t += nw) {
@@ -110,7 +149,7 @@ __global__ void readout_bwd_kernel(const float* __restrict__ gout, const float* 
         du = du_t;
       }
     __syncthreads();
-    for (int i = tid; i < n; i += blockDim.x) dI[base + i] = sx[i];
+    block_copy(dI + base, sx, n);
     __syncthreads();
   }
   if (live) p_alpha[b * C + tid] = pa;
@@ -151,7 +190,7 @@ int sparch_readout_bwd(const float* gout, const float* U, const float* alpha, co
   int threads = ((C + 31) / 32) * 32;
   if (threads < 128) threads = 128;
   const int tch = readout_chunk(T, C, 2);
-  readout_bwd_kernel<<<B, threads, (size_t)(2 * tch + 1) * C * sizeof(float), as_stream(st)>>>(gout, U, alpha, u0, dI,
+  readout_bwd_kernel<<<B, threads, (size_t)(2 * tch + 1) * C * sizeof(float) + 32, as_stream(st)>>>(gout, U, alpha, u0, dI,
                                                                                                 p_alpha, T, C, tch);
   SPARCH_LAUNCH_OK();
   return SPARCH_OK;
