@@ -32,15 +32,18 @@ constexpr int VSCALE_EXP = 13;
 
 // meta[0] = E with max|V0| < 2^E (int), set by vmax_kernel.
 __global__ void vmax_kernel(const float* __restrict__ V, int H, int* __restrict__ meta) {
+  // one warp per row (no per-element division); the diagonal does not count (snns.py:566/712 zeroes it)
   float m = 0.f;
-  int64_t n = (int64_t)H * H;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int r = (int)(i / H), c = (int)(i % H);
-    if (r != c) m = fmaxf(m, fabsf(V[i]));
+  const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < H; row += gridDim.x * wpb) {
+    const float* __restrict__ r = V + (int64_t)row * H;
+#pragma unroll 4
+    for (int c = lane; c < H; c += 32)
+      if (c != row) m = fmaxf(m, fabsf(r[c]));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(&meta[1], __float_as_int(m));
+  if (lane == 0) atomicMax(&meta[1], __float_as_int(m));
 }
 
 __global__ void vmax_finish_kernel(int* meta) {
@@ -744,7 +747,7 @@ int sparch_recur_prepare(const float* V, int H, uint32_t* img_fwd, uint32_t* img
   cudaStream_t st = as_stream(st_);
   const int Hp = sparch_recur_padded(H);
   SPARCH_CUDA(cudaMemsetAsync(meta, 0, 2 * sizeof(int), st));
-  int nb = (int)(((int64_t)H * H + 255) / 256);
+  int nb = (H + 7) / 8;                       // 8 warps per block, one row per warp
   if (nb > sm_count() * 8) nb = sm_count() * 8;
   vmax_kernel<<<nb, 256, 0, st>>>(V, H, meta);
   SPARCH_LAUNCH_OK();

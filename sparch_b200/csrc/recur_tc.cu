@@ -71,20 +71,31 @@ struct RecBwdTcArgs {
 // K = (bx % 4) Hp / 4 + 64 kb + k; element (n, k) of a tile: halves offset n*64 + ((k/8) ^ (n&7))*8 + k%8.
 __global__ void vprep_umma_kernel(const float* __restrict__ V, int H, int Hp, int KB, const int* __restrict__ meta,
                                   __half* __restrict__ img) {
-  const int64_t per_cta = (int64_t)KB * 2 * (TC_N * 64);
-  const int64_t total = per_cta * (Hp / TC_COLS);
+  // one thread per 16-byte swizzle chunk (8 consecutive K of one row n): reads 32 contiguous bytes of V once and
+  // writes the chunk of the hi tile and of the lo tile
+  const int64_t per_cta8 = (int64_t)KB * (TC_N * 8);             // chunks per CTA and part
+  const int64_t total8 = per_cta8 * (Hp / TC_COLS);
   const float sc = ldexpf(1.0f, TC_VSCALE_EXP - meta[0]);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int bx = (int)(i / per_cta);
-    int r = (int)(i % per_cta);
-    const int e = r & 7, chunk_sw = (r >> 3) & 7, n = (r >> 6) & (TC_N - 1), part = (r >> 13) & 1, kb = r >> 14;
-    const int k = ((chunk_sw ^ (n & 7)) << 3) + e;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int bx = (int)(i / per_cta8);
+    const int r = (int)(i - (int64_t)bx * per_cta8);
+    const int chunk_sw = r & 7, n = (r >> 3) & (TC_N - 1), kb = r >> 10;
+    const int k0 = (chunk_sw ^ (n & 7)) << 3;
     const int row = (bx / TC_CL) * TC_N + n;                      // V[row = presynaptic j][col = neuron c]
-    const int col = (bx % TC_CL) * (Hp / TC_CL) + kb * 64 + k;
-    float x = 0.f;
-    if (row < H && col < H && row != col) x = V[(int64_t)row * H + col] * sc;
-    const __half hi = __float2half_rn(x);
-    img[i] = part ? __float2half_rn(x - __half2float(hi)) : hi;
+    const int col0 = (bx % TC_CL) * (Hp / TC_CL) + kb * 64 + k0;
+    __align__(16) __half hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int col = col0 + e;
+      float x = 0.f;
+      if (row < H && col < H && row != col) x = V[(int64_t)row * H + col] * sc;
+      hi[e] = __float2half_rn(x);
+      lo[e] = __float2half_rn(x - __half2float(hi[e]));
+    }
+    // halves offset inside the CTA's image: ((kb * 2 + part) * TC_N + n) * 64 + chunk_sw * 8
+    __half* base = img + ((int64_t)bx * per_cta8 * 2 + ((int64_t)(kb * 2) * TC_N + n) * 8 + chunk_sw) * 8;
+    *reinterpret_cast<uint4*>(base) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(base + (int64_t)TC_N * 64) = *reinterpret_cast<const uint4*>(lo);
   }
 }
 
@@ -522,7 +533,7 @@ size_t sparch_recur_bwd_tc_workspace(int Be, int T, int H) {
 int sparch_recur_prepare_tc(const float* V, int H, void* img, const int* meta, sparch_stream_t st_) {
   SPARCH_REQUIRE(V && H > 0 && img && meta, "null pointer");
   const int Hp = sparch_recur_tc_padded(H), KB = Hp / (64 * TC_CL);
-  int64_t total = (int64_t)Hp * Hp * 2;
+  int64_t total = (int64_t)Hp * Hp / 8;   // one thread per 8-element chunk (hi and lo)
   int nb = (int)((total + 255) / 256);
   if (nb > sm_count() * 16) nb = sm_count() * 16;
   vprep_umma_kernel<<<nb, 256, 0, as_stream(st_)>>>(V, H, Hp, KB, meta, reinterpret_cast<__half*>(img));
