@@ -42,6 +42,35 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().sparch_abi_version() >= 1
 
 
+def test_ctypes_prototypes_match_the_header():
+    """Every ctypes prototype in sparch_b200/_lib.py has the arity and argument classes (pointer / int / int64 /
+    float) of the declaration in include/sparch_b200.h: a hand-edited signature cannot drift unnoticed."""
+    from sparch_b200 import _lib
+    src = ""
+    inc = os.path.join(ROOT, "include")
+    for fn in sorted(os.listdir(inc)):
+        if fn.endswith(".h"):
+            src += open(os.path.join(inc, fn)).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    decls = re.findall(r"SPARCH_API\s+[\w\s\*]+?\b(sparch_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S)
+    assert len(decls) >= 30
+
+    def cls(param):
+        param = " ".join(param.split())
+        if param in ("void", ""):
+            return ""
+        if "*" in param or "sparch_stream_t" in param:
+            return "p"
+        base = param.rsplit(" ", 1)[0].replace("const ", "").strip()
+        return {"int": "i", "int64_t": "l", "size_t": "l", "float": "f", "long long": "l"}[base]
+
+    for name, params in decls:
+        sig = "".join(cls(x) for x in params.split(","))
+        if name == "sparch_last_error":
+            continue
+        assert _lib._PROTOS[name] == sig, f"{name}: header says {sig!r}, _lib.py binds {_lib._PROTOS[name]!r}"
+
+
 def test_init_rng_and_state_dict_contract():
     """Same seed -> same parameters, in the same state_dict order, as the reference."""
     import sparch_b200
