@@ -710,3 +710,15 @@ def test_single_launch_adam_matches_torch():
     cpu_p.grad = torch.ones(3)
     with pytest.raises(RuntimeError):
         Adam([cpu_p], 1e-2).step()
+
+
+@pytest.mark.parametrize("name", ["radlif_bn", "lif_bn"])
+def test_three_bf16_term_mode_against_reference_fixture(name):
+    """set_precision("fp32-bf16x3") -- the first operand scheme, kept for comparison -- meets the same fixture
+    tolerances as the default two-term fp16 scheme (the post pass and BatchNorm backward take their bf16 paths)."""
+    import sparch_b200
+    try:
+        sparch_b200.set_precision("fp32-bf16x3")
+        test_whole_model_against_reference_fixture(name)
+    finally:
+        sparch_b200.set_precision("fp32")
