@@ -722,3 +722,17 @@ def test_three_bf16_term_mode_against_reference_fixture(name):
         test_whole_model_against_reference_fixture(name)
     finally:
         sparch_b200.set_precision("fp32")
+
+
+def test_reference_checkpoint_runs_on_the_gpu():
+    """The whole-module checkpoint written by the reference (tests/golden/reference_module.pt) unpickled into these
+    classes, moved to the GPU and run: outputs and firing rates as the reference recorded them."""
+    from tests.test_host_contract import _load_reference_checkpoint
+    import os
+    from tests.helpers import GOLDEN_DIR
+    net = _load_reference_checkpoint().to(DEV)
+    run = np.load(os.path.join(GOLDEN_DIR, "reference_module_run.npz"))
+    torch.manual_seed(42)
+    out, rates = net(torch.from_numpy(run["x"]).to(DEV))
+    np.testing.assert_allclose(out.detach().cpu().numpy(), run["out"], rtol=5e-5, atol=2e-6)
+    np.testing.assert_allclose(rates.detach().cpu().numpy(), run["rates"], rtol=1e-6, atol=1e-7)

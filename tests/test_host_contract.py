@@ -137,6 +137,45 @@ def test_whole_module_pickle_round_trip():
     assert pickle.loads(pickle.dumps(net.snn[0].spike_fct)) is not None
 
 
+def _load_reference_checkpoint():
+    """Unpickle tests/golden/reference_module.pt -- a torch.save(net) of the UNTOUCHED reference SNN
+    (oracle/make_pickle_fixture.py, exp.py:462) -- with sparch.models.snns re-pointed at sparch_b200.snns."""
+    import sys
+    import types
+    import sparch_b200.snns as ours
+    saved = {k: sys.modules.get(k) for k in ("sparch", "sparch.models", "sparch.models.snns")}
+    try:
+        pkg, models = types.ModuleType("sparch"), types.ModuleType("sparch.models")
+        pkg.models, models.snns = models, ours
+        sys.modules.update({"sparch": pkg, "sparch.models": models, "sparch.models.snns": ours})
+        return torch.load(os.path.join(GOLDEN_DIR, "reference_module.pt"), weights_only=False)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_reference_checkpoint_unpickles_into_these_classes():
+    """SURVEY.md 8b pickle contract: a whole-module checkpoint written by the reference loads after the one-line
+    switch of INTEGRATION.md -- same classes by name, same attributes, same state_dict."""
+    import sparch_b200.snns as ours
+    net = _load_reference_checkpoint()
+    assert type(net) is ours.SNN and net.is_snn and net.neuron_type == "RadLIF"
+    assert [type(l) for l in net.snn] == [ours.RadLIFLayer, ours.RadLIFLayer, ours.ReadoutLayer]
+    run = np.load(os.path.join(GOLDEN_DIR, "reference_module_run.npz"))
+    sd = net.state_dict()
+    want = {k[4:]: run[k] for k in run.files if k.startswith("sd0.")}
+    assert list(sd) == list(want)
+    for k, v in want.items():
+        np.testing.assert_array_equal(sd[k].numpy(), v)
+    lay = net.snn[0]
+    assert lay.threshold == 1.0 and lay.normalize and lay.drop.p == 0.0 and not lay.bidirectional
+    with pytest.raises(RuntimeError):          # still no CPU path
+        net(torch.zeros(4, 3, 7))
+
+
 def test_product_never_imports_the_oracle():
     """The oracle is test infrastructure: nothing under sparch_b200/ may reference it."""
     pkg = os.path.join(ROOT, "sparch_b200")
