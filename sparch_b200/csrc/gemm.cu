@@ -289,15 +289,18 @@ gemm_tn_bf16_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
         }
         if (STATS && nb < p.N) {  // warp-uniform: fused BatchNorm statistics of the finished output
           float a[32], b[32];
+          const bool row_ok = row < p.M;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a[i] = __uint_as_float(v[i]) * inv_a * inv_b * p.alpha;
+          if (p.bias) {   // uniform branch (see above)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (nb + i < p.N) a[i] += p.bias[nb + i];
+          }
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            float x = 0.f;
-            if (row < p.M && nb + i < p.N) {
-              x = __uint_as_float(v[i]) * inv_a * inv_b * p.alpha;
-              if (p.bias) x += p.bias[nb + i];
-            }
-            a[i] = x;
-            b[i] = x * x;
+            a[i] = (row_ok && nb + i < p.N) ? a[i] : 0.f;
+            b[i] = a[i] * a[i];
           }
           const float cs = warp_colsum32(a, lane), cq = warp_colsum32(b, lane);
           sstat[quarter][c * 32 + lane] = make_float2(cs, cq);

@@ -128,11 +128,12 @@ class SpikeFunctionBoxcar(torch.autograd.Function):
         return gx
 
 
-# BatchNorm statistics can ride in the projection GEMM's epilogue (gemm_tn_bf16_kernel<true>) when a tile's main
-# loop has at least this many (pass, k-block) iterations.  Measured at cfg 4 with the persistent two-pass fp16
-# GEMM: the fused epilogue costs more than a separate sparch_col_stats pass over the L2-warm output (5.01 vs
-# 4.95 ms per graphed train step), so it is off by default; SPARCH_B200_FUSED_STATS_MIN_ITERS=8 switches it on.
-FUSED_STATS_MIN_ITERS = int(os.environ.get("SPARCH_B200_FUSED_STATS_MIN_ITERS", "1000000"))
+# BatchNorm statistics ride in the projection GEMM's epilogue (gemm_tn_bf16_kernel<true>) when a tile's main loop
+# has at least this many (pass, k-block) iterations to hide the butterfly column sums under (the epilogue of tile j
+# overlaps the main loop of tile j + 1).  Measured at cfg 4: 4.16 vs 4.20 ms per train step against a separate
+# sparch_col_stats pass (layer 1 and the readout qualify; the K = 40 input layer does not).  Before the epilogue lost
+# its predicated-off bias loads the fused variant was the slower one (5.01 vs 4.95 ms).
+FUSED_STATS_MIN_ITERS = int(os.environ.get("SPARCH_B200_FUSED_STATS_MIN_ITERS", "8"))
 
 
 class LinearFunction(torch.autograd.Function):
