@@ -102,11 +102,6 @@ def _f32c(t):
     return t.contiguous()
 
 
-def _clamp_mask(p, lim):
-    """clamp backward: gradient flows on the closed interval [lo, hi]."""
-    return ((p >= lim[0]) & (p <= lim[1])).to(p.dtype)
-
-
 class SpikeFunctionBoxcar(torch.autograd.Function):
     """snns.py:20-36.  forward: x.gt(0).float(); backward: pass-through on -0.5 < x <= 0.5."""
 
