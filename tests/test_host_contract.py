@@ -185,3 +185,39 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dp, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|snn_oracle", src, re.M), \
                     os.path.join(dp, fn)
+
+
+def test_host_side_guards_without_a_gpu():
+    """Host logic that needs no kernel: operand-term pairings, precision-mode switch, and the loud failures of the
+    CUDA-only entry points on CPU tensors (no silent fallback anywhere)."""
+    import sparch_b200
+    from sparch_b200 import functional as F, gemm
+    from sparch_b200.graphs import GraphedTrainStep
+    from sparch_b200.optim import Adam
+    # every (general, general) pairing drops only the lowest-order product; spikes need one term
+    assert gemm.pairs_for(2, 2) == [(1, 0), (0, 1), (0, 0)] and gemm.pairs_for(1, 2) == [(0, 1), (0, 0)]
+    assert len(gemm.pairs_for(3, 3)) == 6 and gemm.pairs_for(1, 1) == [(0, 0)]
+    try:
+        for mode, gm in (("fp32", "f16x2"), ("fp32-bf16x3", "bf16x3"), ("bf16", "bf16x1")):
+            sparch_b200.set_precision(mode)
+            assert gemm.MODE == gm
+        with pytest.raises(ValueError):
+            sparch_b200.set_precision("fp64")
+    finally:
+        sparch_b200.set_precision("fp32")
+    with pytest.raises(ValueError):
+        sparch_b200.set_state_init("host")
+    x = torch.zeros(2, 3, 4)
+    with pytest.raises(RuntimeError):
+        F.spike_post(x, 0.1, F.NormState("none"), recurrent=False)
+    with pytest.raises(RuntimeError):
+        F.SpikeFunctionBoxcar.apply(x)
+    p = torch.zeros(3, requires_grad=True)
+    p.grad = torch.ones(3)
+    with pytest.raises(RuntimeError):
+        Adam([p], 1e-2).step()
+    with pytest.raises(ValueError):
+        Adam([p], -1.0)
+    net = sparch_b200.SNN((2, None, 4), layer_sizes=[8, 8, 3])
+    with pytest.raises(RuntimeError):          # needs device state init and CUDA tensors
+        GraphedTrainStep(net, Adam(net.parameters(), 1e-2), torch.nn.CrossEntropyLoss(), x, torch.zeros(2, dtype=torch.long))
