@@ -203,6 +203,25 @@ SPARCH_API int sparch_recur_fwd(int kind, const float* Z, const float* scale, co
                                 const float* s0, float theta, float* S, float* U, float* W,
                                 uint32_t* bits, int reduced, int Be, int T, int H,
                                 sparch_stream_t st);
+/* The same layer pass (snns.py:572, 718-724; one persistent cooperative kernel for all T steps) with
+ * s_{t-1} @ V0 on tcgen05 integer tensor cores.  A CTA owns 128 batch rows x 16 neurons; its columns of V0 sit in
+ * shared memory as three int8 digit planes of a 23-bit fixed-point image (one power-of-two scale per column);
+ * the spikes of step t-1 are expanded from the exchanged bit words into a uint8 A operand in TENSOR MEMORY
+ * (tcgen05.st) and multiplied by tcgen05.mma.kind::i8 (M = 128, N = 48, exact int32 sums in TMEM).  H <=
+ * sparch_recur_fwd_tc_max_h().  img: sparch_recur_fwd_tc_image_bytes(H) bytes filled by
+ * sparch_recur_prepare_fwd_tc (digit planes + column scales).  bits: sparch_recur_fwd_tc_bits_bytes() bytes,
+ * receives the packed spike tensor [T][ceil(Be/128)][ceil(H/16)][128] of 32-bit words {0xFF, spikes 8..15, 0xFF,
+ * spikes 0..7} (zeroed here; these words are also the inter-CTA exchange).  rec0 = s0 @ V0 as for
+ * sparch_recur_fwd.  reduced != 0: two digit planes (15-bit image of V0).  Writes the tapes S, U (W).           */
+SPARCH_API int sparch_recur_fwd_tc_max_h(void);
+SPARCH_API size_t sparch_recur_fwd_tc_image_bytes(int H);
+SPARCH_API size_t sparch_recur_fwd_tc_bits_bytes(int Be, int T, int H);
+SPARCH_API int sparch_recur_prepare_fwd_tc(const float* V, int H, void* img, sparch_stream_t st);
+SPARCH_API int sparch_recur_fwd_tc(int kind, const float* Z, const float* scale, const float* shift,
+                                   const float* alpha, const float* beta, const float* a, const float* b,
+                                   const float* rec0, const void* img, const float* u0, const float* w0,
+                                   const float* s0, float theta, float* S, float* U, float* W,
+                                   uint32_t* bits, int reduced, int Be, int T, int H, sparch_stream_t st);
 /* Profiling aid: device buffer of T*4 int64 that receives, per timestep, the SM clock of CTA (0,0)
  * after the spike-word wait, after the MMA loop, after the reduction and at the end of the step
  * for the following sparch_recur_fwd launches (NULL switches it off).                          */

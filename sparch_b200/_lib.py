@@ -38,6 +38,11 @@ _PROTOS = {
     "sparch_recur_sync_words": "i",
     "sparch_recur_debug_clocks": "p",
     "sparch_recur_fwd": "i" + "p" * 13 + "f" + "pppp" + "iiii" + "p",
+    "sparch_recur_fwd_tc_max_h": "",
+    "sparch_recur_fwd_tc_image_bytes": "i",
+    "sparch_recur_fwd_tc_bits_bytes": "iii",
+    "sparch_recur_prepare_fwd_tc": "pipp",
+    "sparch_recur_fwd_tc": "i" + "p" * 12 + "f" + "pppp" + "iiii" + "p",
     "sparch_recur_bwd_workspace": "ii",
     "sparch_recur_bwd": "i" + "p" * 12 + "f" + "p" * 7 + "iiii" + "p",
     "sparch_recur_tc_padded": "i",

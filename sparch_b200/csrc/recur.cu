@@ -743,7 +743,7 @@ int sparch_recur_debug_clocks(long long* buf) {
 
 int sparch_recur_prepare(const float* V, int H, uint32_t* img_fwd, uint32_t* img_bwd, int* meta,
                          sparch_stream_t st_) {
-  SPARCH_REQUIRE(V && H > 0 && meta && (img_fwd || img_bwd), "null pointer");
+  SPARCH_REQUIRE(V && H > 0 && meta, "null pointer");  // both images NULL: meta (max|V0|) only
   cudaStream_t st = as_stream(st_);
   const int Hp = sparch_recur_padded(H);
   SPARCH_CUDA(cudaMemsetAsync(meta, 0, 2 * sizeof(int), st));

@@ -30,6 +30,38 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Same, with a suspend-time hint: the warp sleeps in hardware until the phase completes instead of re-issuing the
+// test (a hot try_wait loop of several warps starves the other warps of their scheduler).
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+// 3-D tiled TMA: global (x fastest) <-> shared box, no swizzle
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int x, int y, int z, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(x), "r"(y), "r"(z)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -78,6 +110,28 @@ inline EncodeTiledFn get_encode() {
 // bf16 matrix (rows, cols) row-major with row stride ld elements; box = (64 cols, box_rows rows), 128B swizzle.
 inline int make_map(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows,
                     CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+
+// fp32 tensor (d2, d1, d0) row-major (d0 fastest) viewed through boxes of (b2, 1, b0) elements, no swizzle: the
+// (batch row, time, neuron) activations of the recurrence kernels.  Needs d0 % 4 == 0 (16-byte global strides).
+inline int make_map3d_f32(CUtensorMap* m, const void* ptr, long long d2, long long d1, long long d0, int b2, int b0) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return SPARCH_ERR_DEVICE;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t strides[2] = {(cuuint64_t)d0 * 4, (cuuint64_t)d0 * d1 * 4};
+  cuuint32_t box[3] = {(cuuint32_t)b0, 1u, (cuuint32_t)b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3-D fp32) failed (%d): dims=%lld,%lld,%lld", (int)r, d2, d1, d0);
+    return SPARCH_ERR_CUDA;
+  }
+  return SPARCH_OK;
+}
 
 // MN-major operand: the matrix in memory is (K rows, MN cols) row-major; one box = 64 K rows x 64 MN cols.
 inline int make_map_mn(CUtensorMap* m, const void* ptr, long long krows, long long mncols, long long ld) {

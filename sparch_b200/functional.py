@@ -312,6 +312,10 @@ RECUR_MAX_H = 1184
 # panels, per-chunk scales; also serves RECUR_TC_MAX_H < H <= RECUR_MAX_H).
 RECUR_BWD = os.environ.get("SPARCH_B200_BWD", "tc")
 RECUR_TC_MAX_H = 1024
+# Forward recurrence kernel: "tc" = tcgen05 kernel (csrc/recur_fwd_tc.cu: int8 digit planes of V0, spike operand in
+# tensor memory, 128 rows x 16 neurons per CTA; H <= 1536), "mma" = mma.sync kernel (csrc/recur.cu).
+RECUR_FWD = os.environ.get("SPARCH_B200_FWD", "tc")
+RECUR_FWD_TC_MAX_H = 1536
 
 
 class SpikingCellFunction(torch.autograd.Function):
@@ -368,11 +372,13 @@ class SpikingCellFunction(torch.autograd.Function):
                 # persistent tensor-core kernels: s_{t-1} @ V0 from packed spike planes (csrc/recur.cu)
                 Hp = _lib.lib().sparch_recur_padded(H)
                 use_tc = RECUR_BWD == "tc" and H <= RECUR_TC_MAX_H
-                img_f = torch.empty(Hp * Hp, device=dev, dtype=torch.int32)
+                fwd_tc = RECUR_FWD == "tc" and H <= RECUR_FWD_TC_MAX_H
+                Vc = V.detach().contiguous()
+                img_f = None if fwd_tc else torch.empty(Hp * Hp, device=dev, dtype=torch.int32)
                 img_b = None if use_tc else torch.empty(Hp * Hp, device=dev, dtype=torch.int32)
                 meta = torch.empty(2, device=dev, dtype=torch.int32)
-                call("sparch_recur_prepare", ptr(V.detach().contiguous()), H, ptr(img_f), ptr(img_b),
-                     ptr(meta), st)
+                if img_f is not None or img_b is not None or use_tc:   # (meta: max|V0| for the fp16 images)
+                    call("sparch_recur_prepare", ptr(Vc), H, ptr(img_f), ptr(img_b), ptr(meta), st)
                 if use_tc:  # V0 as swizzled UMMA tiles for the tcgen05 reverse kernel (csrc/recur_tc.cu)
                     img_b = torch.empty(_lib.lib().sparch_recur_bwd_tc_image_bytes(H), device=dev, dtype=torch.uint8)
                     call("sparch_recur_prepare_tc", ptr(V.detach().contiguous()), H, ptr(img_b), ptr(meta), st)
@@ -380,12 +386,22 @@ class SpikingCellFunction(torch.autograd.Function):
                 ctx.rec = (img_b, meta)
                 ctx.reduced = int(_PRECISION == "bf16")
                 rec0 = torch.matmul(s0, V0)        # t = 0: s_{-1} is real-valued (snns.py:702)
-                bits = torch.empty(T, Be, Hp // 32, 2, device=dev, dtype=torch.int32)
-                with _region("recurrence_fwd"):
-                    call("sparch_recur_fwd", k, ptr(Z), ptr(scale), ptr(shift), ptr(al), ptr(be), ptr(aa),
-                         ptr(bb), ptr(rec0), ptr(img_f), ptr(meta), ptr(u0), ptr(w0), ptr(s0),
-                         float(theta), ptr(S), ptr(U), ptr(Wt), ptr(bits), int(_PRECISION == "bf16"), Be, T, H,
-                         st)
+                if fwd_tc:
+                    L = _lib.lib()
+                    img_i8 = torch.empty(L.sparch_recur_fwd_tc_image_bytes(H), device=dev, dtype=torch.uint8)
+                    call("sparch_recur_prepare_fwd_tc", ptr(Vc), H, ptr(img_i8), st)
+                    bits = torch.empty(L.sparch_recur_fwd_tc_bits_bytes(Be, T, H) // 4, device=dev, dtype=torch.int32)
+                    with _region("recurrence_fwd"):
+                        call("sparch_recur_fwd_tc", k, ptr(Z), ptr(scale), ptr(shift), ptr(al), ptr(be), ptr(aa),
+                             ptr(bb), ptr(rec0), ptr(img_i8), ptr(u0), ptr(w0), ptr(s0), float(theta), ptr(S),
+                             ptr(U), ptr(Wt), ptr(bits), int(_PRECISION == "bf16"), Be, T, H, st)
+                else:
+                    bits = torch.empty(T, Be, Hp // 32, 2, device=dev, dtype=torch.int32)
+                    with _region("recurrence_fwd"):
+                        call("sparch_recur_fwd", k, ptr(Z), ptr(scale), ptr(shift), ptr(al), ptr(be), ptr(aa),
+                             ptr(bb), ptr(rec0), ptr(img_f), ptr(meta), ptr(u0), ptr(w0), ptr(s0),
+                             float(theta), ptr(S), ptr(U), ptr(Wt), ptr(bits), int(_PRECISION == "bf16"), Be, T, H,
+                             st)
         ctx.k, ctx.theta, ctx.norm = k, float(theta), norm
         ctx.has = (gamma is not None, bn_beta is not None)
         ctx.save_for_backward(Z, gamma, bn_beta, alpha, beta, a, b, V0, u0, w0, s0, S, U, Wt, al, be,

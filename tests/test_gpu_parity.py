@@ -402,6 +402,31 @@ def test_both_reverse_recurrence_kernels_against_oracle(kind, Be, T, H, mode):
         F.RECUR_BWD = old
 
 
+@pytest.mark.parametrize("mode", ["tc", "mma"])
+@pytest.mark.parametrize("kind,Be,T,H", [
+    ("RadLIF", 300, 7, 96),     # 3 row groups of 128, ragged last one; 6 slices: one partial batch of producers
+    ("RadLIF", 70, 5, 1000),    # H not a multiple of 16: dead neurons in the last slice, K padded to 1024
+    ("RLIF", 3, 1, 40),         # single timestep: no UMMA at all
+    ("RLIF", 33, 60, 130),      # longer chain, odd sizes
+    ("RadLIF", 640, 4, 512),    # 5 row groups x 32 slices = 160 CTAs > 148: two cooperative launches
+    ("RadLIF", 256, 12, 1024),  # the cfg4 layer width: 4 batches of 16 producers
+    ("RLIF", 130, 6, 1100),     # 5 batches, the last one partial (69 slices)
+])
+def test_both_forward_recurrence_kernels_against_oracle(kind, Be, T, H, mode):
+    """The tcgen05 forward recurrence (sparch_recur_fwd_tc: int8 digit planes of V0, spike operand in tensor memory;
+    the default up to H = 1536) and the mma.sync one (sparch_recur_fwd) meet the same bar: spike trains against the
+    oracle (<= 1e-3 flips, observed 0) and, where they coincide, the gradients of the given-mask backward."""
+    _, F = _mods()
+    old = F.RECUR_FWD
+    F.RECUR_FWD = mode
+    try:
+        n0 = F.native_launches()
+        _oracle_cell_check(kind, Be, T, H, seed=Be + T + H)
+        assert F.native_launches() > n0
+    finally:
+        F.RECUR_FWD = old
+
+
 def test_empty_batch_and_time_are_tolerated():
     _, F = _mods()
     for Be, T in ((0, 5), (4, 0)):
