@@ -291,13 +291,14 @@ SPARCH_API int sparch_param_grads(const float* part, const float* alpha, const f
 
 /* ---- train-step glue: Adam, exp.py:89 ------------------------------------------- */
 /* One launch updates up to 48 parameter tensors (torch.optim.Adam defaults: no weight decay, no amsgrad):
- * m += (1-b1)(g-m); v = b2 v + (1-b2) g^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps), t = *step (device
- * int64, already incremented by the caller).  params/grads/exp_avg/exp_avg_sq/numel are HOST arrays of `count`
- * device pointers / element counts.                                                                  */
+ * g' = g * hyper[4]; m += (1-b1)(g'-m); v = b2 v + (1-b2) g'^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps),
+ * t = *step (device int64, already incremented by the caller).  hyper = DEVICE float[5] {lr, beta1, beta2, eps,
+ * gradient scale}: a scheduler (exp.py:92-96) changes lr between replays of a captured step without re-capture; the
+ * gradient scale is 1/world_size when the gradients hold an all-reduced sum.  params/grads/exp_avg/exp_avg_sq/numel
+ * are HOST arrays of `count` device pointers / element counts.                                              */
 SPARCH_API int sparch_adam_step(int count, float* const* params, const float* const* grads,
                                 float* const* exp_avg, float* const* exp_avg_sq, const int64_t* numel,
-                                const int64_t* step, float lr, float beta1, float beta2, float eps,
-                                sparch_stream_t st);
+                                const int64_t* step, const float* hyper, sparch_stream_t st);
 
 /* ---- ReadoutLayer cell (snns.py:807-825) ---------------------------------------------- */
 /* u_t = alpha*u_{t-1} + (1-alpha)*I_t ; out = sum_t softmax(u_t, dim=1).  U (B,T,C) tape.  */

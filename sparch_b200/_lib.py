@@ -54,7 +54,7 @@ _PROTOS = {
     "sparch_spike_post_bwd": "plifpppp",
     "sparch_neuron_params": "pppppiipp",
     "sparch_param_grads": "ppppppiiipp",
-    "sparch_adam_step": "ippppppffffp",
+    "sparch_adam_step": "ippppppp" "p",
     "sparch_readout_fwd": "p" * 7 + "iii" + "p",
     "sparch_readout_bwd": "p" * 6 + "iii" + "p",
 }

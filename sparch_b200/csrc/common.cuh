@@ -33,7 +33,22 @@ int cuda_fail(const char* what, cudaError_t e);
 
 inline cudaStream_t as_stream(sparch_stream_t st) { return reinterpret_cast<cudaStream_t>(st); }
 
-int sm_count();
+// Device-dependent one-time work (cudaFuncSetAttribute, SM count) is cached PER DEVICE: a process may drive several
+// GPUs (a model on cuda:1 while cuda:0 is current), and a per-process flag would leave the second device without
+// its > 48 KB dynamic shared memory attribute.
+constexpr int SPARCH_MAX_DEVICES = 64;
+int current_device();  // cudaGetDevice(), 0 when it fails
+int sm_count();        // of the current device
+struct PerDeviceOnce {
+  bool done[SPARCH_MAX_DEVICES] = {};
+  bool first() {       // true exactly once per device (always true for an out-of-range ordinal)
+    const int d = current_device();
+    if (d < 0 || d >= SPARCH_MAX_DEVICES) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
 long long* recur_debug_buffer();  // profiling aid set by sparch_recur_debug_clocks (recur.cu), normally NULL
 int recur_debug_flags();
 

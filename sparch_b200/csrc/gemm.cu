@@ -637,11 +637,10 @@ int sparch_gemm_terms(int fp16, const void* const* A_parts, int na, const uint32
   } else {
     p.C = C; p.ldc = ldc; p.split_stride = 0; p.alpha = alpha; p.bias = bias;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     SPARCH_CUDA(cudaFuncSetAttribute(gemm_tn_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
     SPARCH_CUDA(cudaFuncSetAttribute(gemm_tn_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
-    attr_set = true;
   }
   // (A 2-stage ring with two CTAs per SM for short contractions was measured: no gain.)
   p.splits = splits;

@@ -28,15 +28,22 @@ int cuda_fail(const char* what, cudaError_t e) {
   return SPARCH_ERR_CUDA;
 }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  return dev;
+}
+
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
+  static int n[SPARCH_MAX_DEVICES] = {};
+  const int dev = current_device();
+  const int slot = (dev >= 0 && dev < SPARCH_MAX_DEVICES) ? dev : 0;
+  if (n[slot] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[slot] = v;
   }
-  return n;
+  return n[slot];
 }
 
 // ------------------------------------------------------------------ boxcar

@@ -20,7 +20,10 @@ struct AdamTable {
 };
 
 __global__ void __launch_bounds__(256)
-adam_kernel(const AdamTable tb, const long long* __restrict__ step, float lr, float beta1, float beta2, float eps) {
+adam_kernel(const AdamTable tb, const long long* __restrict__ step, const float* __restrict__ hyper) {
+  // hyper-parameters live on the device (lr, beta1, beta2, eps, gradient scale): a learning-rate scheduler
+  // (exp.py:92-96, ReduceLROnPlateau) changes them between replays of a captured step without re-capturing
+  const float lr = hyper[0], beta1 = hyper[1], beta2 = hyper[2], eps = hyper[3], gscale = hyper[4];
   // tensor of this block: binary search over first_block
   int lo = 0, hi = tb.count;
   while (hi - lo > 1) {
@@ -40,7 +43,7 @@ adam_kernel(const AdamTable tb, const long long* __restrict__ step, float lr, fl
   for (int k = 0; k < ADAM_BLOCK_ELEMS / 256; ++k) {
     const long long i = base + k * 256 + threadIdx.x;
     if (i < n) {
-      const float gi = g[i];
+      const float gi = g[i] * gscale;    // gscale = 1 / world size when the gradients hold an all-reduced SUM
       const float mi = m[i] + (1.0f - beta1) * (gi - m[i]);           // lerp, as ATen's fused kernel
       const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
       m[i] = mi;
@@ -57,11 +60,11 @@ using namespace sparch;
 extern "C" {
 
 int sparch_adam_step(int count, float* const* params, const float* const* grads, float* const* exp_avg,
-                     float* const* exp_avg_sq, const int64_t* numel, const int64_t* step, float lr, float beta1,
-                     float beta2, float eps, sparch_stream_t st) {
+                     float* const* exp_avg_sq, const int64_t* numel, const int64_t* step, const float* hyper,
+                     sparch_stream_t st) {
   SPARCH_REQUIRE(count >= 0 && count <= ADAM_MAX_TENSORS, "at most 48 tensors per call");
   if (count == 0) return SPARCH_OK;
-  SPARCH_REQUIRE(params && grads && exp_avg && exp_avg_sq && numel && step, "null pointer");
+  SPARCH_REQUIRE(params && grads && exp_avg && exp_avg_sq && numel && step && hyper, "null pointer");
   AdamTable tb;
   int blocks = 0, used = 0;
   for (int i = 0; i < count; ++i) {
@@ -76,7 +79,7 @@ int sparch_adam_step(int count, float* const* params, const float* const* grads,
   tb.first_block[used] = blocks;
   tb.count = used;
   if (blocks == 0) return SPARCH_OK;
-  adam_kernel<<<blocks, 256, 0, as_stream(st)>>>(tb, reinterpret_cast<const long long*>(step), lr, beta1, beta2, eps);
+  adam_kernel<<<blocks, 256, 0, as_stream(st)>>>(tb, reinterpret_cast<const long long*>(step), hyper);
   SPARCH_LAUNCH_OK();
   return SPARCH_OK;
 }

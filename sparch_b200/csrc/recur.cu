@@ -785,12 +785,12 @@ int sparch_recur_fwd(int kind, const float* Z, const float* scale, const float* 
   RecFwdArgs p{Z, scale, shift, alpha, beta, a, b, rec0, u0, w0, s0, img_fwd, meta, theta, S, U, W,
                reinterpret_cast<uint2*>(bits), Be, T, H, Hp, g_dbg, g_dbg_flags, reduced ? 1 : 0};
   cudaStream_t st = as_stream(st_);
-  static int max_ctas = 0;
-  if (max_ctas == 0) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     SPARCH_CUDA(cudaFuncSetAttribute(rec_fwd_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     SPARCH_CUDA(cudaFuncSetAttribute(rec_fwd_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-    max_ctas = sm_count();  // one CTA per SM (shared memory bound)
   }
+  const int max_ctas = sm_count();  // one CTA per SM (shared memory bound)
   const int slices = Hp / RC, groups = (Be + RB - 1) / RB;
   SPARCH_REQUIRE(slices <= max_ctas, "hidden size needs more co-resident CTAs than the GPU has SMs");
   const int gmax = TEAMS * (max_ctas / slices);   // row groups (of 32) per cooperative launch
@@ -837,12 +837,12 @@ int sparch_recur_bwd(int kind, const float* G, const float* U, const float* W, c
   cudaStream_t st = as_stream(st_);
   const size_t psmem = rec_bwd_persist_smem(Hp);
   SPARCH_REQUIRE(psmem <= 225 * 1024, "hidden size too large for the resident V0^T slice");
-  static int max_ctas = 0;
-  if (max_ctas == 0) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-    max_ctas = sm_count();
   }
+  const int max_ctas = sm_count();
   const int slices = Hp / RC;
   SPARCH_REQUIRE(slices <= max_ctas, "hidden size needs more co-resident CTAs than the GPU has SMs");
   const int gmax = TEAMS * (max_ctas / slices);

@@ -594,11 +594,10 @@ int sparch_recur_fwd_tc(int kind, const float* Z, const float* scale, const floa
   const int groups = (Be + FT_ROWS - 1) / FT_ROWS;
   const size_t smem = (size_t)Hp * FT_N + FT_TMA_SMEM + 1024;
   cudaStream_t st = as_stream(st_);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     SPARCH_CUDA(cudaFuncSetAttribute(rec_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     SPARCH_CUDA(cudaFuncSetAttribute(rec_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   const int max_ctas = sm_count();  // one CTA per SM: each allocates all 512 TMEM columns
   SPARCH_REQUIRE(ns <= max_ctas, "hidden size needs more co-resident CTAs than the GPU has SMs");

@@ -112,6 +112,12 @@ __global__ void gmax_kernel(const float* __restrict__ G, int Be, int T, int H, f
   if (lane == 0) gmax[w] = m;
 }
 
+__device__ __forceinline__ bool tc_elect_one() {
+  uint32_t e;
+  asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\nselp.u32 %0, 1, 0, q;\n}" : "=r"(e));
+  return e != 0;
+}
+
 __device__ __forceinline__ void upd_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ float scale_from_max(float m) {
@@ -247,36 +253,41 @@ rec_bwd_tc_kernel(const __grid_constant__ TcMaps maps, const RecBwdTcArgs p, con
       asm volatile("bar.arrive 2, 288;" ::: "memory");    // the update warps may read the chunk maxima now
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the warp stays converged, one elected lane issues each K block's UMMAs as straight-line code
+    // (under a plain `if (lane == 0)` ptxas wraps every UMMA in an ELECT / PLOP3 / BRA.U.ANY retry loop, ~45 cycles
+    // per instruction whatever its shape: measured with tools/ubench/umma_i8_ts.cu) =====
+    {
       // kind::f16, fp16 x fp16 -> fp32, both K-major, M = 64, N = 128
       const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+      const uint64_t ring_desc = make_desc_k_sw128(ring), v_desc = make_desc_k_sw128(vimg);
       int it = 0, step = 0;
       for (int t = p.T - 2; t >= 0; --t, ++step) {
-        mbar_wait(bars + 8 * B_ACC_EMPTY, (step & 1) ^ 1);  // D drained by the update warps
+        mbar_wait_sleep(bars + 8 * B_ACC_EMPTY, (step & 1) ^ 1);  // D drained by the update warps
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int kb = 0; kb < p.KB; ++kb, ++it) {
           const int s = it % TC_STAGES;
           const uint32_t ph = (it / TC_STAGES) & 1;
-          mbar_wait(bars + 8 * s, ph);
+          mbar_wait_sleep(bars + 8 * s, ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          if (dbg_cta && kb == 0) p.dbg[t * 8 + 1] = clock64();
-          const uint32_t sa = ring + s * TC_STAGE_BYTES;
-          const uint64_t a_hi = make_desc_k_sw128(sa), a_lo = make_desc_k_sw128(sa + 8192);
-          const uint64_t b_hi = make_desc_k_sw128(vimg + (uint32_t)(kb * 2 + 0) * (TC_N * 128));
-          const uint64_t b_lo = make_desc_k_sw128(vimg + (uint32_t)(kb * 2 + 1) * (TC_N * 128));
+          if (dbg_cta && lane == 0 && kb == 0) p.dbg[t * 8 + 1] = clock64();
+          __syncwarp();
+          if (tc_elect_one()) {
+            const uint64_t a_hi = ring_desc + (uint64_t)(s * (TC_STAGE_BYTES >> 4)), a_lo = a_hi + (8192 >> 4);
+            const uint64_t b_hi = v_desc + (uint64_t)((kb * 2) * (TC_N * 128 >> 4)), b_lo = b_hi + (TC_N * 128 >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (p.dbg_flags & 16) continue;
-            umma_f16(tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            if (p.reduced) continue;  // reduced-precision mode: hi * hi only
-            umma_f16(tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-            umma_f16(tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+            for (int k = 0; k < 4; ++k) {
+              if (p.dbg_flags & 16) continue;
+              umma_f16(tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              if (p.reduced) continue;  // reduced-precision mode: hi * hi only
+              umma_f16(tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+              umma_f16(tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+            }
+            umma_commit(bars + 8 * (TC_STAGES + s));
+            if (kb == p.KB - 1) umma_commit(bars + 8 * B_ACC_FULL);
           }
-          umma_commit(bars + 8 * (TC_STAGES + s));
+          __syncwarp();
         }
-        umma_commit(bars + 8 * B_ACC_FULL);
-        if (dbg_cta) p.dbg[t * 8 + 2] = clock64();
+        if (dbg_cta && lane == 0) p.dbg[t * 8 + 2] = clock64();
       }
     }
   } else {
@@ -350,7 +361,7 @@ rec_bwd_tc_kernel(const __grid_constant__ TcMaps maps, const RecBwdTcArgs p, con
       if (t < p.T - 1) {
         // ---- partial D = dI_{t+1}[:, K quarter] (scaled) @ V0^T (scaled): this warp holds rows 16q..16q+15
         // (lanes 0..15) x columns 64 half .. 64 half + 63 = the column quarters of ranks 2 half, 2 half + 1
-        mbar_wait(bars + 8 * B_ACC_FULL, step & 1);
+        mbar_wait_sleep(bars + 8 * B_ACC_FULL, step & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (dbg_on) p.dbg[t * 8 + 3] = clock64();
 #pragma unroll
@@ -557,11 +568,10 @@ int sparch_recur_bwd_tc(int kind, const float* G, const float* U, const float* W
   const size_t smem = rec_bwd_tc_smem(KB);
   SPARCH_REQUIRE(smem + 768 <= 227 * 1024, "hidden size too large for the resident V0 tiles");
   cudaStream_t st = as_stream(st_);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 768));
     SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 768));
-    attr_set = true;
   }
   const int groups = (Be + TC_ROWS - 1) / TC_ROWS, slices = Hp / TC_COLS;
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);

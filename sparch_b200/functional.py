@@ -6,6 +6,7 @@ loops (sparch/models/snns.py:282-303, 419-445, 554-578, 696-727, 807-825) and it
 CPU path (``RuntimeError`` otherwise).
 """
 import ctypes
+import functools
 import math
 import os
 
@@ -94,6 +95,20 @@ def _require_cuda(*ts):
                                "move the module and its inputs to a B200 device")
 
 
+def _on_device(fn):
+    """Run a Function's forward / backward with the CUDA device of its first CUDA tensor argument current: the C ABI
+    launches on the current device's stream and caches per-device attributes, so a model on cuda:1 must not be driven
+    while cuda:0 is current (the launch would land on the wrong GPU with foreign pointers)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        t = next((a for a in args if isinstance(a, torch.Tensor) and a.is_cuda), None)
+        if t is None or t.device.index == torch.cuda.current_device():
+            return fn(*args, **kw)
+        with torch.cuda.device(t.device):
+            return fn(*args, **kw)
+    return wrapper
+
+
 def _f32c(t):
     if t is None:
         return None
@@ -106,6 +121,7 @@ class SpikeFunctionBoxcar(torch.autograd.Function):
     """snns.py:20-36.  forward: x.gt(0).float(); backward: pass-through on -0.5 < x <= 0.5."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, x):
         _require_cuda(x)
         x = _f32c(x)
@@ -115,6 +131,7 @@ class SpikeFunctionBoxcar(torch.autograd.Function):
         return s
 
     @staticmethod
+    @_on_device
     def backward(ctx, grad_spikes):
         (x,) = ctx.saved_tensors
         g = _f32c(grad_spikes)
@@ -138,6 +155,7 @@ class LinearFunction(torch.autograd.Function):
     dropout) so that one exact bf16 term {0,1} suffices and c moves into the epilogue."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, x, weight, bias, in_scale, norm=None, x_terms=None):
         """norm: the layer's NormState; in 'bn_train' mode the GEMM epilogue can also accumulate the
         BatchNorm column statistics of the output and leave them in ``norm.stats``.
@@ -180,6 +198,7 @@ class LinearFunction(torch.autograd.Function):
         return Z.view(*x.shape[:-1], N)
 
     @staticmethod
+    @_on_device
     def backward(ctx, gZ):
         xa, wb = gemm.Terms(*ctx.saved_tensors[:2]), gemm.Terms(*ctx.saved_tensors[2:])
         M, N, K = ctx.dims
@@ -328,6 +347,7 @@ class SpikingCellFunction(torch.autograd.Function):
     """
 
     @staticmethod
+    @_on_device
     def forward(ctx, Z, gamma, bn_beta, alpha, beta, a, b, V, u0, w0, s0, kind, theta, norm):
         _require_cuda(Z, alpha, u0, s0)
         k = KINDS[kind]
@@ -409,6 +429,7 @@ class SpikingCellFunction(torch.autograd.Function):
         return S
 
     @staticmethod
+    @_on_device
     def backward(ctx, gS):
         (Z, gamma, bn_beta, alpha, beta, a, b, V0, u0, w0, s0, S, U, Wt, al, be, aa, bb, scale, mean,
          rstd) = ctx.saved_tensors
@@ -502,11 +523,13 @@ class FiringRateFunction(torch.autograd.Function):
     """mean over (B, T) of a spike tensor whose non-zero values all equal ``scale * rows``, from integer counts."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, out, counts, factor):
         ctx.shape = out.shape
         return counts.to(torch.float32) * factor
 
     @staticmethod
+    @_on_device
     def backward(ctx, g):
         B, T, H = ctx.shape
         return (g / (B * T)).expand(B, T, H), None, None
@@ -518,6 +541,7 @@ class _DropoutPostFunction(torch.autograd.Function):
     reverse recurrence in ``cell_state.gmax``."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, S, p, seed, out_bufs, cell_state, want_gmax):
         Be, T, H = S.shape
         out, term, sterm, counts = out_bufs
@@ -527,6 +551,7 @@ class _DropoutPostFunction(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, g):
         g = _f32c(g)
         Be, T, H = g.shape
@@ -537,6 +562,7 @@ class _DropoutPostFunction(torch.autograd.Function):
         return gS, None, None, None, None, None
 
 
+@_on_device
 def spike_post(S, p, cell_state, recurrent):
     """Post pass of a spiking layer: returns (out, SpikePost).  p: dropout probability in effect (0 in eval
     mode).  cell_state: the NormState the layer's cell Function was called with."""
@@ -571,6 +597,7 @@ class ReadoutCellFunction(torch.autograd.Function):
     """Normalisation fold + ReadoutLayer cell (snns.py:807-825): out = sum_t softmax(u_t)."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, Z, gamma, bn_beta, alpha, u0, norm):
         _require_cuda(Z, alpha, u0)
         Z = _f32c(Z)
@@ -591,6 +618,7 @@ class ReadoutCellFunction(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, gout):
         Z, gamma, bn_beta, alpha, u0, U, al, scale, mean, rstd = ctx.saved_tensors
         B, T, C = Z.shape

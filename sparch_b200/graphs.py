@@ -61,8 +61,17 @@ class GraphedTrainStep:
         """Copy the batch into the static buffers and replay; returns the (device) loss tensor."""
         self.x.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
+        self._refresh_hyper()
         self.graph.replay()
         return self.loss
+
+    def _refresh_hyper(self):
+        """sparch_b200.optim.Adam keeps lr / betas / eps in device words the captured kernel reads: a scheduler's change of
+        ``param_groups[i]["lr"]`` (exp.py:92-96) reaches the replay through this copy.  (torch.optim.Adam(capturable=True)
+        needs ``lr`` as a tensor for the same effect.)"""
+        sync = getattr(self.opt, "sync_hyper", None)
+        if sync is not None:
+            sync()
 
     # ---- input double-buffering: the next batch's host->device copy runs on a copy stream under the current step
     def stage(self, x_host, y_host):
@@ -85,5 +94,6 @@ class GraphedTrainStep:
         self.x.copy_(self._sx, non_blocking=True)             # device-to-device, a few microseconds
         self.y.copy_(self._sy, non_blocking=True)
         self._consumed.record()
+        self._refresh_hyper()
         self.graph.replay()
         return self.loss

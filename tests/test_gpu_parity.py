@@ -347,12 +347,21 @@ def _oracle_cell_check(kind, Be, T, H, seed, drive=(3.0, 1.2), stable=True):
     flips = float((s_gpu != r["s"]).mean())
     assert Be * T * H < 1000 or 0.005 < rate < 0.95, rate
     assert flips <= (FLIP_TOL if recurrent else 0.0), (kind, Be, T, H, flips)
-    if flips > 0:
-        return flips
+    # Given-mask backward on the CUDA forward's OWN tapes: with them the reverse pass is linear and well-posed even
+    # when a membrane value straddles the threshold or an edge of the surrogate window by one ulp (at cfg3's 6.5 M
+    # elements one does: identical spike trains, one differing window bit, 1 % error in dI through either reverse
+    # kernel when the oracle used its own tape).  The tapes themselves are compared with the oracle's first.
+    sv = S.grad_fn.saved_tensors          # (..., S, U, W, ...) as saved by SpikingCellFunction.forward
+    U_gpu = sv[12].cpu().numpy()
+    W_gpu = sv[13].cpu().numpy() if adaptive else None
+    if flips == 0:
+        assert rel_err(U_gpu, r["u"]) < U_RTOL
+        if adaptive:
+            assert rel_err(W_gpu, r["w"]) < U_RTOL
     gs = rng.standard_normal(s_gpu.shape).astype(np.float32)
     S.backward(torch.from_numpy(gs).to(DEV))
     bw = orc.cell_backward(kind, gs, I, p["alpha"], p.get("beta"), p.get("a"), p.get("b"), V0, u0,
-                           w0 if adaptive else None, s0, U=r["u"], W=r["w"], S=r["s"])
+                           w0 if adaptive else None, s0, U=U_gpu, W=W_gpu, S=s_gpu)
     tol = 5e-5  # longer chains than the fixtures: fp32 accumulation over T*Be terms
     assert rel_err(It.grad.cpu().numpy(), bw["dI"]) < tol
     assert rel_err(al.grad.cpu().numpy(), bw["dalpha"] * orc.clamp_grad_mask(alpha, orc.ALPHA_LIM)) < tol
@@ -737,6 +746,52 @@ def test_single_launch_adam_matches_torch():
         Adam([cpu_p], 1e-2).step()
 
 
+def test_adam_lr_change_reaches_graph_replays_and_step_round_trips():
+    """exp.py:92-96 drives the learning rate with ReduceLROnPlateau, which edits param_groups[i]["lr"].  The captured
+    Adam launch reads lr from a device word, so the change takes effect on the next replay (a by-value scalar would be
+    frozen into the graph); the step count lives in optimizer.state and survives state_dict() / load_state_dict()."""
+    from sparch_b200.optim import Adam
+    g = torch.Generator(device=DEV).manual_seed(5)
+    pa = [torch.randn(64, 33, device=DEV, generator=g).requires_grad_(True), torch.randn(17, device=DEV, generator=g).requires_grad_(True)]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    grads = [torch.randn(*p.shape, device=DEV, generator=g) for p in pa]
+    for x, y, gr in zip(pa, pb, grads):
+        x.grad, y.grad = gr.clone(), gr.clone()
+    oa, ob = Adam(pa, 1e-2), torch.optim.Adam(pb, 1e-2)
+    oa.step(); ob.step()                       # eager warm-up step (creates the state and the device words)
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        oa.step(); ob.step()
+    torch.cuda.current_stream().wait_stream(side)
+    with torch.cuda.graph(graph):
+        oa.step()
+    ob.step()                                  # the captured launch did not run: torch is one step ahead on purpose
+    graph.replay()                             # ... and now level again (3 steps each)
+    for lr in (1e-3, 5e-2):
+        for grp in oa.param_groups + ob.param_groups:
+            grp["lr"] = lr
+        before = pa[0].detach().clone()
+        oa.sync_hyper()                        # what GraphedTrainStep.step() does before every replay
+        graph.replay()
+        ob.step()
+        upd = float((pa[0].detach() - before).abs().max())
+        assert 0.2 * lr < upd < 5 * lr, (lr, upd)          # the update magnitude follows the new learning rate
+        for x, y in zip(pa, pb):
+            assert rel_err(x.detach().cpu().numpy(), y.detach().cpu().numpy()) < 2e-6
+    sd = oa.state_dict()
+    assert int(sd["state"][0]["step"]) == 5
+    oc = Adam(pa, 1e-2)
+    oc.load_state_dict(sd)
+    for grp in oc.param_groups:
+        grp["lr"] = 5e-2
+    oc.step(); ob.step()                       # resumes at step 6 with the right bias correction
+    assert int(oc.state[pa[0]]["step"]) == 6
+    for x, y in zip(pa, pb):
+        assert rel_err(x.detach().cpu().numpy(), y.detach().cpu().numpy()) < 2e-6
+
+
 @pytest.mark.parametrize("name", ["radlif_bn", "lif_bn"])
 def test_three_bf16_term_mode_against_reference_fixture(name):
     """set_precision("fp32-bf16x3") -- the first operand scheme, kept for comparison -- meets the same fixture
@@ -761,3 +816,212 @@ def test_reference_checkpoint_runs_on_the_gpu():
     out, rates = net(torch.from_numpy(run["x"]).to(DEV))
     np.testing.assert_allclose(out.detach().cpu().numpy(), run["out"], rtol=5e-5, atol=2e-6)
     np.testing.assert_allclose(rates.detach().cpu().numpy(), run["rates"], rtol=1e-6, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Round-2 regression net (VERDICT r01, "What's weak" 1-4): headline-shape gradients, the reference's default
+# (unstable) adaptation draw, dropout > 0 at value level, the cfg3 and cfg5 shapes.
+# ---------------------------------------------------------------------------------------------------------------
+
+def _bwd_tc_direct(kind, G, U, W, cl, V, u0, w0, s0, theta=1.0):
+    """sparch_recur_bwd_tc through the C ABI on GIVEN tapes (the oracle's): returns dI and the batch-summed raw
+    parameter gradients.  The reverse pass is linear given the tapes, so it is comparable to the fp64 oracle whatever
+    the forward dynamics are -- including the reference's default draw a ~ U(-1, 1), where free-running trains of two
+    implementations diverge (SURVEY.md 7 #1)."""
+    from sparch_b200._lib import call, lib, ptr
+    from sparch_b200.functional import KINDS
+    L = lib()
+    Be, T, H = G.shape
+    adaptive = KINDS[kind] & 1
+    st = torch.cuda.current_stream().cuda_stream
+    meta = torch.empty(2, device=DEV, dtype=torch.int32)
+    call("sparch_recur_prepare", ptr(V), H, None, None, ptr(meta), st)
+    img = torch.empty(L.sparch_recur_bwd_tc_image_bytes(H), device=DEV, dtype=torch.uint8)
+    call("sparch_recur_prepare_tc", ptr(V), H, ptr(img), ptr(meta), st)
+    ws = torch.empty(L.sparch_recur_bwd_tc_workspace(Be, T, H), device=DEV, dtype=torch.uint8)
+    dI = torch.empty_like(G)
+    part = torch.zeros(4, Be, H, device=DEV)
+    on = lambda z: ptr(z) if adaptive else None
+    call("sparch_recur_bwd_tc", KINDS[kind], ptr(G), ptr(U), on(W), ptr(cl["alpha"]), on(cl.get("beta")),
+         on(cl.get("a")), on(cl.get("b")), ptr(img), ptr(meta), ptr(u0), on(w0), ptr(s0), theta, ptr(dI), ptr(part[0]),
+         on(part[1]), on(part[2]), on(part[3]), ptr(ws), 0, Be, T, H, None, st)
+    torch.cuda.synchronize()
+    return dI, part.sum(1)
+
+
+@pytest.mark.parametrize("kind,Be,T,H,stable", [
+    ("RadLIF", 256, 100, 1024, False),   # BASELINE cfg4's layer, the reference's default a ~ U(-1, 1)
+    ("RadLIF", 256, 100, 1024, True),
+    ("RLIF", 128, 100, 512, True),       # cfg3's layer
+])
+def test_given_tape_bptt_at_headline_shapes(kind, Be, T, H, stable):
+    """Gradient parity at the benchmark shapes through the tcgen05 reverse kernel: oracle forward (fp32, numpy) ->
+    tapes -> CUDA reverse pass on those tapes vs the fp64 oracle.  T = 100 is where the kernel's one-step-late
+    per-row scale meets growing adjoints (48 % of the default-init neurons are linearly unstable).  Tolerances:
+    5e-5 of the tensor maximum; dI additionally 2e-4 of its own (row, step) maximum for every row."""
+    rng = np.random.default_rng(Be + T + H + int(stable))
+    adaptive, recurrent = orc.kind_flags(kind)
+    I = (rng.standard_normal((Be, T, H)) * 3.0 + 1.2).astype(np.float32)
+    alpha = rng.uniform(np.exp(-1 / 5), np.exp(-1 / 25), H).astype(np.float32)      # snns.py:229, 644-647
+    beta = rng.uniform(np.exp(-1 / 30), np.exp(-1 / 120), H).astype(np.float32)
+    a = rng.uniform(0.0 if stable else -1.0, 1.0, H).astype(np.float32)
+    b = rng.uniform(0.0, 2.0, H).astype(np.float32)
+    V0 = torch.nn.init.orthogonal_(torch.empty(H, H), generator=torch.Generator().manual_seed(3)).numpy().copy()
+    np.fill_diagonal(V0, 0)
+    u0, w0, s0 = (rng.uniform(0, 1, (Be, H)).astype(np.float32) for _ in range(3))
+    r = orc.cell_forward(kind, I, alpha, beta, a, b, V0, u0, w0 if adaptive else None, s0)
+    assert np.isfinite(r["u"]).all()
+    if not stable:
+        assert np.abs(r["u"]).max() > 1e3, "the unstable draw did not grow: the test would not cover it"
+    gs = rng.standard_normal((Be, T, H)).astype(np.float32)
+    bw = orc.cell_backward(kind, gs, I, alpha, beta, a, b, V0, u0, w0 if adaptive else None, s0,
+                           U=r["u"], W=r["w"], S=r["s"])
+    t_ = lambda z: None if z is None else torch.from_numpy(np.ascontiguousarray(z)).to(DEV)
+    cl = {"alpha": t_(alpha), "beta": t_(beta), "a": t_(a), "b": t_(b)}
+    dI, pg = _bwd_tc_direct(kind, t_(gs), t_(r["u"]), t_(r["w"]) if adaptive else None, cl, t_(V0), t_(u0),
+                            t_(w0), t_(s0))
+    dI = dI.cpu().numpy().astype(np.float64)
+    assert np.isfinite(dI).all()
+    assert rel_err(dI, bw["dI"]) < 5e-5
+    row_max = np.abs(bw["dI"]).max(axis=2, keepdims=True)
+    row_err = (np.abs(dI - bw["dI"]) / np.maximum(row_max, 1e-300)).max()
+    assert row_err < 2e-4, row_err
+    names = ("dalpha", "dbeta", "da", "db") if adaptive else ("dalpha",)
+    for i, k in enumerate(names):
+        assert rel_err(pg[i].cpu().numpy(), bw[k]) < 5e-5, k
+
+
+@pytest.mark.parametrize("kind,Be,T,H", [("RadLIF", 70, 16, 1000), ("RadLIF", 300, 7, 96), ("adLIF", 65, 33, 77),
+                                         ("RadLIF", 256, 12, 1024), ("RadLIF", 33, 40, 130)])
+def test_cells_with_the_default_unstable_adaptation_draw(kind, Be, T, H):
+    """`stable=False`: a ~ U(-1.2, 1.2) as the reference's default init draws it (snns.py:647).  Spike trains are
+    compared as everywhere; the gradients whenever the trains coincide (they do at these lengths)."""
+    _oracle_cell_check(kind, Be, T, H, seed=7 * Be + T + H, stable=False)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_recurrent_cells_random_shape_sweep_unstable(seed):
+    rng = np.random.default_rng(2000 + seed)
+    kind = ("RLIF", "RadLIF", "RadLIF")[seed % 3]
+    Be = int(rng.choice([2, 33, 64, 129, 200]))
+    H = int(rng.choice([16, 33, 48, 100, 260, 512]))
+    T = int(rng.integers(2, 12))
+    _oracle_cell_check(kind, Be, T, H, seed=seed, drive=(3.0, 1.5), stable=False)
+
+
+def test_rlif_cfg3_layer_free_running_against_oracle():
+    """BASELINE cfg3's layer shape (RLIF, B = 128, T = 100, H = 512) free-running against the numpy oracle, then
+    the gradients of the given-mask backward."""
+    _oracle_cell_check("RLIF", 128, 100, 512, seed=3, drive=(3.0, 1.2))
+
+
+@pytest.mark.parametrize("kind,Be,T,H,p", [("RadLIF", 64, 20, 256, 0.1), ("adLIF", 32, 25, 96, 0.25),
+                                           ("RadLIF", 256, 12, 1024, 0.1)])
+def test_dropout_gradients_at_value_level(kind, Be, T, H, p):
+    """cfg4 trains with dropout 0.1 (snns.py:692).  The mask is not stored (Philox keyed by a seed word and the
+    element position), so it is read back by running the same post pass with the same seed over a tensor of ones;
+    the oracle then applies out = S * mask / (1 - p) and its adjoint, and every gradient of the cell is compared."""
+    _, F = _mods()
+    rng = np.random.default_rng(Be + T + H)
+    adaptive, recurrent = orc.kind_flags(kind)
+    I = (rng.standard_normal((Be, T, H)) * 3.0 + 1.2).astype(np.float32)
+    alpha = rng.uniform(0.80, 0.97, H).astype(np.float32)
+    beta = rng.uniform(0.96, 0.995, H).astype(np.float32)
+    a = rng.uniform(0.0, 1.2, H).astype(np.float32)
+    b = rng.uniform(-0.2, 2.2, H).astype(np.float32)
+    V = (rng.standard_normal((H, H)) / np.sqrt(H)).astype(np.float32)
+    u0, w0, s0 = (rng.uniform(0, 1, (Be, H)).astype(np.float32) for _ in range(3))
+    cp = orc.clamp_params(kind, alpha, beta, a, b)
+    V0 = None
+    if recurrent:
+        V0 = V.copy()
+        np.fill_diagonal(V0, 0)
+    r = orc.cell_forward(kind, I, cp["alpha"], cp.get("beta"), cp.get("a"), cp.get("b"), V0, u0,
+                         w0 if adaptive else None, s0)
+    t = lambda z, g=False: torch.from_numpy(z).to(DEV).requires_grad_(g)
+    It, al, be, aa, bb, Vt = t(I, True), t(alpha, True), t(beta, True), t(a, True), t(b, True), t(V, True)
+    norm = F.NormState("none")
+    S = F.SpikingCellFunction.apply(It, None, None, al, be if adaptive else None, aa if adaptive else None,
+                                    bb if adaptive else None, Vt if recurrent else None, t(u0),
+                                    t(w0) if adaptive else None, t(s0), kind, 1.0, norm)
+    assert float((S.detach().cpu() != torch.from_numpy(r["s"])).float().mean()) <= (FLIP_TOL if recurrent else 0.0)
+    sv = S.grad_fn.saved_tensors          # the CUDA forward's own tapes (see _oracle_cell_check)
+    s_gpu, U_gpu = S.detach().cpu().numpy(), sv[12].cpu().numpy()
+    W_gpu = sv[13].cpu().numpy() if adaptive else None
+    torch.manual_seed(99)
+    out, post = F.spike_post(S, p, norm, recurrent)
+    torch.manual_seed(99)                                   # same seed word -> same mask
+    ones_out, _ = F.spike_post(torch.ones_like(S), p, F.NormState("none"), recurrent)
+    mask = (ones_out.detach() != 0).cpu().numpy().astype(np.float64)
+    keep = mask.mean()
+    assert abs(keep - (1 - p)) < 0.01
+    np.testing.assert_allclose(out.detach().cpu().numpy(), s_gpu * mask / (1 - p), rtol=1e-6, atol=0)
+    g_out = rng.standard_normal(S.shape).astype(np.float32)
+    out.backward(torch.from_numpy(g_out).to(DEV))
+    gs = (g_out.astype(np.float64) * mask / (1 - p)).astype(np.float32)      # dropout's adjoint, as ATen does it
+    bw = orc.cell_backward(kind, gs, I, cp["alpha"], cp.get("beta"), cp.get("a"), cp.get("b"), V0, u0,
+                           w0 if adaptive else None, s0, U=U_gpu, W=W_gpu, S=s_gpu)
+    tol = 5e-5
+    assert rel_err(It.grad.cpu().numpy(), bw["dI"]) < tol
+    assert rel_err(al.grad.cpu().numpy(), bw["dalpha"] * orc.clamp_grad_mask(alpha, orc.ALPHA_LIM)) < tol
+    if adaptive:
+        for k, g_, raw, lim in (("beta", be, beta, orc.BETA_LIM), ("a", aa, a, orc.A_LIM), ("b", bb, b, orc.B_LIM)):
+            assert rel_err(g_.grad.cpu().numpy(), bw["d" + k] * orc.clamp_grad_mask(raw, lim)) < tol, k
+    if recurrent:
+        assert rel_err(Vt.grad.cpu().numpy(), bw["dV"]) < tol
+
+
+@pytest.mark.parametrize("precision,flip_tol,loss_tol", [("fp32", FLIP_TOL, 0.10), ("bf16", 2e-2, 0.10)])
+def test_bidirectional_long_sequence_cfg5_shape(precision, flip_tol, loss_tol):
+    """BASELINE cfg5's structure at a batch the oracle can hold: bidirectional RadLIF 3x1024, T = 500, B = 8
+    (Be = 16 after the direction doubling, second layer fed by 2H = 2048 features), a <- |a| (the reference is
+    non-finite at T = 500 with its default draw, SURVEY.md 7 #2).  Layer-0 spike trains and the loss against the
+    oracle's torch restatement on the same device, in the fp32-equivalent mode and in the reduced (bf16) mode with its
+    stated tolerance; every gradient of our model is finite.  The loss band is 10 %: over 500 steps a handful of
+    threshold straddlers in layer 0 reshuffle layer 1 (through its BatchNorm over only 16 x 500 rows) -- the reference
+    differs from ITSELF by 5-8 % in its logits between two thread counts (SURVEY.md 7 #1); firing rates agree to 0.02."""
+    import sparch_b200
+    sp, _ = _mods()
+    kw = dict(layer_sizes=[1024, 1024, 35], neuron_type="RadLIF", normalization="batchnorm", bidirectional=True)
+    torch.manual_seed(0)
+    net = sp.SNN((8, None, 40), **kw)
+    ref = orc.build_oracle_snn((8, None, 40), **kw)
+    ref.load_state_dict(net.state_dict())
+    for m in (net, ref):
+        with torch.no_grad():
+            for lay in m.snn:
+                if hasattr(lay, "a"):
+                    lay.a.abs_()
+                if isinstance(getattr(lay, "norm", None), torch.nn.BatchNorm1d):
+                    lay.norm.weight.fill_(3.0)
+                    lay.norm.bias.fill_(0.8)
+    net, ref = net.to(DEV), ref.to(DEV)
+    ref.snn[0].capture = {}
+    torch.manual_seed(1234)
+    x = torch.randn(8, 500, 40, device=DEV)
+    y = torch.randint(0, 35, (8,), device=DEV)
+    got = {}
+    h = net.snn[0].register_forward_hook(lambda m, i, o: got.__setitem__(0, o.detach()))
+    try:
+        sparch_b200.set_precision(precision)
+        torch.manual_seed(42)
+        out, rates = net(x)
+        loss = torch.nn.functional.cross_entropy(out, y)
+        loss.backward()
+    finally:
+        sparch_b200.set_precision("fp32")
+        h.remove()
+    with torch.no_grad():
+        torch.manual_seed(42)
+        out_r, rates_r = ref(x)
+    assert got[0].shape == (8, 500, 2048)
+    s_ref = ref.snn[0].capture["s"]                 # (2B, T, H) before the direction merge (snns.py:686-689)
+    s_f, s_b = s_ref[:8], s_ref[8:].flip(1)
+    merged = torch.cat([s_f, s_b], dim=2)
+    flips = float((got[0] != merged).float().mean())
+    assert 0.005 < float(merged.mean()) < 0.9
+    assert flips <= flip_tol, flips
+    loss_r = torch.nn.functional.cross_entropy(out_r, y)
+    assert abs(float(loss) - float(loss_r)) <= loss_tol * abs(float(loss_r)), (float(loss), float(loss_r))
+    assert float((rates - rates_r).abs().max()) < 0.02
+    assert all(q.grad is not None and torch.isfinite(q.grad).all() for q in net.parameters())
