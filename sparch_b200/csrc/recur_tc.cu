@@ -1,33 +1,37 @@
-// Reverse-time recurrence of the recurrent kinds with dI_{t+1} @ V0^T on tcgen05 (alternative to
-// rec_bwd_persist_kernel in recur.cu; same BPTT update, same hand-over idea), split-K over a cluster.
+// Reverse-time recurrence of the recurrent kinds (BPTT of snns.py:554-578 / 696-727) with recb_t = dI_{t+1} @ V0^T on
+// tcgen05, split-K over a thread-block cluster, tagged-word hand-over between the steps.
 //
-//   Cluster of 4 CTAs = 64 batch rows x 128 presynaptic neurons j, persistent over all T steps.  CTA
-//   rank r of the cluster multiplies over its QUARTER of K (neurons c in [r Hp/4, (r+1) Hp/4)) for all
-//   128 columns, then the four 64 x 128 partial products are reduce-scattered through distributed
-//   shared memory: rank r sums and owns columns 32 r .. 32 r + 31 (so CTA bx updates neurons 32 bx ..).
-//   B operand: V0[128 j][Hp/4 c] as fp16 hi + lo, K-major SWIZZLE_128B tiles resident in shared memory
+//   Cluster of 4 CTAs = 64 batch rows x 128 presynaptic neurons j, persistent over all T steps.  CTA rank r of the
+//   cluster multiplies over its QUARTER of K (neurons c in [r Hp/4, (r+1) Hp/4)) for all 128 neurons j of the cluster,
+//   then the four partial products are reduce-scattered through distributed shared memory: rank d sums and owns 32 of
+//   the 128 neurons.  The neurons a CTA owns lie INSIDE the K quarter it consumes (cluster c, rank r owns neurons
+//   r Hp/4 + 32 c .. + 31), so the all-gather of dI_{t+1} closes over groups of Hp/128 CTAs (rank r of every cluster):
+//   a CTA waits only for the producers whose data it multiplies.
+//
+//   The product is issued TRANSPOSED: D^T[j][row] = sum_c V0[j][c] dI[row][c], i.e. A = the resident V0 tile (M = 128
+//   neurons, full-rate UMMA shape), B = the dI panel (N = 64 rows), D = 128 TMEM lanes x 64 fp32 columns.  Every TMEM
+//   lane is used, a warp's tcgen05.ld returns one neuron per lane (32 rows each), and the lane quarter q of TMEM holds
+//   exactly the neurons of cluster rank q: the reduce-scatter is 8 st.async per update warp.  (The first version
+//   computed D = dI V0^T with M = 64: half-rate UMMA, half of the TMEM lanes idle, 16 stores per warp.)
+//
+//   A operand: V0[128 j][Hp/4 c] as fp16 hi + lo, K-major SWIZZLE_128B tiles resident in shared memory
 //              (Hp/256 x 2 x 16 KB = 128 KB at H = 1024).
-//   A operand: dI_{t+1} of the 64 rows, handed over through L2 as two plain row-major fp16 matrices
-//              (hi, lo); each CTA fetches only its K quarter by TMA (64 x 64 boxes, SWIZZLE_128B).
-//   D: 64 x 128 fp32 in 128 TMEM columns; per K16 three UMMAs (hi*hi, hi*lo, lo*hi) with N = 128, issued
-//      by one thread; the update warps read D with tcgen05.ld (M = 64 layout: rows 16q..16q+15 live in
-//      TMEM lanes 32q..32q+15) and scatter the column quarters to their owners (st.shared::cluster +
-//      remote mbarrier arrive).
+//   B operand: dI_{t+1} of the 64 rows x this rank's K quarter, fp16 hi + lo, written into shared memory by the update
+//              warps themselves (K-major SWIZZLE_128B, one 16 KB stage per 64-neuron K block, no ring).
+//   Hand-over through L2 without flags, fences or TMA: a producer stores one 32-bit word {hi, lo} per element with
+//   st.relaxed.gpu; the least significant bit of lo is a TAG that toggles every time the (double-buffered) word is
+//   rewritten, so a consumer polls the data itself (ld.relaxed.gpu.v4, 16 loads in flight per thread) and knows from
+//   the word alone whether it is this step's value -- one L2 round trip from "dI_t computed" to "operand in shared
+//   memory" (the first version: panel stores, red.release, ld.acquire poll, fence.proxy.async, TMA = three round trips,
+//   ~5.5 k of its 13.5 k cycles per step).  lo keeps 10 of its 11 significant bits: 21 bits per element.
 //
-// Why split K instead of N (measured on B200 with the first version of this kernel, one CTA = 64 rows x
-// 32 neurons over the whole K range): a tcgen05.mma at M = 64 costs ~58 cycles whether N is 32 or 128,
-// so the 192 UMMAs a whole-K CTA needs per step took 11.3 k cycles, more than the mma.sync kernel.  With
-// N = 128 and a quarter of K a CTA issues 48 per step, and the panel traffic out of L2 drops from 256 KB
-// to 64 KB per CTA per step.
-//
-// Scaling.  fp16 needs a scale, and the tensor core accumulates over the whole K range without
-// intervention, so the scale must be per ROW (not per 32-column chunk as in the mma.sync kernel).  The
-// row maximum of |dI_t| is only known once all slices have produced their part, so the scale of step t
-// is derived one step late: M_t = max(rowmax|dI_{t+1}|, 0.25 * rowmax|g_t|), s_t = 2^(4 - exp(M_t)).
-// |dI_t| can exceed M_t by the growth of one step (bounded by a few hundred), far inside fp16's range
-// above 16; values below it only lose ABSOLUTE precision (fp16 hi + lo keeps 2^-25 of the scaled unit),
-// i.e. <= 2^-29 of the row maximum -- below fp32 rounding of the dominant terms.  Every slice computes
-// the same s_t from the same published chunk maxima, so producer and consumers agree.
+// Scaling.  fp16 needs a scale, and the tensor core accumulates over the whole K range without intervention, so the
+// scale is per ROW.  The row maximum of |dI_t| is only known once all slices have produced their part, so the scale of
+// step t is derived one step late: M_t = max(rowmax|dI_{t+1}|, 0.25 * rowmax|g_t|), s_t = 2^(4 - exp(M_t)).
+// |dI_t| can exceed M_t by the growth of one step (bounded by a few hundred), far inside fp16's range above 16; values
+// below it only lose ABSOLUTE precision.  rowmax|dI_{t+1}| costs no extra exchange: each rank takes the maximum of the
+// K quarter it has just loaded and sends it to its three cluster peers with the reduce-scatter (4 ranks = 4 quarters =
+// the whole row); every CTA of the row group derives the same s_t from the same numbers.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -37,20 +41,17 @@
 
 namespace sparch {
 
-constexpr int TC_ROWS = 64;            // batch rows per CTA
+constexpr int TC_ROWS = 64;            // batch rows per CTA (UMMA N)
 constexpr int TC_COLS = 32;            // neurons updated per CTA
 constexpr int TC_CL = 4;               // CTAs per cluster = K quarters
-constexpr int TC_N = TC_COLS * TC_CL;  // UMMA N: neurons per cluster
-constexpr int TC_STAGES = 3;           // A ring depth (a fourth stage leaves too little L1: measured slower)
-constexpr int TC_RS = 65;              // receive buffer: float4 row stride (64 rows + 1: conflict-free reads)
-constexpr int TC_RECV_BYTES = TC_CL * 8 * TC_RS * 16;
+constexpr int TC_N = TC_COLS * TC_CL;  // neurons per cluster (UMMA M)
 constexpr int TC_STAGE_BYTES = 16384;  // 64 rows x 64 K x (hi, lo) fp16
-constexpr int TC_THREADS = 320;        // warp 0 TMA, warp 1 MMA, warps 2..9 update
+constexpr int TC_RECV_BYTES = TC_CL * TC_COLS * TC_ROWS * 4;  // [source rank][row quad][neuron][4 rows] fp32
+constexpr int TC_QMAX_BYTES = TC_CL * TC_ROWS * 4;            // [source rank][row] quarter maxima of |dI_{t+1}|
+constexpr int TC_THREADS = 320;        // warp 0 spare, warp 1 MMA, warps 2..9 load + update
 constexpr int TC_VSCALE_EXP = 13;
-
-struct TcMaps {
-  CUtensorMap hi, lo;
-};
+constexpr uint32_t TC_RECV_TX = TC_RECV_BYTES + TC_QMAX_BYTES;
+constexpr uint32_t TC_D_COL = 256;      // TMEM: V0 hi / lo in columns [0, 256), two accumulators in [256, 320), [320, 384)
 
 struct RecBwdTcArgs {
   const float *G, *U, *W, *alpha, *beta, *a, *b, *u0, *w0, *s0;
@@ -59,16 +60,21 @@ struct RecBwdTcArgs {
   const float* gmax;     // [Be][T] row maxima of |G|
   float theta;
   float *dI, *p_alpha, *p_beta, *p_a, *p_b;
-  __half *panel_hi, *panel_lo;  // [2][groups*64][Hp]
-  float* cmax;                  // [2][groups][Hp/32][64] chunk maxima of |dI_t|
+  uint32_t* panel;       // [2][groups*64][Hp] words {fp16 hi, fp16 lo with the tag in its least significant bit}
   int Be, T, H, Hp, KB;  // Hp: H padded to 256; KB = Hp / 256 k-blocks of 64 per CTA
   int reduced;
-  long long* dbg;  // optional [T][8] phase clocks of CTA (0,0) (profiling aid), normally NULL
-  int dbg_flags;   // profiling experiments (results invalid): 4 no TMA traffic, 16 no UMMA
+  long long* dbg;  // optional [2T][8] phase clocks of CTA (0,0) (profiling aid), normally NULL
+  int dbg_flags;   // profiling experiments (results invalid): 16 no UMMA
 };
 
-// V0 as UMMA B tiles.  CTA bx = (cluster bx / 4, rank bx % 4) holds rows j = 128 (bx / 4) + n, n < 128, and
-// K = (bx % 4) Hp / 4 + 64 kb + k; element (n, k) of a tile: halves offset n*64 + ((k/8) ^ (n&7))*8 + k%8.
+// First neuron owned by CTA `slice` = (cluster slice / 4, rank slice % 4): inside the K quarter the rank consumes.
+__host__ __device__ __forceinline__ int tc_own0(int slice, int Hp) {
+  return (slice % TC_CL) * (Hp / TC_CL) + TC_COLS * (slice / TC_CL);
+}
+
+// V0 as UMMA tiles.  CTA bx = (cluster bx / 4, rank bx % 4) holds tile rows n = 32 d + i <-> neuron i of cluster rank
+// d (presynaptic j = tc_own0(4 (bx / 4) + d) + i) and K = (bx % 4) Hp / 4 + 64 kb + k; element (n, k) of a tile: halves
+// offset n*64 + ((k/8) ^ (n&7))*8 + k%8.
 __global__ void vprep_umma_kernel(const float* __restrict__ V, int H, int Hp, int KB, const int* __restrict__ meta,
                                   __half* __restrict__ img) {
   // one thread per 16-byte swizzle chunk (8 consecutive K of one row n): reads 32 contiguous bytes of V once and
@@ -81,7 +87,7 @@ __global__ void vprep_umma_kernel(const float* __restrict__ V, int H, int Hp, in
     const int r = (int)(i - (int64_t)bx * per_cta8);
     const int chunk_sw = r & 7, n = (r >> 3) & (TC_N - 1), kb = r >> 10;
     const int k0 = (chunk_sw ^ (n & 7)) << 3;
-    const int row = (bx / TC_CL) * TC_N + n;                      // V[row = presynaptic j][col = neuron c]
+    const int row = tc_own0((bx / TC_CL) * TC_CL + n / TC_COLS, Hp) + (n % TC_COLS);  // V[row = presynaptic j][col = neuron c]
     const int col0 = (bx % TC_CL) * (Hp / TC_CL) + kb * 64 + k0;
     __align__(16) __half hi[8], lo[8];
 #pragma unroll
@@ -118,389 +124,508 @@ __device__ __forceinline__ bool tc_elect_one() {
   return e != 0;
 }
 
-__device__ __forceinline__ void upd_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-__device__ __forceinline__ float scale_from_max(float m) {
+// Exponent E of the power-of-two scale 2^E that brings m into [8, 16) (4 minus the binary exponent of m, clamped): pure
+// bit operations, the same result in every CTA that sees the same m.  -123 <= E <= 104.
+__device__ __forceinline__ int scale_exp(float m) {
   int e = 0;
-  if (m > 0.f && m <= 3.0e38f) frexpf(m, &e);
-  e = max(e, -100);
-  return ldexpf(1.0f, 4 - e);
+  if (m > 0.f && m <= 3.0e38f) {
+    const int ef = (int)((__float_as_uint(m) >> 23) & 0xffu);
+    e = ef ? ef - 126 : -126;
+  }
+  return 4 - max(e, -100);
 }
+
+// Tape values are read once: non-coherent path, no L1 allocation (with 225 KB of shared memory in use the L1 holds
+// a fraction of one step's 32 KB).
+__device__ __forceinline__ float ld_stream(const float* a) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(a));
+  return v;
+}
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* a) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ uint4 ld_relaxed_v4(const uint32_t* a) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a) : "memory");
+  return v;
+}
+
+#define TC_LD32(taddr, v)                                                                                                   \
+  asm volatile(                                                                                                            \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "      \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                             \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),         \
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),              \
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),             \
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                           \
+      : "r"(taddr))
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+__device__ __forceinline__ uint32_t tc_mapa(uint32_t addr, int rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (!done) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+// Tag of the words of panel(t): the buffer (t & 1) is rewritten every second step, its n-th use carries tag (n & 1) ^ 1
+// (the buffers start zeroed: tag 0).
+__device__ __forceinline__ uint32_t tc_tag(int T, int t) { return ((((T - 1 - t) >> 1) & 1) ^ 1); }
 
 template <bool ADAPT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-rec_bwd_tc_kernel(const __grid_constant__ TcMaps maps, const RecBwdTcArgs p, const int group0, const int ngroups_total,
-                  int* __restrict__ counters) {
+rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_total) {
   extern __shared__ unsigned char tsm_raw[];
   const uint32_t raw = smem_u32(tsm_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   unsigned char* tsm = tsm_raw + (base - raw);
-  const size_t v_bytes = (size_t)p.KB * 2 * (TC_N * 128);       // KB x (hi, lo) x 16 KB
-  const uint32_t vimg = base;
-  const uint32_t ring = base + (uint32_t)v_bytes;               // TC_STAGES * 16 KB
-  const uint32_t recv = ring + TC_STAGES * TC_STAGE_BYTES;      // [4 source ranks][8 column groups][65] float4
-  const uint32_t bars = recv + TC_RECV_BYTES;                   // full[4], empty[4], acc_full, acc_empty, recv_full
-  unsigned char* tail = tsm + v_bytes + TC_STAGES * TC_STAGE_BYTES + TC_RECV_BYTES;
-  const float4* recv_f4 = reinterpret_cast<const float4*>(tail - TC_RECV_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 128);
-  __shared__ float sprm[6][TC_COLS];
-  constexpr int B_ACC_FULL = 2 * TC_STAGES, B_ACC_EMPTY = 2 * TC_STAGES + 1, B_RECV = 2 * TC_STAGES + 2;
+  const uint32_t v_bytes = (uint32_t)p.KB * 2 * (TC_N * 128);     // KB x (hi, lo) x 16 KB of V0 tiles per CTA (global image)
+  const uint32_t stage = base;                                    // KB x 16 KB: dI_{t+1} tiles (hi 8 KB, lo 8 KB)
+  const uint32_t recv = stage + (uint32_t)p.KB * TC_STAGE_BYTES;  // partial products from the four ranks
+  const uint32_t qmax = recv + TC_RECV_BYTES;                     // quarter maxima from the four ranks
+  const uint32_t bars = qmax + TC_QMAX_BYTES;                     // full[4], acc_full, recv, free
+  unsigned char* tail = tsm + (size_t)p.KB * TC_STAGE_BYTES;
+  const unsigned char* recv_p = tail;
+  const float* qmax_p = reinterpret_cast<const float*>(tail + TC_RECV_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + TC_RECV_BYTES + TC_QMAX_BYTES + 64);
+  constexpr int B_ACC_FULL = 4, B_RECV = 5, B_FREE = 6;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slice = blockIdx.x, group = group0 + blockIdx.y, row0 = group * TC_ROWS;
   const int rank = blockIdx.x % TC_CL;  // == %cluster_ctarank for cluster dims (4, 1, 1)
-  const int nslices = gridDim.x, NCH = p.Hp / 32;
-  // Hand-over flags: one arrival counter per (row group, 64-neuron K block); the two slices that produce a K block
-  // add 1 each per step.  A consumer waits per K block of its own K quarter (and not for all 32 slices of the group):
-  // less skew to wait out, and two instead of 32 CTAs contend for an address.
-  const int NKB = p.Hp / 64;                           // K blocks per row = flags per group (<= 16 for H <= 1024)
-  int* flags = counters + (size_t)group * NKB;
-  int* my_flag = flags + slice / 2;
+  const int own0 = tc_own0(slice, p.Hp);
   const bool dbg_cta = p.dbg && blockIdx.x == 0 && blockIdx.y == 0;
 
-  {  // resident V0 tiles
-    const uint4* src = reinterpret_cast<const uint4*>(p.img) + (size_t)slice * (v_bytes / 16);
-    uint4* dst = reinterpret_cast<uint4*>(tsm);
-    for (int i = tid; i < (int)(v_bytes / 16); i += TC_THREADS) {
-      uint32_t sa = smem_u32(dst + i);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + i));
-    }
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-  }
-  if (tid < TC_COLS) {
-    const int col = min(slice * TC_COLS + tid, p.H - 1);
-    const NeuronParams q0 = load_params<ADAPT>(p.alpha, p.beta, p.a, p.b, col);
-    sprm[0][tid] = q0.alpha; sprm[1][tid] = q0.oma; sprm[2][tid] = q0.beta; sprm[3][tid] = q0.a;
-    sprm[4][tid] = q0.b; sprm[5][tid] = 1.0f / q0.oma;
-  }
   if (tid == 0) {
-    for (int st = 0; st < TC_STAGES; ++st) {
-      mbar_init(bars + 8 * st, 1);
-      mbar_init(bars + 8 * (TC_STAGES + st), 1);
-    }
-    mbar_init(bars + 8 * B_ACC_FULL, 1);    // one tcgen05.commit
-    mbar_init(bars + 8 * B_ACC_EMPTY, 8);   // one arrival per update warp
-    mbar_init(bars + 8 * B_RECV, 1);  // armed per step with the 32 KB the four ranks deliver (st.async complete_tx)
-    mbar_expect_tx(bars + 8 * B_RECV, TC_CL * TC_ROWS * TC_COLS * 4);
+    for (int kb = 0; kb < 4; ++kb) mbar_init(bars + 8 * kb, 8);   // one arrival per update warp
+    mbar_init(bars + 8 * B_ACC_FULL, 1);                          // one tcgen05.commit
+    mbar_init(bars + 8 * B_RECV, 1);  // armed per step with the bytes the four ranks deliver (st.async complete_tx)
+    mbar_init(bars + 8 * B_FREE, TC_CL * 8);                      // every update warp of the cluster has read its buffers
+    mbar_expect_tx(bars + 8 * B_RECV, TC_RECV_TX);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // make the cp.async-written tiles visible to the tensor core's (async proxy) reads
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  // cluster-wide: nobody may arrive on a peer's recv barrier before it is initialised
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_d = tmem + TC_D_COL;
+  if (warp >= 2) {
+    // ---- resident V0: this CTA's 128 neurons x K quarter, fp16 hi and lo, as the A operand IN TENSOR MEMORY (lane =
+    // neuron n, 32-bit column = two consecutive K): hi at columns [0, 32 KB), lo at [32 KB, 64 KB).  The tensor core then
+    // reads only the 2 KB of dI per UMMA from shared memory and runs at its full rate (A from shared memory: 6 KB per
+    // UMMA, 68 cycles instead of 32 at M = 128, N = 64).  Warp (q, part) copies part (hi / lo) of the neurons of TMEM
+    // lane quarter q out of the global image: each lane reads the 128 contiguous bytes of its tile row, un-swizzled by
+    // address.
+    const int q = warp & 3, part = (warp - 2) >> 2, n = 32 * q + lane;
+    const unsigned char* img = reinterpret_cast<const unsigned char*>(p.img) + (size_t)slice * v_bytes;
+    for (int kb = 0; kb < p.KB; ++kb) {
+      const unsigned char* rowp = img + ((size_t)(kb * 2 + part) * TC_N + n) * 128;
+      uint32_t w[32];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 x = *reinterpret_cast<const uint4*>(rowp + ((c ^ (n & 7)) << 4));
+        w[4 * c] = x.x; w[4 * c + 1] = x.y; w[4 * c + 2] = x.z; w[4 * c + 3] = x.w;
+      }
+      const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(part * 32 * p.KB + kb * 32);
+      asm volatile(
+          "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
+          "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+          "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]), "r"(w[9]),
+          "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]), "r"(w[16]), "r"(w[17]), "r"(w[18]),
+          "r"(w[19]), "r"(w[20]), "r"(w[21]), "r"(w[22]), "r"(w[23]), "r"(w[24]), "r"(w[25]), "r"(w[26]), "r"(w[27]),
+          "r"(w[28]), "r"(w[29]), "r"(w[30]), "r"(w[31])
+          : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  // cluster-wide: nobody may arrive on a peer's barriers before they are initialised
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const float rs = ldexpf(1.0f, p.meta[0] - TC_VSCALE_EXP);
 
-  if (warp == 0) {
-    // ===== TMA producer (whole warp walks the steps; lane 0 does the work) =====
-    int it = 0;
-    for (int t = p.T - 2; t >= 0; --t) {
-      const int rbuf = (t + 1) & 1;
-      const int target = 2 * (p.T - 1 - t);            // both producer slices of a K block have published panel(t+1)
-      const int y = (rbuf * ngroups_total + group) * TC_ROWS;
-      // lanes 0..KB-1: wait for K block `lane` of this rank's quarter, then fetch it (each lane drives its own ring
-      // slot).  Rounds of TC_STAGES lanes: two fills of the same slot must reach its empty barrier one after the other,
-      // a parity wait cannot tell "one phase behind" from "three behind".
-      for (int base_kb = 0; base_kb < p.KB; base_kb += TC_STAGES) {
-      if (lane >= base_kb && lane < min(base_kb + TC_STAGES, p.KB)) {
-        const int kb = lane;
-        const int* f = flags + rank * p.KB + kb;
-        const long long t0 = clock64();
-        while (true) {
-          int v;
-          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-          if (v >= target) break;
-          if (clock64() - t0 > 4000000000LL) __trap();
-        }
-        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of other SMs -> TMA reads
-        if (dbg_cta && kb == 0) p.dbg[t * 8 + 0] = clock64();
-        const int it_kb = it + kb;
-        const int s = it_kb % TC_STAGES;
-        const uint32_t ph = (it_kb / TC_STAGES) & 1;
-        mbar_wait(bars + 8 * (TC_STAGES + s), ph ^ 1);
-        if (p.dbg_flags & 4) {
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8 * s) : "memory");
-        } else {
-          mbar_expect_tx(bars + 8 * s, TC_STAGE_BYTES);
-          const uint32_t sa = ring + s * TC_STAGE_BYTES;
-          const int x = rank * (p.Hp / TC_CL) + kb * 64;  // this rank's K quarter
-          tma_load_2d(sa, &maps.hi, x, y, bars + 8 * s);
-          tma_load_2d(sa + 8192, &maps.lo, x, y, bars + 8 * s);
-        }
-      }
-      __syncwarp();
-      }
-      it += p.KB;
-      // the chunk maxima of ALL slices feed the row scale: wait for the rest of the group's flags (off the MMA's path)
-      if (lane < NKB) {
-        const int* f = flags + lane;
-        const long long t0 = clock64();
-        while (true) {
-          int v;
-          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-          if (v >= target) break;
-          if (clock64() - t0 > 4000000000LL) __trap();
-        }
-      }
-      __syncwarp();
-      asm volatile("bar.arrive 2, 288;" ::: "memory");    // the update warps may read the chunk maxima now
-    }
-  } else if (warp == 1) {
+  if (warp == 1) {
     // ===== MMA issuer: the warp stays converged, one elected lane issues each K block's UMMAs as straight-line code
     // (under a plain `if (lane == 0)` ptxas wraps every UMMA in an ELECT / PLOP3 / BRA.U.ANY retry loop, ~45 cycles
     // per instruction whatever its shape: measured with tools/ubench/umma_i8_ts.cu) =====
-    {
-      // kind::f16, fp16 x fp16 -> fp32, both K-major, M = 64, N = 128
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
-      const uint64_t ring_desc = make_desc_k_sw128(ring), v_desc = make_desc_k_sw128(vimg);
-      int it = 0, step = 0;
-      for (int t = p.T - 2; t >= 0; --t, ++step) {
-        mbar_wait_sleep(bars + 8 * B_ACC_EMPTY, (step & 1) ^ 1);  // D drained by the update warps
+    // kind::f16, fp16 x fp16 -> fp32, both K-major, M = 128 (neurons), N = 64 (batch rows)
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_ROWS >> 3) << 17) | ((uint32_t)(TC_N >> 4) << 24);
+    const uint64_t x_desc = make_desc_k_sw128(stage);
+    const uint32_t lo_col = 32 * p.KB;
+    int step = 0;
+    for (int t = p.T - 2; t >= 0; --t, ++step) {
+      for (int kb = 0; kb < p.KB; ++kb) {
+        mbar_wait_sleep(bars + 8 * kb, step & 1);   // the update warps wrote this K block of dI_{t+1} (and drained D)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int kb = 0; kb < p.KB; ++kb, ++it) {
-          const int s = it % TC_STAGES;
-          const uint32_t ph = (it / TC_STAGES) & 1;
-          mbar_wait_sleep(bars + 8 * s, ph);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          if (dbg_cta && lane == 0 && kb == 0) p.dbg[t * 8 + 1] = clock64();
-          __syncwarp();
-          if (tc_elect_one()) {
-            const uint64_t a_hi = ring_desc + (uint64_t)(s * (TC_STAGE_BYTES >> 4)), a_lo = a_hi + (8192 >> 4);
-            const uint64_t b_hi = v_desc + (uint64_t)((kb * 2) * (TC_N * 128 >> 4)), b_lo = b_hi + (TC_N * 128 >> 4);
+        if (dbg_cta && lane == 0 && kb == 0) p.dbg[(p.T + t) * 8 + 0] = clock64();
+        __syncwarp();
+        if (tc_elect_one()) {
+          const uint64_t x_hi = x_desc + (uint64_t)(kb * (TC_STAGE_BYTES >> 4)), x_lo = x_hi + (8192 >> 4);
+          const uint32_t v_hi = tmem + (uint32_t)(kb * 32), v_lo = v_hi + lo_col;
+          // Two accumulators, alternating: back-to-back UMMAs into the SAME accumulator issue ~57 cycles apart whatever
+          // their shape (measured: 48 per step took 2.76 k cycles); N = 64 is 32 cycles of tensor work.
+          if (!(p.dbg_flags & 16)) {
+            if (p.reduced) {  // reduced-precision mode: hi * hi only
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (p.dbg_flags & 16) continue;
-              umma_f16(tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              if (p.reduced) continue;  // reduced-precision mode: hi * hi only
-              umma_f16(tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-              umma_f16(tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+              for (int k = 0; k < 4; ++k)
+                umma_f16_ts(tmem_d + 64 * (k & 1), v_hi + 8 * k, x_hi + 2 * k, idesc, (kb > 0 || k > 1) ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_f16_ts(tmem_d + 64 * (k & 1), v_hi + 8 * k, x_hi + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                umma_f16_ts(tmem_d + 64 * ((k + 1) & 1), v_lo + 8 * k, x_hi + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                umma_f16_ts(tmem_d + 64 * (k & 1), v_hi + 8 * k, x_lo + 2 * k, idesc, 1u);
+              }
             }
-            umma_commit(bars + 8 * (TC_STAGES + s));
-            if (kb == p.KB - 1) umma_commit(bars + 8 * B_ACC_FULL);
           }
-          __syncwarp();
+          if (kb == p.KB - 1) umma_commit(bars + 8 * B_ACC_FULL);
         }
-        if (dbg_cta && lane == 0) p.dbg[t * 8 + 2] = clock64();
+        __syncwarp();
       }
+      if (dbg_cta && lane == 0) p.dbg[(p.T + t) * 8 + 1] = clock64();
     }
-  } else {
-    // ===== update warps: BPTT for the 64 x 32 block, 8 neurons of one row per thread =====
-    const int uw = warp - 2, q = warp & 3, half = uw >> 2;  // TMEM lane quarter of this warp, column half
-    // (q, half) only address TMEM; the update itself maps 4 consecutive lanes to the 4 column quarters of a row
-    const int r = 8 * uw + (lane >> 2), cq = lane & 3;
-    const int row = row0 + r;
-    const int col0 = slice * TC_COLS + cq * 8;
-    const bool live = row < p.Be && col0 < p.H;
-    const bool vec = ((p.H & 3) == 0) && (col0 + 8 <= p.H);
-    const int nv = live ? min(8, p.H - col0) : 0;
-    const int64_t idx0 = (int64_t)row * p.H + col0;
-    float du[8], dw[8], pa[8], pb[8], pc[8], pd[8], ut[8];
+  } else if (warp >= 2) {
+    // ===== load + update warps.  Warp uw owns batch rows 8 uw .. 8 uw + 7 of the group; lane = neuron own0 + lane
+    // (BPTT state of 8 (row, neuron) pairs per thread, coalesced 128-byte rows of G / U / W / dI per warp access).
+    // As a loader the warp brings rows 8 uw .. + 7 of dI_{t+1}[:, K quarter] into the stage tiles; as TMEM reader it
+    // holds lane quarter q = warp % 4 (= the neurons of cluster rank q) x rows 32 half .. 32 half + 31.
+    const int uw = warp - 2, q = warp & 3, half = uw >> 2;
+    const int col = own0 + lane, colc = min(col, p.H - 1);
+    const bool col_live = col < p.H;
+    const NeuronParams prm = load_params<ADAPT>(p.alpha, p.beta, p.a, p.b, min(col, p.H - 1));
+    const float inv_oma = 1.0f / prm.oma;
+    const int rowb = row0 + 8 * uw;                // first of this warp's 8 batch rows
+    const int TH = p.T * p.H;                      // elements per batch row of the tapes (Be * T * H < 2^31 is checked)
+    float du[8], dw[8], ut[8];
+    float pa = 0.f, pb = 0.f, pc = 0.f, pd = 0.f;  // parameter-gradient sums over this thread's 8 rows and all steps
+    // The hand-over scale of row 8 uw + k is computed by lane k alone (it reads the quarter maxima and the row maximum of
+    // g) and travels as an exponent: e_cur = exponent of s_t, e_next = exponent of s_{t+1} (the scale of the panel that
+    // is multiplied at step t).
+    int e_next = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) du[i] = dw[i] = pa[i] = pb[i] = pc[i] = pd[i] = ut[i] = 0.f;
-    if (live && p.T > 0) {
-      const float* src = p.U + ((int64_t)row * p.T + (p.T - 1)) * p.H + col0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) ut[i] = i < nv ? src[i] : 0.f;
+    for (int k = 0; k < 8; ++k) {
+      du[k] = dw[k] = 0.f;
+      const bool live = col_live && rowb + k < p.Be;
+      ut[k] = (live && p.T > 0) ? __ldcg(p.U + ((int64_t)(rowb + k) * p.T + (p.T - 1)) * p.H + col) : 0.f;
     }
-    float inv_s_next = 1.0f;  // 1 / s_{t+1}: unscales D at step t
+    // loader geometry: load i = (kb = i / 4, j = i % 4) covers row 8 uw + 2 j + (lane / 16), columns 4 (lane % 16) ..
+    // + 3 of K block kb: a half-warp reads the 256 contiguous bytes of one (row, K block)
+    const int lrow = 8 * uw + (lane >> 4), c16 = lane & 15;
+    const uint32_t* pan_rd0 = p.panel + ((size_t)group * TC_ROWS + lrow) * p.Hp + rank * (p.Hp / TC_CL) + 4 * c16;
+    uint32_t* pan_wr0 = p.panel + ((size_t)group * TC_ROWS + 8 * uw) * p.Hp + col;
+    const size_t pan_buf = (size_t)ngroups_total * TC_ROWS * p.Hp;   // words per buffer
+    uint32_t sa_j[4];                              // stage address of this thread's 8 bytes of row lrow + 2 j (K block 0, hi tile)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = lrow + 2 * j;
+      sa_j[j] = stage + r * 128 + ((((uint32_t)c16 >> 1) ^ ((uint32_t)r & 7)) << 4) + ((c16 & 1) << 3);
+    }
+    const int myrow = min(rowb + (lane & 7), p.Be - 1);     // the row whose scale this lane computes
+    const bool myrow_live = rowb + (lane & 7) < p.Be;
+    const bool dbg_on = dbg_cta && tid == 64;
     int step = 0;
     for (int t = p.T - 1; t >= 0; --t) {
-      const int64_t o0 = ((int64_t)row * p.T + t) * p.H + col0;
-      const int rbuf = (t + 1) & 1, wbuf = t & 1;
-      float gq[8], up[8], wp[8], sp[8], recb[8], d[8];
-      const bool dbg_on = dbg_cta && tid == 64;
-      if (dbg_on) p.dbg[t * 8 + 5] = clock64();
+      // ---- this step's tape values.  Issued AFTER the panel load phase, in flight while the tensor core multiplies: the
+      // loader's 64 registers of panel words are dead by then (with both live, ptxas spilled loaded values at once,
+      // which serialises the loads: 4.7 k cycles to issue 32 of them).  Always-valid addresses (clamped rows / column),
+      // the select comes after the load: straight-line code; 32-bit element offsets.
+      float gq[8], up[8], wp[8], grow_l;
+      const int toff = t * p.H + colc;
+      auto load_tape = [&]() {
+        const float* up_base = t > 0 ? p.U + (toff - p.H) : p.u0 + colc;
+        const float* wp_base = ADAPT ? (t > 0 ? p.W + (toff - p.H) : p.w0 + colc) : nullptr;
+        const int rs_prev = t > 0 ? TH : p.H;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) gq[i] = up[i] = wp[i] = sp[i] = recb[i] = d[i] = 0.f;
-      if (live) {
-        const float* gp = p.G + o0;
-        const float* upp = t > 0 ? p.U + o0 - p.H : p.u0 + idx0;
-        const float* wpp = ADAPT ? (t > 0 ? p.W + o0 - p.H : p.w0 + idx0) : nullptr;
-        if (vec) {
-          const float4 a0 = *reinterpret_cast<const float4*>(gp), a1 = *reinterpret_cast<const float4*>(gp + 4);
-          gq[0] = a0.x; gq[1] = a0.y; gq[2] = a0.z; gq[3] = a0.w; gq[4] = a1.x; gq[5] = a1.y; gq[6] = a1.z; gq[7] = a1.w;
-          const float4 b0 = *reinterpret_cast<const float4*>(upp), b1 = *reinterpret_cast<const float4*>(upp + 4);
-          up[0] = b0.x; up[1] = b0.y; up[2] = b0.z; up[3] = b0.w; up[4] = b1.x; up[5] = b1.y; up[6] = b1.z; up[7] = b1.w;
-          if (ADAPT) {
-            const float4 c0 = *reinterpret_cast<const float4*>(wpp), c1 = *reinterpret_cast<const float4*>(wpp + 4);
-            wp[0] = c0.x; wp[1] = c0.y; wp[2] = c0.z; wp[3] = c0.w; wp[4] = c1.x; wp[5] = c1.y; wp[6] = c1.z; wp[7] = c1.w;
-          }
-        } else {
+        for (int k = 0; k < 8; ++k) {
+          const int rowc = min(rowb + k, p.Be - 1);
+          gq[k] = ld_stream(p.G + toff + rowc * TH);
+          up[k] = ld_stream(up_base + rowc * rs_prev);
+          wp[k] = ADAPT ? ld_stream(wp_base + rowc * rs_prev) : 0.f;
+        }
+        grow_l = ld_stream(p.gmax + myrow * p.T + t);
+      };
+      float recb[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (i < nv) {
-              gq[i] = gp[i];
-              up[i] = upp[i];
-              if (ADAPT) wp[i] = wpp[i];
+      for (int k = 0; k < 8; ++k) recb[k] = 0.f;
+      float m_next_l = 0.f;                        // lanes 0..7: maximum of |dI_{t+1}| over row 8 uw + lane
+      if (dbg_on) p.dbg[t * 8 + 0] = clock64();
+      if (t < p.T - 1) {
+        // ---- dI_{t+1}[rows of this warp][K quarter] -> stage tiles: poll the tagged words themselves
+        const uint32_t* src = pan_rd0 + (size_t)((t + 1) & 1) * pan_buf;
+        const uint32_t em = tc_tag(p.T, t + 1) << 16;
+        // Polling all 64 KB would load the L2 with 8 MB per round over the grid; the warp polls one word of every 128-byte
+        // LINE instead (a line = one row of one producer warp = one store instruction of that warp: 8 rows x 8
+        // producers = 64 lines, two per lane: lane l takes producer l % 8, rows l / 8 and l / 8 + 4).  Fresh lines say
+        // "the data is there"; every data word is still checked by its own tag (and re-read until fresh), so nothing
+        // rests on the line assumption.
+        const uint32_t* smp = p.panel + (size_t)((t + 1) & 1) * pan_buf + ((size_t)group * TC_ROWS + 8 * uw + (lane >> 3)) * p.Hp +
+                              rank * (p.Hp / TC_CL) + 32 * (lane & 7);
+        uint4 v[16];
+        __half2 mj[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mj[j] = __float2half2_rn(0.f);
+        int issued = 0;
+        const long long t0 = clock64();
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          if (kb < p.KB) {
+            while (issued <= kb) {
+              bool ok = true;
+              if ((lane & 7) < 2 * p.KB) {
+                const uint32_t w0 = ld_relaxed_u32(smp), w1 = ld_relaxed_u32(smp + 4 * p.Hp);
+                ok = (((w0 ^ em) | (w1 ^ em)) & 0x10000u) == 0;
+              }
+              const uint32_t fresh = __ballot_sync(0xffffffffu, ok);
+              int n = issued;
+              while (n < p.KB && ((fresh >> (2 * n)) & 0x03030303u) == 0x03030303u) ++n;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if ((i >> 2) >= issued && (i >> 2) < n) v[i] = ld_relaxed_v4(src + (2 * (i & 3)) * p.Hp + (i >> 2) * 64);
+              issued = n;
+              if (dbg_on) p.dbg[2 * p.T * 8 + kb] += 1;          // sample rounds entered at K block kb
+              if (clock64() - t0 > 4000000000LL) __trap();
             }
+            while (true) {
+              uint32_t bad = 0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 x = v[kb * 4 + j];
+                bad |= (x.x ^ em) | (x.y ^ em) | (x.z ^ em) | (x.w ^ em);
+              }
+              if (!(bad & 0x10000u)) break;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) v[kb * 4 + j] = ld_relaxed_v4(src + (2 * j) * p.Hp + kb * 64);
+              if (dbg_on) p.dbg[2 * p.T * 8 + 4 + kb] += 1;      // data re-reads at K block kb
+              if (clock64() - t0 > 4000000000LL) __trap();
+            }
+            if (dbg_on && kb == 0) p.dbg[t * 8 + 1] = clock64();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 x = v[kb * 4 + j];
+              const uint32_t h01 = __byte_perm(x.x, x.y, 0x5410), h23 = __byte_perm(x.z, x.w, 0x5410);
+              const uint32_t l01 = __byte_perm(x.x, x.y, 0x7632) & 0xFFFEFFFEu, l23 = __byte_perm(x.z, x.w, 0x7632) & 0xFFFEFFFEu;
+              const uint32_t sa = sa_j[j] + kb * TC_STAGE_BYTES;
+              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(sa), "r"(h01), "r"(h23) : "memory");
+              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(sa + 8192), "r"(l01), "r"(l23) : "memory");
+              const __half2 a01 = __habs2(*reinterpret_cast<const __half2*>(&h01));
+              const __half2 a23 = __habs2(*reinterpret_cast<const __half2*>(&h23));
+              mj[j] = __hmax2(mj[j], __hmax2(a01, a23));
+            }
+            // generic-proxy stores -> the tensor core's async-proxy reads; the preceding tcgen05.ld of D (previous
+            // step) is ordered before the MMA warp's next UMMA by the same arrival
+            if (!(p.dbg_flags & 32)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8 * kb) : "memory");
+            if (dbg_on) p.dbg[(p.T + t) * 8 + 4 + kb] = clock64();
+          }
         }
-        if (t == 0) {
+        if (dbg_on) p.dbg[t * 8 + 2] = clock64();
+        // ---- maxima of |dI_{t+1}| over this K quarter: mj[j] covers row 2 j + lane / 16 of the warp (in units of
+        // s_{t+1}); lanes 0 and 16 send them to all four ranks
+        float mf[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (i < nv) sp[i] = p.s0[idx0 + i];
+        for (int j = 0; j < 4; ++j) {
+          mf[j] = fmaxf(__low2float(mj[j]), __high2float(mj[j]));
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) mf[j] = fmaxf(mf[j], __shfl_xor_sync(0xffffffffu, mf[j], o));
         }
-      }
-      // ---- row scale of this step's hand-over: M_t = max(rowmax |dI_{t+1}|, 0.25 rowmax |g_t|)
-      float m_next = 0.f;
-      if (t < p.T - 1) {
-        asm volatile("bar.sync 2, 288;" ::: "memory");  // producer saw the group's counter: chunk maxima are visible
-        const float* cm = p.cmax + ((size_t)rbuf * ngroups_total + group) * NCH * TC_ROWS;
-        for (int c = cq; c < NCH; c += 4) m_next = fmaxf(m_next, __ldcg(&cm[c * TC_ROWS + r]));
-      }
-      m_next = fmaxf(m_next, __shfl_xor_sync(0xffffffffu, m_next, 1));
-      m_next = fmaxf(m_next, __shfl_xor_sync(0xffffffffu, m_next, 2));
-      const float g_row = row < p.Be ? p.gmax[(size_t)row * p.T + t] : 0.f;
-      const float s_t = scale_from_max(fmaxf(m_next, 0.25f * g_row));
-      if (t < p.T - 1) {
-        // ---- partial D = dI_{t+1}[:, K quarter] (scaled) @ V0^T (scaled): this warp holds rows 16q..16q+15
-        // (lanes 0..15) x columns 64 half .. 64 half + 63 = the column quarters of ranks 2 half, 2 half + 1
-        mbar_wait_sleep(bars + 8 * B_ACC_FULL, step & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (dbg_on) p.dbg[t * 8 + 3] = clock64();
+        // the peers' buffers are free once every update warp of the cluster has read the previous step's data
+        if (step > 0) mbar_wait_cluster(bars + 8 * B_FREE, (step - 1) & 1);
+        {
+          // rows 8 uw .. + 7 in units of 1 (not of s_{t+1}); lane d < 4 sends the 32 bytes to rank d: two 16-byte remote
+          // stores per destination (one 4-byte store per row and destination cost ~2 k cycles of DSMEM transactions)
+          float val[8];
 #pragma unroll
-        for (int dq = 0; dq < 2; ++dq) {
-          const int dest = 2 * half + dq;
-          uint32_t v[32];
-          const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * dest);
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-              : "r"(taddr));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (lane < 16) {
-            // row 16q + lane, 32 columns -> slot [this rank] of the owner's receive buffer, laid out
-            // [rank][4-column group j][row] so that one store instruction covers contiguous bytes.
-            // (Spreading the stores over all 32 lanes by shuffles was measured: no faster, more registers.)
-            const uint32_t la = recv + (uint32_t)((rank * 8 * TC_RS) + 16 * q + lane) * 16;
-            uint32_t ra, rb;
-            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(dest));
-            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(bars + 8 * B_RECV), "r"(dest));
+          for (int j = 0; j < 4; ++j) {
+            val[2 * j] = __shfl_sync(0xffffffffu, mf[j], 0);
+            val[2 * j + 1] = __shfl_sync(0xffffffffu, mf[j], 16);
+          }
 #pragma unroll
-            for (int j = 0; j < 8; ++j)  // each store reports its 16 bytes to the owner's barrier: no fence, no arrival
+          for (int k = 0; k < 8; ++k)
+            val[k] *= __uint_as_float((uint32_t)(127 - __shfl_sync(0xffffffffu, e_next, k)) << 23);
+          if (lane < TC_CL) {
+            const uint32_t ra = tc_mapa(qmax + (uint32_t)(rank * TC_ROWS + 8 * uw) * 4, lane);
+            const uint32_t rb = tc_mapa(bars + 8 * B_RECV, lane);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
               asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
-                               ra + 16 * TC_RS * j),
-                           "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]), "r"(rb)
+                               ra + 16 * hh),
+                           "r"(__float_as_uint(val[4 * hh])), "r"(__float_as_uint(val[4 * hh + 1])),
+                           "r"(__float_as_uint(val[4 * hh + 2])), "r"(__float_as_uint(val[4 * hh + 3])), "r"(rb)
                            : "memory");
           }
         }
-        if (dbg_on) p.dbg[(p.T + t) * 8 + 4] = clock64();
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8 * B_ACC_EMPTY) : "memory");
-        if (dbg_on) p.dbg[(p.T + t) * 8 + 5] = clock64();
-        // ---- this CTA's column quarter from the four ranks, summed in rank order
+        // ---- partial D^T = V0[128 neurons][K quarter] dI_{t+1}[rows][K quarter]^T: this warp reads neurons 32 q + lane
+        // (= neuron `lane` of cluster rank q), rows 32 half .. 32 half + 31, and sends them to their owner
+        if (dbg_on) p.dbg[t * 8 + 7] = clock64();
+        mbar_wait_sleep(bars + 8 * B_ACC_FULL, step & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (dbg_on) p.dbg[t * 8 + 3] = clock64();
         {
-          uint32_t done = 0;
-          const long long t0 = clock64();
-          while (!done) {
-            asm volatile(
-                "{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
-                "selp.u32 %0, 1, 0, p;\n}"
-                : "=r"(done)
-                : "r"(bars + 8 * B_RECV), "r"((uint32_t)(step & 1))
-                : "memory");
-            if (!done && clock64() - t0 > 4000000000LL) __trap();
-          }
+          uint32_t x[32], y[32];
+          const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * half);
+          TC_LD32(taddr, x);
+          TC_LD32(taddr + 64, y);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = __float_as_uint(__uint_as_float(x[i]) + __uint_as_float(y[i]));
+          // rows 32 half + 4 jj .. + 3 of neuron `lane` -> rank q's receive buffer, laid out [source rank][row quad][neuron]
+          // [4 rows]: the 32 lanes of a store cover 512 contiguous bytes (DSMEM moves contiguous bytes as whole packets;
+          // a layout with one 16-byte piece per lane and 256-byte stride took twice as long)
+          const uint32_t la = recv + (uint32_t)((rank * 16 + 8 * half) * TC_COLS + lane) * 16;
+          const uint32_t ra = tc_mapa(la, q), rb = tc_mapa(bars + 8 * B_RECV, q);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj)  // each store reports its 16 bytes to the owner's barrier: no fence, no arrival
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                             ra + (uint32_t)(jj * TC_COLS * 16)),
+                         "r"(x[4 * jj]), "r"(x[4 * jj + 1]), "r"(x[4 * jj + 2]), "r"(x[4 * jj + 3]), "r"(rb)
+                         : "memory");
         }
-        if (tid == 64 && t > 0) mbar_expect_tx(bars + 8 * B_RECV, TC_CL * TC_ROWS * TC_COLS * 4);  // arm the next phase
-        if (dbg_on) p.dbg[t * 8 + 6] = clock64();
-        const float k = inv_s_next * rs;
+        if (dbg_on) p.dbg[t * 8 + 4] = clock64();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        // the tape values travel while the partial products cross the cluster (issued earlier they queue behind the
+        // 64 KB of panel words in the SM's load path and delay this warp's arrival at the accumulator by ~2 k cycles)
+        load_tape();
+        // ---- this CTA's neurons from the four ranks, summed in rank order; the quarter maxima with them
+        mbar_wait_cluster(bars + 8 * B_RECV, step & 1);
+        if (tid == 64 && t > 0) mbar_expect_tx(bars + 8 * B_RECV, TC_RECV_TX);  // arm the next phase
+        if (dbg_on) p.dbg[t * 8 + 5] = clock64();
         float acc[8];
 #pragma unroll
-        for (int src = 0; src < TC_CL; ++src) {
-          const float4* rp = recv_f4 + (src * 8 + 2 * cq) * TC_RS + r;
-          const float4 x0 = rp[0], x1 = rp[TC_RS];
+        for (int s = 0; s < TC_CL; ++s) {
+          const unsigned char* rp = recv_p + (size_t)((s * 16 + 2 * uw) * TC_COLS + lane) * 16;
+          const float4 x0 = *reinterpret_cast<const float4*>(rp);
+          const float4 x1 = *reinterpret_cast<const float4*>(rp + TC_COLS * 16);
           const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) acc[jj] = src == 0 ? xs[jj] : acc[jj] + xs[jj];
+          for (int k = 0; k < 8; ++k) acc[k] = s == 0 ? xs[k] : acc[k] + xs[k];
+          m_next_l = fmaxf(m_next_l, qmax_p[s * TC_ROWS + 8 * uw + (lane & 7)]);
         }
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) recb[jj] = acc[jj] * k;
-        ++step;
-      }
-      if (live) {
-        if (t > 0) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) sp[i] = spike_of(__fsub_rn(up[i], p.theta));
+        for (int k = 0; k < 8; ++k) {
+          const int e_row = __shfl_sync(0xffffffffu, e_next, k);
+          recb[k] = acc[k] * (__uint_as_float((uint32_t)(127 - e_row) << 23) * rs);
         }
+        // the receive buffers are free for the next step once every update warp of the cluster has read them.  A relaxed
+        // arrival: it signals completed shared-memory READS (their values are consumed above), there is nothing to
+        // release -- mbarrier.arrive.release.cluster compiles to MEMBAR.ALL.GPU per arrival.
+        __syncwarp();
+        if (lane == 0 && t > 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (i < nv) {
-            const int lc = cq * 8 + i;
-            NeuronParams npi;
-            npi.alpha = sprm[0][lc]; npi.oma = sprm[1][lc]; npi.beta = sprm[2][lc]; npi.a = sprm[3][lc];
-            npi.b = sprm[4][lc];
-            float dwi = dw[i], pbi = pb[i], pci = pc[i], pdi = pd[i];
-            d[i] = step_bwd<ADAPT>(npi, sprm[5][lc], p.theta, gq[i], recb[i], ut[i], up[i], sp[i], wp[i], du[i], dwi,
-                                   pa[i], pbi, pci, pdi);
-            dw[i] = dwi; pb[i] = pbi; pc[i] = pci; pd[i] = pdi;
-            ut[i] = up[i];
-          }
+          for (int d = 0; d < TC_CL; ++d)
+            asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(tc_mapa(bars + 8 * B_FREE, d)) : "memory");
         }
-      }
-      if (dbg_on) p.dbg[(p.T + t) * 8 + 0] = clock64();
-      if (t > 0) {
-        // ---- hand dI_t over: chunk maximum (for the next scale) and fp16 hi/lo rows scaled by s_t
-        float m = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) m = fmaxf(m, fabsf(d[i]));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-        if (dbg_on) p.dbg[(p.T + t) * 8 + 1] = clock64();
-        if (cq == 0) {
-          p.cmax[(((size_t)wbuf * ngroups_total + group) * NCH + slice) * TC_ROWS + r] = m;
-        }
-        __align__(16) __half hh[8], hl[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float x = d[i] * s_t;
-          hh[i] = __float2half_rn(x);
-          hl[i] = __float2half_rn(x - __half2float(hh[i]));
-        }
-        const size_t po = ((size_t)(wbuf * ngroups_total + group) * TC_ROWS + r) * p.Hp + slice * TC_COLS + cq * 8;
-        *reinterpret_cast<uint4*>(p.panel_hi + po) = *reinterpret_cast<const uint4*>(hh);
-        *reinterpret_cast<uint4*>(p.panel_lo + po) = *reinterpret_cast<const uint4*>(hl);
         if (dbg_on) p.dbg[(p.T + t) * 8 + 2] = clock64();
-        upd_sync();                       // every update thread's panel stores are issued
-        if (dbg_on) p.dbg[(p.T + t) * 8 + 3] = clock64();
-        if (tid == 64) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(my_flag) : "memory");
-        if (dbg_on) p.dbg[t * 8 + 4] = clock64();
+        ++step;
+      } else {
+        load_tape();
       }
-      if (live) {
-        float* dp = p.dI + o0;
-        if (vec) {
-          *reinterpret_cast<float4*>(dp) = make_float4(d[0], d[1], d[2], d[3]);
-          *reinterpret_cast<float4*>(dp + 4) = make_float4(d[4], d[5], d[6], d[7]);
-        } else {
+      // ---- scale of this step's hand-over (lane k: row k): s_t = 2^e_cur brings max(rowmax|dI_{t+1}|, rowmax|g_t| / 4)
+      // into [8, 16)
+      const int e_cur = scale_exp(fmaxf(m_next_l, myrow_live ? 0.25f * grow_l : 0.f));
+      // ---- BPTT update of the 8 (row, neuron) pairs (cell_math.cuh: step_bwd, same operations in the same order), in
+      // two parts: first what dI_t needs, then its hand-over, and only then what nobody waits for (parameter-gradient
+      // sums, the adjoint of w, the dI tape) -- that part runs while the published words travel to the L2.
+      const uint32_t tag = tc_tag(p.T, t) << 16;
+      uint32_t* dst = pan_wr0 + (size_t)(t & 1) * pan_buf;
+      float d[8], sc[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (i < nv) dp[i] = d[i];
+      for (int k = 0; k < 8; ++k) sc[k] = __uint_as_float((uint32_t)(127 + __shfl_sync(0xffffffffu, e_cur, k)) << 23);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const bool live = col_live && rowb + k < p.Be;
+        gq[k] = live ? gq[k] : 0.f;
+        up[k] = live ? up[k] : 0.f;
+        wp[k] = live ? wp[k] : 0.f;
+        float ds = gq[k] - prm.alpha * du[k] + recb[k];
+        if (ADAPT) ds += prm.b * dw[k];
+        float du_t = (window_of(__fsub_rn(ut[k], p.theta)) ? ds : 0.0f) + prm.alpha * du[k];
+        if (ADAPT) du_t += prm.a * dw[k];
+        du[k] = du_t;
+        d[k] = prm.oma * du_t;
+      }
+      if (t > 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float x = d[k] * sc[k];
+          const __half hh = __float2half_rn(x);
+          const __half hl = p.reduced ? __float2half_rn(0.f) : __float2half_rn(x - __half2float(hh));
+          const uint32_t word = (uint32_t)__half_as_ushort(hh) | (((uint32_t)__half_as_ushort(hl) << 16) & 0xFFFE0000u) | tag;
+          asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(dst), "r"(word) : "memory");
+          dst += p.Hp;
         }
       }
-      inv_s_next = 1.0f / s_t;
+      e_next = e_cur;
+      if (dbg_on) p.dbg[t * 8 + 6] = clock64();
+      float sp[8];
+      if (t > 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sp[k] = spike_of(__fsub_rn(up[k], p.theta));
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          sp[k] = (col_live && rowb + k < p.Be) ? p.s0[(int64_t)(rowb + k) * p.H + col] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float dd = up[k] - sp[k];
+        pa += du[k] * ((dd - ut[k]) * inv_oma);
+        if (ADAPT) {
+          const float dw_t = prm.beta * dw[k] - d[k];
+          pb += dw_t * wp[k];
+          pc += dw_t * up[k];
+          pd += dw_t * sp[k];
+          dw[k] = dw_t;
+        }
+        ut[k] = up[k];
+        if (col_live && rowb + k < p.Be) __stcg(p.dI + toff + (rowb + k) * TH, d[k]);
+      }
+      if (dbg_on) p.dbg[(p.T + t) * 8 + 3] = clock64();
     }
-    if (live) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i < nv) {
-          p.p_alpha[idx0 + i] = pa[i];
-          if (ADAPT) {
-            p.p_beta[idx0 + i] = pb[i];
-            p.p_a[idx0 + i] = pc[i];
-            p.p_b[idx0 + i] = pd[i];
-          }
+    for (int k = 0; k < 8; ++k) {
+      const int row = rowb + k;
+      if (col_live && row < p.Be) {
+        // the sums cover the thread's 8 rows: they go to the first one, the buffers are reduced over the batch anyway
+        const int64_t o1 = (int64_t)row * p.H + col;
+        p.p_alpha[o1] = k == 0 ? pa : 0.f;
+        if (ADAPT) {
+          p.p_beta[o1] = k == 0 ? pb : 0.f;
+          p.p_a[o1] = k == 0 ? pc : 0.f;
+          p.p_b[o1] = k == 0 ? pd : 0.f;
         }
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -508,12 +633,12 @@ rec_bwd_tc_kernel(const __grid_constant__ TcMaps maps, const RecBwdTcArgs p, con
   __syncwarp();
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
 }
 
 static size_t rec_bwd_tc_smem(int KB) {
-  return (size_t)KB * 2 * (TC_N * 128) + TC_STAGES * TC_STAGE_BYTES + TC_RECV_BYTES + 256 + 1024;
+  return (size_t)KB * TC_STAGE_BYTES + TC_RECV_BYTES + TC_QMAX_BYTES + 256 + 1024;
 }
 
 }  // namespace sparch
@@ -533,10 +658,9 @@ size_t sparch_recur_bwd_tc_image_bytes(int H) {
 size_t sparch_recur_bwd_tc_workspace(int Be, int T, int H) {
   const int Hp = sparch_recur_tc_padded(H);
   const size_t groups = (size_t)(Be + TC_ROWS - 1) / TC_ROWS;
-  return 2 * (2 * groups * TC_ROWS * Hp * sizeof(__half))  // panels hi, lo
-         + 2 * groups * (Hp / 32) * TC_ROWS * sizeof(float)  // chunk maxima
-         + (size_t)Be * T * sizeof(float)                    // gmax
-         + groups * (Hp / 64) * sizeof(int) + 256;
+  return 2 * groups * TC_ROWS * Hp * sizeof(uint32_t)  // double-buffered panel of {hi, lo | tag} words
+         + (size_t)Be * T * sizeof(float)              // gmax
+         + 256;
 }
 
 // V (H,H) raw recurrent weight -> swizzled fp16 hi/lo UMMA tiles of V0 (zero diagonal); meta from
@@ -566,23 +690,20 @@ int sparch_recur_bwd_tc(int kind, const float* G, const float* U, const float* W
                  "adaptive kind needs W, beta, a, b, w0 and the partial buffers");
   const int Hp = sparch_recur_tc_padded(H), KB = Hp / (64 * TC_CL);
   const size_t smem = rec_bwd_tc_smem(KB);
-  SPARCH_REQUIRE(smem + 768 <= 227 * 1024, "hidden size too large for the resident V0 tiles");
+  SPARCH_REQUIRE(KB <= 4 && smem <= 227 * 1024, "hidden size too large for the resident V0 tiles");
+  SPARCH_REQUIRE((long long)Be * T * H < (1LL << 31), "tape larger than 2^31 elements: split the batch");
   cudaStream_t st = as_stream(st_);
   static PerDeviceOnce attr_once;
   if (attr_once.first()) {
-    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 768));
-    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 768));
+    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   const int groups = (Be + TC_ROWS - 1) / TC_ROWS, slices = Hp / TC_COLS;
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
-  const size_t panel_bytes = (size_t)2 * groups * TC_ROWS * Hp * sizeof(__half);
-  __half* panel_hi = reinterpret_cast<__half*>(ws);
-  __half* panel_lo = reinterpret_cast<__half*>(ws + panel_bytes);
-  float* cmax = reinterpret_cast<float*>(ws + 2 * panel_bytes);
-  float* gmax = cmax + (size_t)2 * groups * (Hp / 32) * TC_ROWS;
-  int* counters = reinterpret_cast<int*>(gmax + (size_t)Be * T);
-  SPARCH_CUDA(cudaMemsetAsync(ws, 0, 2 * panel_bytes, st));  // rows beyond Be / columns beyond H read as zero
-  SPARCH_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * groups * (Hp / 64), st));
+  const size_t panel_bytes = (size_t)2 * groups * TC_ROWS * Hp * sizeof(uint32_t);
+  uint32_t* panel = reinterpret_cast<uint32_t*>(ws);
+  float* gmax = reinterpret_cast<float*>(ws + panel_bytes);
+  SPARCH_CUDA(cudaMemsetAsync(ws, 0, panel_bytes, st));  // tag 0 everywhere: the first use of a buffer writes tag 1
   if (gmax_in) {  // the producer of G already left the row maxima (sparch_spike_post_bwd)
     gmax = const_cast<float*>(gmax_in);
   } else {
@@ -590,21 +711,15 @@ int sparch_recur_bwd_tc(int kind, const float* G, const float* U, const float* W
     gmax_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(G, Be, T, H, gmax);
     SPARCH_LAUNCH_OK();
   }
-  TcMaps maps;
-  memset(&maps, 0, sizeof maps);
-  if (int e = make_map(&maps.hi, panel_hi, (long long)2 * groups * TC_ROWS, Hp, Hp, TC_ROWS, CU_TENSOR_MAP_DATA_TYPE_FLOAT16))
-    return e;
-  if (int e = make_map(&maps.lo, panel_lo, (long long)2 * groups * TC_ROWS, Hp, Hp, TC_ROWS, CU_TENSOR_MAP_DATA_TYPE_FLOAT16))
-    return e;
   RecBwdTcArgs p{G, U, W, alpha, beta, a, b, u0, w0, s0, reinterpret_cast<const uint32_t*>(img), meta, gmax, theta,
-                 dI, p_alpha, p_beta, p_a, p_b, panel_hi, panel_lo, cmax, Be, T, H, Hp, KB, reduced ? 1 : 0, recur_debug_buffer(), recur_debug_flags()};
+                 dI, p_alpha, p_beta, p_a, p_b, panel, Be, T, H, Hp, KB, reduced ? 1 : 0, recur_debug_buffer(), recur_debug_flags()};
   const void* fn = adapt ? (const void*)rec_bwd_tc_kernel<true> : (const void*)rec_bwd_tc_kernel<false>;
   cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = TC_CL;
   attrs[0].val.clusterDim.y = 1;
   attrs[0].val.clusterDim.z = 1;
-  attrs[1].id = cudaLaunchAttributeCooperative;  // every CTA of a launch must be resident: they wait on each other
+  attrs[1].id = cudaLaunchAttributeCooperative;
   attrs[1].val.cooperative = 1;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
@@ -612,9 +727,12 @@ int sparch_recur_bwd_tc(int kind, const float* G, const float* U, const float* W
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cfg.attrs = attrs;
-  // Nsight Compute (2025.2) cannot replay a launch that is both clustered and cooperative; SPARCH_B200_TC_COOP=0
-  // drops the cooperative attribute for profiling runs (co-residency then rests on the occupancy query below alone).
-  static const bool coop = !(getenv("SPARCH_B200_TC_COOP") && getenv("SPARCH_B200_TC_COOP")[0] == '0');
+  // The CTAs of a launch wait on each other, so all of them must be resident.  The grid of one launch never exceeds
+  // what cudaOccupancyMaxActiveClusters reports for an empty GPU, and whatever else occupies SMs when it starts
+  // (the tail of the previous kernel, a collective on another stream) finishes without needing this kernel: the
+  // launch needs no cooperative attribute (Nsight Compute cannot replay a launch that is both clustered and
+  // cooperative).  SPARCH_B200_TC_COOP=1 adds the attribute (gang scheduling by the driver).
+  static const bool coop = getenv("SPARCH_B200_TC_COOP") && getenv("SPARCH_B200_TC_COOP")[0] == '1';
   cfg.numAttrs = coop ? 2 : 1;
   cfg.gridDim = dim3(slices, 1);
   int max_clusters = 0;
@@ -625,7 +743,7 @@ int sparch_recur_bwd_tc(int kind, const float* G, const float* U, const float* W
     int gn = groups - g0 < gmaxl ? groups - g0 : gmaxl;
     cfg.gridDim = dim3(slices, gn);
     int group0 = g0, ngt = groups;
-    void* args[] = {(void*)&maps, (void*)&p, (void*)&group0, (void*)&ngt, (void*)&counters};
+    void* args[] = {(void*)&p, (void*)&group0, (void*)&ngt};
     SPARCH_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
   }
   return SPARCH_OK;

@@ -50,17 +50,24 @@ for mode in ("mma", "tc"):
         S.backward(g)
         torch.cuda.synchronize()
         call("sparch_recur_debug_clocks", None)
-        e = dbg.cpu().double()[T + 2:2 * T - 3]
-        c = dbg.cpu().double()[2:T - 3]   # rows t = 2 .. T-4; step t-1 follows step t in time
+        c = dbg.cpu().double()[2:T - 3]            # update thread 64 of CTA (0,0), rows t = 2 .. T-4 (step t-1 follows step t)
+        e = dbg.cpu().double()[T + 2:2 * T - 3]    # MMA warp of the same CTA
         m = lambda x: float(x.mean())
-        print("tc phases, cycles/step (CTA 0,0): step start -> counter seen %.0f | -> first k-block landed %.0f | "
-              "-> last UMMA issued %.0f | -> D complete %.0f | -> quarters received %.0f | -> released %.0f | total %.0f"
-              % (m(c[:, 0] - c[:, 5]), m(c[:, 1] - c[:, 0]), m(c[:, 2] - c[:, 1]), m(c[:, 3] - c[:, 2]),
-                 m(c[:, 6] - c[:, 3]), m(c[:, 4] - c[:, 6]), m(c[:-1, 5] - c[1:, 5])))
-        print("  D complete -> TMEM read + scatter stores issued %.0f | -> arrivals sent %.0f | -> quarters received %.0f | "
-              "-> BPTT update done %.0f | -> chunk max exchanged %.0f | -> panel stores issued %.0f | -> all warps' stores issued %.0f "
-              "| -> released %.0f" % (m(e[:, 4] - c[:, 3]), m(e[:, 5] - e[:, 4]), m(c[:, 6] - e[:, 5]), m(e[:, 0] - c[:, 6]),
-                                     m(e[:, 1] - e[:, 0]), m(e[:, 2] - e[:, 1]), m(e[:, 3] - e[:, 2]), m(c[:, 4] - e[:, 3])))
+        print("tc phases, cycles/step (CTA 0,0): step start (tape loads issued) -> first K block of dI_{t+1} valid %.0f | "
+              "-> all K blocks in shared memory %.0f | -> D complete %.0f | -> scatter stores issued %.0f | "
+              "-> quarters received %.0f | -> update done + dI_t published %.0f | -> next step start %.0f | total %.0f"
+              % (m(c[:, 1] - c[:, 0]), m(c[:, 2] - c[:, 1]), m(c[:, 3] - c[:, 2]), m(c[:, 4] - c[:, 3]),
+                 m(c[:, 5] - c[:, 4]), m(c[:, 6] - c[:, 5]), m(c[:-1, 0] - c[1:, 6]), m(c[:-1, 0] - c[1:, 0])))
+        print("  all K blocks stored -> quarter maxima sent %.0f | quarters received -> sums + buffers released %.0f | "
+              "update done -> dI stores issued %.0f | -> next step's tape loads issued %.0f"
+              % (m(c[:, 7] - c[:, 2]), m(e[:, 2] - c[:, 5]), m(e[:, 3] - c[:, 6]), m(c[:-1, 0] - e[1:, 3])))
+        print("  first K block valid -> K block 0 / 1 / 2 / 3 stored and signalled %.0f / %.0f / %.0f / %.0f"
+              % tuple(m(e[:, 4 + i] - c[:, 1]) for i in range(4)))
+        print("  warp 2 of CTA (0,0), all steps: sample rounds entered at K block 0..3", dbg.cpu()[2 * T, :4].tolist(),
+              "data re-reads at K block 0..3", dbg.cpu()[2 * T, 4:8].tolist())
+        print("  MMA warp: first K block seen -> last UMMA issued %.0f | update warps: last K block stored -> first K block "
+              "seen by the MMA warp %.0f | last UMMA issued -> D complete seen %.0f"
+              % (m(e[:, 1] - e[:, 0]), m(e[:, 0] - c[:, 2]), m(c[:, 3] - e[:, 1])))
 names = ("dI", "dalpha", "dbeta", "da", "db", "dV") if adaptive else ("dI", "dalpha", "dV")
 for n, x, y in zip(names, out["mma"], out["tc"]):
     den = float(x.abs().max())
