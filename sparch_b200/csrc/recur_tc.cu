@@ -14,10 +14,15 @@
 //   exactly the neurons of cluster rank q: the reduce-scatter is 8 st.async per update warp.  (The first version
 //   computed D = dI V0^T with M = 64: half-rate UMMA, half of the TMEM lanes idle, 16 stores per warp.)
 //
-//   A operand: V0[128 j][Hp/4 c] as fp16 hi + lo, K-major SWIZZLE_128B tiles resident in shared memory
-//              (Hp/256 x 2 x 16 KB = 128 KB at H = 1024).
+//   A operand: V0[128 j][Hp/4 c] as fp16 hi + lo, resident in TENSOR MEMORY (lane = neuron, 32-bit column = two K;
+//              Hp/256 x 2 x 32 columns = 256 of the 512 columns at H = 1024), copied once per launch from the swizzled
+//              global image with tcgen05.st.  With A in TMEM the tensor core reads only the 1-2 KB of dI per UMMA from
+//              shared memory: 32 cycles per M128 N64 K16 UMMA instead of 48 (tools/ubench/umma_f16_rate.cu).
 //   B operand: dI_{t+1} of the 64 rows x this rank's K quarter, fp16 hi + lo, written into shared memory by the update
 //              warps themselves (K-major SWIZZLE_128B, one 16 KB stage per 64-neuron K block, no ring).
+//   Two CHAINS per CTA: rows 0..31 and 32..63 of the group are different batch rows, i.e. independent recurrences.
+//              Each half has its own four update warps, barriers, accumulator (N = 32) and step counter; the MMA warp
+//              serves whichever chain has a K block ready.
 //   Hand-over through L2 without flags, fences or TMA: a producer stores one 32-bit word {hi, lo} per element with
 //   st.relaxed.gpu; the least significant bit of lo is a TAG that toggles every time the (double-buffered) word is
 //   rewritten, so a consumer polls the data itself (ld.relaxed.gpu.v4, 16 loads in flight per thread) and knows from
@@ -50,8 +55,8 @@ constexpr int TC_RECV_BYTES = TC_CL * TC_COLS * TC_ROWS * 4;  // [source rank][r
 constexpr int TC_QMAX_BYTES = TC_CL * TC_ROWS * 4;            // [source rank][row] quarter maxima of |dI_{t+1}|
 constexpr int TC_THREADS = 320;        // warp 0 spare, warp 1 MMA, warps 2..9 load + update
 constexpr int TC_VSCALE_EXP = 13;
-constexpr uint32_t TC_RECV_TX = TC_RECV_BYTES + TC_QMAX_BYTES;
-constexpr uint32_t TC_D_COL = 256;      // TMEM: V0 hi / lo in columns [0, 256), two accumulators in [256, 320), [320, 384)
+constexpr uint32_t TC_RECV_TX = (TC_RECV_BYTES + TC_QMAX_BYTES) / 2;   // per chain (32 of the 64 rows) and step
+constexpr uint32_t TC_D_COL = 256;      // TMEM: V0 hi / lo in columns [0, 256), D of chain c in [256 + 32 c, 288 + 32 c)
 
 struct RecBwdTcArgs {
   const float *G, *U, *W, *alpha, *beta, *a, *b, *u0, *w0, *s0;
@@ -212,8 +217,9 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
   unsigned char* tail = tsm + (size_t)p.KB * TC_STAGE_BYTES;
   const unsigned char* recv_p = tail;
   const float* qmax_p = reinterpret_cast<const float*>(tail + TC_RECV_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + TC_RECV_BYTES + TC_QMAX_BYTES + 64);
-  constexpr int B_ACC_FULL = 4, B_RECV = 5, B_FREE = 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + TC_RECV_BYTES + TC_QMAX_BYTES + 192);
+  // barriers of chain c (the 32-row half c of the group) at index 8 c + {0..3 full[kb], 4 acc_full, 5 recv, 6 free}
+  constexpr int B_ACC_FULL = 4, B_RECV = 5, B_FREE = 6, B_CHAIN = 8;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slice = blockIdx.x, group = group0 + blockIdx.y, row0 = group * TC_ROWS;
@@ -222,11 +228,14 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
   const bool dbg_cta = p.dbg && blockIdx.x == 0 && blockIdx.y == 0;
 
   if (tid == 0) {
-    for (int kb = 0; kb < 4; ++kb) mbar_init(bars + 8 * kb, 8);   // one arrival per update warp
-    mbar_init(bars + 8 * B_ACC_FULL, 1);                          // one tcgen05.commit
-    mbar_init(bars + 8 * B_RECV, 1);  // armed per step with the bytes the four ranks deliver (st.async complete_tx)
-    mbar_init(bars + 8 * B_FREE, TC_CL * 8);                      // every update warp of the cluster has read its buffers
-    mbar_expect_tx(bars + 8 * B_RECV, TC_RECV_TX);
+    for (int c = 0; c < 2; ++c) {
+      const uint32_t cb = bars + 8 * B_CHAIN * c;
+      for (int kb = 0; kb < 4; ++kb) mbar_init(cb + 8 * kb, 4);   // one arrival per update warp of the chain
+      mbar_init(cb + 8 * B_ACC_FULL, 1);                          // one tcgen05.commit
+      mbar_init(cb + 8 * B_RECV, 1);  // armed per step with the bytes the four ranks deliver (st.async complete_tx)
+      mbar_init(cb + 8 * B_FREE, TC_CL * 4);                      // every update warp of the chain, cluster-wide, has read
+      mbar_expect_tx(cb + 8 * B_RECV, TC_RECV_TX);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -279,40 +288,54 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
     // (under a plain `if (lane == 0)` ptxas wraps every UMMA in an ELECT / PLOP3 / BRA.U.ANY retry loop, ~45 cycles
     // per instruction whatever its shape: measured with tools/ubench/umma_i8_ts.cu) =====
     // kind::f16, fp16 x fp16 -> fp32, both K-major, M = 128 (neurons), N = 64 (batch rows)
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_ROWS >> 3) << 17) | ((uint32_t)(TC_N >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | ((uint32_t)((TC_ROWS / 2) >> 3) << 17) | ((uint32_t)(TC_N >> 4) << 24);
     const uint64_t x_desc = make_desc_k_sw128(stage);
     const uint32_t lo_col = 32 * p.KB;
-    int step = 0;
-    for (int t = p.T - 2; t >= 0; --t, ++step) {
-      for (int kb = 0; kb < p.KB; ++kb) {
-        mbar_wait_sleep(bars + 8 * kb, step & 1);   // the update warps wrote this K block of dI_{t+1} (and drained D)
+    // The two 32-row chains of the group advance independently (different batch rows): the warp serves whichever has a
+    // K block ready, so one chain's tensor work fills the other's L2 / DSMEM / update time.
+    int cstep[2] = {0, 0}, ckb[2] = {0, 0};
+    const int nsteps = p.T - 1;
+    while (cstep[0] < nsteps || cstep[1] < nsteps) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (cstep[c] >= nsteps) continue;
+        const uint32_t cb = bars + 8 * B_CHAIN * c;
+        const int kb = ckb[c];
+        uint32_t ready;
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ready)
+            : "r"(cb + 8 * kb), "r"((uint32_t)(cstep[c] & 1))
+            : "memory");
+        ready = __shfl_sync(0xffffffffu, ready, 0);   // one answer for the warp
+        if (!ready) continue;   // the update warps have not yet written this K block of dI_{t+1} (and drained D)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (dbg_cta && lane == 0 && kb == 0) p.dbg[(p.T + t) * 8 + 0] = clock64();
+        if (dbg_cta && lane == 0 && c == 0 && kb == 0) p.dbg[(p.T + (p.T - 2 - cstep[0])) * 8 + 0] = clock64();
         __syncwarp();
         if (tc_elect_one()) {
-          const uint64_t x_hi = x_desc + (uint64_t)(kb * (TC_STAGE_BYTES >> 4)), x_lo = x_hi + (8192 >> 4);
+          const uint64_t x_hi = x_desc + (uint64_t)(kb * (TC_STAGE_BYTES >> 4) + c * (4096 >> 4)), x_lo = x_hi + (8192 >> 4);
           const uint32_t v_hi = tmem + (uint32_t)(kb * 32), v_lo = v_hi + lo_col;
-          // Two accumulators, alternating: back-to-back UMMAs into the SAME accumulator issue ~57 cycles apart whatever
-          // their shape (measured: 48 per step took 2.76 k cycles); N = 64 is 32 cycles of tensor work.
+          const uint32_t dcol = tmem_d + 32 * c;
           if (!(p.dbg_flags & 16)) {
-            if (p.reduced) {  // reduced-precision mode: hi * hi only
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16_ts(tmem_d + 64 * (k & 1), v_hi + 8 * k, x_hi + 2 * k, idesc, (kb > 0 || k > 1) ? 1u : 0u);
-            } else {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_f16_ts(tmem_d + 64 * (k & 1), v_hi + 8 * k, x_hi + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                umma_f16_ts(tmem_d + 64 * ((k + 1) & 1), v_lo + 8 * k, x_hi + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                umma_f16_ts(tmem_d + 64 * (k & 1), v_hi + 8 * k, x_lo + 2 * k, idesc, 1u);
-              }
+            for (int k = 0; k < 4; ++k) {
+              umma_f16_ts(dcol, v_hi + 8 * k, x_hi + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              if (p.reduced) continue;  // reduced-precision mode: hi * hi only
+              umma_f16_ts(dcol, v_lo + 8 * k, x_hi + 2 * k, idesc, 1u);
+              umma_f16_ts(dcol, v_hi + 8 * k, x_lo + 2 * k, idesc, 1u);
             }
           }
-          if (kb == p.KB - 1) umma_commit(bars + 8 * B_ACC_FULL);
+          if (kb == p.KB - 1) umma_commit(cb + 8 * B_ACC_FULL);
         }
         __syncwarp();
+        if (kb == p.KB - 1) {
+          if (dbg_cta && lane == 0 && c == 0) p.dbg[(p.T + (p.T - 2 - cstep[0])) * 8 + 1] = clock64();
+          ckb[c] = 0;
+          ++cstep[c];
+        } else {
+          ckb[c] = kb + 1;
+        }
       }
-      if (dbg_cta && lane == 0) p.dbg[(p.T + t) * 8 + 1] = clock64();
     }
   } else if (warp >= 2) {
     // ===== load + update warps.  Warp uw owns batch rows 8 uw .. 8 uw + 7 of the group; lane = neuron own0 + lane
@@ -320,6 +343,7 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
     // As a loader the warp brings rows 8 uw .. + 7 of dI_{t+1}[:, K quarter] into the stage tiles; as TMEM reader it
     // holds lane quarter q = warp % 4 (= the neurons of cluster rank q) x rows 32 half .. 32 half + 31.
     const int uw = warp - 2, q = warp & 3, half = uw >> 2;
+    const uint32_t cbar = bars + 8 * B_CHAIN * half;   // this warp's chain = the 32-row half of the group it belongs to
     const int col = own0 + lane, colc = min(col, p.H - 1);
     const bool col_live = col < p.H;
     const NeuronParams prm = load_params<ADAPT>(p.alpha, p.beta, p.a, p.b, min(col, p.H - 1));
@@ -399,41 +423,43 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
           if (kb < p.KB) {
-            while (issued <= kb) {
-              bool ok = true;
-              if ((lane & 7) < 2 * p.KB) {
-                const uint32_t w0 = ld_relaxed_u32(smp), w1 = ld_relaxed_u32(smp + 4 * p.Hp);
-                ok = (((w0 ^ em) | (w1 ^ em)) & 0x10000u) == 0;
-              }
-              const uint32_t fresh = __ballot_sync(0xffffffffu, ok);
-              int n = issued;
-              while (n < p.KB && ((fresh >> (2 * n)) & 0x03030303u) == 0x03030303u) ++n;
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if ((i >> 2) >= issued && (i >> 2) < n) v[i] = ld_relaxed_v4(src + (2 * (i & 3)) * p.Hp + (i >> 2) * 64);
-              issued = n;
-              if (dbg_on) p.dbg[2 * p.T * 8 + kb] += 1;          // sample rounds entered at K block kb
-              if (clock64() - t0 > 4000000000LL) __trap();
-            }
             while (true) {
-              uint32_t bad = 0;
+              while (issued <= kb) {
+                bool ok = true;
+                if ((lane & 7) < 2 * p.KB) {
+                  const uint32_t w0 = ld_relaxed_u32(smp), w1 = ld_relaxed_u32(smp + 4 * p.Hp);
+                  ok = (((w0 ^ em) | (w1 ^ em)) & 0x10000u) == 0;
+                }
+                const uint32_t fresh = __ballot_sync(0xffffffffu, ok);
+                int n = issued;
+                while (n < p.KB && ((fresh >> (2 * n)) & 0x03030303u) == 0x03030303u) ++n;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if ((i >> 2) >= issued && (i >> 2) < n) v[i] = ld_relaxed_v4(src + (2 * (i & 3)) * p.Hp + (i >> 2) * 64);
+                issued = n;
+                if (dbg_on) p.dbg[2 * p.T * 8 + kb] += 1;          // sample rounds entered at K block kb
+                if (clock64() - t0 > 4000000000LL) __trap();
+              }
+              // every word carries its own tag (a balanced tree: the update warps are ALU-latency bound here)
+              uint32_t bj[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const uint4 x = v[kb * 4 + j];
-                bad |= (x.x ^ em) | (x.y ^ em) | (x.z ^ em) | (x.w ^ em);
+                bj[j] = ((x.x ^ em) | (x.y ^ em)) | ((x.z ^ em) | (x.w ^ em));
               }
-              if (!(bad & 0x10000u)) break;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) v[kb * 4 + j] = ld_relaxed_v4(src + (2 * j) * p.Hp + kb * 64);
-              if (dbg_on) p.dbg[2 * p.T * 8 + 4 + kb] += 1;      // data re-reads at K block kb
-              if (clock64() - t0 > 4000000000LL) __trap();
+              const bool bad = (((bj[0] | bj[1]) | (bj[2] | bj[3])) & 0x10000u) != 0;
+              if (!__any_sync(0xffffffffu, bad)) break;
+              issued = kb;                                         // a stale word after fresh lines: read the K block again
+              if (dbg_on) p.dbg[2 * p.T * 8 + 4 + kb] += 1;
             }
             if (dbg_on && kb == 0) p.dbg[t * 8 + 1] = clock64();
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
+              // {hi, lo | tag} words -> hi pairs and lo pairs (the tag stays in lo's last bit: 2^-22 of the element, with
+              // the 21 bits that survive the tagging anyway)
               const uint4 x = v[kb * 4 + j];
               const uint32_t h01 = __byte_perm(x.x, x.y, 0x5410), h23 = __byte_perm(x.z, x.w, 0x5410);
-              const uint32_t l01 = __byte_perm(x.x, x.y, 0x7632) & 0xFFFEFFFEu, l23 = __byte_perm(x.z, x.w, 0x7632) & 0xFFFEFFFEu;
+              const uint32_t l01 = __byte_perm(x.x, x.y, 0x7632), l23 = __byte_perm(x.z, x.w, 0x7632);
               const uint32_t sa = sa_j[j] + kb * TC_STAGE_BYTES;
               asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(sa), "r"(h01), "r"(h23) : "memory");
               asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(sa + 8192), "r"(l01), "r"(l23) : "memory");
@@ -441,12 +467,11 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
               const __half2 a23 = __habs2(*reinterpret_cast<const __half2*>(&h23));
               mj[j] = __hmax2(mj[j], __hmax2(a01, a23));
             }
-            // generic-proxy stores -> the tensor core's async-proxy reads; the preceding tcgen05.ld of D (previous
-            // step) is ordered before the MMA warp's next UMMA by the same arrival
-            if (!(p.dbg_flags & 32)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            // generic-proxy stores -> the tensor core's async-proxy reads.  (The tcgen05.ld of D of the previous step was
+            // fenced right after the drain: tcgen05.fence::before_thread_sync precedes this arrival in program order.)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8 * kb) : "memory");
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cbar + 8 * kb) : "memory");
             if (dbg_on) p.dbg[(p.T + t) * 8 + 4 + kb] = clock64();
           }
         }
@@ -461,7 +486,7 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
           for (int o = 8; o > 0; o >>= 1) mf[j] = fmaxf(mf[j], __shfl_xor_sync(0xffffffffu, mf[j], o));
         }
         // the peers' buffers are free once every update warp of the cluster has read the previous step's data
-        if (step > 0) mbar_wait_cluster(bars + 8 * B_FREE, (step - 1) & 1);
+        if (step > 0) mbar_wait_cluster(cbar + 8 * B_FREE, (step - 1) & 1);
         {
           // rows 8 uw .. + 7 in units of 1 (not of s_{t+1}); lane d < 4 sends the 32 bytes to rank d: two 16-byte remote
           // stores per destination (one 4-byte store per row and destination cost ~2 k cycles of DSMEM transactions)
@@ -476,7 +501,7 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
             val[k] *= __uint_as_float((uint32_t)(127 - __shfl_sync(0xffffffffu, e_next, k)) << 23);
           if (lane < TC_CL) {
             const uint32_t ra = tc_mapa(qmax + (uint32_t)(rank * TC_ROWS + 8 * uw) * 4, lane);
-            const uint32_t rb = tc_mapa(bars + 8 * B_RECV, lane);
+            const uint32_t rb = tc_mapa(cbar + 8 * B_RECV, lane);
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh)
               asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
@@ -489,22 +514,19 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
         // ---- partial D^T = V0[128 neurons][K quarter] dI_{t+1}[rows][K quarter]^T: this warp reads neurons 32 q + lane
         // (= neuron `lane` of cluster rank q), rows 32 half .. 32 half + 31, and sends them to their owner
         if (dbg_on) p.dbg[t * 8 + 7] = clock64();
-        mbar_wait_sleep(bars + 8 * B_ACC_FULL, step & 1);
+        mbar_wait_sleep(cbar + 8 * B_ACC_FULL, step & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (dbg_on) p.dbg[t * 8 + 3] = clock64();
         {
-          uint32_t x[32], y[32];
+          uint32_t x[32];
           const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * half);
           TC_LD32(taddr, x);
-          TC_LD32(taddr + 64, y);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = __float_as_uint(__uint_as_float(x[i]) + __uint_as_float(y[i]));
           // rows 32 half + 4 jj .. + 3 of neuron `lane` -> rank q's receive buffer, laid out [source rank][row quad][neuron]
           // [4 rows]: the 32 lanes of a store cover 512 contiguous bytes (DSMEM moves contiguous bytes as whole packets;
           // a layout with one 16-byte piece per lane and 256-byte stride took twice as long)
           const uint32_t la = recv + (uint32_t)((rank * 16 + 8 * half) * TC_COLS + lane) * 16;
-          const uint32_t ra = tc_mapa(la, q), rb = tc_mapa(bars + 8 * B_RECV, q);
+          const uint32_t ra = tc_mapa(la, q), rb = tc_mapa(cbar + 8 * B_RECV, q);
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj)  // each store reports its 16 bytes to the owner's barrier: no fence, no arrival
             asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
@@ -518,8 +540,8 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
         // 64 KB of panel words in the SM's load path and delay this warp's arrival at the accumulator by ~2 k cycles)
         load_tape();
         // ---- this CTA's neurons from the four ranks, summed in rank order; the quarter maxima with them
-        mbar_wait_cluster(bars + 8 * B_RECV, step & 1);
-        if (tid == 64 && t > 0) mbar_expect_tx(bars + 8 * B_RECV, TC_RECV_TX);  // arm the next phase
+        mbar_wait_cluster(cbar + 8 * B_RECV, step & 1);
+        if ((uw & 3) == 0 && lane == 0 && t > 0) mbar_expect_tx(cbar + 8 * B_RECV, TC_RECV_TX);  // arm the next phase
         if (dbg_on) p.dbg[t * 8 + 5] = clock64();
         float acc[8];
 #pragma unroll
@@ -544,7 +566,7 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
         if (lane == 0 && t > 0) {
 #pragma unroll
           for (int d = 0; d < TC_CL; ++d)
-            asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(tc_mapa(bars + 8 * B_FREE, d)) : "memory");
+            asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(tc_mapa(cbar + 8 * B_FREE, d)) : "memory");
         }
         if (dbg_on) p.dbg[(p.T + t) * 8 + 2] = clock64();
         ++step;
