@@ -289,6 +289,22 @@ SPARCH_API int sparch_param_grads(const float* part, const float* alpha, const f
                                   const float* b, const float* lims, int nk, int Be, int H, float* grads,
                                   sparch_stream_t st);
 
+/* C (M,N) = [C +] sum_k A(m,k) B[k][n] in fp32 FFMA for the Be-sized products of a recurrent layer: rec_0 = s0 @ V0
+ * (snns.py:702, 720: A = s0 (M = Be, K = H), B = V, flags = 1) and the t = 0 frames of dV (A = sparch_dv_boundary's
+ * output stored (K = Be, M = H): a_km = 1, B = dI[:, 0, :] with ldb = T * H, flags = 2 | 4).  a_km: A is (K, M)
+ * row-major.  flags: 1 read B with a zero diagonal, 2 zero the diagonal of C, 4 accumulate into C, 8 B is stored
+ * (N, K) row-major (product with B^T: the stepwise reverse pass dI_{t+1} @ V0^T of hidden sizes beyond the persistent kernels). */
+SPARCH_API int sparch_small_gemm(const float* A, int64_t lda, int a_km, const float* B, int64_t ldb, float* C,
+                                 int64_t ldc, int M, int N, int K, int flags, sparch_stream_t st);
+/* Small helpers of the recurrent layers.  sparch_recur_v0: V0 = V with a zero diagonal (snns.py:712, 566).
+ * sparch_zero_diag: A[i][i] = 0 (the backward of that masking, applied to dV).  sparch_dv_boundary: first[b] = s0[b] -
+ * S[b-1][T-1] (b > 0), S (Be,T,H): the dV GEMM pairs frame m of dI with frame m-1 of the (b,t)-flattened spikes, this
+ * is the correction operand of the Be frames t = 0, whose true partner is the real-valued s0 (snns.py:702).        */
+SPARCH_API int sparch_recur_v0(const float* V, int H, float* V0, sparch_stream_t st);
+SPARCH_API int sparch_zero_diag(float* A, int H, sparch_stream_t st);
+SPARCH_API int sparch_dv_boundary(const float* s0, const float* S, int Be, int T, int H, float* first,
+                                  sparch_stream_t st);
+
 /* ---- train-step glue: Adam, exp.py:89 ------------------------------------------- */
 /* One launch updates up to 48 parameter tensors (torch.optim.Adam defaults: no weight decay, no amsgrad):
  * g' = g * hyper[4]; m += (1-b1)(g'-m); v = b2 v + (1-b2) g'^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps),
@@ -308,6 +324,15 @@ SPARCH_API int sparch_readout_fwd(const float* Z, const float* scale, const floa
 /* gout (B,C) -> dI (B,T,C), p_alpha (B,C) partials.                                       */
 SPARCH_API int sparch_readout_bwd(const float* gout, const float* U, const float* alpha, const float* u0,
                        float* dI, float* p_alpha, int B, int T, int C, sparch_stream_t st);
+
+/* ---- loss of the train step (exp.py:83 nn.CrossEntropyLoss(), exp.py:362) -------------------------------- */
+/* *loss = mean_b(logsumexp(logits[b]) - logits[b][target[b]]), lse[b] kept for the backward; targets outside
+ * [0, C) contribute zero.  dlogits = (softmax - onehot) * *gloss / B.  One launch each instead of ATen's
+ * log_softmax + nll_loss pairs.                                                                              */
+SPARCH_API int sparch_ce_fwd(const float* logits, const int64_t* target, int B, int C, float* loss, float* lse,
+                             sparch_stream_t st);
+SPARCH_API int sparch_ce_bwd(const float* logits, const int64_t* target, const float* lse, const float* gloss, int B,
+                             int C, float* dlogits, sparch_stream_t st);
 
 #ifdef __cplusplus
 }

@@ -5,10 +5,10 @@
 (hand-written sm_100a CUDA, C ABI in include/sparch_b200.h).  Importing the package does
 not load the native library; the first kernel call does, and fails loudly if it is absent.
 """
-from .functional import set_precision
+from .functional import CrossEntropyLoss, set_precision
 from .snns import (SNN, LIFLayer, RadLIFLayer, ReadoutLayer, RLIFLayer, SpikeFunctionBoxcar,
                    adLIFLayer, set_state_init)
 
 __all__ = ["SNN", "LIFLayer", "adLIFLayer", "RLIFLayer", "RadLIFLayer", "ReadoutLayer",
-           "SpikeFunctionBoxcar", "set_state_init", "set_precision"]
+           "SpikeFunctionBoxcar", "set_state_init", "set_precision", "CrossEntropyLoss"]
 __version__ = "0.1.0"

@@ -54,9 +54,15 @@ _PROTOS = {
     "sparch_spike_post_bwd": "plifpppp",
     "sparch_neuron_params": "pppppiipp",
     "sparch_param_grads": "ppppppiiipp",
+    "sparch_small_gemm": "pliplpliiiip",
+    "sparch_recur_v0": "pipp",
+    "sparch_zero_diag": "pip",
+    "sparch_dv_boundary": "ppiiipp",
     "sparch_adam_step": "ippppppp" "p",
     "sparch_readout_fwd": "p" * 7 + "iii" + "p",
     "sparch_readout_bwd": "p" * 6 + "iii" + "p",
+    "sparch_ce_fwd": "ppiippp",
+    "sparch_ce_bwd": "ppppiipp",
 }
 _CT = {"p": _P, "i": _I, "l": _L, "f": _F}
 

@@ -497,6 +497,113 @@ __global__ void split_rows_f16_kernel(const float* __restrict__ X, long long ldx
   }
 }
 
+// ---------------------------------------------------------------- small fp32 products of the recurrent layers
+// C[M][N] (=, +=) sum_k A(m, k) B[k][n] in plain fp32 FFMA: the two Be-sized products of a recurrent layer
+// (rec_0 = s0 @ V0 at t = 0, snns.py:702 / 720, and the t = 0 frames of dV), each ~0.5 GFLOP -- too small to repay
+// splitting their operands into 16-bit terms for the tensor pipe, and exact in fp32 whatever the precision mode.
+// A_KM: A is stored (K, M) row-major (A(m, k) = A[k * lda + m]), else (M, K).  64 x 64 tile, K step 16, 4 x 4 per thread.
+constexpr int SG_T = 64, SG_K = 16;
+
+// four consecutive elements of a row: one 16-byte load when aligned and inside the matrix, guarded scalars otherwise
+__device__ __forceinline__ float4 sg_ld4(const float* __restrict__ P, int64_t ld, int r, int c, int R, int Cn, bool vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r >= R) return v;
+  const float* q = P + r * ld + c;
+  if (vec && c + 3 < Cn) return *reinterpret_cast<const float4*>(q);
+  if (c < Cn) v.x = q[0];
+  if (c + 1 < Cn) v.y = q[1];
+  if (c + 2 < Cn) v.z = q[2];
+  if (c + 3 < Cn) v.w = q[3];
+  return v;
+}
+
+template <bool A_KM>
+__global__ void __launch_bounds__(256)
+small_gemm_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, float* __restrict__ C,
+                  int64_t ldc, int M, int N, int K, int flags, int kper) {
+  __shared__ __align__(16) float As[SG_K][SG_T + 4], Bs[SG_K][SG_T + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * SG_T, n0 = blockIdx.x * SG_T;
+  const int kbeg = blockIdx.z * kper, kend = min(K, kbeg + kper);
+  const bool b_nk = flags & 8;                      // B stored (N, K) row-major: the product with B^T
+  const bool va = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  const bool vb = ((ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  // each thread moves one float4 of A and one of B per K step: (row = tid / 4, 4 columns at 4 (tid % 4)) of a
+  // [64][16] block for a K-contiguous operand, (row = tid / 16, 4 columns at 4 (tid % 16)) of a [16][64] block otherwise
+  auto fetch_a = [&](int k0) {
+    return A_KM ? sg_ld4(A, lda, k0 + (tid >> 4), m0 + 4 * (tid & 15), kend, M, va)
+                : sg_ld4(A, lda, m0 + (tid >> 2), k0 + 4 * (tid & 3), M, kend, va);
+  };
+  auto fetch_b = [&](int k0) {
+    return b_nk ? sg_ld4(B, ldb, n0 + (tid >> 2), k0 + 4 * (tid & 3), N, kend, vb)
+                : sg_ld4(B, ldb, k0 + (tid >> 4), n0 + 4 * (tid & 15), kend, N, vb);
+  };
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float4 ra = fetch_a(kbeg), rb = fetch_b(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += SG_K) {
+    if (A_KM) {
+      *reinterpret_cast<float4*>(&As[tid >> 4][4 * (tid & 15)]) = ra;
+    } else {
+      const int mm = tid >> 2, kk = 4 * (tid & 3);
+      As[kk][mm] = ra.x; As[kk + 1][mm] = ra.y; As[kk + 2][mm] = ra.z; As[kk + 3][mm] = ra.w;
+    }
+    if (b_nk) {
+      const int nn = tid >> 2, kk = 4 * (tid & 3);
+      float bv[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) Bs[kk + e][nn] = ((flags & 1) && k0 + kk + e == n0 + nn) ? 0.f : bv[e];
+    } else {
+      const int kk = tid >> 4, nn = 4 * (tid & 15);
+      if (flags & 1) {                              // B with a zero diagonal (V0 of snns.py:712)
+        const int dn = k0 + kk - (n0 + nn);
+        if (dn == 0) rb.x = 0.f;
+        if (dn == 1) rb.y = 0.f;
+        if (dn == 2) rb.z = 0.f;
+        if (dn == 3) rb.w = 0.f;
+      }
+      *reinterpret_cast<float4*>(&Bs[kk][nn]) = rb;
+    }
+    __syncthreads();
+    if (k0 + SG_K < kend) {                         // next block's global loads fly under this block's FFMAs
+      ra = fetch_a(k0 + SG_K);
+      rb = fetch_b(k0 + SG_K);
+    }
+#pragma unroll
+    for (int kk = 0; kk < SG_K; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (gridDim.z > 1) {                          // two K halves into a zeroed C: x + y is the same in either order
+        atomicAdd(&C[m * ldc + n], v);
+        continue;
+      }
+      if (flags & 4) v += C[m * ldc + n];
+      if ((flags & 2) && m == n) v = 0.f;
+      C[m * ldc + n] = v;
+    }
+  }
+}
+
 }  // namespace sparch
 
 using namespace sparch;
@@ -660,6 +767,24 @@ int sparch_gemm_terms(int fp16, const void* const* A_parts, int na, const uint32
                                                                         amax_b);
     SPARCH_LAUNCH_OK();
   }
+  return SPARCH_OK;
+}
+
+int sparch_small_gemm(const float* A, int64_t lda, int a_km, const float* B, int64_t ldb, float* C, int64_t ldc, int M,
+                      int N, int K, int flags, sparch_stream_t st) {
+  SPARCH_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "bad argument");
+  SPARCH_REQUIRE(lda >= (a_km ? M : K) && ldb >= ((flags & 8) ? K : N) && ldc >= N, "leading dimension smaller than the row");
+  dim3 grid((N + SG_T - 1) / SG_T, (M + SG_T - 1) / SG_T, 1);
+  int kper = K;
+  // few tiles and a long contraction (rec_0: 64 tiles, K = H): two K halves, added into a zeroed C by atomics
+  if (!(flags & (2 | 4)) && (int)(grid.x * grid.y) < sm_count() && K >= 8 * SG_K && ldc == N) {
+    grid.z = 2;
+    kper = ((K + 2 * SG_K - 1) / (2 * SG_K)) * SG_K;
+    SPARCH_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), as_stream(st)));
+  }
+  if (a_km) small_gemm_kernel<true><<<grid, 256, 0, as_stream(st)>>>(A, lda, B, ldb, C, ldc, M, N, K, flags, kper);
+  else small_gemm_kernel<false><<<grid, 256, 0, as_stream(st)>>>(A, lda, B, ldb, C, ldc, M, N, K, flags, kper);
+  SPARCH_LAUNCH_OK();
   return SPARCH_OK;
 }
 

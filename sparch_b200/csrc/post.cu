@@ -188,6 +188,32 @@ __global__ void __launch_bounds__(256) param_grads_kernel(const float* __restric
   }
 }
 
+
+// ---- small helpers of the recurrent layers (snns.py:712, 702): no library kernel on the product path
+__global__ void v0_copy_kernel(const float* __restrict__ V, int H, float* __restrict__ V0) {
+  const int64_t n = (int64_t)H * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    V0[i] = (i / H == i % H) ? 0.f : V[i];
+}
+
+__global__ void zero_diag_kernel(float* __restrict__ A, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < H) A[(int64_t)i * H + i] = 0.f;
+}
+
+// first[b] = s0[b] - S[b-1][T-1] (b > 0): what frame (b, 0) of dI must be paired with INSTEAD of the frame before it
+// in the (b, t)-flattened spike matrix (the dV GEMM pairs frame m of dI with frame m - 1 of S)
+__global__ void dv_boundary_kernel(const float* __restrict__ s0, const float* __restrict__ S, int Be, int T, int H,
+                                   float* __restrict__ first) {
+  const int64_t n = (int64_t)Be * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / H, h = i - b * H;
+    float x = s0[i];
+    if (b > 0) x -= S[((b - 1) * T + (T - 1)) * H + h];
+    first[i] = x;
+  }
+}
+
 }  // namespace sparch
 
 using namespace sparch;
@@ -260,6 +286,33 @@ int sparch_param_grads(const float* part, const float* alpha, const float* beta,
                  "bad argument");
   const ParamSet ps = make_param_set(alpha, beta, a, b, lims, nk);
   param_grads_kernel<<<dim3((H + 31) / 32, nk), dim3(32, 8), 0, as_stream(st)>>>(part, ps, nk, Be, H, grads);
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+int sparch_recur_v0(const float* V, int H, float* V0, sparch_stream_t st) {
+  SPARCH_REQUIRE(V && V0 && H > 0, "bad argument");
+  const int64_t n = (int64_t)H * H;
+  int nb = (int)((n + 255) / 256);
+  if (nb > sm_count() * 8) nb = sm_count() * 8;
+  v0_copy_kernel<<<nb, 256, 0, as_stream(st)>>>(V, H, V0);
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+int sparch_zero_diag(float* A, int H, sparch_stream_t st) {
+  SPARCH_REQUIRE(A && H > 0, "bad argument");
+  zero_diag_kernel<<<(H + 255) / 256, 256, 0, as_stream(st)>>>(A, H);
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+int sparch_dv_boundary(const float* s0, const float* S, int Be, int T, int H, float* first, sparch_stream_t st) {
+  SPARCH_REQUIRE(s0 && S && first && Be > 0 && T > 0 && H > 0, "bad argument");
+  const int64_t n = (int64_t)Be * H;
+  int nb = (int)((n + 255) / 256);
+  if (nb > sm_count() * 8) nb = sm_count() * 8;
+  dv_boundary_kernel<<<nb, 256, 0, as_stream(st)>>>(s0, S, Be, T, H, first);
   SPARCH_LAUNCH_OK();
   return SPARCH_OK;
 }

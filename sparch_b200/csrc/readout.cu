@@ -161,6 +161,51 @@ static int readout_chunk(int T, int C, int arrays) {
   return tch < 1 ? 1 : tch;
 }
 
+// ---- cross-entropy of the readout's output (exp.py:83 nn.CrossEntropyLoss(), exp.py:362): mean over the batch of
+// logsumexp(x_b) - x_b[y_b], and its gradient (softmax(x_b) - onehot(y_b)) * gloss / B.  One block; a warp per row
+// (lane-strided classes, shuffle reductions), the B row losses are summed in row order by thread 0: deterministic.
+__global__ void ce_fwd_kernel(const float* __restrict__ X, const long long* __restrict__ y, int B, int C,
+                              float* __restrict__ loss, float* __restrict__ lse) {
+  extern __shared__ float row_loss[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int b = warp; b < B; b += nw) {
+    const float* x = X + (int64_t)b * C;
+    float m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, x[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float z = 0.f;
+    for (int c = lane; c < C; c += 32) z += expf(x[c] - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+    if (lane == 0) {
+      const float l = m + logf(z);
+      const long long t = y[b];
+      lse[b] = l;
+      row_loss[b] = (t >= 0 && t < C) ? l - x[t] : 0.f;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sum = 0.f;
+    for (int b = 0; b < B; ++b) sum += row_loss[b];
+    *loss = sum / (float)B;
+  }
+}
+
+__global__ void ce_bwd_kernel(const float* __restrict__ X, const long long* __restrict__ y, const float* __restrict__ lse,
+                              const float* __restrict__ gloss, int B, int C, float* __restrict__ dX) {
+  const int64_t n = (int64_t)B * C;
+  const float g = *gloss / (float)B;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / C;
+    const int c = (int)(i - b * C);
+    const long long t = y[b];
+    const bool valid = t >= 0 && t < C;
+    dX[i] = valid ? (expf(X[i] - lse[b]) - (c == t ? 1.f : 0.f)) * g : 0.f;
+  }
+}
+
 }  // namespace sparch
 
 using namespace sparch;
@@ -192,6 +237,28 @@ int sparch_readout_bwd(const float* gout, const float* U, const float* alpha, co
   const int tch = readout_chunk(T, C, 2);
   readout_bwd_kernel<<<B, threads, (size_t)(2 * tch + 1) * C * sizeof(float) + 32, as_stream(st)>>>(gout, U, alpha, u0, dI,
                                                                                                 p_alpha, T, C, tch);
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+int sparch_ce_fwd(const float* logits, const int64_t* target, int B, int C, float* loss, float* lse, sparch_stream_t st) {
+  SPARCH_REQUIRE(logits && target && loss && lse && B > 0 && C > 0, "bad argument");
+  SPARCH_REQUIRE((size_t)B * sizeof(float) <= 200 * 1024, "batch too large for the one-block loss kernel");
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) SPARCH_CUDA(cudaFuncSetAttribute(ce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ce_fwd_kernel<<<1, 1024, (size_t)B * sizeof(float), as_stream(st)>>>(logits, reinterpret_cast<const long long*>(target), B, C,
+                                                                      loss, lse);
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+int sparch_ce_bwd(const float* logits, const int64_t* target, const float* lse, const float* gloss, int B, int C,
+                  float* dlogits, sparch_stream_t st) {
+  SPARCH_REQUIRE(logits && target && lse && gloss && dlogits && B > 0 && C > 0, "bad argument");
+  const int64_t n = (int64_t)B * C;
+  int nb = (int)((n + 255) / 256);
+  if (nb > sm_count() * 8) nb = sm_count() * 8;
+  ce_bwd_kernel<<<nb, 256, 0, as_stream(st)>>>(logits, reinterpret_cast<const long long*>(target), lse, gloss, B, C, dlogits);
   SPARCH_LAUNCH_OK();
   return SPARCH_OK;
 }

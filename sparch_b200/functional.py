@@ -362,7 +362,10 @@ class SpikingCellFunction(torch.autograd.Function):
             call("sparch_neuron_params", ptr(alpha), ptr(beta), ptr(a), ptr(b), _LIMS, cl.shape[0], H, ptr(cl), st)
             al, be, aa, bb = cl[0], (cl[1] if adaptive else None), (cl[2] if adaptive else None), \
                 (cl[3] if adaptive else None)
-            V0 = V.detach().clone().fill_diagonal_(0) if recurrent else None  # snns.py:712
+            V0 = None
+            if recurrent and H > RECUR_MAX_H:                                   # snns.py:712 (stepwise path only)
+                V0 = torch.empty(H, H, device=dev, dtype=torch.float32)
+                call("sparch_recur_v0", ptr(V.detach().contiguous()), H, ptr(V0), st)
             u0, w0, s0 = _f32c(u0), _f32c(w0) if adaptive else None, _f32c(s0)
             Z2d = Z.view(Be * T, H)
             scale, shift, mean, rstd = _fold_norm(Z2d, gamma, bn_beta, norm)
@@ -377,12 +380,13 @@ class SpikingCellFunction(torch.autograd.Function):
                          ptr(bb), ptr(u0), ptr(w0), ptr(s0), float(theta), ptr(S), ptr(U), ptr(Wt), Be, T,
                          H, st)
             elif H > RECUR_MAX_H:
-                # V0 slice too large for shared memory: general stepwise path, one launch per timestep
-                # with s_{t-1} @ V0 as a library GEMM (sparch_cell_step_fwd)
+                # V0 slice too large for shared memory: general stepwise path, two launches per timestep
+                # (s_{t-1} @ V0 in fp32 FFMA, then sparch_cell_step_fwd)
                 rec = torch.empty(Be, H, device=dev, dtype=torch.float32)
                 region = _region("recurrence_fwd").__enter__()
                 for t in range(T):
-                    torch.matmul(s0 if t == 0 else S[:, t - 1, :], V0, out=rec)  # snns.py:720
+                    sp_ = s0 if t == 0 else S[:, t - 1, :]                      # snns.py:720
+                    call("sparch_small_gemm", ptr(sp_), sp_.stride(0), 0, ptr(V0), H, ptr(rec), H, Be, H, H, 0, st)
                     call("sparch_cell_step_fwd", k, t, ptr(Z), ptr(scale), ptr(shift), ptr(al),
                          ptr(be), ptr(aa), ptr(bb), ptr(rec), ptr(u0), ptr(w0), ptr(s0), float(theta),
                          ptr(S), ptr(U), ptr(Wt), Be, T, H, st)
@@ -405,7 +409,10 @@ class SpikingCellFunction(torch.autograd.Function):
                 ctx.tc = use_tc
                 ctx.rec = (img_b, meta)
                 ctx.reduced = int(_PRECISION == "bf16")
-                rec0 = torch.matmul(s0, V0)        # t = 0: s_{-1} is real-valued (snns.py:702)
+                # t = 0: s_{-1} is real-valued (snns.py:702): rec_0 = s0 @ V0, V0's zero diagonal applied on the fly
+                rec0 = torch.empty(Be, H, device=dev, dtype=torch.float32)
+                with _region("gemm_fwd"):
+                    call("sparch_small_gemm", ptr(s0), H, 0, ptr(Vc), H, ptr(rec0), H, Be, H, H, 1, st)
                 if fwd_tc:
                     L = _lib.lib()
                     img_i8 = torch.empty(L.sparch_recur_fwd_tc_image_bytes(H), device=dev, dtype=torch.uint8)
@@ -459,10 +466,9 @@ class SpikingCellFunction(torch.autograd.Function):
         elif ctx.rec is None:
             carry = torch.zeros(2, Be, H, device=dev, dtype=torch.float32)
             recb = torch.empty(Be, H, device=dev, dtype=torch.float32)
-            V0t = V0.t()
             for t in range(T - 1, -1, -1):
                 if t < T - 1:
-                    torch.matmul(dI[:, t + 1, :], V0t, out=recb)
+                    call("sparch_small_gemm", ptr(dI[:, t + 1, :]), T * H, 0, ptr(V0), H, ptr(recb), H, Be, H, H, 8, st)
                 call("sparch_cell_step_bwd", k, t, ptr(G), ptr(U), ptr(Wt), ptr(al), ptr(be), ptr(aa),
                      ptr(bb), ptr(recb) if t < T - 1 else None, ptr(u0), ptr(w0), ptr(s0), theta,
                      ptr(dI), ptr(carry[0]), ptr(carry[1]) if adaptive else None, pp[0], pp[1], pp[2],
@@ -487,15 +493,16 @@ class SpikingCellFunction(torch.autograd.Function):
                 # frame m of dI pairs with frame m-1 of S (a_koff = -1).  Inside a batch row that is
                 # s_{t-1}; across rows it pairs dI[b, 0] with S[b-1, T-1], which is replaced below by
                 # the real-valued initial state s0 (snns.py:702).
-                first = s0.clone()
-                if Be > 1:
-                    first[1:] -= S[:-1, T - 1, :]
-                dV = first.t() @ dI[:, 0, :]
+                first = torch.empty(Be, H, device=dev, dtype=torch.float32)
+                call("sparch_dv_boundary", ptr(s0), ptr(S), Be, T, H, ptr(first), st)
+                dV = torch.empty(H, H, device=dev, dtype=torch.float32)
                 if Be * T > 1:
                     sp = norm.sterm if norm.sterm is not None else gemm.split_binary(S.view(Be * T, H))
                     dit = gemm.split_general(dI.view(Be * T, H), amax=di_amax)
-                    dV += gemm.gemm_parts(sp, dit, Be * T, a_mn=True, b_mn=True, a_koff=-1, M=H, N=H)
-                dV.fill_diagonal_(0)
+                    gemm.gemm_parts(sp, dit, Be * T, a_mn=True, b_mn=True, a_koff=-1, M=H, N=H, out=dV)
+                # + first^T dI[:, 0, :], then the zero diagonal (backward of snns.py:712), in the same epilogue
+                call("sparch_small_gemm", ptr(first), H, 1, ptr(dI), T * H, ptr(dV), H, H, H, Be,
+                     2 | (4 if Be * T > 1 else 0), st)
         norm.gmax = None     # consumed: belongs to this backward pass only
         pg = torch.empty(npart, H, device=dev, dtype=torch.float32)
         call("sparch_param_grads", ptr(part), ptr(alpha), ptr(beta), ptr(a), ptr(b), _LIMS, npart, Be, H, ptr(pg), st)
@@ -632,6 +639,43 @@ class ReadoutCellFunction(torch.autograd.Function):
         dgamma, dbnb = _norm_backward(dI.view(B * T, C), Z.view(B * T, C), gamma, bn_beta, ctx.norm,
                                       scale, mean, rstd)
         return dI, dgamma, dbnb, dalpha, None, None
+
+
+class CrossEntropyFunction(torch.autograd.Function):
+    """Mean cross-entropy of (B, C) logits against int64 class targets: what ``nn.CrossEntropyLoss()`` (exp.py:83) computes
+    at exp.py:362, as one launch forward and one backward (ATen: log_softmax + nll_loss, twice)."""
+
+    @staticmethod
+    @_on_device
+    def forward(ctx, logits, target):
+        _require_cuda(logits, target)
+        if logits.dim() != 2 or target.dim() != 1 or target.dtype != torch.int64 or target.shape[0] != logits.shape[0]:
+            raise ValueError("CrossEntropyFunction takes (B, C) logits and (B,) int64 targets")
+        x = _f32c(logits.detach())
+        y = target.contiguous()
+        B, C = x.shape
+        loss = torch.empty((), device=x.device, dtype=torch.float32)
+        lse = torch.empty(B, device=x.device, dtype=torch.float32)
+        call("sparch_ce_fwd", ptr(x), ptr(y), B, C, ptr(loss), ptr(lse), _stream())
+        ctx.save_for_backward(x, y, lse)
+        return loss
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, gloss):
+        x, y, lse = ctx.saved_tensors
+        B, C = x.shape
+        g = _f32c(gloss).reshape(1)
+        dx = torch.empty_like(x)
+        call("sparch_ce_bwd", ptr(x), ptr(y), ptr(lse), ptr(g), B, C, ptr(dx), _stream())
+        return dx, None
+
+
+class CrossEntropyLoss(torch.nn.Module):
+    """Drop-in for the ``nn.CrossEntropyLoss()`` of exp.py:83 (default arguments: mean reduction, class-index targets)."""
+
+    def forward(self, logits, target):
+        return CrossEntropyFunction.apply(logits, target)
 
 
 def native_launches():

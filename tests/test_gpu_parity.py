@@ -1025,3 +1025,80 @@ def test_bidirectional_long_sequence_cfg5_shape(precision, flip_tol, loss_tol):
     assert abs(float(loss) - float(loss_r)) <= loss_tol * abs(float(loss_r)), (float(loss), float(loss_r))
     assert float((rates - rates_r).abs().max()) < 0.02
     assert all(q.grad is not None and torch.isfinite(q.grad).all() for q in net.parameters())
+
+
+@pytest.mark.parametrize("B,C", [(256, 35), (1, 20), (7, 1), (300, 1000)])
+def test_cross_entropy_against_torch(B, C):
+    """sparch_b200.CrossEntropyLoss = nn.CrossEntropyLoss() (exp.py:83, 362): loss and gradient to 1e-6 of torch's fp32
+    result, through the C ABI (one launch each way)."""
+    import sparch_b200
+    g = torch.Generator(device=DEV).manual_seed(B + C)
+    x = (torch.randn(B, C, device=DEV, generator=g) * 4).requires_grad_(True)
+    xr = x.detach().clone().requires_grad_(True)
+    y = torch.randint(0, C, (B,), device=DEV, generator=g)
+    loss = sparch_b200.CrossEntropyLoss()(x, y)
+    loss_r = torch.nn.CrossEntropyLoss()(xr, y)
+    (loss * 1.7).backward()
+    (loss_r * 1.7).backward()
+    assert abs(float(loss) - float(loss_r)) <= 2e-6 * max(1.0, abs(float(loss_r)))
+    assert rel_err(x.grad.cpu().numpy(), xr.grad.cpu().numpy()) < 2e-6 or float(xr.grad.abs().max()) < 1e-12
+    with pytest.raises(RuntimeError):
+        sparch_b200.CrossEntropyLoss()(torch.zeros(2, 3), torch.zeros(2, dtype=torch.long))
+
+
+def test_recurrent_helper_kernels():
+    """sparch_recur_v0 (snns.py:712), sparch_dv_boundary, sparch_zero_diag against their torch one-liners."""
+    from sparch_b200._lib import call, ptr
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device=DEV).manual_seed(3)
+    for H, Be, T in ((9, 3, 4), (256, 5, 1), (100, 1, 7)):
+        V = torch.randn(H, H, device=DEV, generator=g)
+        V0 = torch.empty_like(V)
+        call("sparch_recur_v0", ptr(V), H, ptr(V0), st)
+        assert torch.equal(V0, V.clone().fill_diagonal_(0))
+        s0 = torch.rand(Be, H, device=DEV, generator=g)
+        S = (torch.rand(Be, T, H, device=DEV, generator=g) > 0.7).float()
+        first = torch.empty_like(s0)
+        call("sparch_dv_boundary", ptr(s0), ptr(S), Be, T, H, ptr(first), st)
+        ref = s0.clone()
+        if Be > 1:
+            ref[1:] -= S[:-1, T - 1, :]
+        assert torch.equal(first, ref)
+        call("sparch_zero_diag", ptr(V), H, st)
+        assert torch.equal(V, V0)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 1024, 1024), (1024, 1024, 256), (5, 9, 9), (3, 130, 130), (70, 33, 1)])
+def test_small_fp32_gemm_against_fp64(M, N, K):
+    """sparch_small_gemm (rec_0 = s0 @ V0 with V0's zero diagonal on the fly, the t = 0 frames of dV accumulated into the
+    main product with the diagonal masked, the stepwise paths' products): every layout / flag against fp64, 2e-6 of the
+    largest entry (plain fp32 FFMA accumulation)."""
+    from sparch_b200._lib import call, ptr
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    r = lambda *s: torch.randn(*s, device=DEV, generator=g)
+    def check(C, ref):
+        ref = ref.double()
+        assert float((C.double() - ref).abs().max()) <= 2e-6 * max(float(ref.abs().max()), 1e-30)
+    A, B = r(M, K), r(K, N)
+    C = torch.full((M, N), 7.0, device=DEV)
+    call("sparch_small_gemm", ptr(A), K, 0, ptr(B), N, ptr(C), N, M, N, K, 0, st)
+    check(C, A.double() @ B.double())
+    if N == K:                                                     # B = V read with a zero diagonal
+        call("sparch_small_gemm", ptr(A), K, 0, ptr(B), N, ptr(C), N, M, N, K, 1, st)
+        check(C, A.double() @ B.double().clone().fill_diagonal_(0))
+    At = A.t().contiguous()                                        # A stored (K, M); accumulate; zero diagonal of C
+    C0 = r(M, N)
+    C = C0.clone()
+    call("sparch_small_gemm", ptr(At), M, 1, ptr(B), N, ptr(C), N, M, N, K, 4, st)
+    check(C, C0.double() + A.double() @ B.double())
+    if M == N:
+        C = C0.clone()
+        call("sparch_small_gemm", ptr(At), M, 1, ptr(B), N, ptr(C), N, M, N, K, 2 | 4, st)
+        check(C, (C0.double() + A.double() @ B.double()).fill_diagonal_(0))
+    Bt = B.t().contiguous()                                        # B stored (N, K)
+    call("sparch_small_gemm", ptr(A), K, 0, ptr(Bt), K, ptr(C), N, M, N, K, 8, st)
+    check(C, A.double() @ B.double())
+    big = r(M, 3, K)                                               # strided rows (a time slice of a (Be, T, H) tensor)
+    call("sparch_small_gemm", ptr(big[:, 1, :]), 3 * K, 0, ptr(B), N, ptr(C), N, M, N, K, 0, st)
+    check(C, big[:, 1, :].double() @ B.double())
