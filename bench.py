@@ -188,6 +188,9 @@ def run_ours(args, cfg, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # the persistent recurrence kernels occupy 128 of the 148 SMs for most of the step: a collective that asks for
+        # more CTAs than the 20 SMs left either waits for them or delays their launch (NCCL's default is up to 32)
+        os.environ.setdefault("NCCL_MAX_CTAS", "16")
         dist.init_process_group("nccl", device_id=dev)
     B = cfg["B"]
     sparch_b200.set_state_init(args.state_init)
@@ -205,10 +208,10 @@ def run_ours(args, cfg, rank, local_rank, world):
     # (sparch_b200/optim.py); --adam torch uses torch.optim.Adam(fused=True)
     if args.adam == "sparch":
         from sparch_b200.optim import Adam
-        opt = Adam(net.parameters(), 1e-2)
+        opt = Adam(net.parameters(), 1e-2, grad_scale=1.0 / world)   # .grad holds the all-reduced SUM (no division pass)
     else:
         opt = torch.optim.Adam(net.parameters(), 1e-2, capturable=use_graph, fused=True)
-    sync = parallel.GradSync(net) if world > 1 else None
+    sync = parallel.GradSync(net, average=args.adam != "sparch") if world > 1 else None
     x_h, y_h = make_batch(cfg, B, 1234 + rank)
     x_h, y_h = x_h.pin_memory(), y_h.pin_memory()
     x_d, y_d = x_h.to(dev), y_h.to(dev)

@@ -3,10 +3,15 @@
 The reference is single-process (sparch/exp.py:81); batch rows are independent inside every
 layer, so the path shards over the batch with ONE exchange per train step: a
 sum all-reduce of the parameter gradients, averaged over ranks.  Gradients are bucketed per
-layer of ``SNN.snn`` and each bucket's all-reduce is launched asynchronously from a
-post-accumulate-grad hook as soon as the last gradient of that layer exists, so the transfer
-over NVLink overlaps the BPTT of the layers below it.  BatchNorm uses local (per-rank) batch
-statistics -- plain data-parallel semantics.
+layer of ``SNN.snn`` -- two buckets per layer: the projection ``W`` (its gradient is the LAST thing a
+layer's backward produces) and everything else (recurrent ``V``, neuron parameters, normalisation:
+produced by the cell's backward, before the projection's GEMMs) -- and each bucket's all-reduce is
+launched asynchronously from a post-accumulate-grad hook as soon as its last gradient exists, so the
+transfer over NVLink overlaps the BPTT of the layers below it and, inside the first layer, the 4 MB of
+dV travel under the dW GEMM: only the small dW bucket of the first layer is left exposed at the end of
+the backward pass.  ``average=False`` leaves the SUM in ``.grad`` (no division pass): the optimizer
+applies 1 / world (``sparch_b200.optim.Adam(grad_scale=1 / world)``).  BatchNorm uses local (per-rank)
+batch statistics -- plain data-parallel semantics.
 
 Works with any backend ("nccl" on GPUs; "gloo" in the CPU tests).
 """
@@ -15,19 +20,23 @@ import torch.distributed as dist
 
 
 class GradSync:
-    def __init__(self, module, group=None, broadcast=True):
+    def __init__(self, module, group=None, broadcast=True, average=True):
         if not dist.is_initialized():
             raise RuntimeError("GradSync needs an initialised torch.distributed process group")
         self.group = group
         self.world = dist.get_world_size(group)
+        self.average = average
         self.buckets = []
         layers = list(module.snn) if hasattr(module, "snn") else [module]
         seen = set()
         for lay in layers:
             ps = [p for p in lay.parameters() if p.requires_grad and id(p) not in seen]
             seen.update(id(p) for p in ps)
-            if ps:
-                self._add_bucket(ps)
+            proj = getattr(lay, "W", None)
+            wids = {id(p) for p in proj.parameters()} if isinstance(proj, torch.nn.Module) else set()
+            for part in ([p for p in ps if id(p) not in wids], [p for p in ps if id(p) in wids]):
+                if part:
+                    self._add_bucket(part)
         rest = [p for p in module.parameters() if p.requires_grad and id(p) not in seen]
         if rest:
             self._add_bucket(rest)
@@ -69,7 +78,8 @@ class GradSync:
                                             async_op=True)
         for b in self.buckets:
             b["work"].wait()
-            b["flat"].div_(self.world)
+            if self.average:
+                b["flat"].div_(self.world)
             for v, p in zip(b["views"], b["params"]):
                 p.grad = v
             b["pending"] = len(b["params"])

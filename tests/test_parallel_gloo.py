@@ -14,10 +14,22 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 
+class _Lay(torch.nn.Module):
+    """Shaped like a spiking layer: a projection ``W`` plus other parameters (two buckets in GradSync)."""
+
+    def __init__(self, i, o):
+        super().__init__()
+        self.W = torch.nn.Linear(i, o)
+        self.gain = torch.nn.Parameter(torch.ones(o))
+
+    def forward(self, x):
+        return self.W(x) * self.gain
+
+
 class _Toy(torch.nn.Module):
     def __init__(self):
         super().__init__()
-        self.snn = torch.nn.ModuleList([torch.nn.Linear(6, 5), torch.nn.Linear(5, 4), torch.nn.Linear(4, 3)])
+        self.snn = torch.nn.ModuleList([_Lay(6, 5), torch.nn.Linear(5, 4), _Lay(4, 3)])
         self.unused = torch.nn.Parameter(torch.ones(2))
         self.register_buffer("stat", torch.zeros(3))
 
@@ -33,7 +45,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, average=True):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -41,7 +53,8 @@ def _worker(rank, world, port, out):
         torch.manual_seed(100 + rank)          # different init per rank: broadcast must fix it
         net = _Toy()
         net.stat.fill_(float(rank + 1))
-        sync = GradSync(net)
+        sync = GradSync(net, average=average)
+        assert len(sync.buckets) == 6   # (gain | W) x 2 layers + one plain layer + the module's own parameter
         torch.manual_seed(7)
         ref = _Toy()                            # what rank 0 had (seed 100) is unknown here; compare via gather
         p0 = [p.detach().clone() for p in net.parameters()]
@@ -63,7 +76,7 @@ def _worker(rank, world, port, out):
                     continue
                 parts = [torch.zeros_like(lg) for _ in range(world)]
                 dist.all_gather(parts, lg)
-                want = sum(parts) / world
+                want = sum(parts) / (world if average else 1)
                 assert torch.allclose(p.grad, want, rtol=1e-6, atol=1e-7)
         out.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
@@ -72,11 +85,12 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_gradsync_world2_gloo():
+@pytest.mark.parametrize("average", [True, False])
+def test_gradsync_world2_gloo(average):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, average)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
