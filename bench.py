@@ -324,6 +324,39 @@ def run_ours(args, cfg, rank, local_rank, world):
         torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None            # samples cover the timed + e2e (+ filler) load
 
+    # ---- the drop-in figure: what sparch/exp.py's own loop gets after INTEGRATION.md's one-line switch, nothing else
+    # changed -- default (reference-exact, CPU generator) state draws, eager launches, torch.optim.Adam as exp.py:89
+    # builds it, nn.CrossEntropyLoss, x.to(device) / y.to(device) from pinned host tensors and loss.item() every step
+    # (exp.py:355-363, 375-377).  Single GPU only (the reference loop has no gradient exchange); a few steps.
+    dropin = None
+    if world == 1 and not args.no_dropin:
+        sparch_b200.set_state_init("cpu")
+        torch.manual_seed(0)
+        net2 = sparch_b200.SNN((B, None, cfg["F"]), **model_kwargs(cfg)).to(dev)
+        net2.train()
+        opt2 = torch.optim.Adam(net2.parameters(), 1e-2)
+        loss2 = torch.nn.CrossEntropyLoss()
+
+        def dropin_step():
+            x, y = x_h.to(dev), y_h.to(dev)
+            out, _ = net2(x)
+            l = loss2(out, y)
+            v = l.item()
+            opt2.zero_grad()
+            l.backward()
+            opt2.step()
+            return v
+
+        for _ in range(3):
+            dropin_step()
+        nd = max(3, min(args.steps, 10))
+        ms_d = timed(dropin_step, nd)
+        dropin = {"value": B * nd / (ms_d * 1e-3), "unit": "samples/s", "ms_per_step": ms_d / nd, "steps": nd,
+                  "what": "sparch/exp.py's loop unchanged (reference-exact CPU-generator state draws, eager, "
+                          "torch.optim.Adam, nn.CrossEntropyLoss, .to(device) + loss.item() per step)"}
+        sparch_b200.set_state_init(args.state_init)
+        del net2, opt2
+
     if rank != 0:
         # Hard exit: tearing down a process group whose collectives live inside a captured CUDA graph was seen to
         # hang at interpreter exit; this rank's measured work is complete and synchronised.
@@ -391,6 +424,8 @@ def run_ours(args, cfg, rank, local_rank, world):
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "regions_ms_per_step": {k: v / args.steps for k, v in rec_ms.items()},
     }
+    if dropin is not None:
+        line["e2e_dropin"] = dropin
     print(json.dumps(line), flush=True)
     if world > 1:
         sys.stderr.flush()
@@ -417,6 +452,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly, launch by launch")
     ap.add_argument("--adam", default="sparch", choices=["sparch", "torch"],
                     help="optimizer of the train step: sparch_b200.optim.Adam (one launch) or torch.optim.Adam(fused=True)")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the e2e_dropin leg (exp.py's loop unchanged)")
     ap.add_argument("--profile", action="store_true",
                     help="profiling run (under ncu): exactly --warmup warm-up and --steps timed steps of "
                          "the device-resident loop, no e2e leg, no CPU baseline; prints no bench value")

@@ -1102,3 +1102,36 @@ def test_small_fp32_gemm_against_fp64(M, N, K):
     big = r(M, 3, K)                                               # strided rows (a time slice of a (Be, T, H) tensor)
     call("sparch_small_gemm", ptr(big[:, 1, :]), 3 * K, 0, ptr(B), N, ptr(C), N, M, N, K, 0, st)
     check(C, big[:, 1, :].double() @ B.double())
+
+
+@pytest.mark.parametrize("neuron_type,reg", [("RadLIF", False), ("LIF", True)])
+def test_reference_training_loop_drop_in(neuron_type, reg):
+    """INTEGRATION.md's claim, end to end: the reference's train / validation loops (sparch/exp.py:341-459, restated in
+    oracle/exp_loop.py and pinned there against the reference's own functions) drive ``sparch_b200.SNN`` exactly as
+    they drive ``sparch.models.snns.SNN`` -- constructor call of exp.py:305-314, ``self.net(x)`` returning
+    (output, firing_rates), ``is_snn``, torch.optim.Adam + ReduceLROnPlateau + nn.CrossEntropyLoss, the optional
+    firing-rate regularisers, ``.item()`` every step, default (reference) state initialisation.  Two epochs on a
+    learnable synthetic task: finite losses that decrease, a scheduler step, rates in (0, 1)."""
+    from oracle import exp_loop
+    sp, _ = _mods()
+    torch.manual_seed(0)
+    net = sp.SNN(input_shape=(8, None, 40), layer_sizes=[64, 64, 10], neuron_type=neuron_type, dropout=0.1,
+                 normalization="batchnorm", use_bias=False, bidirectional=False, use_readout_layer=True).to(DEV)
+    with torch.no_grad():
+        for lay in net.snn:
+            if hasattr(lay, "a"):
+                lay.a.abs_()
+    ex = exp_loop.stub_experiment(net, torch.device(DEV), lr=5e-3, batches=12, use_regularizers=reg)
+    first = last = None
+    best = (0, 0)
+    for e in (1, 2, 3):
+        losses, accs = exp_loop.train_one_epoch(ex, e)
+        assert all(np.isfinite(losses))
+        first = first if first is not None else float(np.mean(losses[:4]))
+        last = float(np.mean(losses[-4:]))
+        best = exp_loop.valid_one_epoch(ex, e, *best)
+    assert last < first, (first, last)
+    assert any("train mean act rate" in m for m in ex.log)
+    out, rates = net(ex.train_loader[0][0].to(DEV))
+    assert out.shape == (8, 10) and 0.0 < float(rates.mean()) < 1.0
+    assert best[0] in (1, 2, 3) and 0.0 <= best[1] <= 1.0

@@ -221,3 +221,65 @@ def test_host_side_guards_without_a_gpu():
     net = sparch_b200.SNN((2, None, 4), layer_sizes=[8, 8, 3])
     with pytest.raises(RuntimeError):          # needs device state init and CUDA tensors
         GraphedTrainStep(net, Adam(net.parameters(), 1e-2), torch.nn.CrossEntropyLoss(), x, torch.zeros(2, dtype=torch.long))
+
+
+def test_restated_training_loop_equals_the_references_own():
+    """oracle/exp_loop.py against the reference's unbound Experiment.train_one_epoch / valid_one_epoch (exp.py:341-459) on
+    the same CPU model (the torch restatement of the reference SNN), stub loaders, optimizer and scheduler: identical
+    per-step losses, learning rate and parameters after two epochs, with and without the firing-rate regularisers.
+    Needs /root/reference (build container only)."""
+    import copy
+    import sys
+    if not os.path.isdir("/root/reference/sparch"):
+        pytest.skip("the reference is not on this machine")
+    import types
+    # exp.py:26-27 imports the dataloaders, which need torchaudio / h5py packages this image does not have: the loops
+    # under test never touch them, so two empty stand-ins take their place for the duration of the import
+    stubs = {}
+    for name, fn in (("sparch.dataloaders.nonspiking_datasets", "load_hd_or_sc"),
+                     ("sparch.dataloaders.spiking_datasets", "load_shd_or_ssc")):
+        m = types.ModuleType(name)
+        setattr(m, fn, lambda *a, **k: None)
+        stubs[name] = m
+    had = {k for k in sys.modules if k == "sparch" or k.startswith("sparch.")}
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    sys.path.insert(0, "/root/reference")
+    try:
+        from sparch.exp import Experiment
+    finally:
+        sys.path.remove("/root/reference")
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        for k in [k for k in sys.modules if (k == "sparch" or k.startswith("sparch.")) and k not in had]:
+            del sys.modules[k]                                  # (Experiment keeps its own references)
+    from oracle import exp_loop
+    from oracle import snn_oracle as orc
+    for reg in (False, True):
+        kw = dict(layer_sizes=[24, 24, 10], neuron_type="RadLIF", normalization="batchnorm", dropout=0.0)
+        torch.manual_seed(0)
+        net_a = orc.build_oracle_snn((8, None, 40), **kw)
+        net_b = copy.deepcopy(net_a)
+        exps = [exp_loop.stub_experiment(n, torch.device("cpu"), use_regularizers=reg) for n in (net_a, net_b)]
+        losses = []
+        for i, ex in enumerate(exps):
+            torch.manual_seed(5)                               # the initial-state draws (snns.py:700-702)
+            ls = []
+            for e in (1, 2):
+                if i == 0:
+                    before = [b[0].clone() for b in ex.train_loader]
+                    Experiment.train_one_epoch(ex, e)          # the reference's own function on the stub
+                    best = Experiment.valid_one_epoch(ex, e, 0, 0)
+                    assert all(torch.equal(a, b[0]) for a, b in zip(before, ex.train_loader))
+                else:
+                    l, _ = exp_loop.train_one_epoch(ex, e)
+                    ls += l
+                    best = exp_loop.valid_one_epoch(ex, e, 0, 0)
+            losses.append((ls, best, ex.opt.param_groups[-1]["lr"]))
+        assert losses[0][1] == losses[1][1] and losses[0][2] == losses[1][2]
+        for pa, pb in zip(net_a.parameters(), net_b.parameters()):
+            assert torch.equal(pa, pb)
+        assert len(losses[1][0]) == 8 and all(np.isfinite(losses[1][0]))
