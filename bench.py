@@ -377,12 +377,39 @@ def run_ours(args, cfg, rank, local_rank, world):
     rec_total_ms = (rec_ms.get("recurrence_fwd", 0.0) + rec_ms.get("recurrence_bwd", 0.0)) / args.steps
     achieved = alg_bytes / (rec_total_ms * 1e-3) / 1e9 if rec_total_ms > 0 else None
     traffic = None
-    try:                                                      # from the committed ncu --set full capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_recur_traffic.json")))
-        if tj.get("config") == args.config:
-            traffic = tj["traffic_bytes_per_step"]
+    for name in ("r02_recur_traffic.json", "r01_recur_traffic.json"):   # from the committed ncu --set full capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if tj.get("config") == args.config:
+                traffic = tj["traffic_bytes_per_step"]
+                break
+        except Exception:
+            pass
+    # The recurrence is a chain of 2 T dependent steps per layer; a step cannot be shorter than one inter-CTA
+    # hand-over through L2 (measured by tools/ubench/exchange_rtt.cu: an EMPTY persistent kernel on the same grid that
+    # only publishes and polls tagged words, profiles/r02_ubench_exchange_rtt.txt) nor than its tensor work at the
+    # measured dense peak.  floor = T * layers * (t_fwd + t_bwd), t = max(hand-over, tensor time).
+    latency = None
+    try:
+        import re as _re
+        rtts = [float(x) for x in _re.findall(r"tagged words \(64 loads in flight\) grid 32 x 4.*?= ([0-9.]+) ns/step",
+                                              open(os.path.join(ROOT, "profiles", "r02_ubench_exchange_rtt.txt")).read())]
+        rtt_us = min(rtts) * 1e-3
+        tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1387.7)))
+        hs = [h for h in cfg["layer_sizes"][:n_spiking]]
+        rec_layers = [h for h in hs] if cfg["neuron_type"] in ("RLIF", "RadLIF") else []
+        if rec_layers:
+            t_f = [max(rtt_us, 2.0 * Be * h * h * 2 / (tf * 1e12) * 1e6) for h in rec_layers]   # spikes x (hi, lo) of V0
+            t_b = [max(rtt_us, 2.0 * Be * h * h * 3 / (tf * 1e12) * 1e6) for h in rec_layers]   # three fp16 passes
+            floor_ms = cfg["T"] * (sum(t_f) + sum(t_b)) * 1e-3
+            latency = {"exchange_rtt_us": rtt_us, "t_step_floor_us": {"fwd": t_f, "bwd": t_b}, "floor_ms": floor_ms,
+                       "frac_of_floor": floor_ms / rec_total_ms if rec_total_ms else None,
+                       "measured_us_per_layer_step": {"fwd": rec_ms.get("recurrence_fwd", 0.0) / args.steps /
+                                                      (cfg["T"] * len(rec_layers)) * 1e3,
+                                                      "bwd": rec_ms.get("recurrence_bwd", 0.0) / args.steps /
+                                                      (cfg["T"] * len(rec_layers)) * 1e3}}
     except Exception:
-        pass
+        latency = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "kernel": "membrane recurrence fwd+bwd (all launches of one train step)",
@@ -394,8 +421,9 @@ def run_ours(args, cfg, rank, local_rank, world):
                 "timed": ("CUDA events around the recurrence launches of the same steps issued eagerly right after "
                           "the graphed timed region") if graphed is not None else
                          "CUDA events around the recurrence launches inside the timed region",
+                "latency": latency,
                 "note": "the recurrence is bounded by its 2*T dependent steps per layer (exchange latency + tensor "
-                        "issue), not by HBM: see DESIGN.md section 5 for the latency floor"}
+                        "issue), not by HBM: `latency` holds the floor from the measured hand-over round trip"}
 
     # ---- CPU baseline beside it (bounded sample: the full config batch, 2 timed steps) --------
     cpu = None
