@@ -334,6 +334,17 @@ SPARCH_API int sparch_ce_fwd(const float* logits, const int64_t* target, int B, 
 SPARCH_API int sparch_ce_bwd(const float* logits, const int64_t* target, const float* lse, const float* gloss, int B,
                              int C, float* dlogits, sparch_stream_t st);
 
+/* ---- on-device data path of the spiking datasets (sparch/dataloaders/spiking_datasets.py:66-78) ------------- */
+/* A batch of B event lists, concatenated: times[e] (seconds, fp32), units[e] (int32), offsets[b] .. offsets[b+1] the
+ * events of example b (offsets[B] = nev).  dense (B, nb_steps, nb_units) fp32 is zeroed and receives, per example, the
+ * reference's x.to_dense(): the NUMBER of events of unit u whose time falls into bin np.digitize(t, bins) (bins:
+ * nb_steps increasing float64 edges, np.linspace(0, max_time, nb_steps), compared in float64 as numpy does).  *bad
+ * (device int) becomes non-zero if an event lies at or beyond the last edge, has a unit outside [0, nb_units) or a NaN
+ * time -- where the reference's sparse-tensor constructor raises.                                                   */
+SPARCH_API int sparch_events_to_dense(const float* times, const int* units, const int64_t* offsets, const double* bins,
+                                      int B, int nb_steps, int nb_units, int64_t nev, float* dense, int* bad,
+                                      sparch_stream_t st);
+
 #ifdef __cplusplus
 }
 #endif

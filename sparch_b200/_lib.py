@@ -63,6 +63,7 @@ _PROTOS = {
     "sparch_readout_bwd": "p" * 6 + "iii" + "p",
     "sparch_ce_fwd": "ppiippp",
     "sparch_ce_bwd": "ppppiipp",
+    "sparch_events_to_dense": "ppppiiilppp",
 }
 _CT = {"p": _P, "i": _I, "l": _L, "f": _F}
 

@@ -1135,3 +1135,34 @@ def test_reference_training_loop_drop_in(neuron_type, reg):
     out, rates = net(ex.train_loader[0][0].to(DEV))
     assert out.shape == (8, 10) and 0.0 < float(rates.mean()) < 1.0
     assert best[0] in (1, 2, 3) and 0.0 <= best[1] <= 1.0
+
+
+@pytest.mark.parametrize("B,rate,nb_steps", [(16, 8000, 100), (1, 10, 100), (5, 3000, 250), (3, 0, 100)])
+def test_events_to_dense_against_the_data_oracle(B, rate, nb_steps):
+    """sparch_b200.data.SpikingBatcher (csrc/data.cu) = the reference's SpikingDataset.__getitem__ + generateBatch
+    (spiking_datasets.py:66-86, restated in oracle/data_oracle.py and pinned there against the reference): bit-exact dense
+    count tensors from SHD-shaped event lists, incl. duplicates in a bin, an example without events, events on the first
+    bin edge; an event at / beyond the last edge raises as the reference's sparse constructor does."""
+    from oracle import data_oracle as dor
+    from sparch_b200.data import SpikingBatcher
+    if rate:
+        T, U, y = dor.synthetic_events(B, seed=B + rate, rate=rate)
+        T[0][:2] = 0.0
+        U[0][:2] = 3
+    else:
+        T, U, y = [np.zeros(0, np.float16)] * B, [np.zeros(0, np.uint16)] * B, np.arange(B)
+    if B > 2 and rate:
+        T[2], U[2] = T[2][:0], U[2][:0]                    # an empty example in the middle
+    bat = SpikingBatcher(nb_steps=nb_steps, device=DEV)
+    x, xlens, yy = bat(T, U, y)
+    ox, olens, oy = dor.batch_to_dense(T, U, y, nb_steps=nb_steps)
+    assert x.shape == (B, nb_steps, 700) and x.dtype == torch.float32
+    assert np.array_equal(x.cpu().numpy(), ox)
+    assert np.array_equal(xlens.numpy(), olens) and np.array_equal(yy.cpu().numpy(), oy)
+    if rate:
+        T[-1] = np.append(T[-1], np.float16(1.4))           # np.digitize -> bin nb_steps: outside the grid
+        U[-1] = np.append(U[-1], np.uint16(0))
+        with pytest.raises(ValueError):
+            bat(T, U, y)
+        with pytest.raises(IndexError):
+            dor.batch_to_dense(T, U, y, nb_steps=nb_steps)

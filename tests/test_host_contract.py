@@ -283,3 +283,48 @@ def test_restated_training_loop_equals_the_references_own():
         for pa, pb in zip(net_a.parameters(), net_b.parameters()):
             assert torch.equal(pa, pb)
         assert len(losses[1][0]) == 8 and all(np.isfinite(losses[1][0]))
+
+
+def test_data_oracle_equals_the_references_spiking_dataset():
+    """oracle/data_oracle.py against the reference's own SpikingDataset.__getitem__ / generateBatch
+    (spiking_datasets.py:66-86) on synthetic SHD-shaped events (float16 times, duplicates in a bin, events in the first and
+    in the last bin): identical dense tensors, lengths and labels.  Needs /root/reference (build container only)."""
+    import sys
+    import types
+    if not os.path.isdir("/root/reference/sparch"):
+        pytest.skip("the reference is not on this machine")
+    had = {k for k in sys.modules if k == "sparch" or k.startswith("sparch.")}
+    fake_h5 = "h5py" not in sys.modules
+    try:
+        import h5py  # noqa: F401
+        fake_h5 = False
+    except Exception:
+        sys.modules["h5py"] = types.ModuleType("h5py")
+    sys.path.insert(0, "/root/reference")
+    try:
+        from sparch.dataloaders.spiking_datasets import SpikingDataset
+    finally:
+        sys.path.remove("/root/reference")
+        if fake_h5:
+            sys.modules.pop("h5py", None)
+        for k in [k for k in sys.modules if (k == "sparch" or k.startswith("sparch.")) and k not in had]:
+            del sys.modules[k]
+    from oracle import data_oracle as dor
+    T, U, y = dor.synthetic_events(5, seed=3, rate=3000)
+    T[0][:3] = 0.0                                          # first bin edge, three times (duplicates sum)
+    U[0][:3] = 7
+    T[1][-1] = np.float16(1.39)                             # last bin
+    stub = types.SimpleNamespace(firing_times=T, units_fired=U, labels=np.asarray(y), device="cpu", nb_steps=100,
+                                 nb_units=700, time_bins=np.linspace(0, 1.4, num=100))
+    items = [SpikingDataset.__getitem__(stub, i) for i in range(5)]
+    xs, xlens, ys = SpikingDataset.generateBatch(stub, items)
+    ox, olens, oy = dor.batch_to_dense(T, U, y)
+    assert xs.shape == (5, 100, 700) and np.array_equal(xs.numpy(), ox)
+    assert ox[0, 1, 7] >= 3.0                               # digitize puts t = 0 into bin 1; duplicates are counts
+    assert np.array_equal(xlens.numpy(), olens) and np.array_equal(ys.numpy(), oy)
+
+
+def test_spiking_batcher_is_cuda_only():
+    from sparch_b200.data import SpikingBatcher
+    with pytest.raises(RuntimeError):
+        SpikingBatcher(device="cpu")
