@@ -123,7 +123,5 @@ int main() {
   if (run<32, 3>("i8,  A in TMEM, one accumulator")) return 1;
   if (run<128, 0>("f16, A in TMEM, one accumulator")) return 1;
   if (run<128, 2>("f16, A in shared memory")) return 1;
-  if (run<256, 0>("f16, A in TMEM, one accumulator")) return 1;
-  if (run<256, 2>("f16, A in shared memory")) return 1;
   return 0;
 }
