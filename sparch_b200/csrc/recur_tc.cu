@@ -56,6 +56,7 @@ constexpr int TC_QMAX_BYTES = TC_CL * TC_ROWS * 4;            // [source rank][r
 constexpr int TC_THREADS = 320;        // warp 0 spare, warp 1 MMA, warps 2..9 load + update
 constexpr int TC_VSCALE_EXP = 13;
 constexpr uint32_t TC_RECV_TX = (TC_RECV_BYTES + TC_QMAX_BYTES) / 2;   // per chain (32 of the 64 rows) and step
+constexpr int TC_NBUF = 2;               // hand-over buffers in rotation (see tc_tag)
 constexpr uint32_t TC_D_COL = 256;      // TMEM: V0 hi / lo in columns [0, 256), D of chain c in [256 + 32 c, 288 + 32 c)
 
 struct RecBwdTcArgs {
@@ -154,6 +155,12 @@ __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* a) {
   return v;
 }
 
+__device__ __forceinline__ uint4 ld_weak_v4(const uint32_t* a) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ uint4 ld_relaxed_v4(const uint32_t* a) {
   uint4 v;
   asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a) : "memory");
@@ -198,9 +205,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
   }
 }
 
-// Tag of the words of panel(t): the buffer (t & 1) is rewritten every second step, its n-th use carries tag (n & 1) ^ 1
-// (the buffers start zeroed: tag 0).
-__device__ __forceinline__ uint32_t tc_tag(int T, int t) { return ((((T - 1 - t) >> 1) & 1) ^ 1); }
+// panel(t) lives in buffer (T - 1 - t) % TC_NBUF; the n-th use of a buffer carries tag (n & 1) ^ 1 (the buffers start
+// zeroed: tag 0).  Two buffers are enough: a producer overwrites panel(t + 2) only after all its consumers have published
+// panel(t + 1), which they do after reading it.  (Eight buffers in rotation were measured: no faster -- the ~25 B/clk
+// at which a CTA's 64 KB arrive per step is not an effect of re-reading recently read addresses, although an isolated
+// SM shows one: tools/ubench/l2_gather.cu.)
+__device__ __forceinline__ uint32_t tc_tag(int T, int t) { return ((((T - 1 - t) / TC_NBUF) & 1) ^ 1); }
+__device__ __forceinline__ int tc_buf(int T, int t) { return (T - 1 - t) % TC_NBUF; }
 
 template <bool ADAPT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -405,14 +416,14 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
       if (dbg_on) p.dbg[t * 8 + 0] = clock64();
       if (t < p.T - 1) {
         // ---- dI_{t+1}[rows of this warp][K quarter] -> stage tiles: poll the tagged words themselves
-        const uint32_t* src = pan_rd0 + (size_t)((t + 1) & 1) * pan_buf;
+        const uint32_t* src = pan_rd0 + (size_t)tc_buf(p.T, t + 1) * pan_buf;
         const uint32_t em = tc_tag(p.T, t + 1) << 16;
         // Polling all 64 KB would load the L2 with 8 MB per round over the grid; the warp polls one word of every 128-byte
         // LINE instead (a line = one row of one producer warp = one store instruction of that warp: 8 rows x 8
         // producers = 64 lines, two per lane: lane l takes producer l % 8, rows l / 8 and l / 8 + 4).  Fresh lines say
         // "the data is there"; every data word is still checked by its own tag (and re-read until fresh), so nothing
         // rests on the line assumption.
-        const uint32_t* smp = p.panel + (size_t)((t + 1) & 1) * pan_buf + ((size_t)group * TC_ROWS + 8 * uw + (lane >> 3)) * p.Hp +
+        const uint32_t* smp = p.panel + (size_t)tc_buf(p.T, t + 1) * pan_buf + ((size_t)group * TC_ROWS + 8 * uw + (lane >> 3)) * p.Hp +
                               rank * (p.Hp / TC_CL) + 32 * (lane & 7);
         uint4 v[16];
         __half2 mj[4];
@@ -435,7 +446,10 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
                 while (n < p.KB && ((fresh >> (2 * n)) & 0x03030303u) == 0x03030303u) ++n;
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                  if ((i >> 2) >= issued && (i >> 2) < n) v[i] = ld_relaxed_v4(src + (2 * (i & 3)) * p.Hp + (i >> 2) * 64);
+                  if ((i >> 2) >= issued && (i >> 2) < n) {
+                    const uint32_t* q_ = src + (2 * (i & 3)) * p.Hp + (i >> 2) * 64;
+                    v[i] = ld_relaxed_v4(q_);
+                  }
                 issued = n;
                 if (dbg_on) p.dbg[2 * p.T * 8 + kb] += 1;          // sample rounds entered at K block kb
                 if (clock64() - t0 > 4000000000LL) __trap();
@@ -580,7 +594,7 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
       // two parts: first what dI_t needs, then its hand-over, and only then what nobody waits for (parameter-gradient
       // sums, the adjoint of w, the dI tape) -- that part runs while the published words travel to the L2.
       const uint32_t tag = tc_tag(p.T, t) << 16;
-      uint32_t* dst = pan_wr0 + (size_t)(t & 1) * pan_buf;
+      uint32_t* dst = pan_wr0 + (size_t)tc_buf(p.T, t) * pan_buf;
       float d[8], sc[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) sc[k] = __uint_as_float((uint32_t)(127 + __shfl_sync(0xffffffffu, e_cur, k)) << 23);
@@ -680,7 +694,7 @@ size_t sparch_recur_bwd_tc_image_bytes(int H) {
 size_t sparch_recur_bwd_tc_workspace(int Be, int T, int H) {
   const int Hp = sparch_recur_tc_padded(H);
   const size_t groups = (size_t)(Be + TC_ROWS - 1) / TC_ROWS;
-  return 2 * groups * TC_ROWS * Hp * sizeof(uint32_t)  // double-buffered panel of {hi, lo | tag} words
+  return TC_NBUF * groups * TC_ROWS * Hp * sizeof(uint32_t)  // rotating panels of {hi, lo | tag} words
          + (size_t)Be * T * sizeof(float)              // gmax
          + 256;
 }
@@ -712,17 +726,21 @@ int sparch_recur_bwd_tc(int kind, const float* G, const float* U, const float* W
                  "adaptive kind needs W, beta, a, b, w0 and the partial buffers");
   const int Hp = sparch_recur_tc_padded(H), KB = Hp / (64 * TC_CL);
   const size_t smem = rec_bwd_tc_smem(KB);
-  SPARCH_REQUIRE(KB <= 4 && smem <= 227 * 1024, "hidden size too large for the resident V0 tiles");
+  SPARCH_REQUIRE(KB <= 4 && smem <= 112 * 1024, "hidden size too large for the resident V0 tiles");
   SPARCH_REQUIRE((long long)Be * T * H < (1LL << 31), "tape larger than 2^31 elements: split the batch");
   cudaStream_t st = as_stream(st_);
   static PerDeviceOnce attr_once;
   if (attr_once.first()) {
-    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    // 98.5 KB at H = 1024 (V0 lives in tensor memory): the rest of the SM's 256 KB stays L1, whose lines buffer the
+    // 64 KB of panel words a CTA has in flight per step
+    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
+    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
   }
   const int groups = (Be + TC_ROWS - 1) / TC_ROWS, slices = Hp / TC_COLS;
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
-  const size_t panel_bytes = (size_t)2 * groups * TC_ROWS * Hp * sizeof(uint32_t);
+  const size_t panel_bytes = (size_t)TC_NBUF * groups * TC_ROWS * Hp * sizeof(uint32_t);
   uint32_t* panel = reinterpret_cast<uint32_t*>(ws);
   float* gmax = reinterpret_cast<float*>(ws + panel_bytes);
   SPARCH_CUDA(cudaMemsetAsync(ws, 0, panel_bytes, st));  // tag 0 everywhere: the first use of a buffer writes tag 1
