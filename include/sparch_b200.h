@@ -106,6 +106,17 @@ SPARCH_API int sparch_cell_step_fwd(int kind, int t, const float* Z, const float
                          const float* w0, const float* s0, float theta, float* S, float* U,
                          float* W, int Be, int T, int H, sparch_stream_t st);
 
+/* ---- LayerNorm (normalization="layernorm": nn.LayerNorm(H) on W x, snns.py:98-99, 678-680) ------------------- */
+/* Y[m] = (X[m] - mean_m) * rstd_m * gamma + beta over rows of H <= 2048 values (biased variance, eps inside the root);
+ * mean / rstd (M) are kept for the backward.  gamma / beta may be NULL (elementwise_affine=False).               */
+SPARCH_API int sparch_layernorm_fwd(const float* X, const float* gamma, const float* beta, float eps, int64_t M, int H,
+                                    float* Y, float* mean, float* rstd, sparch_stream_t st);
+/* dX, and (when asked for) dgamma = sum_m dY * xhat, dbeta = sum_m dY (fp64 partial sums, fixed order).            */
+SPARCH_API size_t sparch_layernorm_bwd_workspace(int64_t M, int H);
+SPARCH_API int sparch_layernorm_bwd(const float* dY, const float* X, const float* gamma, const float* mean,
+                                    const float* rstd, int64_t M, int H, float* dX, float* dgamma, float* dbeta,
+                                    void* workspace, sparch_stream_t st);
+
 /* ---- membrane recurrence, reverse-time BPTT (autograd of the above) ----- */
 /* Non-recurrent kinds: whole reverse loop.  G = dL/dS (Be,T,H).  Writes dI (Be,T,H) and the
  * per-(b,h) partial parameter gradients pa,pb,pc,pd (Be,H each; pb..pd NULL for LIF) which

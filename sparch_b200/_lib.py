@@ -22,6 +22,9 @@ _PROTOS = {
     "sparch_bn_bwd_apply_f16": "pppppppli" "ppppplpp",
     "sparch_bn_fold_train": "pplppffppppppip",
     "sparch_bn_bwd_apply": "pppppppli" "pp",
+    "sparch_layernorm_fwd": "pppfliPPPp".replace("P", "p"),
+    "sparch_layernorm_bwd_workspace": "li",
+    "sparch_layernorm_bwd": "ppppplipppp" "p",
     "sparch_cell_fwd": "i" + "p" * 10 + "f" + "ppp" + "iii" + "p",
     "sparch_cell_step_fwd": "ii" + "p" * 11 + "f" + "ppp" + "iii" + "p",
     "sparch_cell_bwd": "i" + "p" * 10 + "f" + "p" * 5 + "iii" + "p",

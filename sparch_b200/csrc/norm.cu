@@ -420,6 +420,121 @@ static int ew_grid(int64_t n, int block) {
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
+// ------------------------------------------------------------------ LayerNorm (normalization="layernorm", snns.py:98-99)
+// nn.LayerNorm(H) over the last dimension of W x (snns.py:678-680): y = (x - mean) * rstd * gamma + beta with the
+// biased row variance.  One warp per row: the row is read once into registers (H <= 32 * LN_MAX values per lane),
+// two-pass mean / variance like ATen's RowwiseMoments for short rows, mean and rstd kept for the backward.
+constexpr int LN_MAX = 64;   // row length <= 2048
+
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ X, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float eps, int64_t M, int H,
+                                                     float* __restrict__ Y, float* __restrict__ mean, float* __restrict__ rstd) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* x = X + row * H;
+  float v[LN_MAX];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < H ? x[c] : 0.f;
+    s += v[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mu = s / (float)H;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX; ++i) {
+    const float d = (lane + 32 * i < H) ? v[i] - mu : 0.f;
+    q += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rs = rsqrtf(q / (float)H + eps);
+  float* y = Y + row * H;
+#pragma unroll
+  for (int i = 0; i < LN_MAX; ++i) {
+    const int c = lane + 32 * i;
+    if (c < H) {
+      const float xh = (v[i] - mu) * rs;
+      y[c] = (gamma ? xh * gamma[c] : xh) + (beta ? beta[c] : 0.f);
+    }
+  }
+  if (lane == 0) {
+    mean[row] = mu;
+    rstd[row] = rs;
+  }
+}
+
+// dx = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)), g = dy * gamma; one warp per row
+__global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const float* __restrict__ dY, const float* __restrict__ X,
+                                                        const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                        const float* __restrict__ rstd, int64_t M, int H,
+                                                        float* __restrict__ dX) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float mu = mean[row], rs = rstd[row];
+  const float* x = X + row * H;
+  const float* dy = dY + row * H;
+  float g[LN_MAX], xh[LN_MAX];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX; ++i) {
+    const int c = lane + 32 * i;
+    const bool in = c < H;
+    xh[i] = in ? (x[c] - mu) * rs : 0.f;
+    g[i] = in ? dy[c] * (gamma ? gamma[c] : 1.f) : 0.f;
+    s1 += g[i];
+    s2 += g[i] * xh[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  const float m1 = s1 / (float)H, m2 = s2 / (float)H;
+  float* dx = dX + row * H;
+#pragma unroll
+  for (int i = 0; i < LN_MAX; ++i) {
+    const int c = lane + 32 * i;
+    if (c < H) dx[c] = rs * (g[i] - m1 - xh[i] * m2);
+  }
+}
+
+// dgamma[c] = sum_rows dy * xhat, dbeta[c] = sum_rows dy: a thread per column, a block per slab of rows, per-block partials
+// in fp64 written to part[2][nblocks][H] and summed in block order by ln_bwd_finish_kernel (deterministic)
+__global__ void __launch_bounds__(256) ln_bwd_param_kernel(const float* __restrict__ dY, const float* __restrict__ X,
+                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           int64_t M, int H, int rows_per_block, double* __restrict__ part) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= H) return;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  double sg = 0.0, sb = 0.0;
+  for (int64_t r = r0; r < r1; ++r) {
+    const float dy = dY[r * H + c];
+    sg += (double)(dy * ((X[r * H + c] - mean[r]) * rstd[r]));
+    sb += (double)dy;
+  }
+  part[((size_t)0 * gridDim.y + blockIdx.y) * H + c] = sg;
+  part[((size_t)1 * gridDim.y + blockIdx.y) * H + c] = sb;
+}
+
+__global__ void ln_bwd_finish_kernel(const double* __restrict__ part, int nb, int H, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= H) return;
+  double sg = 0.0, sb = 0.0;
+  for (int b = 0; b < nb; ++b) {
+    sg += part[((size_t)0 * nb + b) * H + c];
+    sb += part[((size_t)1 * nb + b) * H + c];
+  }
+  if (dgamma) dgamma[c] = (float)sg;
+  if (dbeta) dbeta[c] = (float)sb;
+}
+
 }  // namespace sparch
 
 using namespace sparch;
@@ -494,6 +609,42 @@ int sparch_bn_bwd_apply_f16(const float* dI, const float* Z, const float* mean, 
   bn_bwd_apply_f16_kernel<<<ew_grid(M * (ldp / 8), 256), 256, 0, as_stream(st)>>>(
       dI, Z, mean, rstd, scale, coef, M, H, bound, (__half*)P0, (__half*)P1, ldp, dZ32);
   SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+int sparch_layernorm_fwd(const float* X, const float* gamma, const float* beta, float eps, int64_t M, int H, float* Y,
+                         float* mean, float* rstd, sparch_stream_t st) {
+  SPARCH_REQUIRE(M >= 0 && H > 0 && H <= 32 * LN_MAX, "row length must be 1..2048");
+  if (M == 0) return SPARCH_OK;
+  SPARCH_REQUIRE(X && Y && mean && rstd, "null pointer");
+  ln_fwd_kernel<<<(unsigned)((M * 32 + 255) / 256), 256, 0, as_stream(st)>>>(X, gamma, beta, eps, M, H, Y, mean, rstd);
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+size_t sparch_layernorm_bwd_workspace(int64_t M, int H) {
+  const int64_t nb = M < 148 * 4 ? (M > 0 ? M : 1) : 148 * 4;
+  return (size_t)2 * nb * H * sizeof(double);
+}
+
+int sparch_layernorm_bwd(const float* dY, const float* X, const float* gamma, const float* mean, const float* rstd,
+                         int64_t M, int H, float* dX, float* dgamma, float* dbeta, void* workspace, sparch_stream_t st) {
+  SPARCH_REQUIRE(M >= 0 && H > 0 && H <= 32 * LN_MAX, "row length must be 1..2048");
+  if (M == 0) return SPARCH_OK;
+  SPARCH_REQUIRE(dY && X && mean && rstd && dX, "null pointer");
+  ln_bwd_dx_kernel<<<(unsigned)((M * 32 + 255) / 256), 256, 0, as_stream(st)>>>(dY, X, gamma, mean, rstd, M, H, dX);
+  SPARCH_LAUNCH_OK();
+  if (dgamma || dbeta) {
+    SPARCH_REQUIRE(workspace, "the parameter gradients need the workspace");
+    const int nb = (int)(M < 148 * 4 ? M : 148 * 4);
+    const int rpb = (int)((M + nb - 1) / nb);
+    const int nbu = (int)((M + rpb - 1) / rpb);
+    double* part = reinterpret_cast<double*>(workspace);
+    ln_bwd_param_kernel<<<dim3((H + 255) / 256, nbu), 256, 0, as_stream(st)>>>(dY, X, mean, rstd, M, H, rpb, part);
+    SPARCH_LAUNCH_OK();
+    ln_bwd_finish_kernel<<<(H + 255) / 256, 256, 0, as_stream(st)>>>(part, nbu, H, dgamma, dbeta);
+    SPARCH_LAUNCH_OK();
+  }
   return SPARCH_OK;
 }
 

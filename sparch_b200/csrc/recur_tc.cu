@@ -307,6 +307,7 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
     int cstep[2] = {0, 0}, ckb[2] = {0, 0};
     const int nsteps = p.T - 1;
     while (cstep[0] < nsteps || cstep[1] < nsteps) {
+      bool idle = true;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         if (cstep[c] >= nsteps) continue;
@@ -320,6 +321,7 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
             : "memory");
         ready = __shfl_sync(0xffffffffu, ready, 0);   // one answer for the warp
         if (!ready) continue;   // the update warps have not yet written this K block of dI_{t+1} (and drained D)
+        idle = false;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (dbg_cta && lane == 0 && c == 0 && kb == 0) p.dbg[(p.T + (p.T - 2 - cstep[0])) * 8 + 0] = clock64();
         __syncwarp();
@@ -347,6 +349,9 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
           ckb[c] = kb + 1;
         }
       }
+      // nothing ready: stay off the schedulers and the shared-memory pipe for a moment (a hot try_wait loop competes
+      // with the update warps' loads and stores)
+      if (idle) __nanosleep(40);
     }
   } else if (warp >= 2) {
     // ===== load + update warps.  Warp uw owns batch rows 8 uw .. 8 uw + 7 of the group; lane = neuron own0 + lane

@@ -641,6 +641,44 @@ class ReadoutCellFunction(torch.autograd.Function):
         return dI, dgamma, dbnb, dalpha, None, None
 
 
+class LayerNormFunction(torch.autograd.Function):
+    """``nn.LayerNorm(H)`` on the pre-activations W x (normalization="layernorm", snns.py:98-99, 678-680): a row kernel
+    each way (csrc/norm.cu) instead of ATen's; parameter gradients from fp64 partial sums in a fixed order."""
+
+    @staticmethod
+    @_on_device
+    def forward(ctx, x, weight, bias, eps):
+        _require_cuda(x)
+        x = _f32c(x)
+        H = x.shape[-1]
+        M = x.numel() // H
+        y = torch.empty_like(x)
+        stats = torch.empty(2, M, device=x.device, dtype=torch.float32)
+        w, b = _f32c(weight), _f32c(bias)
+        call("sparch_layernorm_fwd", ptr(x), ptr(w), ptr(b), float(eps), M, H, ptr(y), ptr(stats[0]), ptr(stats[1]),
+             _stream())
+        ctx.save_for_backward(x, w, stats)
+        ctx.has = (weight is not None, bias is not None)
+        return y
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, gy):
+        x, w, stats = ctx.saved_tensors
+        H = x.shape[-1]
+        M = x.numel() // H
+        g = _f32c(gy)
+        dx = torch.empty_like(x)
+        dw = torch.empty(H, device=x.device, dtype=torch.float32) if ctx.has[0] else None
+        db = torch.empty(H, device=x.device, dtype=torch.float32) if ctx.has[1] else None
+        ws = None
+        if dw is not None or db is not None:
+            ws = torch.empty(_lib.lib().sparch_layernorm_bwd_workspace(M, H), device=x.device, dtype=torch.uint8)
+        call("sparch_layernorm_bwd", ptr(g), ptr(x), ptr(w), ptr(stats[0]), ptr(stats[1]), M, H, ptr(dx), ptr(dw), ptr(db),
+             ptr(ws), _stream())
+        return dx, dw, db, None
+
+
 class CrossEntropyFunction(torch.autograd.Function):
     """Mean cross-entropy of (B, C) logits against int64 class targets: what ``nn.CrossEntropyLoss()`` (exp.py:83) computes
     at exp.py:362, as one launch forward and one backward (ATen: log_softmax + nll_loss, twice)."""

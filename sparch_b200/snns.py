@@ -14,7 +14,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .functional import (LinearFunction, NormState, ReadoutCellFunction, SpikeFunctionBoxcar,
+from .functional import (LayerNormFunction, LinearFunction, NormState, ReadoutCellFunction, SpikeFunctionBoxcar,
                          SpikingCellFunction, spike_post)
 
 # Where the per-forward initial states u_{-1}, w_{-1}, s_{-1} ~ U[0,1) are drawn.
@@ -145,7 +145,10 @@ class _SpikingLayerBase(nn.Module):
         gamma, bn_beta, norm = _norm_args(self)
         Wx = LinearFunction.apply(x, self.W.weight, self.W.bias, in_scale, norm, x_terms)   # snns.py:675
         if norm is None:                                         # layernorm, snns.py:678-680
-            Wx = self.norm(Wx)
+            if isinstance(self.norm, nn.LayerNorm) and Wx.shape[-1] <= 2048:
+                Wx = LayerNormFunction.apply(Wx, self.norm.weight, self.norm.bias, self.norm.eps)
+            else:
+                Wx = self.norm(Wx)
             norm = NormState("none")
         s = self._cell(Wx, gamma, bn_beta, norm)
         p = self.drop.p if self.drop.training else 0.0
@@ -245,7 +248,10 @@ class ReadoutLayer(nn.Module):
         gamma, bn_beta, norm = _norm_args(self)
         Wx = LinearFunction.apply(x, self.W.weight, self.W.bias, in_scale, norm, x_terms)   # snns.py:796
         if norm is None:
-            Wx = self.norm(Wx)
+            if isinstance(self.norm, nn.LayerNorm) and Wx.shape[-1] <= 2048:
+                Wx = LayerNormFunction.apply(Wx, self.norm.weight, self.norm.bias, self.norm.eps)
+            else:
+                Wx = self.norm(Wx)
             norm = NormState("none")
         return self._readout_cell(Wx, gamma, bn_beta, norm)
 

@@ -1166,3 +1166,30 @@ def test_events_to_dense_against_the_data_oracle(B, rate, nb_steps):
             bat(T, U, y)
         with pytest.raises(IndexError):
             dor.batch_to_dense(T, U, y, nb_steps=nb_steps)
+
+
+@pytest.mark.parametrize("M,H,affine", [(2560, 1024, True), (7, 9, True), (300, 130, False), (64, 2048, True), (1, 35, True)])
+def test_layernorm_kernels_against_torch(M, H, affine):
+    """LayerNormFunction (csrc/norm.cu) = nn.LayerNorm(H) (normalization="layernorm", snns.py:98-99, 678-680): output
+    2e-6, dX / dgamma / dbeta 1e-5 of torch's fp32 results (fp64 reference for the gradients)."""
+    _, F = _mods()
+    g = torch.Generator(device=DEV).manual_seed(M + H)
+    x = (torch.randn(M, H, device=DEV, generator=g) * 3 + 1).requires_grad_(True)
+    ln = torch.nn.LayerNorm(H, elementwise_affine=affine).to(DEV)
+    if affine:
+        with torch.no_grad():
+            ln.weight.copy_(torch.randn(H, device=DEV, generator=g))
+            ln.bias.copy_(torch.randn(H, device=DEV, generator=g))
+    y = F.LayerNormFunction.apply(x, ln.weight, ln.bias, ln.eps)
+    x64 = x.detach().double().requires_grad_(True)
+    ln64 = torch.nn.LayerNorm(H, elementwise_affine=affine).to(DEV).double()
+    if affine:
+        ln64.load_state_dict({k: v.double() for k, v in ln.state_dict().items()})
+    y64 = ln64(x64)
+    assert rel_err(y.detach().cpu().numpy(), y64.detach().cpu().numpy()) < 2e-6
+    gy = torch.randn(M, H, device=DEV, generator=g)
+    params = [ln.weight, ln.bias] if affine else []
+    grads = torch.autograd.grad(y, [x] + params, gy)
+    grads64 = torch.autograd.grad(y64, [x64] + (list(ln64.parameters()) if affine else []), gy.double())
+    for a, b in zip(grads, grads64):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
