@@ -247,6 +247,7 @@ class NormState:
         # forward and before it in the backward):
         self.sterm = None    # gemm.Terms: the {0,1} 16-bit image of S, the S_prev operand of dV
         self.gmax = None     # (Be*T,) row maxima of |dL/dS| for the tcgen05 reverse recurrence
+        self.gmax_of = None  # (data_ptr, version) of the tensor those maxima were taken from
 
 
 def _fold_norm(Z2d, gamma, bn_beta, norm):
@@ -475,9 +476,15 @@ class SpikingCellFunction(torch.autograd.Function):
                      pp[3], Be, T, H, st)
         elif ctx.tc:
             img_b, meta = ctx.rec
+            # the row maxima left by the dropout backward describe exactly the tensor that pass produced: a hook or a
+            # gradient scaling between the two nodes hands over another tensor (or a modified one) -- then the kernel
+            # computes the maxima itself (they fix the fp16 scale of the hand-over: a stale bound could overflow it)
+            gmax = norm.gmax
+            if gmax is not None and getattr(norm, "gmax_of", None) != (G.data_ptr(), G._version):
+                gmax = None
             call("sparch_recur_bwd_tc", k, ptr(G), ptr(U), ptr(Wt), ptr(al), ptr(be), ptr(aa), ptr(bb),
                  ptr(img_b), ptr(meta), ptr(u0), ptr(w0), ptr(s0), theta, ptr(dI), pp[0], pp[1], pp[2],
-                 pp[3], ptr(ws), ctx.reduced, Be, T, H, ptr(norm.gmax), st)
+                 pp[3], ptr(ws), ctx.reduced, Be, T, H, ptr(gmax), st)
         else:
             img_b, meta = ctx.rec
             call("sparch_recur_bwd", k, ptr(G), ptr(U), ptr(Wt), ptr(al), ptr(be), ptr(aa), ptr(bb),
@@ -566,6 +573,7 @@ class _DropoutPostFunction(torch.autograd.Function):
         gmax = torch.empty(Be * T, device=g.device, dtype=torch.float32) if ctx.want_gmax else None
         call("sparch_spike_post_bwd", ptr(g), Be * T, H, ctx.p, ptr(ctx.seed), ptr(gS), ptr(gmax), _stream())
         ctx.cell_state.gmax = gmax
+        ctx.cell_state.gmax_of = (gS.data_ptr(), gS._version) if gmax is not None else None
         return gS, None, None, None, None, None
 
 

@@ -159,6 +159,9 @@ def test_cell_free_running_and_given_mask_backward(name):
             assert rel_err(lay.V.weight.grad.cpu().numpy(), bw["dV"]) < G_RTOL, (name, i, "dV")
 
 
+_FLIPPED_FIXTURES = []
+
+
 @pytest.mark.parametrize("name", golden_names())
 def test_whole_model_against_reference_fixture(name):
     """Same weights, same seeds, same input as the reference run that wrote the fixture."""
@@ -181,8 +184,13 @@ def test_whole_model_against_reference_fixture(name):
             flipped += int((got != ref).sum())
     assert flipped <= FLIP_TOL * total, (name, flipped, total)
     if flipped:
-        pytest.skip(f"{flipped}/{total} spikes straddled the threshold: downstream values are "
-                    "not comparable to the fixture (reference self-noise, SURVEY.md 7 #1)")
+        # threshold straddlers (reference self-noise): values downstream of a flipped spike are not
+        # comparable element by element; what stays well-defined is checked -- the firing rates move by at most the
+        # flipped share -- and the fixture is counted: test_fixture_flip_budget fails if this happens to more than one
+        _FLIPPED_FIXTURES.append(name)
+        np.testing.assert_allclose(rates.detach().cpu().numpy(), g.z["rates"], rtol=0, atol=2.0 * flipped / total + 1e-6)
+        assert np.isfinite(out.detach().cpu().numpy()).all()
+        return
     np.testing.assert_allclose(out.detach().cpu().numpy(), g.z["out"], rtol=5e-5, atol=2e-6)
     np.testing.assert_allclose(rates.detach().cpu().numpy(), g.z["rates"], rtol=1e-6, atol=1e-7)
     if g.eval:
@@ -200,6 +208,12 @@ def test_whole_model_against_reference_fixture(name):
             np.testing.assert_allclose(v.cpu().numpy(), g.z["sd1." + k], rtol=2e-5, atol=1e-6)
         if "num_batches" in k:
             assert int(v) == int(g.z["sd1." + k])
+
+
+def test_fixture_flip_budget():
+    """At most one of the reference's fixtures may have taken the threshold-straddler exit above (observed: none -- the
+    forward recurrence accumulates s @ V0 exactly in int32)."""
+    assert len(_FLIPPED_FIXTURES) <= 1, _FLIPPED_FIXTURES
 
 
 @pytest.mark.parametrize("kind,H,B,T,F", [("LIF", 128, 16, 50, 70), ("adLIF", 96, 16, 50, 70),
@@ -1193,3 +1207,53 @@ def test_layernorm_kernels_against_torch(M, H, affine):
     grads64 = torch.autograd.grad(y64, [x64] + (list(ln64.parameters()) if affine else []), gy.double())
     for a, b in zip(grads, grads64):
         assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
+
+
+def test_graphed_step_equals_eager_step():
+    """One replay of GraphedTrainStep = one eager step from the same parameters, seeds and batch: same loss, same
+    parameters afterwards (the graph replays the launches the eager step issues; state draws and dropout seeds come
+    from the CUDA generator in both)."""
+    import copy
+    import sparch_b200
+    from sparch_b200.graphs import GraphedTrainStep
+    from sparch_b200.optim import Adam
+    sp, _ = _mods()
+    sparch_b200.set_state_init("device")
+    try:
+        torch.manual_seed(0)
+        net_a = sp.SNN((16, None, 40), layer_sizes=[128, 128, 10], neuron_type="RadLIF", normalization="batchnorm",
+                       dropout=0.1).to(DEV)
+        with torch.no_grad():
+            for lay in net_a.snn:
+                if hasattr(lay, "a"):
+                    lay.a.abs_()
+        net_b = copy.deepcopy(net_a)
+        g = torch.Generator(device=DEV).manual_seed(1)
+        x = torch.randn(16, 30, 40, device=DEV, generator=g)
+        y = torch.randint(0, 10, (16,), device=DEV, generator=g)
+        loss_fn = sparch_b200.CrossEntropyLoss()
+        opt_a, opt_b = Adam(net_a.parameters(), 1e-2), Adam(net_b.parameters(), 1e-2)
+        graphed = GraphedTrainStep(net_a, opt_a, loss_fn, x, y, warmup=3)     # 3 eager warm-up steps + capture
+        for _ in range(3):                                                      # the same three steps on the copy
+            out, _ = net_b(x)
+            l = loss_fn(out, y)
+            opt_b.zero_grad()
+            l.backward()
+            opt_b.step()
+        # both nets went through three eager steps with different random draws; level them again
+        net_b.load_state_dict(net_a.state_dict())
+        opt_b.load_state_dict(copy.deepcopy(opt_a.state_dict()))
+        torch.manual_seed(77)
+        la = float(graphed.step(x, y))
+        torch.manual_seed(77)
+        net_b.train()
+        out, _ = net_b(x)
+        lb = loss_fn(out, y)
+        opt_b.zero_grad()
+        lb.backward()
+        opt_b.step()
+        assert abs(la - float(lb)) <= 1e-6 * max(1.0, abs(la)), (la, float(lb))
+        for (k, pa), pb in zip(net_a.named_parameters(), net_b.parameters()):
+            assert rel_err(pa.detach().cpu().numpy(), pb.detach().cpu().numpy()) < 1e-5, k
+    finally:
+        sparch_b200.set_state_init("cpu")
