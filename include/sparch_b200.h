@@ -286,6 +286,13 @@ SPARCH_API int sparch_recur_bwd_tc(int kind, const float* G, const float* U, con
 SPARCH_API int sparch_spike_post_fwd(const float* S, int64_t M, int H, float p_drop, const void* seed,
                                      float* out, void* term, void* sterm, int fp16_terms, int* counts,
                                      sparch_stream_t st);
+/* The same pass fed by the PACKED spike planes the tcgen05 forward recurrence published (sparch_recur_fwd_tc called with
+ * S = NULL: [T][group of 128 rows][slice of 16 neurons][128 rows] words, spike i of a slice at bit 2 i) instead of an
+ * fp32 spike tensor: the spikes cross HBM as 0.25 B/elt.  out (Be,T,H) is always written (the layer's output);
+ * s_last (Be,H), optional, receives the spikes of the last step (operand of sparch_dv_boundary).              */
+SPARCH_API int sparch_spike_post_fwd_bits(const uint32_t* bits, int Be, int T, int H, float p_drop, const void* seed,
+                                          float* out, void* term, void* sterm, int fp16_terms, int* counts,
+                                          float* s_last, sparch_stream_t st);
 /* GS = G * mask / (1-p_drop) with the same mask; gmax (M floats, may be NULL; zeroed here) receives the
  * row maxima of |GS| (input of sparch_recur_bwd_tc).                                              */
 SPARCH_API int sparch_spike_post_bwd(const float* G, int64_t M, int H, float p_drop, const void* seed,

@@ -54,6 +54,7 @@ _PROTOS = {
     "sparch_recur_prepare_tc": "pippp",
     "sparch_recur_bwd_tc": "i" + "p" * 12 + "f" + "p" * 6 + "iiii" + "pp",
     "sparch_spike_post_fwd": "plifppppipp",
+    "sparch_spike_post_fwd_bits": "piiifppppippp",
     "sparch_spike_post_bwd": "plifpppp",
     "sparch_neuron_params": "pppppiipp",
     "sparch_param_grads": "ppppppiiipp",

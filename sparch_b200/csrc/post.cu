@@ -36,8 +36,16 @@ __device__ __forceinline__ void keep8(const unsigned long long* __restrict__ see
   keep[4] = b.x >= thresh; keep[5] = b.y >= thresh; keep[6] = b.z >= thresh; keep[7] = b.w >= thresh;
 }
 
+// Where the spikes come from when the forward recurrence did not write them as fp32: the words it published
+// (csrc/recur_fwd_tc.cu: [T][group][slice][128 rows], 16 spikes per word as 2-bit fields, spike i at bit 2 i).
+struct SpikeBits {
+  const uint32_t* words;   // NULL: read S
+  int T, groups, nsl;
+  float* s_last;           // optional (Be, H): the spikes of the last step as fp32 (the dV boundary operand needs them)
+};
+
 __global__ void __launch_bounds__(256)
-spike_post_fwd_kernel(const float* __restrict__ S, long long M, int H, long long ld, float scale, uint32_t thresh,
+spike_post_fwd_kernel(const float* __restrict__ S, const SpikeBits sb_, long long M, int H, long long ld, float scale, uint32_t thresh,
                       const unsigned long long* __restrict__ seed, float* __restrict__ out,
                       uint16_t* __restrict__ term, uint16_t* __restrict__ sterm, uint16_t one_bits,
                       int* __restrict__ counts, int use_hist) {
@@ -54,7 +62,20 @@ spike_post_fwd_kernel(const float* __restrict__ S, long long M, int H, long long
     const int c = (int)(i - r * segs) * 8;
     const float* src = S + r * H + c;
     float x[8];
-    if (vec && c + 8 <= H) {
+    if (sb_.words) {
+      // row r = (b, t); the 8 columns c .. c + 7 are one byte of the word of slice c / 16
+      const long long b = r / sb_.T;
+      const int t = (int)(r - b * sb_.T);
+      const uint32_t w = c < H ? sb_.words[(((size_t)t * sb_.groups + (size_t)(b >> 7)) * sb_.nsl + (c >> 4)) * 128 + (b & 127)] : 0u;
+      const uint32_t f = w >> (2 * (c & 15));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = (c + j < H && ((f >> (2 * j)) & 1u)) ? 1.f : 0.f;
+      if (sb_.s_last && t == sb_.T - 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c + j < H) sb_.s_last[b * H + c + j] = x[j];
+      }
+    } else if (vec && c + 8 <= H) {
       const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
       x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
     } else {
@@ -234,7 +255,31 @@ int sparch_spike_post_fwd(const float* S, int64_t M, int H, float p_drop, const 
   const int use_hist = counts && H <= 8192;
   const uint32_t thresh = p_drop > 0.f ? (uint32_t)fmin((double)p_drop * 4294967296.0, 4294967295.0) : 0u;
   spike_post_fwd_kernel<<<(unsigned)(g < cap ? g : cap), 256, use_hist ? sizeof(int) * H : 0, st>>>(
-      S, M, H, ld, 1.0f / (1.0f - p_drop), thresh, reinterpret_cast<const unsigned long long*>(seed), out,
+      S, SpikeBits{nullptr, 0, 0, 0, nullptr}, M, H, ld, 1.0f / (1.0f - p_drop), thresh,
+      reinterpret_cast<const unsigned long long*>(seed), out,
+      reinterpret_cast<uint16_t*>(term), reinterpret_cast<uint16_t*>(sterm), fp16_terms ? (uint16_t)0x3C00 : (uint16_t)0x3F80,
+      counts, use_hist);
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+int sparch_spike_post_fwd_bits(const uint32_t* bits, int Be, int T, int H, float p_drop, const void* seed, float* out,
+                               void* term, void* sterm, int fp16_terms, int* counts, float* s_last, sparch_stream_t st_) {
+  SPARCH_REQUIRE(Be >= 0 && T >= 0 && H > 0 && p_drop >= 0.f && p_drop < 1.f, "bad argument");
+  SPARCH_REQUIRE(p_drop == 0.f || seed, "dropout needs the seed word");
+  cudaStream_t st = as_stream(st_);
+  if (counts) SPARCH_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * H, st));
+  const int64_t M = (int64_t)Be * T;
+  if (M == 0) return SPARCH_OK;
+  SPARCH_REQUIRE(bits && out, "null pointer");
+  const int64_t ld = ((int64_t)H + 7) / 8 * 8;
+  const int64_t n = M * (ld / 8);
+  int64_t g = (n + 255) / 256, cap = (int64_t)sm_count() * 8;
+  const int use_hist = counts && H <= 8192;
+  const uint32_t thresh = p_drop > 0.f ? (uint32_t)fmin((double)p_drop * 4294967296.0, 4294967295.0) : 0u;
+  const SpikeBits sb{bits, T, (Be + 127) / 128, (H + 15) / 16, s_last};
+  spike_post_fwd_kernel<<<(unsigned)(g < cap ? g : cap), 256, use_hist ? sizeof(int) * H : 0, st>>>(
+      nullptr, sb, M, H, ld, 1.0f / (1.0f - p_drop), thresh, reinterpret_cast<const unsigned long long*>(seed), out,
       reinterpret_cast<uint16_t*>(term), reinterpret_cast<uint16_t*>(sterm), fp16_terms ? (uint16_t)0x3C00 : (uint16_t)0x3F80,
       counts, use_hist);
   SPARCH_LAUNCH_OK();

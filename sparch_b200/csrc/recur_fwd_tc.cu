@@ -396,7 +396,8 @@ rec_fwd_tc_kernel(const __grid_constant__ FtMaps maps, const RecFwdTcArgs p, con
     // the bulk copies stay off the publish -> poll chain (placed right after the publish they cost ~2000 cycles there).
     auto hand_over = [&](int ts) {
       const uint32_t sb = stile + (uint32_t)(ts & 1) * (3 * FT_TILE_BYTES) + tile_off;
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb), "f"(s[0]), "f"(s[1]), "f"(s[2]), "f"(s[3]) : "memory");
+      if (p.S)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb), "f"(s[0]), "f"(s[1]), "f"(s[2]), "f"(s[3]) : "memory");
       asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + FT_TILE_BYTES), "f"(u[0]), "f"(u[1]), "f"(u[2]), "f"(u[3])
                    : "memory");
       if (ADAPT)
@@ -409,7 +410,7 @@ rec_fwd_tc_kernel(const __grid_constant__ FtMaps maps, const RecFwdTcArgs p, con
       if (issuer) {
         const uint32_t tb = stile + (uint32_t)(ts & 1) * (3 * FT_TILE_BYTES) + qoff;
         if (!(p.dbg_flags & 2)) {
-          tma_store_3d(&maps.s, slice * FT_NEUR, ts, row0 + 32 * q, tb);
+          if (p.S) tma_store_3d(&maps.s, slice * FT_NEUR, ts, row0 + 32 * q, tb);
           tma_store_3d(&maps.u, slice * FT_NEUR, ts, row0 + 32 * q, tb + FT_TILE_BYTES);
           if (ADAPT) tma_store_3d(&maps.w, slice * FT_NEUR, ts, row0 + 32 * q, tb + 2 * FT_TILE_BYTES);
         }
@@ -501,7 +502,7 @@ rec_fwd_tc_kernel(const __grid_constant__ FtMaps maps, const RecFwdTcArgs p, con
       }
       if (dbg_w) p.dbg[t * 8 + 5] = clock64();
       if (!tma && nv > 0 && !(p.dbg_flags & 2)) {
-        st4(p.S + o0, s);
+        if (p.S) st4(p.S + o0, s);
         st4(p.U + o0, u);
         if (ADAPT) st4(p.W + o0, w);
       }
@@ -587,7 +588,7 @@ int sparch_recur_fwd_tc(int kind, const float* Z, const float* scale, const floa
   SPARCH_REQUIRE((scale == nullptr) == (shift == nullptr), "scale and shift go together");
   SPARCH_REQUIRE(H <= sparch_recur_fwd_tc_max_h(), "hidden size too large for the tcgen05 forward recurrence");
   if (Be == 0 || T == 0) return SPARCH_OK;
-  SPARCH_REQUIRE(Z && alpha && rec0 && img && u0 && s0 && S && U && bits, "null pointer");
+  SPARCH_REQUIRE(Z && alpha && rec0 && img && u0 && s0 && U && bits, "null pointer");   // S may be NULL: bits only
   const bool adapt = kind & 1;
   SPARCH_REQUIRE(!adapt || (beta && a && b && w0 && W), "adaptive kind needs beta, a, b, w0, W");
   const int ns = ft_slices(H), NB = ft_batches(H), Hp = NB * 256;
@@ -609,7 +610,8 @@ int sparch_recur_fwd_tc(int kind, const float* Z, const float* scale, const floa
   memset(&maps, 0, sizeof maps);
   if (use_tma) {
     if (int e = make_map3d_f32(&maps.z, Z, Be, T, H, 32, FT_NEUR)) return e;
-    if (int e = make_map3d_f32(&maps.s, S, Be, T, H, 32, FT_NEUR)) return e;
+    if (S)
+      if (int e = make_map3d_f32(&maps.s, S, Be, T, H, 32, FT_NEUR)) return e;
     if (int e = make_map3d_f32(&maps.u, U, Be, T, H, 32, FT_NEUR)) return e;
     if (int e = make_map3d_f32(&maps.w, adapt ? W : U, Be, T, H, 32, FT_NEUR)) return e;
   }

@@ -248,6 +248,14 @@ class NormState:
         self.sterm = None    # gemm.Terms: the {0,1} 16-bit image of S, the S_prev operand of dV
         self.gmax = None     # (Be*T,) row maxima of |dL/dS| for the tcgen05 reverse recurrence
         self.gmax_of = None  # (data_ptr, version) of the tensor those maxima were taken from
+        # Packed-plane hand-over (first step): with ``lazy_spikes`` set (by the layer module, which calls
+        # spike_post right after the cell) the tcgen05 forward recurrence does NOT write the fp32 spike tensor; the
+        # post pass builds the layer's output and the operand terms from the published bit planes (0.25 B/elt).  The
+        # tensor the cell Function returns is then uninitialised until spike_post has run (p = 0: it becomes the
+        # output itself; p > 0: it is never read).
+        self.lazy_spikes = False
+        self.bits = None     # the planes of this forward (consumed by spike_post)
+        self.s_last = None   # (Be, H) spikes of the last step, for the t = 0 frames of dV
 
 
 def _fold_norm(Z2d, gamma, bn_beta, norm):
@@ -419,10 +427,13 @@ class SpikingCellFunction(torch.autograd.Function):
                     img_i8 = torch.empty(L.sparch_recur_fwd_tc_image_bytes(H), device=dev, dtype=torch.uint8)
                     call("sparch_recur_prepare_fwd_tc", ptr(Vc), H, ptr(img_i8), st)
                     bits = torch.empty(L.sparch_recur_fwd_tc_bits_bytes(Be, T, H) // 4, device=dev, dtype=torch.int32)
+                    lazy = bool(norm.lazy_spikes)
                     with _region("recurrence_fwd"):
                         call("sparch_recur_fwd_tc", k, ptr(Z), ptr(scale), ptr(shift), ptr(al), ptr(be), ptr(aa),
-                             ptr(bb), ptr(rec0), ptr(img_i8), ptr(u0), ptr(w0), ptr(s0), float(theta), ptr(S),
-                             ptr(U), ptr(Wt), ptr(bits), int(_PRECISION == "bf16"), Be, T, H, st)
+                             ptr(bb), ptr(rec0), ptr(img_i8), ptr(u0), ptr(w0), ptr(s0), float(theta),
+                             None if lazy else ptr(S), ptr(U), ptr(Wt), ptr(bits), int(_PRECISION == "bf16"), Be, T, H, st)
+                    if lazy:
+                        norm.bits = bits
                 else:
                     bits = torch.empty(T, Be, Hp // 32, 2, device=dev, dtype=torch.int32)
                     with _region("recurrence_fwd"):
@@ -430,6 +441,8 @@ class SpikingCellFunction(torch.autograd.Function):
                              ptr(bb), ptr(rec0), ptr(img_f), ptr(meta), ptr(u0), ptr(w0), ptr(s0),
                              float(theta), ptr(S), ptr(U), ptr(Wt), ptr(bits), int(_PRECISION == "bf16"), Be, T, H,
                              st)
+        if norm.bits is None:
+            norm.lazy_spikes = False      # another forward kernel ran: S is an ordinary tensor
         ctx.k, ctx.theta, ctx.norm = k, float(theta), norm
         ctx.has = (gamma is not None, bn_beta is not None)
         ctx.save_for_backward(Z, gamma, bn_beta, alpha, beta, a, b, V0, u0, w0, s0, S, U, Wt, al, be,
@@ -501,9 +514,15 @@ class SpikingCellFunction(torch.autograd.Function):
                 # s_{t-1}; across rows it pairs dI[b, 0] with S[b-1, T-1], which is replaced below by
                 # the real-valued initial state s0 (snns.py:702).
                 first = torch.empty(Be, H, device=dev, dtype=torch.float32)
-                call("sparch_dv_boundary", ptr(s0), ptr(S), Be, T, H, ptr(first), st)
+                if norm.s_last is not None:   # packed-plane forward: S was never written, its last step was kept
+                    call("sparch_dv_boundary", ptr(s0), ptr(norm.s_last), Be, 1, H, ptr(first), st)
+                else:
+                    call("sparch_dv_boundary", ptr(s0), ptr(S), Be, T, H, ptr(first), st)
                 dV = torch.empty(H, H, device=dev, dtype=torch.float32)
                 if Be * T > 1:
+                    if norm.sterm is None and norm.s_last is not None:
+                        raise RuntimeError("packed-plane forward without the post pass's operand image: call "
+                                           "spike_post(S, p, norm, recurrent=True) after the cell Function")
                     sp = norm.sterm if norm.sterm is not None else gemm.split_binary(S.view(Be * T, H))
                     dit = gemm.split_general(dI.view(Be * T, H), amax=di_amax)
                     gemm.gemm_parts(sp, dit, Be * T, a_mn=True, b_mn=True, a_koff=-1, M=H, N=H, out=dV)
@@ -559,8 +578,11 @@ class _DropoutPostFunction(torch.autograd.Function):
     def forward(ctx, S, p, seed, out_bufs, cell_state, want_gmax):
         Be, T, H = S.shape
         out, term, sterm, counts = out_bufs
-        call("sparch_spike_post_fwd", ptr(S), Be * T, H, float(p), ptr(seed), ptr(out), ptr(term), ptr(sterm),
-             int(term.dtype == torch.float16), ptr(counts), _stream())
+        if cell_state.bits is not None:
+            _post_from_bits(cell_state, Be, T, H, float(p), seed, out, term, sterm, counts)
+        else:
+            call("sparch_spike_post_fwd", ptr(S), Be * T, H, float(p), ptr(seed), ptr(out), ptr(term), ptr(sterm),
+                 int(term.dtype == torch.float16), ptr(counts), _stream())
         ctx.p, ctx.seed, ctx.cell_state, ctx.want_gmax = float(p), seed, cell_state, want_gmax
         return out
 
@@ -575,6 +597,15 @@ class _DropoutPostFunction(torch.autograd.Function):
         ctx.cell_state.gmax = gmax
         ctx.cell_state.gmax_of = (gS.data_ptr(), gS._version) if gmax is not None else None
         return gS, None, None, None, None, None
+
+
+def _post_from_bits(cell_state, Be, T, H, p, seed, out, term, sterm, counts):
+    """The post pass fed by the packed spike planes of the tcgen05 forward (csrc/post.cu: sparch_spike_post_fwd_bits)."""
+    s_last = torch.empty(Be, H, device=out.device, dtype=torch.float32)
+    call("sparch_spike_post_fwd_bits", ptr(cell_state.bits), Be, T, H, p, ptr(seed), ptr(out), ptr(term), ptr(sterm),
+         int(term.dtype == torch.float16), ptr(counts), ptr(s_last), _stream())
+    cell_state.bits = None
+    cell_state.s_last = s_last
 
 
 @_on_device
@@ -600,8 +631,11 @@ def spike_post(S, p, cell_state, recurrent):
         scale = 1.0 / (1.0 - p)
     else:
         with torch.no_grad():
-            call("sparch_spike_post_fwd", ptr(S), M, H, 0.0, None, None, ptr(term), None,
-                 int(dt == torch.float16), ptr(counts), _stream())
+            if cell_state.bits is not None:     # S is still uninitialised: this pass writes it (it IS the output)
+                _post_from_bits(cell_state, Be, T, H, 0.0, None, S, term, None, counts)
+            else:
+                call("sparch_spike_post_fwd", ptr(S), M, H, 0.0, None, None, ptr(term), None,
+                     int(dt == torch.float16), ptr(counts), _stream())
         if recurrent and need_grad:
             cell_state.sterm = gemm.Terms(term)
         out, scale = S, 1.0

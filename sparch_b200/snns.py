@@ -17,6 +17,10 @@ import torch.nn as nn
 from .functional import (LayerNormFunction, LinearFunction, NormState, ReadoutCellFunction, SpikeFunctionBoxcar,
                          SpikingCellFunction, spike_post)
 
+# SPARCH_B200_LAZY_SPIKES=0: the forward recurrence writes the fp32 spike tensor even where the post pass could read the
+# packed planes (comparison / debugging).
+_LAZY_SPIKES = os.environ.get("SPARCH_B200_LAZY_SPIKES", "1") != "0"
+
 # Where the per-forward initial states u_{-1}, w_{-1}, s_{-1} ~ U[0,1) are drawn.
 #   "cpu"    (default): torch.rand on the CPU default generator, then copied to the device --
 #            exactly the reference's draws (snns.py:700-702), so a given torch.manual_seed gives the
@@ -150,8 +154,11 @@ class _SpikingLayerBase(nn.Module):
             else:
                 Wx = self.norm(Wx)
             norm = NormState("none")
-        s = self._cell(Wx, gamma, bn_beta, norm)
         p = self.drop.p if self.drop.training else 0.0
+        # the post pass below runs on the cell's own output: the forward recurrence may hand the spikes over as packed
+        # planes instead of an fp32 tensor (functional.NormState.lazy_spikes)
+        norm.lazy_spikes = self._recurrent and not self.bidirectional and p < 1.0 and _LAZY_SPIKES
+        s = self._cell(Wx, gamma, bn_beta, norm)
         if self.bidirectional:                                   # snns.py:686-689
             s_f, s_b = s.chunk(2, dim=0)
             s = torch.cat([s_f, s_b.flip(1)], dim=2)

@@ -1257,3 +1257,42 @@ def test_graphed_step_equals_eager_step():
             assert rel_err(pa.detach().cpu().numpy(), pb.detach().cpu().numpy()) < 1e-5, k
     finally:
         sparch_b200.set_state_init("cpu")
+
+
+@pytest.mark.parametrize("kind,H,p,B,T", [("RadLIF", 256, 0.1, 70, 20), ("RLIF", 100, 0.0, 130, 7), ("RadLIF", 1024, 0.25, 256, 12)])
+def test_packed_plane_hand_over_equals_fp32_spike_tensor(kind, H, p, B, T):
+    """SURVEY 8 N1, first step: with the layer's post pass reading the PACKED spike planes the tcgen05 forward published
+    (no fp32 spike tensor is written: 0.25 instead of 8 B/elt between the two kernels), outputs, firing rates and every
+    gradient are bit-identical to the path that writes and re-reads fp32 spikes (same seeds, same kernels otherwise)."""
+    import sparch_b200.snns as snns_mod
+    sp, _ = _mods()
+    res = []
+    for lazy in (True, False):
+        snns_mod._LAZY_SPIKES = lazy
+        try:
+            torch.manual_seed(0)
+            net = sp.SNN((B, None, 40), layer_sizes=[H, H, 10], neuron_type=kind, normalization="batchnorm",
+                         dropout=p).to(DEV)
+            with torch.no_grad():
+                for lay in net.snn:
+                    if hasattr(lay, "a"):
+                        lay.a.abs_()
+                    if isinstance(getattr(lay, "norm", None), torch.nn.BatchNorm1d):
+                        lay.norm.weight.fill_(3.0)
+                        lay.norm.bias.fill_(0.8)
+            g = torch.Generator(device=DEV).manual_seed(5)
+            x = torch.randn(B, T, 40, device=DEV, generator=g)
+            y = torch.randint(0, 10, (B,), device=DEV, generator=g)
+            torch.manual_seed(11)
+            out, rates = net(x)
+            loss = torch.nn.functional.cross_entropy(out, y) + 0.1 * rates.sum()
+            loss.backward()
+            res.append((out.detach().clone(), rates.detach().clone(),
+                        {k: q.grad.detach().clone() for k, q in net.named_parameters()}))
+        finally:
+            snns_mod._LAZY_SPIKES = True
+    (oa, ra, ga), (ob, rb, gb) = res
+    assert 0.005 < float(ra.mean()) < 0.9
+    assert torch.equal(oa, ob) and torch.equal(ra, rb)
+    for k in ga:
+        assert torch.equal(ga[k], gb[k]), k
