@@ -50,6 +50,19 @@ int main() {
   CK(cudaMalloc(&dc, 2 * 148 * 8)); CK(cudaMalloc(&sink, 4));
   long long h[2 * 148];
   const char* names[4] = {"ld.global.nc.L1::no_allocate", "ld.relaxed.gpu            ", "ld.global (weak)          ", "ld.volatile.global        "};
+  CK(cudaFuncSetAttribute(gather_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  for (int smem_kb : {0, 100, 200}) {
+    for (int n : {16})
+      for (int grid : {128}) {
+        gather_kernel<1><<<grid, 256, smem_kb * 1024>>>(panel, Hp, 1, n, dc, sink, 50);
+        CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(h, dc, sizeof(long long) * 2 * grid, cudaMemcpyDeviceToHost));
+        double avg = 0;
+        for (int b = 0; b < grid; ++b) avg += h[2 * b + 1];
+        avg /= grid;
+        printf("ld.relaxed.gpu, %3d KB of dynamic shared memory per CTA, 64 KB per CTA, 128 CTAs: avg %6.0f cycles = %5.1f B/clk/SM\n", smem_kb, avg, n * 4096.0 / avg);
+      }
+  }
   for (int strong = 0; strong < 4; ++strong)
     for (int share = 1; share < 2; ++share)
       for (int n : {4, 16})
