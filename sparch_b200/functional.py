@@ -256,6 +256,7 @@ class NormState:
         self.lazy_spikes = False
         self.bits = None     # the planes of this forward (consumed by spike_post)
         self.s_last = None   # (Be, H) spikes of the last step, for the t = 0 frames of dV
+        self.prep = None     # functional.CellPrep made ahead of this call by SNN.forward's side stream (or None)
 
 
 def _fold_norm(Z2d, gamma, bn_beta, norm):
@@ -346,6 +347,73 @@ RECUR_FWD = os.environ.get("SPARCH_B200_FWD", "tc")
 RECUR_FWD_TC_MAX_H = 1536
 
 
+class CellPrep:
+    """What a spiking layer's forward needs that depends on its PARAMETERS (and the initial states) only: the clamped
+    neuron parameters (snns.py:706-709), the images of V0 the recurrence kernels read (snns.py:712), rec_0 = s0 @ V0.
+    None of it depends on the layer's input, so ``SNN.forward`` computes it for all layers on a side stream at the
+    start of the step, under the first projection and the first layer's recurrence (``event``: recorded on that stream
+    when this layer's share is complete; None when the work was issued on the consumer's own stream)."""
+    __slots__ = ("cl", "V0", "Vc", "img_f", "img_b", "meta", "rec0", "img_i8", "use_tc", "fwd_tc", "path", "states",
+                 "event", "key")
+
+
+def prepare_cell(k, alpha, beta, a, b, V, Be, H, states=None):
+    """The parameter-only launches of SpikingCellFunction.forward (same kernels, same order); ``states`` = (u0, w0, s0)
+    when they are already drawn (rec_0 needs s0)."""
+    adaptive, recurrent = bool(k & 1), bool(k & 2)
+    dev = alpha.device
+    st = _stream()
+    pr = CellPrep()
+    pr.event = None
+    pr.states = states
+    pr.key = (k, Be, H, _PRECISION, RECUR_BWD, RECUR_FWD)
+    with torch.no_grad():
+        alpha, beta, a, b = _f32c(alpha), _f32c(beta), _f32c(a), _f32c(b)
+        cl = torch.empty(4 if adaptive else 1, H, device=dev, dtype=torch.float32)   # snns.py:706-709
+        call("sparch_neuron_params", ptr(alpha), ptr(beta), ptr(a), ptr(b), _LIMS, cl.shape[0], H, ptr(cl), st)
+        pr.cl = cl
+        pr.V0 = pr.Vc = pr.img_f = pr.img_b = pr.meta = pr.rec0 = pr.img_i8 = None
+        pr.use_tc = pr.fwd_tc = False
+        if not recurrent:
+            pr.path = "cell"
+        elif H > RECUR_MAX_H:                                                   # snns.py:712 (stepwise path only)
+            pr.path = "stepwise"
+            pr.V0 = torch.empty(H, H, device=dev, dtype=torch.float32)
+            call("sparch_recur_v0", ptr(V.detach().contiguous()), H, ptr(pr.V0), st)
+        else:
+            # persistent tensor-core kernels: s_{t-1} @ V0 from packed spike planes (csrc/recur.cu, recur_fwd_tc.cu)
+            pr.path = "persist"
+            Hp = _lib.lib().sparch_recur_padded(H)
+            use_tc = RECUR_BWD == "tc" and H <= RECUR_TC_MAX_H
+            fwd_tc = RECUR_FWD == "tc" and H <= RECUR_FWD_TC_MAX_H
+            Vc = V.detach().contiguous()
+            img_f = None if fwd_tc else torch.empty(Hp * Hp, device=dev, dtype=torch.int32)
+            img_b = None if use_tc else torch.empty(Hp * Hp, device=dev, dtype=torch.int32)
+            meta = torch.empty(2, device=dev, dtype=torch.int32)
+            # what the forward kernel waits for comes first (the reverse kernel's image is needed a pass later)
+            if fwd_tc:
+                img_i8 = torch.empty(_lib.lib().sparch_recur_fwd_tc_image_bytes(H), device=dev, dtype=torch.uint8)
+                call("sparch_recur_prepare_fwd_tc", ptr(Vc), H, ptr(img_i8), st)
+                pr.img_i8 = img_i8
+            if states is not None:
+                pr.rec0 = _rec0(states[2], Vc, Be, H)
+            if img_f is not None or img_b is not None or use_tc:   # (meta: max|V0| for the fp16 images)
+                call("sparch_recur_prepare", ptr(Vc), H, ptr(img_f), ptr(img_b), ptr(meta), st)
+            if use_tc:  # V0 as swizzled UMMA tiles for the tcgen05 reverse kernel (csrc/recur_tc.cu)
+                img_b = torch.empty(_lib.lib().sparch_recur_bwd_tc_image_bytes(H), device=dev, dtype=torch.uint8)
+                call("sparch_recur_prepare_tc", ptr(Vc), H, ptr(img_b), ptr(meta), st)
+            pr.Vc, pr.img_f, pr.img_b, pr.meta, pr.use_tc, pr.fwd_tc = Vc, img_f, img_b, meta, use_tc, fwd_tc
+    return pr
+
+
+def _rec0(s0, Vc, Be, H):
+    """t = 0: s_{-1} is real-valued (snns.py:702): rec_0 = s0 @ V0, V0's zero diagonal applied on the fly."""
+    rec0 = torch.empty(Be, H, device=s0.device, dtype=torch.float32)
+    with _region("gemm_fwd"):
+        call("sparch_small_gemm", ptr(s0), H, 0, ptr(Vc), H, ptr(rec0), H, Be, H, H, 1, _stream())
+    return rec0
+
+
 class SpikingCellFunction(torch.autograd.Function):
     """Normalisation fold + membrane recurrence of one spiking layer.
 
@@ -367,15 +435,22 @@ class SpikingCellFunction(torch.autograd.Function):
         st = _stream()
         alpha, beta, a, b = _f32c(alpha), _f32c(beta), _f32c(a), _f32c(b)
         with torch.no_grad():
-            cl = torch.empty(4 if adaptive else 1, H, device=dev, dtype=torch.float32)   # snns.py:706-709
-            call("sparch_neuron_params", ptr(alpha), ptr(beta), ptr(a), ptr(b), _LIMS, cl.shape[0], H, ptr(cl), st)
+            u0, w0, s0 = _f32c(u0), _f32c(w0) if adaptive else None, _f32c(s0)
+            # parameter-only launches: taken from the side stream of SNN.forward when it prepared them for exactly this
+            # call (functional.CellPrep), issued here otherwise
+            pr = norm.prep
+            norm.prep = None
+            if pr is not None and (pr.key != (k, Be, H, _PRECISION, RECUR_BWD, RECUR_FWD) or
+                                   (pr.states is not None and pr.states[2].data_ptr() != s0.data_ptr())):
+                pr = None
+            if pr is None:
+                pr = prepare_cell(k, alpha, beta, a, b, V, Be, H)
+            elif pr.event is not None:
+                torch.cuda.current_stream().wait_event(pr.event)
+            cl = pr.cl
             al, be, aa, bb = cl[0], (cl[1] if adaptive else None), (cl[2] if adaptive else None), \
                 (cl[3] if adaptive else None)
-            V0 = None
-            if recurrent and H > RECUR_MAX_H:                                   # snns.py:712 (stepwise path only)
-                V0 = torch.empty(H, H, device=dev, dtype=torch.float32)
-                call("sparch_recur_v0", ptr(V.detach().contiguous()), H, ptr(V0), st)
-            u0, w0, s0 = _f32c(u0), _f32c(w0) if adaptive else None, _f32c(s0)
+            V0 = pr.V0
             Z2d = Z.view(Be * T, H)
             scale, shift, mean, rstd = _fold_norm(Z2d, gamma, bn_beta, norm)
             S = torch.empty_like(Z)
@@ -402,30 +477,16 @@ class SpikingCellFunction(torch.autograd.Function):
                 region.__exit__()
                 ctx.rec = None
             else:
-                # persistent tensor-core kernels: s_{t-1} @ V0 from packed spike planes (csrc/recur.cu)
+                # persistent tensor-core kernels: s_{t-1} @ V0 from packed spike planes (csrc/recur.cu); images of V0 and
+                # rec_0 from prepare_cell
                 Hp = _lib.lib().sparch_recur_padded(H)
-                use_tc = RECUR_BWD == "tc" and H <= RECUR_TC_MAX_H
-                fwd_tc = RECUR_FWD == "tc" and H <= RECUR_FWD_TC_MAX_H
-                Vc = V.detach().contiguous()
-                img_f = None if fwd_tc else torch.empty(Hp * Hp, device=dev, dtype=torch.int32)
-                img_b = None if use_tc else torch.empty(Hp * Hp, device=dev, dtype=torch.int32)
-                meta = torch.empty(2, device=dev, dtype=torch.int32)
-                if img_f is not None or img_b is not None or use_tc:   # (meta: max|V0| for the fp16 images)
-                    call("sparch_recur_prepare", ptr(Vc), H, ptr(img_f), ptr(img_b), ptr(meta), st)
-                if use_tc:  # V0 as swizzled UMMA tiles for the tcgen05 reverse kernel (csrc/recur_tc.cu)
-                    img_b = torch.empty(_lib.lib().sparch_recur_bwd_tc_image_bytes(H), device=dev, dtype=torch.uint8)
-                    call("sparch_recur_prepare_tc", ptr(V.detach().contiguous()), H, ptr(img_b), ptr(meta), st)
+                use_tc, fwd_tc, img_f, img_b, meta, img_i8 = pr.use_tc, pr.fwd_tc, pr.img_f, pr.img_b, pr.meta, pr.img_i8
                 ctx.tc = use_tc
                 ctx.rec = (img_b, meta)
                 ctx.reduced = int(_PRECISION == "bf16")
-                # t = 0: s_{-1} is real-valued (snns.py:702): rec_0 = s0 @ V0, V0's zero diagonal applied on the fly
-                rec0 = torch.empty(Be, H, device=dev, dtype=torch.float32)
-                with _region("gemm_fwd"):
-                    call("sparch_small_gemm", ptr(s0), H, 0, ptr(Vc), H, ptr(rec0), H, Be, H, H, 1, st)
+                rec0 = pr.rec0 if pr.rec0 is not None else _rec0(s0, pr.Vc, Be, H)
                 if fwd_tc:
                     L = _lib.lib()
-                    img_i8 = torch.empty(L.sparch_recur_fwd_tc_image_bytes(H), device=dev, dtype=torch.uint8)
-                    call("sparch_recur_prepare_fwd_tc", ptr(Vc), H, ptr(img_i8), st)
                     bits = torch.empty(L.sparch_recur_fwd_tc_bits_bytes(Be, T, H) // 4, device=dev, dtype=torch.int32)
                     lazy = bool(norm.lazy_spikes)
                     with _region("recurrence_fwd"):

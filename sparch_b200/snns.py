@@ -16,6 +16,7 @@ import torch.nn as nn
 
 from .functional import (LayerNormFunction, LinearFunction, NormState, ReadoutCellFunction, SpikeFunctionBoxcar,
                          SpikingCellFunction, spike_post)
+from . import functional as _F
 
 # SPARCH_B200_LAZY_SPIKES=0: the forward recurrence writes the fp32 spike tensor even where the post pass could read the
 # packed planes (comparison / debugging).
@@ -36,6 +37,20 @@ def set_state_init(mode):
     if mode not in ("cpu", "device"):
         raise ValueError("state init mode must be 'cpu' or 'device'")
     _STATE_INIT = mode
+
+
+# SPARCH_B200_PREP_AHEAD=0: every layer issues its parameter-only launches (clamps, images of V0, rec_0) itself, on the
+# stream of its forward pass, instead of SNN.forward issuing them for all layers on a side stream at the start.
+_PREP_AHEAD = os.environ.get("SPARCH_B200_PREP_AHEAD", "1") != "0"
+_SIDE_STREAMS = {}     # device index -> the side stream of SNN.forward's parameter-only work
+_PENDING_PREP = {}     # id(layer) -> functional.CellPrep made ahead of the layer's forward (cleared by SNN.forward)
+
+
+def _side_stream(device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SIDE_STREAMS:
+        _SIDE_STREAMS[idx] = torch.cuda.Stream(device=idx)
+    return _SIDE_STREAMS[idx]
 
 
 def _rand_state(rows, cols, device):
@@ -173,7 +188,13 @@ class _SpikingLayerBase(nn.Module):
         Be, H = Wx.shape[0], Wx.shape[2]
         # initial states in the reference's order ut, [wt,] st (snns.py:700-702): from the CPU generator (identical
         # draws), or in "device" mode as one draw of the 2-3 states on the CUDA generator
-        if _STATE_INIT == "device":
+        prep = _PENDING_PREP.pop(id(self), None)
+        if prep is not None and prep.key[1:3] != (Be, H):
+            prep = None
+        norm.prep = prep
+        if prep is not None and prep.states is not None:
+            ut, wt, st = prep.states      # drawn on the side stream, in the same order
+        elif _STATE_INIT == "device":
             r = torch.rand(3 if self._adaptive else 2, Be, H, device=device)
             ut, wt, st = r[0], (r[1] if self._adaptive else None), r[-1]
         else:
@@ -322,6 +343,47 @@ class SNN(nn.Module):
                 x = x.reshape(x.shape[0], x.shape[1], x.shape[2] * x.shape[3])
             else:
                 raise NotImplementedError
+        ahead = self._prepare_ahead(x)
+        try:
+            return self._forward_layers(x)
+        finally:
+            if ahead is not None:
+                for lay in self.snn:
+                    _PENDING_PREP.pop(id(lay), None)
+                torch.cuda.current_stream(x.device).wait_stream(ahead)   # (every layer has already waited for its share)
+
+    def _prepare_ahead(self, x):
+        """Issue what the spiking layers' forward passes need from their PARAMETERS alone -- the clamps (snns.py:706-709),
+        the images of V0 the recurrence kernels read (snns.py:712), and in "device" state mode the initial states
+        (snns.py:700-702, same order) with rec_0 = s0 @ V0 -- for all layers at once on a side stream: it runs under the
+        first projection and the first layer's recurrence (which leaves 20 SMs idle) instead of in front of every layer's
+        recurrence.  Returns the side stream, or None when nothing was issued."""
+        if not (_PREP_AHEAD and x.is_cuda and x.ndim == 3):
+            return None
+        layers = [lay for lay in self.snn if isinstance(lay, _SpikingLayerBase)]
+        if not layers:
+            return None
+        dev = x.device
+        with torch.cuda.device(dev):
+            main, side = torch.cuda.current_stream(), _side_stream(dev)
+            side.wait_stream(main)
+            Be = x.shape[0] * (2 if self.bidirectional else 1)
+            with torch.cuda.stream(side), torch.no_grad():
+                for lay in layers:
+                    H = lay.hidden_size
+                    states = None
+                    if _STATE_INIT == "device":
+                        r = torch.rand(3 if lay._adaptive else 2, Be, H, device=dev)
+                        states = (r[0], (r[1] if lay._adaptive else None), r[-1])
+                    pr = _F.prepare_cell(_F.KINDS[lay._kind], lay.alpha, getattr(lay, "beta", None),
+                                         getattr(lay, "a", None), getattr(lay, "b", None),
+                                         lay.V.weight if lay._recurrent else None, Be, H, states)
+                    pr.event = torch.cuda.Event()
+                    pr.event.record(side)
+                    _PENDING_PREP[id(lay)] = pr
+        return side
+
+    def _forward_layers(self, x):
         rates = []
         in_scale = None          # the network input is a general fp32 tensor
         post = None              # the previous spiking layer's post pass (operand terms, spike counts)
