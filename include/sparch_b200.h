@@ -89,6 +89,25 @@ SPARCH_API int sparch_bn_bwd_apply_f16(const float* dI, const float* Z, const fl
                         const uint32_t* amax_dI, uint32_t* bound, float* coef, void* P0, void* P1,
                         int64_t ldp, float* dZ32, sparch_stream_t st);
 
+/* BatchNorm backward of a BIDIRECTIONAL layer whose projection ran once on the un-flipped batch (the reference feeds
+ * cat([x, flip(x)]) through W and the norm, snns.py:666-680: every row of W x appears twice, so batch mean and biased
+ * variance are those of the single copy and the gradient of a row of W x is the sum of its two uses).
+ * dI (2*rev_from*T, H) in the recurrence's order; Z (rev_from*T, H).  col_dot_bidir: the column sums over all M =
+ * 2*rev_from*T rows, row (b, t), b >= rev_from, pairing with Z row (b - rev_from, T-1-t).  apply: M = rev_from*T
+ * OUTPUT rows, dZ[b,t] = scale*((dI[b,t] - c1 - xhat*c2) + (dI[b+rev_from, T-1-t] - c1 - xhat*c2)), c = sums / (2M);
+ * the fp32 variant writes in place on the first M rows of dI, the f16 variant writes the operand terms (dZ32 may
+ * alias dI's first M rows).  H % 4 == 0.                                                                        */
+SPARCH_API int sparch_col_dot_bidir(const float* A, const float* Zn, const float* mean, const float* rstd, int64_t M,
+                                    int H, int T, int64_t rev_from, double* sum1, double* sum2, uint32_t* amax_a,
+                                    sparch_stream_t st);
+SPARCH_API int sparch_bn_bwd_apply_bidir(float* dI, const float* Z, const float* mean, const float* rstd,
+                                         const float* scale, const double* sum1, const double* sum2, int64_t M,
+                                         int H, int T, sparch_stream_t st);
+SPARCH_API int sparch_bn_bwd_apply_f16_bidir(const float* dI, const float* Z, const float* mean, const float* rstd,
+                                             const float* scale, const double* sum1, const double* sum2, int64_t M,
+                                             int H, int T, const uint32_t* amax_dI, uint32_t* bound, float* coef,
+                                             void* P0, void* P1, int64_t ldp, float* dZ32, sparch_stream_t st);
+
 /* ---- membrane recurrence, forward (snns.py:282-303, 419-445, 554-578, 696-727) ------- */
 /* Non-recurrent kinds (LIF, adLIF): whole time loop in one streaming kernel, state in
  * registers.  I_t = Z[b,t,h]*scale[h]+shift[h] (scale/shift NULL => I = Z).  alpha..b are the
@@ -233,6 +252,16 @@ SPARCH_API int sparch_recur_fwd_tc(int kind, const float* Z, const float* scale,
                                    const float* rec0, const void* img, const float* u0, const float* w0,
                                    const float* s0, float theta, float* S, float* U, float* W,
                                    uint32_t* bits, int reduced, int Be, int T, int H, sparch_stream_t st);
+/* Bidirectional layers (snns.py:666-668, 686-689) WITHOUT the flipped / concatenated copies: Z is the projection of the
+ * un-flipped batch, (rev_from, T, H); the kernel runs Be = 2 * rev_from rows, rows b >= rev_from read
+ * Z[b - rev_from][T - 1 - t] (the reversed sequence).  Tapes and planes stay in the kernel's own (Be, T, H) order, which
+ * is what sparch_recur_bwd_tc reads.  rev_from = 0: sparch_recur_fwd_tc.  Needs rev_from % 128 == 0, H % 4 == 0.   */
+SPARCH_API int sparch_recur_fwd_tc_bidir(int kind, const float* Z, const float* scale, const float* shift,
+                                         const float* alpha, const float* beta, const float* a, const float* b,
+                                         const float* rec0, const void* img, const float* u0, const float* w0,
+                                         const float* s0, float theta, float* S, float* U, float* W,
+                                         uint32_t* bits, int reduced, int Be, int T, int H, int rev_from,
+                                         sparch_stream_t st);
 /* Profiling aid: device buffer of T*4 int64 that receives, per timestep, the SM clock of CTA (0,0)
  * after the spike-word wait, after the MMA loop, after the reduction and at the end of the step
  * for the following sparch_recur_fwd launches (NULL switches it off).                          */
@@ -293,6 +322,19 @@ SPARCH_API int sparch_spike_post_fwd(const float* S, int64_t M, int H, float p_d
 SPARCH_API int sparch_spike_post_fwd_bits(const uint32_t* bits, int Be, int T, int H, float p_drop, const void* seed,
                                           float* out, void* term, void* sterm, int fp16_terms, int* counts,
                                           float* s_last, sparch_stream_t st);
+/* ... and with the bidirectional merge fused (snns.py:686-689: cat([s_f, flip(s_b, time)], feature)): rows b >= rev_from
+ * of the planes are the reversed pass of row b - rev_from; out (rev_from, T, 2H), term (rev_from*T, 2*ld) and counts
+ * (2H) are written in the merged layout and the dropout mask is keyed by the merged position; sterm (Be*T, ld) and
+ * s_last (Be, H) stay in the recurrence's own order (operands of this layer's dV).  H % 8 == 0.              */
+SPARCH_API int sparch_spike_post_fwd_bits_bidir(const uint32_t* bits, int Be, int T, int H, float p_drop,
+                                                const void* seed, float* out, void* term, void* sterm,
+                                                int fp16_terms, int* counts, float* s_last, int rev_from,
+                                                sparch_stream_t st);
+/* Backward of that merge + dropout: G (B, T, 2H) -> GS (2B, T, H) in the recurrence's order (columns >= H go to row
+ * b + B at time T-1-t), mask regenerated from the merged position (p_drop = 0: no mask, seed may be NULL); gmax
+ * (2B*T floats, may be NULL) as for sparch_spike_post_bwd.                                                     */
+SPARCH_API int sparch_spike_post_bwd_bidir(const float* G, int B, int T, int H, float p_drop, const void* seed,
+                                           float* GS, float* gmax, sparch_stream_t st);
 /* GS = G * mask / (1-p_drop) with the same mask; gmax (M floats, may be NULL; zeroed here) receives the
  * row maxima of |GS| (input of sparch_recur_bwd_tc).                                              */
 SPARCH_API int sparch_spike_post_bwd(const float* G, int64_t M, int H, float p_drop, const void* seed,

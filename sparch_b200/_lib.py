@@ -21,6 +21,9 @@ _PROTOS = {
     "sparch_col_dot": "pppplipppp",
     "sparch_bn_bwd_apply_f16": "pppppppli" "ppppplpp",
     "sparch_bn_fold_train": "pplppffppppppip",
+    "sparch_col_dot_bidir": "pppplii" + "lpppp",
+    "sparch_bn_bwd_apply_bidir": "pppppppliip",
+    "sparch_bn_bwd_apply_f16_bidir": "pppppppli" "i" "ppppplpp",
     "sparch_bn_bwd_apply": "pppppppli" "pp",
     "sparch_layernorm_fwd": "pppfliPPPp".replace("P", "p"),
     "sparch_layernorm_bwd_workspace": "li",
@@ -46,6 +49,7 @@ _PROTOS = {
     "sparch_recur_fwd_tc_bits_bytes": "iii",
     "sparch_recur_prepare_fwd_tc": "pipp",
     "sparch_recur_fwd_tc": "i" + "p" * 12 + "f" + "pppp" + "iiii" + "p",
+    "sparch_recur_fwd_tc_bidir": "i" + "p" * 12 + "f" + "pppp" + "iiiii" + "p",
     "sparch_recur_bwd_workspace": "ii",
     "sparch_recur_bwd": "i" + "p" * 12 + "f" + "p" * 7 + "iiii" + "p",
     "sparch_recur_tc_padded": "i",
@@ -56,6 +60,8 @@ _PROTOS = {
     "sparch_spike_post_fwd": "plifppppipp",
     "sparch_spike_post_fwd_bits": "piiifppppippp",
     "sparch_spike_post_bwd": "plifpppp",
+    "sparch_spike_post_fwd_bits_bidir": "piiifppppipp" + "ip",
+    "sparch_spike_post_bwd_bidir": "piiifpppp",
     "sparch_neuron_params": "pppppiipp",
     "sparch_param_grads": "ppppppiiipp",
     "sparch_small_gemm": "pliplpliiiip",

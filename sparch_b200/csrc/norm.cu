@@ -115,7 +115,9 @@ template <bool DOT>
 __global__ void __launch_bounds__(256)
 col_reduce4_kernel(const float* __restrict__ A, const float* __restrict__ Zn, const float* __restrict__ mean,
                    const float* __restrict__ rstd, int64_t M, int H, int64_t rows_per_block, double* __restrict__ o1,
-                   double* __restrict__ o2, uint32_t* __restrict__ amax) {
+                   double* __restrict__ o2, uint32_t* __restrict__ amax, const int64_t rev_from = 0, const int T = 1) {
+  // rev_from > 0 (bidirectional layer without a flipped copy of Z): row (b, t) of A with b >= rev_from pairs with row
+  // (b - rev_from, T - 1 - t) of Zn
   __shared__ double sh[2][CS_ROWS][32][4];
   const int h = (blockIdx.x * 32 + threadIdx.x) * 4;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
@@ -135,7 +137,14 @@ col_reduce4_kernel(const float* __restrict__ A, const float* __restrict__ Zn, co
       for (int k = 0; k < 4; ++k) {
         const int64_t rr = r + k * CS_ROWS;
         v[k] = rr < r1 ? *reinterpret_cast<const float4*>(A + rr * H + h) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (DOT) z[k] = rr < r1 ? *reinterpret_cast<const float4*>(Zn + rr * H + h) : mu;
+        if (DOT) {
+          int64_t zr = rr;
+          if (rev_from && rr >= rev_from * T && rr < r1) {
+            const int64_t b = rr / T;
+            zr = (b - rev_from) * T + (T - 1 - (rr - b * T));
+          }
+          z[k] = rr < r1 ? *reinterpret_cast<const float4*>(Zn + zr * H + h) : mu;
+        }
       }
       float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -191,7 +200,7 @@ __global__ void absmax_scalar_kernel(const float* __restrict__ A, int64_t n, uin
 
 static int col_reduce_launch(bool dot, const float* A, const float* Zn, const float* mean,
                              const float* rstd, int64_t M, int H, double* o1, double* o2,
-                             cudaStream_t st, uint32_t* amax = nullptr) {
+                             cudaStream_t st, uint32_t* amax = nullptr, int64_t rev_from = 0, int T = 1) {
   SPARCH_CUDA(cudaMemsetAsync(o1, 0, sizeof(double) * H, st));
   SPARCH_CUDA(cudaMemsetAsync(o2, 0, sizeof(double) * H, st));
   if (amax) SPARCH_CUDA(cudaMemsetAsync(amax, 0, sizeof(uint32_t), st));
@@ -206,12 +215,13 @@ static int col_reduce_launch(bool dot, const float* A, const float* Zn, const fl
     if (rpb4 < 64) rpb4 = 64;
     dim3 grid4(cb4, (unsigned)((M + rpb4 - 1) / rpb4)), block4(32, CS_ROWS);
     if (dot)
-      col_reduce4_kernel<true><<<grid4, block4, 0, st>>>(A, Zn, mean, rstd, M, H, rpb4, o1, o2, amax);
+      col_reduce4_kernel<true><<<grid4, block4, 0, st>>>(A, Zn, mean, rstd, M, H, rpb4, o1, o2, amax, rev_from, T);
     else
       col_reduce4_kernel<false><<<grid4, block4, 0, st>>>(A, nullptr, nullptr, nullptr, M, H, rpb4, o1, o2, amax);
     SPARCH_LAUNCH_OK();
     return SPARCH_OK;
   }
+  SPARCH_REQUIRE(rev_from == 0, "the paired-row reduction needs H % 4 == 0 and 16-byte aligned tensors");
   if (amax) {
     absmax_scalar_kernel<<<sm_count() * 4, 256, 0, st>>>(A, M * (int64_t)H, amax);
     SPARCH_LAUNCH_OK();
@@ -302,13 +312,33 @@ __global__ void bn_bwd_apply_kernel(float* __restrict__ dI, const float* __restr
   }
 }
 
+// Bidirectional layer without a flipped copy (snns.py:666-668 feeds W x twice, once reversed): the gradient of W x is the
+// sum of the two passes' dZ, dZ[b][t] = scale ((dI[b][t] - c1 - xhat c2) + (dI[b + B][T-1-t] - c1 - xhat c2)) with ONE
+// xhat (the same row of Z) and the column sums taken over all 2 B T rows.  In place on the first half of dI.
+__global__ void bn_bwd_apply_bidir_kernel(float* __restrict__ dI, const float* __restrict__ Z,
+                                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                                          const float* __restrict__ scale, const double* __restrict__ s1,
+                                          const double* __restrict__ s2, int64_t M, int H, int T) {
+  const double inv = 1.0 / (double)(2 * M);
+  const int64_t n = M * (int64_t)H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / H;
+    const int h = (int)(i - r * H);
+    const int64_t b = r / T;
+    const int64_t rp = M + b * T + (T - 1 - (r - b * T));
+    const float c1 = (float)(s1[h] * inv), c2 = (float)(s2[h] * inv);
+    const float xh = (Z[i] - mean[h]) * rstd[h];
+    dI[i] = scale[h] * ((dI[i] - c1 - xh * c2) + (dI[rp * H + h] - c1 - xh * c2));
+  }
+}
+
 // bound[0] = bit pattern of an upper bound of max|dZ|: max_h |scale_h| * (max|dI| + max_h |c1_h| + sqrt(M) max_h |c2_h|)
 // (|xhat| <= sqrt(M - 1) for batch statistics).  The bound only positions the fp16 scale; an fp16 hi/lo pair keeps
 // its 22 bits over 2^-20 of the scaled range, so a bound that is loose by two orders of magnitude costs nothing.
 __global__ void __launch_bounds__(1024)
 bn_bwd_bound_kernel(const float* __restrict__ scale, const double* __restrict__ s1, const double* __restrict__ s2,
                     int64_t M, int H, const uint32_t* __restrict__ amax_dI, uint32_t* __restrict__ bound,
-                    float* __restrict__ coef) {
+                    float* __restrict__ coef, const float pair = 1.0f) {   // pair = 2: dZ sums two rows (bidirectional)
   __shared__ float sh[3][32];
   float ms = 0.f, m1 = 0.f, m2 = 0.f;
   const double invM = 1.0 / (double)M;
@@ -334,7 +364,7 @@ bn_bwd_bound_kernel(const float* __restrict__ scale, const double* __restrict__ 
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
       ms = fmaxf(ms, sh[0][w]); m1 = fmaxf(m1, sh[1][w]); m2 = fmaxf(m2, sh[2][w]);
     }
-    const float b = ms * (__uint_as_float(*amax_dI) + m1 + sqrtf((float)M) * m2);
+    const float b = pair * ms * (__uint_as_float(*amax_dI) + m1 + sqrtf((float)M) * m2);
     *bound = __float_as_uint(b);
   }
 }
@@ -345,7 +375,10 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_f16_kernel(const float* __restrict__ dI, const float* __restrict__ Z, const float* __restrict__ mean,
                         const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ coef,
                         int64_t M, int H, const uint32_t* __restrict__ bound,
-                        __half* __restrict__ P0, __half* __restrict__ P1, int64_t ldp, float* __restrict__ dZ32) {
+                        __half* __restrict__ P0, __half* __restrict__ P1, int64_t ldp, float* __restrict__ dZ32,
+                        const int pairT = 0) {
+  // pairT = T > 0: bidirectional layer, M = B T output rows; row (b, t) also takes dI of row (B + b, T - 1 - t) (see
+  // bn_bwd_apply_bidir_kernel; coef holds the column means over all 2 M rows)
   const float sc2 = ldexpf(1.0f, f16_scale_exp(*bound));
   const int64_t segs = ldp / 8, n = M * segs;
   const bool vec = (H & 3) == 0;
@@ -357,6 +390,9 @@ bn_bwd_apply_f16_kernel(const float* __restrict__ dI, const float* __restrict__ 
     float d[8], z[8];
     const float* dp = dI + r * H + c;
     const float* zp = Z + r * H + c;
+    float d2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d2[j] = 0.f;
     if (vec && c + 8 <= H) {
       const float4 a = *reinterpret_cast<const float4*>(dp), b = *reinterpret_cast<const float4*>(dp + 4);
       const float4 e = *reinterpret_cast<const float4*>(zp), f = *reinterpret_cast<const float4*>(zp + 4);
@@ -368,6 +404,12 @@ bn_bwd_apply_f16_kernel(const float* __restrict__ dI, const float* __restrict__ 
         d[j] = c + j < H ? dp[j] : 0.f;
         z[j] = c + j < H ? zp[j] : 0.f;
       }
+    }
+    if (pairT) {
+      const int64_t b = r / pairT;
+      const float* qp = dI + (M + b * pairT + (pairT - 1 - (r - b * pairT))) * H + c;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d2[j] = c + j < H ? qp[j] : 0.f;
     }
     float pm[8], pr[8], ps[8], p1[8], p2[8];
     if (vec && c + 8 <= H) {
@@ -392,7 +434,9 @@ bn_bwd_apply_f16_kernel(const float* __restrict__ dI, const float* __restrict__ 
     __align__(16) __half h0[8], h1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float x = c + j < H ? ps[j] * (d[j] - p1[j] - (z[j] - pm[j]) * pr[j] * p2[j]) : 0.f;
+      const float xh = (z[j] - pm[j]) * pr[j];
+      float x = c + j < H ? ps[j] * (d[j] - p1[j] - xh * p2[j]) : 0.f;
+      if (pairT) x = c + j < H ? ps[j] * ((d[j] - p1[j] - xh * p2[j]) + (d2[j] - p1[j] - xh * p2[j])) : 0.f;
       d[j] = x;
       const float v = x * sc2;
       h0[j] = __float2half_rn(v);
@@ -573,6 +617,14 @@ int sparch_col_dot(const float* A, const float* Zn, const float* mean, const flo
   return col_reduce_launch(true, A, Zn, mean, rstd, M, H, sum1, sum2, as_stream(st), amax_a);
 }
 
+int sparch_col_dot_bidir(const float* A, const float* Zn, const float* mean, const float* rstd, int64_t M, int H, int T,
+                         int64_t rev_from, double* sum1, double* sum2, uint32_t* amax_a, sparch_stream_t st) {
+  SPARCH_REQUIRE(M >= 0 && H > 0 && T > 0 && rev_from > 0 && M == 2 * rev_from * T && sum1 && sum2 && (M == 0 || (A && Zn)),
+                 "bad shape or null pointer");
+  SPARCH_REQUIRE((mean == nullptr) == (rstd == nullptr), "mean and rstd go together");
+  return col_reduce_launch(true, A, Zn, mean, rstd, M, H, sum1, sum2, as_stream(st), amax_a, rev_from, T);
+}
+
 int sparch_bn_fold_train(const double* sum, const double* sumsq, int64_t M, const float* gamma,
                          const float* beta, float eps, float momentum, float* running_mean,
                          float* running_var, float* mean, float* rstd, float* scale, float* shift,
@@ -608,6 +660,32 @@ int sparch_bn_bwd_apply_f16(const float* dI, const float* Z, const float* mean, 
   SPARCH_LAUNCH_OK();
   bn_bwd_apply_f16_kernel<<<ew_grid(M * (ldp / 8), 256), 256, 0, as_stream(st)>>>(
       dI, Z, mean, rstd, scale, coef, M, H, bound, (__half*)P0, (__half*)P1, ldp, dZ32);
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+int sparch_bn_bwd_apply_bidir(float* dI, const float* Z, const float* mean, const float* rstd, const float* scale,
+                              const double* sum1, const double* sum2, int64_t M, int H, int T, sparch_stream_t st) {
+  SPARCH_REQUIRE(M > 0 && H > 0 && T > 0 && M % T == 0 && dI && Z && mean && rstd && scale && sum1 && sum2, "bad argument");
+  bn_bwd_apply_bidir_kernel<<<ew_grid(M * (int64_t)H, 256), 256, 0, as_stream(st)>>>(dI, Z, mean, rstd, scale, sum1, sum2,
+                                                                                    M, H, T);
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+int sparch_bn_bwd_apply_f16_bidir(const float* dI, const float* Z, const float* mean, const float* rstd,
+                                  const float* scale, const double* sum1, const double* sum2, int64_t M, int H, int T,
+                                  const uint32_t* amax_dI, uint32_t* bound, float* coef, void* P0, void* P1,
+                                  int64_t ldp, float* dZ32, sparch_stream_t st) {
+  SPARCH_REQUIRE(M > 0 && H > 0 && T > 0 && M % T == 0 && dI && Z && mean && rstd && scale && sum1 && sum2 && amax_dI &&
+                     bound && coef && P0 && P1,
+                 "bad argument");
+  SPARCH_REQUIRE((ldp % 8) == 0 && ldp >= H, "ldp must be a multiple of 8 covering a row");
+  // column means over all 2 M rows of the two passes
+  bn_bwd_bound_kernel<<<1, 1024, 0, as_stream(st)>>>(scale, sum1, sum2, 2 * M, H, amax_dI, bound, coef, 2.0f);
+  SPARCH_LAUNCH_OK();
+  bn_bwd_apply_f16_kernel<<<ew_grid(M * (ldp / 8), 256), 256, 0, as_stream(st)>>>(
+      dI, Z, mean, rstd, scale, coef, M, H, bound, (__half*)P0, (__half*)P1, ldp, dZ32, T);
   SPARCH_LAUNCH_OK();
   return SPARCH_OK;
 }

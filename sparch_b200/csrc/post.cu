@@ -42,6 +42,9 @@ struct SpikeBits {
   const uint32_t* words;   // NULL: read S
   int T, groups, nsl;
   float* s_last;           // optional (Be, H): the spikes of the last step as fp32 (the dV boundary operand needs them)
+  int rev_from;            // bidirectional merge (snns.py:686-689) fused: rows b >= rev_from are the time-reversed pass of
+                           // row b - rev_from; out / term / counts / the dropout position then live in the merged
+                           // (rev_from, T, 2 H) layout, out[b - rev_from][T - 1 - t][H + h].  0 = off.  (H % 8 == 0.)
 };
 
 __global__ void __launch_bounds__(256)
@@ -50,8 +53,9 @@ spike_post_fwd_kernel(const float* __restrict__ S, const SpikeBits sb_, long lon
                       uint16_t* __restrict__ term, uint16_t* __restrict__ sterm, uint16_t one_bits,
                       int* __restrict__ counts, int use_hist) {
   extern __shared__ int hist[];
+  const int Hc = (sb_.words && sb_.rev_from) ? 2 * H : H;   // columns of the counts
   if (counts && use_hist) {
-    for (int h = threadIdx.x; h < H; h += blockDim.x) hist[h] = 0;
+    for (int h = threadIdx.x; h < Hc; h += blockDim.x) hist[h] = 0;
     __syncthreads();
   }
   const long long segs = ld / 8, n = M * segs;
@@ -82,9 +86,23 @@ spike_post_fwd_kernel(const float* __restrict__ S, const SpikeBits sb_, long lon
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] = c + j < H ? src[j] : 0.f;
     }
+    // where the item goes: its own place, or its place in the merged bidirectional tensor
+    long long ro = r, io = i, Ho = H, ldo = ld;
+    int co = c;
+    if (sb_.words && sb_.rev_from) {
+      const long long b = r / sb_.T;
+      const int t = (int)(r - b * sb_.T);
+      Ho = 2 * (long long)H;
+      ldo = 2 * ld;
+      if (b >= sb_.rev_from) {
+        ro = (b - sb_.rev_from) * sb_.T + (sb_.T - 1 - t);
+        co = c + H;
+      }
+      io = ro * (ldo / 8) + co / 8;
+    }
     bool keep[8];
     if (thresh) {
-      keep8(seed, i, thresh, keep);
+      keep8(seed, io, thresh, keep);
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) keep[j] = true;
@@ -98,7 +116,7 @@ spike_post_fwd_kernel(const float* __restrict__ S, const SpikeBits sb_, long lon
       sb[j] = x[j] != 0.f ? one_bits : (uint16_t)0;
     }
     if (out) {
-      float* dst = out + r * H + c;
+      float* dst = out + ro * Ho + co;
       if (vec && c + 8 <= H) {
         *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
         *reinterpret_cast<float4*>(dst + 4) = make_float4(y[4], y[5], y[6], y[7]);
@@ -108,31 +126,35 @@ spike_post_fwd_kernel(const float* __restrict__ S, const SpikeBits sb_, long lon
           if (c + j < H) dst[j] = y[j];
       }
     }
-    if (term) *reinterpret_cast<uint4*>(term + r * ld + c) = *reinterpret_cast<const uint4*>(tb);
+    if (term) *reinterpret_cast<uint4*>(term + ro * ldo + co) = *reinterpret_cast<const uint4*>(tb);
     if (sterm) *reinterpret_cast<uint4*>(sterm + r * ld + c) = *reinterpret_cast<const uint4*>(sb);
     if (counts) {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (y[j] != 0.f) atomicAdd(use_hist ? &hist[c + j] : &counts[c + j], 1);
+        if (y[j] != 0.f) atomicAdd(use_hist ? &hist[co + j] : &counts[co + j], 1);
     }
   }
   if (counts && use_hist) {
     __syncthreads();
-    for (int h = threadIdx.x; h < H; h += blockDim.x)
+    for (int h = threadIdx.x; h < Hc; h += blockDim.x)
       if (hist[h]) atomicAdd(&counts[h], hist[h]);
   }
 }
 
 __global__ void __launch_bounds__(256)
 spike_post_bwd_kernel(const float* __restrict__ G, long long M, int H, float scale, uint32_t thresh,
-                      const unsigned long long* __restrict__ seed, float* __restrict__ GS, uint32_t* __restrict__ gmax) {
+                      const unsigned long long* __restrict__ seed, float* __restrict__ GS, uint32_t* __restrict__ gmax,
+                      const int rev_from, const int T) {
+  // rev_from > 0: G is the gradient of the MERGED bidirectional output (rev_from, T, H = 2 Hc); GS / gmax are written
+  // in the recurrence's own order (2 rev_from, T, Hc): columns >= Hc go to row b + rev_from at time T - 1 - t
+  const int Hc = rev_from ? H / 2 : H;
   const long long segs = (H + 7) / 8, n = M * segs;
   const bool vec = ((H & 3) == 0) && ((reinterpret_cast<uintptr_t>(G) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(GS) & 15) == 0);
   const long long total = (n + 31) / 32 * 32;  // whole warps walk the loop (shuffles below)
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const bool on = i < n;
-    const long long r = on ? i / segs : -1;
+    long long r = on ? i / segs : -1;
     const int c = on ? (int)(i - r * segs) * 8 : 0;
     float m = 0.f;
     if (on) {
@@ -146,13 +168,24 @@ spike_post_bwd_kernel(const float* __restrict__ G, long long M, int H, float sca
         for (int j = 0; j < 8; ++j) x[j] = c + j < H ? src[j] : 0.f;
       }
       bool keep[8];
-      keep8(seed, i, thresh, keep);
+      if (thresh) {
+        keep8(seed, i, thresh, keep);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) keep[j] = true;
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         x[j] = keep[j] ? x[j] * scale : 0.f;
         m = fmaxf(m, fabsf(x[j]));
       }
       float* dst = GS + r * H + c;
+      if (rev_from) {
+        const long long b = r / T;
+        const int t = (int)(r - b * T);
+        r = c >= Hc ? (b + rev_from) * T + (T - 1 - t) : r;    // from here on: the row of GS / gmax
+        dst = GS + r * Hc + (c >= Hc ? c - Hc : c);
+      }
       if (vec && c + 8 <= H) {
         *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
         *reinterpret_cast<float4*>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
@@ -255,7 +288,7 @@ int sparch_spike_post_fwd(const float* S, int64_t M, int H, float p_drop, const 
   const int use_hist = counts && H <= 8192;
   const uint32_t thresh = p_drop > 0.f ? (uint32_t)fmin((double)p_drop * 4294967296.0, 4294967295.0) : 0u;
   spike_post_fwd_kernel<<<(unsigned)(g < cap ? g : cap), 256, use_hist ? sizeof(int) * H : 0, st>>>(
-      S, SpikeBits{nullptr, 0, 0, 0, nullptr}, M, H, ld, 1.0f / (1.0f - p_drop), thresh,
+      S, SpikeBits{nullptr, 0, 0, 0, nullptr, 0}, M, H, ld, 1.0f / (1.0f - p_drop), thresh,
       reinterpret_cast<const unsigned long long*>(seed), out,
       reinterpret_cast<uint16_t*>(term), reinterpret_cast<uint16_t*>(sterm), fp16_terms ? (uint16_t)0x3C00 : (uint16_t)0x3F80,
       counts, use_hist);
@@ -265,20 +298,29 @@ int sparch_spike_post_fwd(const float* S, int64_t M, int H, float p_drop, const 
 
 int sparch_spike_post_fwd_bits(const uint32_t* bits, int Be, int T, int H, float p_drop, const void* seed, float* out,
                                void* term, void* sterm, int fp16_terms, int* counts, float* s_last, sparch_stream_t st_) {
+  return sparch_spike_post_fwd_bits_bidir(bits, Be, T, H, p_drop, seed, out, term, sterm, fp16_terms, counts, s_last, 0, st_);
+}
+
+int sparch_spike_post_fwd_bits_bidir(const uint32_t* bits, int Be, int T, int H, float p_drop, const void* seed,
+                                     float* out, void* term, void* sterm, int fp16_terms, int* counts, float* s_last,
+                                     int rev_from, sparch_stream_t st_) {
   SPARCH_REQUIRE(Be >= 0 && T >= 0 && H > 0 && p_drop >= 0.f && p_drop < 1.f, "bad argument");
   SPARCH_REQUIRE(p_drop == 0.f || seed, "dropout needs the seed word");
+  SPARCH_REQUIRE(rev_from == 0 || (rev_from > 0 && Be == 2 * rev_from && H % 8 == 0),
+                 "merged bidirectional output: Be = 2 * rev_from and H a multiple of 8");
   cudaStream_t st = as_stream(st_);
-  if (counts) SPARCH_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * H, st));
+  if (counts) SPARCH_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (rev_from ? 2 * H : H), st));
   const int64_t M = (int64_t)Be * T;
   if (M == 0) return SPARCH_OK;
   SPARCH_REQUIRE(bits && out, "null pointer");
   const int64_t ld = ((int64_t)H + 7) / 8 * 8;
   const int64_t n = M * (ld / 8);
   int64_t g = (n + 255) / 256, cap = (int64_t)sm_count() * 8;
-  const int use_hist = counts && H <= 8192;
+  const int Hc = rev_from ? 2 * H : H;
+  const int use_hist = counts && Hc <= 8192;
   const uint32_t thresh = p_drop > 0.f ? (uint32_t)fmin((double)p_drop * 4294967296.0, 4294967295.0) : 0u;
-  const SpikeBits sb{bits, T, (Be + 127) / 128, (H + 15) / 16, s_last};
-  spike_post_fwd_kernel<<<(unsigned)(g < cap ? g : cap), 256, use_hist ? sizeof(int) * H : 0, st>>>(
+  const SpikeBits sb{bits, T, (Be + 127) / 128, (H + 15) / 16, s_last, rev_from};
+  spike_post_fwd_kernel<<<(unsigned)(g < cap ? g : cap), 256, use_hist ? sizeof(int) * Hc : 0, st>>>(
       nullptr, sb, M, H, ld, 1.0f / (1.0f - p_drop), thresh, reinterpret_cast<const unsigned long long*>(seed), out,
       reinterpret_cast<uint16_t*>(term), reinterpret_cast<uint16_t*>(sterm), fp16_terms ? (uint16_t)0x3C00 : (uint16_t)0x3F80,
       counts, use_hist);
@@ -298,7 +340,26 @@ int sparch_spike_post_bwd(const float* G, int64_t M, int H, float p_drop, const 
   const uint32_t thresh = (uint32_t)fmin((double)p_drop * 4294967296.0, 4294967295.0);
   spike_post_bwd_kernel<<<(unsigned)(g < cap ? g : cap), 256, 0, st>>>(G, M, H, 1.0f / (1.0f - p_drop), thresh,
                                                                         reinterpret_cast<const unsigned long long*>(seed),
-                                                                        GS, reinterpret_cast<uint32_t*>(gmax));
+                                                                        GS, reinterpret_cast<uint32_t*>(gmax), 0, 1);
+  SPARCH_LAUNCH_OK();
+  return SPARCH_OK;
+}
+
+int sparch_spike_post_bwd_bidir(const float* G, int B, int T, int H, float p_drop, const void* seed, float* GS,
+                                float* gmax, sparch_stream_t st_) {
+  SPARCH_REQUIRE(B >= 0 && T >= 0 && H > 0 && H % 8 == 0 && p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || seed),
+                 "bad argument");
+  cudaStream_t st = as_stream(st_);
+  const int64_t M = (int64_t)B * T;
+  if (gmax && M > 0) SPARCH_CUDA(cudaMemsetAsync(gmax, 0, sizeof(float) * 2 * M, st));
+  if (M == 0) return SPARCH_OK;
+  SPARCH_REQUIRE(G && GS, "null pointer");
+  const int64_t n = M * (2 * (int64_t)H / 8);
+  int64_t g = (n + 255) / 256, cap = (int64_t)sm_count() * 8;
+  const uint32_t thresh = p_drop > 0.f ? (uint32_t)fmin((double)p_drop * 4294967296.0, 4294967295.0) : 0u;
+  spike_post_bwd_kernel<<<(unsigned)(g < cap ? g : cap), 256, 0, st>>>(G, M, 2 * H, 1.0f / (1.0f - p_drop), thresh,
+                                                                        reinterpret_cast<const unsigned long long*>(seed),
+                                                                        GS, reinterpret_cast<uint32_t*>(gmax), B, T);
   SPARCH_LAUNCH_OK();
   return SPARCH_OK;
 }

@@ -118,6 +118,8 @@ struct RecFwdTcArgs {
   int Be, T, H, Hp, NB, ngroups_total;
   int reduced;     // 1: two digit planes only (15-bit image of V0)
   int use_tma;     // 1: Z tiles in / S, U, W tiles out by TMA (needs H % 4 == 0); 0: per-thread global accesses
+  int rev_from;    // bidirectional layers (snns.py:666-668): rows >= rev_from run the sequence backwards and read the
+                   // input of row - rev_from -- Z is (rev_from, T, H), no flipped copy; 0 = off.  TMA mode only.
   long long* dbg;  // optional [2T][8] phase clocks of CTA (0,0), normally NULL
   int dbg_flags;
 };
@@ -381,10 +383,14 @@ rec_fwd_tc_kernel(const __grid_constant__ FtMaps maps, const RecFwdTcArgs p, con
     const bool issuer = tma && r == 0 && lane == 0;   // one thread per quarter drives its 32-row tiles
     const uint32_t qz = bar_z + 16 * q;               // z_full[q][2]
     const uint32_t qoff = (uint32_t)(32 * q) * (FT_NEUR * 4);
+    // bidirectional second half: this CTA's rows read Z[row - rev_from][T - 1 - t] (a row group lies in one half)
+    const bool rev = p.rev_from > 0 && row0 >= p.rev_from;
+    const int zrow0 = rev ? row0 - p.rev_from : row0;
+    auto zt = [&](int t_) { return rev ? p.T - 1 - t_ : t_; };
     if (issuer) {
       for (int t0 = 0; t0 < 2 && t0 < p.T; ++t0) {
         mbar_expect_tx(qz + 8 * t0, FT_TILE_BYTES / 4);
-        tma_load_3d(ztile + (uint32_t)t0 * FT_TILE_BYTES + qoff, &maps.z, slice * FT_NEUR, t0, row0 + 32 * q, qz + 8 * t0);
+        tma_load_3d(ztile + (uint32_t)t0 * FT_TILE_BYTES + qoff, &maps.z, slice * FT_NEUR, zt(t0), zrow0 + 32 * q, qz + 8 * t0);
       }
     }
     uint8_t* pub = reinterpret_cast<uint8_t*>(p.bits) + ((((size_t)group) * nsl + slice) * FT_ROWS + lrow) * 4 + r;
@@ -418,7 +424,7 @@ rec_fwd_tc_kernel(const __grid_constant__ FtMaps maps, const RecFwdTcArgs p, con
         if (ts + 2 < p.T) {  // Z tile of step ts + 2: its buffer held step ts, read before this barrier by all four warps
           const uint32_t b = qz + 8 * (ts & 1);
           mbar_expect_tx(b, FT_TILE_BYTES / 4);
-          tma_load_3d(ztile + (uint32_t)(ts & 1) * FT_TILE_BYTES + qoff, &maps.z, slice * FT_NEUR, ts + 2, row0 + 32 * q, b);
+          tma_load_3d(ztile + (uint32_t)(ts & 1) * FT_TILE_BYTES + qoff, &maps.z, slice * FT_NEUR, zt(ts + 2), zrow0 + 32 * q, b);
         }
       }
     };
@@ -583,6 +589,15 @@ int sparch_recur_fwd_tc(int kind, const float* Z, const float* scale, const floa
                         const float* beta, const float* a, const float* b, const float* rec0, const void* img,
                         const float* u0, const float* w0, const float* s0, float theta, float* S, float* U, float* W,
                         uint32_t* bits, int reduced, int Be, int T, int H, sparch_stream_t st_) {
+  return sparch_recur_fwd_tc_bidir(kind, Z, scale, shift, alpha, beta, a, b, rec0, img, u0, w0, s0, theta, S, U, W, bits,
+                                   reduced, Be, T, H, 0, st_);
+}
+
+int sparch_recur_fwd_tc_bidir(int kind, const float* Z, const float* scale, const float* shift, const float* alpha,
+                              const float* beta, const float* a, const float* b, const float* rec0, const void* img,
+                              const float* u0, const float* w0, const float* s0, float theta, float* S, float* U,
+                              float* W, uint32_t* bits, int reduced, int Be, int T, int H, int rev_from,
+                              sparch_stream_t st_) {
   SPARCH_REQUIRE(kind == SPARCH_RLIF || kind == SPARCH_RADLIF, "recurrent kinds only");
   SPARCH_REQUIRE(Be >= 0 && T >= 0 && H > 0, "bad shape");
   SPARCH_REQUIRE((scale == nullptr) == (shift == nullptr), "scale and shift go together");
@@ -606,17 +621,22 @@ int sparch_recur_fwd_tc(int kind, const float* Z, const float* scale, const floa
   const float* colscale = reinterpret_cast<const float*>(planes + (size_t)ns * Hp * FT_N);
   static const bool tma_off = getenv("SPARCH_B200_FWD_TMA") && getenv("SPARCH_B200_FWD_TMA")[0] == '0';
   const int use_tma = ((H & 3) == 0 && !tma_off) ? 1 : 0;   // TMA needs 16-byte global strides
+  if (rev_from) {
+    SPARCH_REQUIRE(rev_from > 0 && Be == 2 * rev_from && rev_from % FT_ROWS == 0 && use_tma,
+                   "reversed second half: Be = 2 * rev_from, rev_from a multiple of 128 rows, H a multiple of 4");
+  }
+  const int z_rows = rev_from ? rev_from : Be;
   FtMaps maps;
   memset(&maps, 0, sizeof maps);
   if (use_tma) {
-    if (int e = make_map3d_f32(&maps.z, Z, Be, T, H, 32, FT_NEUR)) return e;
+    if (int e = make_map3d_f32(&maps.z, Z, z_rows, T, H, 32, FT_NEUR)) return e;
     if (S)
       if (int e = make_map3d_f32(&maps.s, S, Be, T, H, 32, FT_NEUR)) return e;
     if (int e = make_map3d_f32(&maps.u, U, Be, T, H, 32, FT_NEUR)) return e;
     if (int e = make_map3d_f32(&maps.w, adapt ? W : U, Be, T, H, 32, FT_NEUR)) return e;
   }
   RecFwdTcArgs p{Z, scale, shift, alpha, beta, a, b, rec0, u0, w0, s0, planes, colscale, theta, S, U, W, bits,
-                 Be, T, H, Hp, NB, groups, reduced ? 1 : 0, use_tma, recur_debug_buffer(), recur_debug_flags()};
+                 Be, T, H, Hp, NB, groups, reduced ? 1 : 0, use_tma, rev_from, recur_debug_buffer(), recur_debug_flags()};
   // a word of all ones means "not yet published" (published halves have zero odd bits): every step has its own words
   SPARCH_CUDA(cudaMemsetAsync(bits, 0xFF, sparch_recur_fwd_tc_bits_bytes(Be, T, H), st));
   const int gmax = max_ctas / ns;  // row groups per cooperative launch (all its CTAs wait on each other)

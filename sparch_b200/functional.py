@@ -257,6 +257,10 @@ class NormState:
         self.bits = None     # the planes of this forward (consumed by spike_post)
         self.s_last = None   # (Be, H) spikes of the last step, for the t = 0 frames of dV
         self.prep = None     # functional.CellPrep made ahead of this call by SNN.forward's side stream (or None)
+        # Bidirectional layer without flipped / concatenated copies: B (rows per direction) when the projection ran once on
+        # the un-flipped batch -- Z is (B, T, H), the recurrence runs 2B rows (the second half reads Z time-reversed), the
+        # post pass writes the merged (B, T, 2H) output, the BatchNorm backward sums a row's two uses.  0 = off.
+        self.bidir = 0
 
 
 def _fold_norm(Z2d, gamma, bn_beta, norm):
@@ -280,6 +284,10 @@ def _fold_norm(Z2d, gamma, bn_beta, norm):
     if sums is None:        # projection not done by LinearFunction (direct use of the cell Function)
         sums = torch.empty(2, H, dtype=torch.float64, device=dev)
         call("sparch_col_stats", ptr(Z2d), M, H, ptr(sums[0]), ptr(sums[1]), _stream())
+    if norm.bidir:
+        # the reference normalises cat([W x, W flip(x)]) (snns.py:666-680): every row twice -- same mean and biased
+        # variance, 2M samples in the unbiased variance of the running statistics
+        sums, M = sums * 2, 2 * M
     out = torch.empty(4, H, dtype=torch.float32, device=dev)
     call("sparch_bn_fold_train", ptr(sums[0]), ptr(sums[1]), M, ptr(gamma), ptr(bn_beta),
          float(norm.eps), float(norm.momentum), ptr(norm.running_mean), ptr(norm.running_var),
@@ -295,8 +303,13 @@ def _norm_backward_reduce(dI2d, Z2d, norm, mean, rstd):
     M, H = dI2d.shape
     sums = torch.empty(2, H, dtype=torch.float64, device=dI2d.device)
     amax = torch.empty(1, device=dI2d.device, dtype=torch.int32) if gemm.MODE == "f16x2" else None
-    call("sparch_col_dot", ptr(dI2d), ptr(Z2d), ptr(mean), ptr(rstd), M, H, ptr(sums[0]),
-         ptr(sums[1]), ptr(amax), _stream())
+    if norm.bidir:
+        T = Z2d.shape[0] // norm.bidir
+        call("sparch_col_dot_bidir", ptr(dI2d), ptr(Z2d), ptr(mean), ptr(rstd), M, H, T, norm.bidir, ptr(sums[0]),
+             ptr(sums[1]), ptr(amax), _stream())
+    else:
+        call("sparch_col_dot", ptr(dI2d), ptr(Z2d), ptr(mean), ptr(rstd), M, H, ptr(sums[0]),
+             ptr(sums[1]), ptr(amax), _stream())
     return sums, amax
 
 
@@ -309,6 +322,26 @@ def _norm_backward_apply(dI2d, Z2d, gamma, bn_beta, norm, scale, mean, rstd, sum
     M, H = dI2d.shape
     dgamma = sums[1].float() if gamma is not None else None
     dbeta = sums[0].float() if bn_beta is not None else None
+    if norm.bidir:
+        # dZ (B*T rows) = the sum of a row's two uses; lands in the first half of dI (and / or as operand terms)
+        M = Z2d.shape[0]
+        T = M // norm.bidir
+        if norm.mode == "bn_train" and gemm.MODE == "f16x2":
+            ld = (H + 7) // 8 * 8
+            parts = torch.empty(2, M, ld, device=dI2d.device, dtype=torch.float16)
+            bound = torch.empty(1, device=dI2d.device, dtype=torch.int32)
+            coef = torch.empty(2, H, device=dI2d.device, dtype=torch.float32)
+            call("sparch_bn_bwd_apply_f16_bidir", ptr(dI2d), ptr(Z2d), ptr(mean), ptr(rstd), ptr(scale), ptr(sums[0]),
+                 ptr(sums[1]), M, H, T, ptr(amax), ptr(bound), ptr(coef), ptr(parts[0]), ptr(parts[1]), ld,
+                 ptr(dI2d) if norm.need_dz32 else None, _stream())
+            norm.dz_terms = gemm.Terms(parts, bound)
+        elif norm.mode == "bn_train":
+            call("sparch_bn_bwd_apply_bidir", ptr(dI2d), ptr(Z2d), ptr(mean), ptr(rstd), ptr(scale),
+                 ptr(sums[0]), ptr(sums[1]), M, H, T, _stream())
+        else:   # running statistics: dZ = scale * (dI_f + flip(dI_b))
+            d3 = dI2d.view(2, norm.bidir, T, H)
+            d3[0].add_(d3[1].flip(1)).mul_(scale)
+        return dgamma, dbeta
     if norm.mode == "bn_train" and gemm.MODE == "f16x2":
         ld = (H + 7) // 8 * 8
         parts = torch.empty(2, M, ld, device=dI2d.device, dtype=torch.float16)
@@ -431,6 +464,10 @@ class SpikingCellFunction(torch.autograd.Function):
         adaptive, recurrent = bool(k & 1), bool(k & 2)
         Z = _f32c(Z)
         Be, T, H = Z.shape
+        if norm.bidir:         # Z is the projection of the un-flipped batch: the recurrence runs both directions
+            if norm.bidir != Be:
+                raise ValueError("NormState.bidir must equal the batch size of Z")
+            Be = 2 * Be
         dev = Z.device
         st = _stream()
         alpha, beta, a, b = _f32c(alpha), _f32c(beta), _f32c(a), _f32c(b)
@@ -451,11 +488,14 @@ class SpikingCellFunction(torch.autograd.Function):
             al, be, aa, bb = cl[0], (cl[1] if adaptive else None), (cl[2] if adaptive else None), \
                 (cl[3] if adaptive else None)
             V0 = pr.V0
-            Z2d = Z.view(Be * T, H)
+            Z2d = Z.view(-1, H)
             scale, shift, mean, rstd = _fold_norm(Z2d, gamma, bn_beta, norm)
-            S = torch.empty_like(Z)
-            U = torch.empty_like(Z)
-            Wt = torch.empty_like(Z) if adaptive else None
+            S = torch.empty(Be, T, H, device=dev, dtype=torch.float32)
+            U = torch.empty_like(S)
+            Wt = torch.empty_like(S) if adaptive else None
+            if norm.bidir and not (recurrent and pr.path == "persist" and pr.fwd_tc and norm.lazy_spikes):
+                raise RuntimeError("the copy-free bidirectional path needs the tcgen05 forward recurrence with the "
+                                   "packed-plane hand-over (the layer module checks this before choosing it)")
             # (the timed regions wrap the recurrence launches only, event records right next to the call, so that an
             # eager pass measures kernel time and not the host's launch gaps)
             if not recurrent:
@@ -490,9 +530,10 @@ class SpikingCellFunction(torch.autograd.Function):
                     bits = torch.empty(L.sparch_recur_fwd_tc_bits_bytes(Be, T, H) // 4, device=dev, dtype=torch.int32)
                     lazy = bool(norm.lazy_spikes)
                     with _region("recurrence_fwd"):
-                        call("sparch_recur_fwd_tc", k, ptr(Z), ptr(scale), ptr(shift), ptr(al), ptr(be), ptr(aa),
+                        call("sparch_recur_fwd_tc_bidir", k, ptr(Z), ptr(scale), ptr(shift), ptr(al), ptr(be), ptr(aa),
                              ptr(bb), ptr(rec0), ptr(img_i8), ptr(u0), ptr(w0), ptr(s0), float(theta),
-                             None if lazy else ptr(S), ptr(U), ptr(Wt), ptr(bits), int(_PRECISION == "bf16"), Be, T, H, st)
+                             None if lazy else ptr(S), ptr(U), ptr(Wt), ptr(bits), int(_PRECISION == "bf16"), Be, T, H,
+                             int(norm.bidir), st)
                     if lazy:
                         norm.bits = bits
                 else:
@@ -517,11 +558,11 @@ class SpikingCellFunction(torch.autograd.Function):
          rstd) = ctx.saved_tensors
         k, theta, norm = ctx.k, ctx.theta, ctx.norm
         adaptive, recurrent = bool(k & 1), bool(k & 2)
-        Be, T, H = Z.shape
+        Be, T, H = U.shape
         dev = Z.device
         st = _stream()
         G = _f32c(gS)
-        dI = torch.empty_like(Z)
+        dI = torch.empty_like(U)
         npart = 4 if adaptive else 1
         part = torch.zeros(npart, Be, H, device=dev, dtype=torch.float32)
         pp = [ptr(part[i]) if i < npart else None for i in range(4)]
@@ -567,7 +608,7 @@ class SpikingCellFunction(torch.autograd.Function):
         if recurrent:
             region.__exit__()
         # BatchNorm backward reductions first: the same pass leaves max|dI| for the dV operand split
-        sums, di_amax = _norm_backward_reduce(dI.view(Be * T, H), Z.view(Be * T, H), norm, mean, rstd)
+        sums, di_amax = _norm_backward_reduce(dI.view(Be * T, H), Z.view(-1, H), norm, mean, rstd)
         if recurrent:
             # dV = sum_t s_{t-1}^T dI_t, diagonal masked (clone().fill_diagonal_(0) backward)
             with _region("gemm_bwd"):
@@ -595,8 +636,12 @@ class SpikingCellFunction(torch.autograd.Function):
         call("sparch_param_grads", ptr(part), ptr(alpha), ptr(beta), ptr(a), ptr(b), _LIMS, npart, Be, H, ptr(pg), st)
         dalpha = pg[0]
         dbeta, da, db = (pg[1], pg[2], pg[3]) if adaptive else (None, None, None)
-        dgamma, dbnb = _norm_backward_apply(dI.view(Be * T, H), Z.view(Be * T, H), gamma, bn_beta, norm,
+        dgamma, dbnb = _norm_backward_apply(dI.view(Be * T, H), Z.view(-1, H), gamma, bn_beta, norm,
                                             scale, mean, rstd, sums, di_amax)
+        if norm.bidir:
+            if norm.mode == "none":      # no normalisation: the gradient of W x is the sum of its two uses
+                dI[:norm.bidir].add_(dI[norm.bidir:].flip(1))
+            dI = dI[:norm.bidir]         # (B, T, H): the BatchNorm backward left dZ in the first half
         return (dI, dgamma, dbnb, dalpha, dbeta, da, db, dV, None, None, None, None, None, None)
 
 
@@ -652,6 +697,14 @@ class _DropoutPostFunction(torch.autograd.Function):
     def backward(ctx, g):
         g = _f32c(g)
         Be, T, H = g.shape
+        if ctx.cell_state.bidir:      # g is the gradient of the merged (B, T, 2H) output: un-merge into the recurrence's rows
+            B, Be, H = Be, 2 * Be, H // 2
+            gS = torch.empty(Be, T, H, device=g.device, dtype=torch.float32)
+            gmax = torch.empty(Be * T, device=g.device, dtype=torch.float32) if ctx.want_gmax else None
+            call("sparch_spike_post_bwd_bidir", ptr(g), B, T, H, ctx.p, ptr(ctx.seed), ptr(gS), ptr(gmax), _stream())
+            ctx.cell_state.gmax = gmax
+            ctx.cell_state.gmax_of = (gS.data_ptr(), gS._version) if gmax is not None else None
+            return gS, None, None, None, None, None
         gS = torch.empty_like(g)
         gmax = torch.empty(Be * T, device=g.device, dtype=torch.float32) if ctx.want_gmax else None
         call("sparch_spike_post_bwd", ptr(g), Be * T, H, ctx.p, ptr(ctx.seed), ptr(gS), ptr(gmax), _stream())
@@ -663,8 +716,8 @@ class _DropoutPostFunction(torch.autograd.Function):
 def _post_from_bits(cell_state, Be, T, H, p, seed, out, term, sterm, counts):
     """The post pass fed by the packed spike planes of the tcgen05 forward (csrc/post.cu: sparch_spike_post_fwd_bits)."""
     s_last = torch.empty(Be, H, device=out.device, dtype=torch.float32)
-    call("sparch_spike_post_fwd_bits", ptr(cell_state.bits), Be, T, H, p, ptr(seed), ptr(out), ptr(term), ptr(sterm),
-         int(term.dtype == torch.float16), ptr(counts), ptr(s_last), _stream())
+    call("sparch_spike_post_fwd_bits_bidir", ptr(cell_state.bits), Be, T, H, p, ptr(seed), ptr(out), ptr(term), ptr(sterm),
+         int(term.dtype == torch.float16), ptr(counts), ptr(s_last), int(cell_state.bidir), _stream())
     cell_state.bits = None
     cell_state.s_last = s_last
 
@@ -681,6 +734,22 @@ def spike_post(S, p, cell_state, recurrent):
     term = torch.empty(1, M, ld, device=dev, dtype=dt)
     counts = torch.empty(H, device=dev, dtype=torch.int32)
     need_grad = torch.is_grad_enabled() and S.requires_grad
+    if cell_state.bidir:
+        # merged (B, T, 2H) output, operand terms and counts straight from the planes (snns.py:686-692 in one pass); the
+        # same node un-merges the gradient, with or without dropout
+        if cell_state.bits is None:
+            raise RuntimeError("the copy-free bidirectional path needs the packed planes of the tcgen05 forward")
+        B = cell_state.bidir
+        term = torch.empty(1, B * T, 2 * ld, device=dev, dtype=dt)
+        counts = torch.empty(2 * H, device=dev, dtype=torch.int32)
+        sterm = torch.empty(1, M, ld, device=dev, dtype=dt) if (recurrent and need_grad) else None
+        seed = torch.empty(1, device=dev, dtype=torch.int64).random_() if p > 0.0 else None
+        out = torch.empty(B, T, 2 * H, device=dev, dtype=torch.float32)
+        want_gmax = recurrent and RECUR_BWD == "tc" and H <= RECUR_TC_MAX_H
+        out = _DropoutPostFunction.apply(S, p, seed, (out, term, sterm, counts), cell_state, want_gmax)
+        if sterm is not None:
+            cell_state.sterm = gemm.Terms(sterm)
+        return out, SpikePost(gemm.Terms(term), counts, 1.0 / (1.0 - p), B * T)
     if p > 0.0:
         sterm = torch.empty(1, M, ld, device=dev, dtype=dt) if (recurrent and need_grad) else None
         seed = torch.empty(1, device=dev, dtype=torch.int64).random_()     # device generator, as nn.Dropout

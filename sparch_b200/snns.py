@@ -42,6 +42,8 @@ def set_state_init(mode):
 # SPARCH_B200_PREP_AHEAD=0: every layer issues its parameter-only launches (clamps, images of V0, rec_0) itself, on the
 # stream of its forward pass, instead of SNN.forward issuing them for all layers on a side stream at the start.
 _PREP_AHEAD = os.environ.get("SPARCH_B200_PREP_AHEAD", "1") != "0"
+# SPARCH_B200_BIDIR_FUSED=0: bidirectional layers take the reference's flip / cat formulation (copies) everywhere.
+_BIDIR_FUSED = os.environ.get("SPARCH_B200_BIDIR_FUSED", "1") != "0"
 _SIDE_STREAMS = {}     # device index -> the side stream of SNN.forward's parameter-only work
 _PENDING_PREP = {}     # id(layer) -> functional.CellPrep made ahead of the layer's forward (cleared by SNN.forward)
 
@@ -153,6 +155,8 @@ class _SpikingLayerBase(nn.Module):
         (``functional.SpikePost`` or None); ``x_terms``: the previous layer's ``SpikePost.terms``."""
         if not x.is_cuda:
             raise RuntimeError("sparch_b200 layers run on CUDA only (no CPU fallback)")
+        if self.bidirectional and self._copy_free_bidir(x):
+            return self._forward_post_bidir(x, in_scale, x_terms)
         if self.bidirectional:                                   # snns.py:666-668
             if x_terms is not None:   # the same batch-wise flip/cat on the 16-bit operand image instead of a re-split
                 n, _, ld = x_terms.parts.shape
@@ -183,9 +187,31 @@ class _SpikingLayerBase(nn.Module):
         # bidirectional tensor is not the cell's own output, so it cannot serve the cell's dV product
         return spike_post(s, p, norm, self._recurrent and not self.bidirectional)
 
+    def _copy_free_bidir(self, x):
+        """Whether this bidirectional layer can run without the flipped / concatenated copies of snns.py:666-668 and
+        686-689: the projection once on the un-flipped batch, the second half of the recurrence reading it
+        time-reversed, the merge written by the post pass (functional.NormState.bidir).  Needs the tcgen05 forward
+        recurrence with its packed planes, whole 128-row groups per direction and 16-byte rows."""
+        H, p = self.hidden_size, (self.drop.p if self.drop.training else 0.0)
+        return (_BIDIR_FUSED and _LAZY_SPIKES and self._recurrent and x.ndim == 3 and x.shape[0] % 128 == 0
+                and H % 8 == 0 and H <= _F.RECUR_MAX_H and _F.RECUR_FWD == "tc" and H <= _F.RECUR_FWD_TC_MAX_H
+                and p < 1.0 and not (self.normalize and isinstance(self.norm, nn.LayerNorm)))
+
+    def _forward_post_bidir(self, x, in_scale, x_terms):
+        B = x.shape[0]
+        if self.batch_size != 2 * B:                             # snns.py:671-672 (the reference sees the doubled batch)
+            self.batch_size = 2 * B
+        gamma, bn_beta, norm = _norm_args(self)
+        Wx = LinearFunction.apply(x, self.W.weight, self.W.bias, in_scale, norm, x_terms)   # snns.py:675, once
+        norm.bidir = B
+        norm.lazy_spikes = True
+        p = self.drop.p if self.drop.training else 0.0
+        s = self._cell(Wx, gamma, bn_beta, norm)                 # (2B, T, H) in the recurrence's order, still planes only
+        return spike_post(s, p, norm, True)                      # snns.py:686-692: merge + dropout, (B, T, 2H)
+
     def _cell(self, Wx, gamma, bn_beta, norm):
         device = Wx.device
-        Be, H = Wx.shape[0], Wx.shape[2]
+        Be, H = Wx.shape[0] * (2 if norm.bidir else 1), Wx.shape[2]
         # initial states in the reference's order ut, [wt,] st (snns.py:700-702): from the CPU generator (identical
         # draws), or in "device" mode as one draw of the 2-3 states on the CUDA generator
         prep = _PENDING_PREP.pop(id(self), None)

@@ -1296,3 +1296,66 @@ def test_packed_plane_hand_over_equals_fp32_spike_tensor(kind, H, p, B, T):
     assert torch.equal(oa, ob) and torch.equal(ra, rb)
     for k in ga:
         assert torch.equal(ga[k], gb[k]), k
+
+
+@pytest.mark.parametrize("kind,norm,p,bias,precision", [
+    ("RadLIF", "batchnorm", 0.1, False, "fp32"), ("RLIF", "batchnorm", 0.0, False, "fp32"),
+    ("RadLIF", "batchnorm", 0.25, True, "fp32"), ("RadLIF", "none", 0.0, False, "fp32"),
+    ("RadLIF", "batchnorm", 0.1, False, "bf16")])
+def test_copy_free_bidirectional_equals_flip_cat(kind, norm, p, bias, precision):
+    """a bidirectional layer WITHOUT the reference's flipped / concatenated copies (snns.py:666-668,
+    686-689) -- one projection of the un-flipped batch, the second half of the recurrence reading it time-reversed, the
+    merge written by the post pass from the packed planes, the BatchNorm backward summing a row's two uses -- against
+    the flip / cat formulation (which the fixtures pin to the reference), same seeds: outputs and firing rates equal
+    (the dropout mask is keyed by the merged position in both), gradients to rel 2e-5 of their maximum (the batch-
+    contracted GEMMs sum the rows in another order; reduced-precision mode: 2e-2)."""
+    import sparch_b200
+    import sparch_b200.snns as snns_mod
+    sp, _ = _mods()
+    B, T, H = 128, 20, 256
+    res = []
+    sparch_b200.set_precision(precision)
+    try:
+        for fused in (True, False):
+            snns_mod._BIDIR_FUSED = fused
+            torch.manual_seed(0)
+            net = sp.SNN((B, None, 40), layer_sizes=[H, H, 10], neuron_type=kind, normalization=norm, dropout=p,
+                         use_bias=bias, bidirectional=True).to(DEV)
+            with torch.no_grad():
+                for lay in net.snn:
+                    if hasattr(lay, "a"):
+                        lay.a.abs_()
+                    if isinstance(getattr(lay, "norm", None), torch.nn.BatchNorm1d):
+                        lay.norm.weight.fill_(3.0)
+                        lay.norm.bias.fill_(0.8)
+            g = torch.Generator(device=DEV).manual_seed(5)
+            x = (torch.randn(B, T, 40, device=DEV, generator=g) * (1.0 if norm == "batchnorm" else 10.0)).requires_grad_(True)
+            y = torch.randint(0, 10, (B,), device=DEV, generator=g)
+            torch.manual_seed(11)
+            out, rates = net(x)
+            loss = torch.nn.functional.cross_entropy(out, y) + 0.1 * rates.sum()
+            loss.backward()
+            grads = {k: q.grad.detach().clone() for k, q in net.named_parameters()}
+            grads["x"] = x.grad.detach().clone()
+            stats = {k: v.detach().clone() for k, v in net.state_dict().items() if "running" in k}
+            net.eval()
+            torch.manual_seed(12)
+            with torch.no_grad():
+                out_e, rates_e = net(x)
+            res.append((out.detach().clone(), rates.detach().clone(), grads, stats, out_e.clone(), rates_e.clone()))
+    finally:
+        snns_mod._BIDIR_FUSED = True
+        sparch_b200.set_precision("fp32")
+    (oa, ra, ga, sa, ea, rea), (ob, rb, gb, sb, eb, reb) = res
+    assert ra.shape == (4 * H,) and 0.005 < float(ra.mean()) < 0.9
+    assert torch.equal(ra, rb) and torch.equal(oa, ob)
+    assert torch.equal(rea, reb) and torch.equal(ea, eb)
+    for k in sa:
+        assert torch.allclose(sa[k], sb[k], rtol=1e-6, atol=1e-7), k
+    tol = 2e-5 if precision == "fp32" else 2e-2
+    for k in ga:
+        # (a bias in front of BatchNorm has a gradient of exactly zero: what is there is rounding noise of the
+        # projection's gradient, so it is measured on that scale)
+        ref = gb[k.replace("W.bias", "W.weight")].abs().max() if k.endswith("W.bias") else gb[k].abs().max()
+        err = float((ga[k] - gb[k]).abs().max() / ref.clamp_min(1e-30))
+        assert err < tol, (k, err)
