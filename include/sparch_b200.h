@@ -255,13 +255,16 @@ SPARCH_API int sparch_recur_fwd_tc(int kind, const float* Z, const float* scale,
 /* Bidirectional layers (snns.py:666-668, 686-689) WITHOUT the flipped / concatenated copies: Z is the projection of the
  * un-flipped batch, (rev_from, T, H); the kernel runs Be = 2 * rev_from rows, rows b >= rev_from read
  * Z[b - rev_from][T - 1 - t] (the reversed sequence).  Tapes and planes stay in the kernel's own (Be, T, H) order, which
- * is what sparch_recur_bwd_tc reads.  rev_from = 0: sparch_recur_fwd_tc.  Needs rev_from % 128 == 0, H % 4 == 0.   */
+ * is what sparch_recur_bwd_tc reads.  rev_from = 0: one direction.  Needs rev_from % 128 == 0, H % 4 == 0.
+ * w_every = C > 0: W is a CHECKPOINT tape (Be, ceil(T/C), H) that receives w_t at the last step of every
+ * chunk of C steps (and at T-1) instead of the full (Be, T, H) tape; sparch_recur_bwd_tc_ck recomputes the steps in
+ * between.  rev_from = w_every = 0 is sparch_recur_fwd_tc.                                                         */
 SPARCH_API int sparch_recur_fwd_tc_bidir(int kind, const float* Z, const float* scale, const float* shift,
                                          const float* alpha, const float* beta, const float* a, const float* b,
                                          const float* rec0, const void* img, const float* u0, const float* w0,
                                          const float* s0, float theta, float* S, float* U, float* W,
                                          uint32_t* bits, int reduced, int Be, int T, int H, int rev_from,
-                                         sparch_stream_t st);
+                                         int w_every, sparch_stream_t st);
 /* Profiling aid: device buffer of T*4 int64 that receives, per timestep, the SM clock of CTA (0,0)
  * after the spike-word wait, after the MMA loop, after the reduction and at the end of the step
  * for the following sparch_recur_fwd launches (NULL switches it off).                          */
@@ -300,6 +303,17 @@ SPARCH_API int sparch_recur_bwd_tc(int kind, const float* G, const float* U, con
                                    float* dI, float* p_alpha, float* p_beta, float* p_a,
                                    float* p_b, void* workspace, int reduced, int Be, int T, int H,
                                    const float* gmax_in, sparch_stream_t st);
+/* The same pass reading the CHECKPOINT adaptation tape of sparch_recur_fwd_tc_bidir(w_every = C): W is (Be, ceil(T/C), H),
+ * w_{t-1} is loaded where step t-1 closes a chunk and recomputed in between by solving snns.py:718 for w_{t-1} (beta >=
+ * e^(-1/30): the rounding error of a step back grows by <= 1.034 and is dropped at the next checkpoint; only d(beta)
+ * reads w).  w_every = 0: the full tape, i.e. sparch_recur_bwd_tc.                                              */
+SPARCH_API int sparch_recur_bwd_tc_ck(int kind, const float* G, const float* U, const float* W,
+                                   const float* alpha, const float* beta, const float* a,
+                                   const float* b, const void* img, const int* meta,
+                                   const float* u0, const float* w0, const float* s0, float theta,
+                                   float* dI, float* p_alpha, float* p_beta, float* p_a,
+                                   float* p_b, void* workspace, int reduced, int Be, int T, int H,
+                                   const float* gmax_in, int w_every, sparch_stream_t st);
 
 /* ---- around the recurrence: dropout, firing-rate counts, operand terms, parameter clamps ------- */
 /* One pass over the spike tensor S (M = Be*T rows, H columns, values exactly 0/1):

@@ -49,7 +49,7 @@ _PROTOS = {
     "sparch_recur_fwd_tc_bits_bytes": "iii",
     "sparch_recur_prepare_fwd_tc": "pipp",
     "sparch_recur_fwd_tc": "i" + "p" * 12 + "f" + "pppp" + "iiii" + "p",
-    "sparch_recur_fwd_tc_bidir": "i" + "p" * 12 + "f" + "pppp" + "iiiii" + "p",
+    "sparch_recur_fwd_tc_bidir": "i" + "p" * 12 + "f" + "pppp" + "iiiiii" + "p",
     "sparch_recur_bwd_workspace": "ii",
     "sparch_recur_bwd": "i" + "p" * 12 + "f" + "p" * 7 + "iiii" + "p",
     "sparch_recur_tc_padded": "i",
@@ -57,6 +57,7 @@ _PROTOS = {
     "sparch_recur_bwd_tc_workspace": "iii",
     "sparch_recur_prepare_tc": "pippp",
     "sparch_recur_bwd_tc": "i" + "p" * 12 + "f" + "p" * 6 + "iiii" + "pp",
+    "sparch_recur_bwd_tc_ck": "i" + "p" * 12 + "f" + "p" * 6 + "iiii" + "pip",
     "sparch_spike_post_fwd": "plifppppipp",
     "sparch_spike_post_fwd_bits": "piiifppppippp",
     "sparch_spike_post_bwd": "plifpppp",

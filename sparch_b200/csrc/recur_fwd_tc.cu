@@ -118,6 +118,9 @@ struct RecFwdTcArgs {
   int Be, T, H, Hp, NB, ngroups_total;
   int reduced;     // 1: two digit planes only (15-bit image of V0)
   int use_tma;     // 1: Z tiles in / S, U, W tiles out by TMA (needs H % 4 == 0); 0: per-thread global accesses
+  int w_every;     // 0: W is the full (Be, T, H) adaptation tape.  C > 0: W is (Be, ceil(T / C), H) and receives w_t only at
+                   // the last step of every chunk of C steps (and at T - 1): the reverse pass recomputes the steps in
+                   // between from u and s by inverting the update (csrc/recur_tc.cu), 4 / C instead of 4 B/elt each way
   int rev_from;    // bidirectional layers (snns.py:666-668): rows >= rev_from run the sequence backwards and read the
                    // input of row - rev_from -- Z is (rev_from, T, H), no flipped copy; 0 = off.  TMA mode only.
   long long* dbg;  // optional [2T][8] phase clocks of CTA (0,0), normally NULL
@@ -406,7 +409,8 @@ rec_fwd_tc_kernel(const __grid_constant__ FtMaps maps, const RecFwdTcArgs p, con
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb), "f"(s[0]), "f"(s[1]), "f"(s[2]), "f"(s[3]) : "memory");
       asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + FT_TILE_BYTES), "f"(u[0]), "f"(u[1]), "f"(u[2]), "f"(u[3])
                    : "memory");
-      if (ADAPT)
+      const bool w_step = ADAPT && (!p.w_every || ts % p.w_every == p.w_every - 1 || ts == p.T - 1);
+      if (w_step)
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + 2 * FT_TILE_BYTES), "f"(w[0]), "f"(w[1]), "f"(w[2]),
                      "f"(w[3])
                      : "memory");
@@ -418,7 +422,7 @@ rec_fwd_tc_kernel(const __grid_constant__ FtMaps maps, const RecFwdTcArgs p, con
         if (!(p.dbg_flags & 2)) {
           if (p.S) tma_store_3d(&maps.s, slice * FT_NEUR, ts, row0 + 32 * q, tb);
           tma_store_3d(&maps.u, slice * FT_NEUR, ts, row0 + 32 * q, tb + FT_TILE_BYTES);
-          if (ADAPT) tma_store_3d(&maps.w, slice * FT_NEUR, ts, row0 + 32 * q, tb + 2 * FT_TILE_BYTES);
+          if (w_step) tma_store_3d(&maps.w, slice * FT_NEUR, p.w_every ? ts / p.w_every : ts, row0 + 32 * q, tb + 2 * FT_TILE_BYTES);
         }
         tma_store_commit();
         if (ts + 2 < p.T) {  // Z tile of step ts + 2: its buffer held step ts, read before this barrier by all four warps
@@ -510,7 +514,12 @@ rec_fwd_tc_kernel(const __grid_constant__ FtMaps maps, const RecFwdTcArgs p, con
       if (!tma && nv > 0 && !(p.dbg_flags & 2)) {
         if (p.S) st4(p.S + o0, s);
         st4(p.U + o0, u);
-        if (ADAPT) st4(p.W + o0, w);
+        if (ADAPT) {
+          if (!p.w_every)
+            st4(p.W + o0, w);
+          else if (t % p.w_every == p.w_every - 1 || t == p.T - 1)
+            st4(p.W + ((int64_t)row * ((p.T + p.w_every - 1) / p.w_every) + t / p.w_every) * p.H + col0, w);
+        }
       }
       // the first poll of the next step
       if (t + 1 < p.T && r < NB) {
@@ -590,13 +599,13 @@ int sparch_recur_fwd_tc(int kind, const float* Z, const float* scale, const floa
                         const float* u0, const float* w0, const float* s0, float theta, float* S, float* U, float* W,
                         uint32_t* bits, int reduced, int Be, int T, int H, sparch_stream_t st_) {
   return sparch_recur_fwd_tc_bidir(kind, Z, scale, shift, alpha, beta, a, b, rec0, img, u0, w0, s0, theta, S, U, W, bits,
-                                   reduced, Be, T, H, 0, st_);
+                                   reduced, Be, T, H, 0, 0, st_);
 }
 
 int sparch_recur_fwd_tc_bidir(int kind, const float* Z, const float* scale, const float* shift, const float* alpha,
                               const float* beta, const float* a, const float* b, const float* rec0, const void* img,
                               const float* u0, const float* w0, const float* s0, float theta, float* S, float* U,
-                              float* W, uint32_t* bits, int reduced, int Be, int T, int H, int rev_from,
+                              float* W, uint32_t* bits, int reduced, int Be, int T, int H, int rev_from, int w_every,
                               sparch_stream_t st_) {
   SPARCH_REQUIRE(kind == SPARCH_RLIF || kind == SPARCH_RADLIF, "recurrent kinds only");
   SPARCH_REQUIRE(Be >= 0 && T >= 0 && H > 0, "bad shape");
@@ -621,6 +630,7 @@ int sparch_recur_fwd_tc_bidir(int kind, const float* Z, const float* scale, cons
   const float* colscale = reinterpret_cast<const float*>(planes + (size_t)ns * Hp * FT_N);
   static const bool tma_off = getenv("SPARCH_B200_FWD_TMA") && getenv("SPARCH_B200_FWD_TMA")[0] == '0';
   const int use_tma = ((H & 3) == 0 && !tma_off) ? 1 : 0;   // TMA needs 16-byte global strides
+  SPARCH_REQUIRE(w_every >= 0, "w_every");
   if (rev_from) {
     SPARCH_REQUIRE(rev_from > 0 && Be == 2 * rev_from && rev_from % FT_ROWS == 0 && use_tma,
                    "reversed second half: Be = 2 * rev_from, rev_from a multiple of 128 rows, H a multiple of 4");
@@ -633,10 +643,10 @@ int sparch_recur_fwd_tc_bidir(int kind, const float* Z, const float* scale, cons
     if (S)
       if (int e = make_map3d_f32(&maps.s, S, Be, T, H, 32, FT_NEUR)) return e;
     if (int e = make_map3d_f32(&maps.u, U, Be, T, H, 32, FT_NEUR)) return e;
-    if (int e = make_map3d_f32(&maps.w, adapt ? W : U, Be, T, H, 32, FT_NEUR)) return e;
+    if (int e = make_map3d_f32(&maps.w, adapt ? W : U, Be, (adapt && w_every) ? (T + w_every - 1) / w_every : T, H, 32, FT_NEUR)) return e;
   }
   RecFwdTcArgs p{Z, scale, shift, alpha, beta, a, b, rec0, u0, w0, s0, planes, colscale, theta, S, U, W, bits,
-                 Be, T, H, Hp, NB, groups, reduced ? 1 : 0, use_tma, rev_from, recur_debug_buffer(), recur_debug_flags()};
+                 Be, T, H, Hp, NB, groups, reduced ? 1 : 0, use_tma, w_every, rev_from, recur_debug_buffer(), recur_debug_flags()};
   // a word of all ones means "not yet published" (published halves have zero odd bits): every step has its own words
   SPARCH_CUDA(cudaMemsetAsync(bits, 0xFF, sparch_recur_fwd_tc_bits_bytes(Be, T, H), st));
   const int gmax = max_ctas / ns;  // row groups per cooperative launch (all its CTAs wait on each other)

@@ -69,6 +69,8 @@ struct RecBwdTcArgs {
   uint32_t* panel;       // [2][groups*64][Hp] words {fp16 hi, fp16 lo with the tag in its least significant bit}
   int Be, T, H, Hp, KB;  // Hp: H padded to 256; KB = Hp / 256 k-blocks of 64 per CTA
   int reduced;
+  int w_every;     // C > 0: W is the checkpoint tape (Be, ceil(T / C), H) of sparch_recur_fwd_tc_bidir: w at the end of
+                   // every chunk of C steps; the steps in between are recomputed here (see the update's second half)
   long long* dbg;  // optional [2T][8] phase clocks of CTA (0,0) (profiling aid), normally NULL
   int dbg_flags;   // profiling experiments (results invalid): 16 no UMMA
 };
@@ -213,7 +215,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ uint32_t tc_tag(int T, int t) { return ((((T - 1 - t) / TC_NBUF) & 1) ^ 1); }
 __device__ __forceinline__ int tc_buf(int T, int t) { return (T - 1 - t) % TC_NBUF; }
 
-template <bool ADAPT>
+template <bool ADAPT, bool WCK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_total) {
   extern __shared__ unsigned char tsm_raw[];
@@ -229,6 +231,9 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
   const unsigned char* recv_p = tail;
   const float* qmax_p = reinterpret_cast<const float*>(tail + TC_RECV_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + TC_RECV_BYTES + TC_QMAX_BYTES + 192);
+  // checkpoint-tape mode: [8 rows][256 update threads] floats w of the step last visited + the same for a freshly loaded
+  // checkpoint (kept out of the register file: touched once per step, in the waiting window)
+  float* wc_sm = reinterpret_cast<float*>(tail + TC_RECV_BYTES + TC_QMAX_BYTES + 256);
   // barriers of chain c (the 32-row half c of the group) at index 8 c + {0..3 full[kb], 4 acc_full, 5 recv, 6 free}
   constexpr int B_ACC_FULL = 4, B_RECV = 5, B_FREE = 6, B_CHAIN = 8;
 
@@ -367,6 +372,9 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
     const int rowb = row0 + 8 * uw;                // first of this warp's 8 batch rows
     const int TH = p.T * p.H;                      // elements per batch row of the tapes (Be * T * H < 2^31 is checked)
     float du[8], dw[8], ut[8];
+    const int NCK = WCK ? (p.T + p.w_every - 1) / p.w_every : 0;
+    const float inv_beta = WCK ? 1.0f / prm.beta : 0.f;
+    float* wc = wc_sm + (tid - 64);                // wc[256 k]: row k of this thread
     float pa = 0.f, pb = 0.f, pc = 0.f, pd = 0.f;  // parameter-gradient sums over this thread's 8 rows and all steps
     // The hand-over scale of row 8 uw + k is computed by lane k alone (it reads the quarter maxima and the row maximum of
     // g) and travels as an exponent: e_cur = exponent of s_t, e_next = exponent of s_{t+1} (the scale of the panel that
@@ -377,6 +385,7 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
       du[k] = dw[k] = 0.f;
       const bool live = col_live && rowb + k < p.Be;
       ut[k] = (live && p.T > 0) ? __ldcg(p.U + ((int64_t)(rowb + k) * p.T + (p.T - 1)) * p.H + col) : 0.f;
+      if (WCK) wc[256 * k] = (live && p.T > 0) ? __ldcg(p.W + ((int64_t)(rowb + k) * NCK + (NCK - 1)) * p.H + col) : 0.f;
     }
     // loader geometry: load i = (kb = i / 4, j = i % 4) covers row 8 uw + 2 j + (lane / 16), columns 4 (lane % 16) ..
     // + 3 of K block kb: a half-warp reads the 256 contiguous bytes of one (row, K block)
@@ -394,6 +403,8 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
     const bool myrow_live = rowb + (lane & 7) < p.Be;
     const bool dbg_on = dbg_cta && tid == 64;
     int step = 0;
+    // t % C and t / C of the checkpoint tape as counters (no division inside the loop)
+    int tm = WCK ? (p.T - 1) % p.w_every : 0, tq = WCK ? (p.T - 1) / p.w_every : 0;
     for (int t = p.T - 1; t >= 0; --t) {
       // ---- this step's tape values.  Issued AFTER the panel load phase, in flight while the tensor core multiplies: the
       // loader's 64 registers of panel words are dead by then (with both live, ptxas spilled loaded values at once,
@@ -403,14 +414,22 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
       const int toff = t * p.H + colc;
       auto load_tape = [&]() {
         const float* up_base = t > 0 ? p.U + (toff - p.H) : p.u0 + colc;
-        const float* wp_base = ADAPT ? (t > 0 ? p.W + (toff - p.H) : p.w0 + colc) : nullptr;
+        // w_{t-1}: from the full tape; or (checkpoint tape) loaded only where step t-1 closes a chunk -- everywhere else
+        // the second half of the update recomputes it from w_t -- and w0 at t = 0
+        const bool w_ck = WCK && t > 0;
+        const bool w_load = ADAPT && (!w_ck || tm == 0);
+        const float* wp_base = !ADAPT ? nullptr
+                               : t == 0 ? p.w0 + colc
+                               : w_ck   ? p.W + (tq - 1) * p.H + colc      // tm == 0: (t - 1) / C = t / C - 1
+                                        : p.W + (toff - p.H);
         const int rs_prev = t > 0 ? TH : p.H;
+        const int rs_w = t == 0 ? p.H : (w_ck ? NCK * p.H : TH);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int rowc = min(rowb + k, p.Be - 1);
           gq[k] = ld_stream(p.G + toff + rowc * TH);
           up[k] = ld_stream(up_base + rowc * rs_prev);
-          wp[k] = ADAPT ? ld_stream(wp_base + rowc * rs_prev) : 0.f;
+          wp[k] = w_load ? ld_stream(wp_base + rowc * rs_w) : 0.f;
         }
         grow_l = ld_stream(p.gmax + myrow * p.T + t);
       };
@@ -533,6 +552,23 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
         // ---- partial D^T = V0[128 neurons][K quarter] dI_{t+1}[rows][K quarter]^T: this warp reads neurons 32 q + lane
         // (= neuron `lane` of cluster rank q), rows 32 half .. 32 half + 31, and sends them to their owner
         if (dbg_on) p.dbg[t * 8 + 7] = clock64();
+        if (WCK) {
+          // ---- checkpoint adaptation tape, while the tensor core multiplies: w_t from w_{t+1} by solving
+          // w_{t+1} = beta w_t + a u_t + b s_t (snns.py:718) -- or from the tape where step t closes a chunk -- and the
+          // term of d(beta) that step t+1 left open, dw_{t+1} w_t.  beta >= 0.967: a rounding error grows by <= 1.034
+          // per step back and is dropped at the next checkpoint; w only enters d(beta).  Everything it needs (u_t, the
+          // adjoint of step t+1) is in registers, w itself waits in shared memory.  Placed HERE because no global load
+          // is in flight: behind load_tape() the shared-memory loads share scoreboards with the 24 tape loads and wait
+          // for DRAM (measured: +1.4 k cycles per step).
+          const bool from_tape = tm == p.w_every - 1;      // (t + 1) % C == 0
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float s_t = spike_of(__fsub_rn(ut[k], p.theta));
+            const float w_t = from_tape ? wc[256 * (8 + k)] : (wc[256 * k] - prm.a * ut[k] - prm.b * s_t) * inv_beta;
+            pb += dw[k] * w_t;
+            wc[256 * k] = w_t;
+          }
+        }
         mbar_wait_sleep(cbar + 8 * B_ACC_FULL, step & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (dbg_on) p.dbg[t * 8 + 3] = clock64();
@@ -638,13 +674,19 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
         for (int k = 0; k < 8; ++k)
           sp[k] = (col_live && rowb + k < p.Be) ? p.s0[(int64_t)(rowb + k) * p.H + col] : 0.f;
       }
+      if (WCK && t > 0 && tm == 0) {
+        // step t-1 closes a chunk: its w came from the checkpoint tape (load_tape); the next step's waiting window
+        // takes it from shared memory instead of recomputing it
+#pragma unroll
+        for (int k = 0; k < 8; ++k) wc[256 * (8 + k)] = wp[k];
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float dd = up[k] - sp[k];
         pa += du[k] * ((dd - ut[k]) * inv_oma);
         if (ADAPT) {
           const float dw_t = prm.beta * dw[k] - d[k];
-          pb += dw_t * wp[k];
+          if (!WCK || t == 0) pb += dw_t * wp[k];   // (checkpoint tape: added a step later, in the waiting window)
           pc += dw_t * up[k];
           pd += dw_t * sp[k];
           dw[k] = dw_t;
@@ -653,6 +695,9 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
         if (col_live && rowb + k < p.Be) __stcg(p.dI + toff + (rowb + k) * TH, d[k]);
       }
       if (dbg_on) p.dbg[(p.T + t) * 8 + 3] = clock64();
+      if (WCK) {
+        if (tm == 0) { tm = p.w_every - 1; --tq; } else { --tm; }
+      }
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -678,8 +723,8 @@ rec_bwd_tc_kernel(const RecBwdTcArgs p, const int group0, const int ngroups_tota
   }
 }
 
-static size_t rec_bwd_tc_smem(int KB) {
-  return (size_t)KB * TC_STAGE_BYTES + TC_RECV_BYTES + TC_QMAX_BYTES + 256 + 1024;
+static size_t rec_bwd_tc_smem(int KB, bool wck = true) {
+  return (size_t)KB * TC_STAGE_BYTES + TC_RECV_BYTES + TC_QMAX_BYTES + 256 + 1024 + (wck ? 16 * 256 * sizeof(float) : 0);
 }
 
 }  // namespace sparch
@@ -722,6 +767,16 @@ int sparch_recur_bwd_tc(int kind, const float* G, const float* U, const float* W
                         const float* u0, const float* w0, const float* s0, float theta, float* dI, float* p_alpha,
                         float* p_beta, float* p_a, float* p_b, void* workspace, int reduced, int Be, int T, int H,
                         const float* gmax_in, sparch_stream_t st_) {
+  return sparch_recur_bwd_tc_ck(kind, G, U, W, alpha, beta, a, b, img, meta, u0, w0, s0, theta, dI, p_alpha, p_beta, p_a,
+                                p_b, workspace, reduced, Be, T, H, gmax_in, 0, st_);
+}
+
+int sparch_recur_bwd_tc_ck(int kind, const float* G, const float* U, const float* W, const float* alpha,
+                           const float* beta, const float* a, const float* b, const void* img, const int* meta,
+                           const float* u0, const float* w0, const float* s0, float theta, float* dI, float* p_alpha,
+                           float* p_beta, float* p_a, float* p_b, void* workspace, int reduced, int Be, int T, int H,
+                           const float* gmax_in, int w_every, sparch_stream_t st_) {
+  SPARCH_REQUIRE(w_every >= 0, "w_every");
   SPARCH_REQUIRE(kind == SPARCH_RLIF || kind == SPARCH_RADLIF, "recurrent kinds only");
   SPARCH_REQUIRE(Be >= 0 && T >= 0 && H > 0, "bad shape");
   if (Be == 0 || T == 0) return SPARCH_OK;
@@ -730,18 +785,20 @@ int sparch_recur_bwd_tc(int kind, const float* G, const float* U, const float* W
   SPARCH_REQUIRE(!adapt || (W && beta && a && b && w0 && p_beta && p_a && p_b),
                  "adaptive kind needs W, beta, a, b, w0 and the partial buffers");
   const int Hp = sparch_recur_tc_padded(H), KB = Hp / (64 * TC_CL);
-  const size_t smem = rec_bwd_tc_smem(KB);
-  SPARCH_REQUIRE(KB <= 4 && smem <= 112 * 1024, "hidden size too large for the resident V0 tiles");
+  const size_t smem = rec_bwd_tc_smem(KB, adapt && w_every > 0) + (getenv("SPARCH_TC_PAD_SMEM") ? atoi(getenv("SPARCH_TC_PAD_SMEM")) : 0);
+  SPARCH_REQUIRE(KB <= 4 && smem <= 128 * 1024, "hidden size too large for the resident V0 tiles");
   SPARCH_REQUIRE((long long)Be * T * H < (1LL << 31), "tape larger than 2^31 elements: split the batch");
   cudaStream_t st = as_stream(st_);
   static PerDeviceOnce attr_once;
   if (attr_once.first()) {
     // 98.5 KB at H = 1024 (V0 lives in tensor memory): the rest of the SM's 256 KB stays L1, whose lines buffer the
     // 64 KB of panel words a CTA has in flight per step
-    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
-    SPARCH_CUDA(cudaFuncSetAttribute(rec_bwd_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
+    const void* fns[3] = {(const void*)rec_bwd_tc_kernel<true, false>, (const void*)rec_bwd_tc_kernel<true, true>,
+                          (const void*)rec_bwd_tc_kernel<false, false>};
+    for (const void* f : fns) {
+      SPARCH_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+      SPARCH_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
+    }
   }
   const int groups = (Be + TC_ROWS - 1) / TC_ROWS, slices = Hp / TC_COLS;
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
@@ -757,8 +814,12 @@ int sparch_recur_bwd_tc(int kind, const float* G, const float* U, const float* W
     SPARCH_LAUNCH_OK();
   }
   RecBwdTcArgs p{G, U, W, alpha, beta, a, b, u0, w0, s0, reinterpret_cast<const uint32_t*>(img), meta, gmax, theta,
-                 dI, p_alpha, p_beta, p_a, p_b, panel, Be, T, H, Hp, KB, reduced ? 1 : 0, recur_debug_buffer(), recur_debug_flags()};
-  const void* fn = adapt ? (const void*)rec_bwd_tc_kernel<true> : (const void*)rec_bwd_tc_kernel<false>;
+                 dI, p_alpha, p_beta, p_a, p_b, panel, Be, T, H, Hp, KB, reduced ? 1 : 0, (kind & 1) ? w_every : 0, recur_debug_buffer(),
+                 recur_debug_flags()};
+  const bool wck = adapt && w_every > 0;
+  const void* fn = wck     ? (const void*)rec_bwd_tc_kernel<true, true>
+                   : adapt ? (const void*)rec_bwd_tc_kernel<true, false>
+                           : (const void*)rec_bwd_tc_kernel<false, false>;
   cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = TC_CL;

@@ -378,6 +378,10 @@ RECUR_TC_MAX_H = 1024
 # tensor memory, 128 rows x 16 neurons per CTA; H <= 1536), "mma" = mma.sync kernel (csrc/recur.cu).
 RECUR_FWD = os.environ.get("SPARCH_B200_FWD", "tc")
 RECUR_FWD_TC_MAX_H = 1536
+# Adaptation tape of the recurrent adaptive kind when both tcgen05 recurrence kernels serve the layer: C > 0
+# keeps w only at the end of every chunk of C steps -- (Be, ceil(T/C), H) instead of (Be, T, H) fp32 -- and the reverse
+# kernel recomputes the steps in between by solving snns.py:718 for w_{t-1}; 0 = the full tape.
+W_TAPE_EVERY = int(os.environ.get("SPARCH_B200_W_EVERY", "16"))
 
 
 class CellPrep:
@@ -492,7 +496,10 @@ class SpikingCellFunction(torch.autograd.Function):
             scale, shift, mean, rstd = _fold_norm(Z2d, gamma, bn_beta, norm)
             S = torch.empty(Be, T, H, device=dev, dtype=torch.float32)
             U = torch.empty_like(S)
-            Wt = torch.empty_like(S) if adaptive else None
+            w_every = W_TAPE_EVERY if (adaptive and recurrent and pr.path == "persist" and pr.fwd_tc and pr.use_tc) else 0
+            ctx.w_every = w_every
+            Wt = (torch.empty(Be, (T + w_every - 1) // w_every, H, device=dev, dtype=torch.float32) if w_every
+                  else torch.empty_like(S)) if adaptive else None
             if norm.bidir and not (recurrent and pr.path == "persist" and pr.fwd_tc and norm.lazy_spikes):
                 raise RuntimeError("the copy-free bidirectional path needs the tcgen05 forward recurrence with the "
                                    "packed-plane hand-over (the layer module checks this before choosing it)")
@@ -533,7 +540,7 @@ class SpikingCellFunction(torch.autograd.Function):
                         call("sparch_recur_fwd_tc_bidir", k, ptr(Z), ptr(scale), ptr(shift), ptr(al), ptr(be), ptr(aa),
                              ptr(bb), ptr(rec0), ptr(img_i8), ptr(u0), ptr(w0), ptr(s0), float(theta),
                              None if lazy else ptr(S), ptr(U), ptr(Wt), ptr(bits), int(_PRECISION == "bf16"), Be, T, H,
-                             int(norm.bidir), st)
+                             int(norm.bidir), w_every, st)
                     if lazy:
                         norm.bits = bits
                 else:
@@ -597,9 +604,9 @@ class SpikingCellFunction(torch.autograd.Function):
             gmax = norm.gmax
             if gmax is not None and getattr(norm, "gmax_of", None) != (G.data_ptr(), G._version):
                 gmax = None
-            call("sparch_recur_bwd_tc", k, ptr(G), ptr(U), ptr(Wt), ptr(al), ptr(be), ptr(aa), ptr(bb),
+            call("sparch_recur_bwd_tc_ck", k, ptr(G), ptr(U), ptr(Wt), ptr(al), ptr(be), ptr(aa), ptr(bb),
                  ptr(img_b), ptr(meta), ptr(u0), ptr(w0), ptr(s0), theta, ptr(dI), pp[0], pp[1], pp[2],
-                 pp[3], ptr(ws), ctx.reduced, Be, T, H, ptr(gmax), st)
+                 pp[3], ptr(ws), ctx.reduced, Be, T, H, ptr(gmax), ctx.w_every, st)
         else:
             img_b, meta = ctx.rec
             call("sparch_recur_bwd", k, ptr(G), ptr(U), ptr(Wt), ptr(al), ptr(be), ptr(aa), ptr(bb),

@@ -331,6 +331,31 @@ def test_eval_mode_and_dropout_train_mode():
     assert torch.equal(o1, o2)
 
 
+def _full_w_tape(W_gpu, U_gpu, s_gpu, u0, w0, s0, cp):
+    """The adaptation tape a reverse pass reads.  When both tcgen05 recurrence kernels serve the layer the forward keeps w
+    only at the end of every chunk of ``F.W_TAPE_EVERY`` steps (and at T-1): the steps in between follow from the
+    membrane tape and the spikes by snns.py:718 in the kernel's own operation order -- which also checks the stored
+    entries bit for bit."""
+    from sparch_b200 import functional as F
+    Be, T, H = U_gpu.shape
+    if W_gpu.shape[1] == T:
+        return W_gpu
+    C = F.W_TAPE_EVERY
+    assert W_gpu.shape[1] == (T + C - 1) // C
+    beta, a, b = (np.asarray(cp[k], dtype=np.float32) for k in ("beta", "a", "b"))
+    full = np.empty_like(U_gpu)
+    w = w0.astype(np.float32)
+    for t in range(T):
+        up = u0 if t == 0 else U_gpu[:, t - 1]
+        sp = s0 if t == 0 else s_gpu[:, t - 1]
+        w = ((beta * w).astype(np.float32) + (a * up).astype(np.float32)).astype(np.float32) + (b * sp).astype(np.float32)
+        w = w.astype(np.float32)
+        full[:, t] = w
+        if t % C == C - 1 or t == T - 1:
+            assert np.array_equal(W_gpu[:, t // C], w), ("checkpoint tape", t)
+    return full
+
+
 def _oracle_cell_check(kind, Be, T, H, seed, drive=(3.0, 1.2), stable=True):
     """Free-running CUDA cell vs the numpy oracle on random inputs: spikes (flip fraction), then the
     given-mask backward when the spike trains agree exactly."""
@@ -367,7 +392,7 @@ def _oracle_cell_check(kind, Be, T, H, seed, drive=(3.0, 1.2), stable=True):
     # kernel when the oracle used its own tape).  The tapes themselves are compared with the oracle's first.
     sv = S.grad_fn.saved_tensors          # (..., S, U, W, ...) as saved by SpikingCellFunction.forward
     U_gpu = sv[12].cpu().numpy()
-    W_gpu = sv[13].cpu().numpy() if adaptive else None
+    W_gpu = _full_w_tape(sv[13].cpu().numpy(), U_gpu, s_gpu, u0, w0, s0, p) if adaptive else None
     if flips == 0:
         assert rel_err(U_gpu, r["u"]) < U_RTOL
         if adaptive:
@@ -961,7 +986,7 @@ def test_dropout_gradients_at_value_level(kind, Be, T, H, p):
     assert float((S.detach().cpu() != torch.from_numpy(r["s"])).float().mean()) <= (FLIP_TOL if recurrent else 0.0)
     sv = S.grad_fn.saved_tensors          # the CUDA forward's own tapes (see _oracle_cell_check)
     s_gpu, U_gpu = S.detach().cpu().numpy(), sv[12].cpu().numpy()
-    W_gpu = sv[13].cpu().numpy() if adaptive else None
+    W_gpu = _full_w_tape(sv[13].cpu().numpy(), U_gpu, s_gpu, u0, w0, s0, cp) if adaptive else None
     torch.manual_seed(99)
     out, post = F.spike_post(S, p, norm, recurrent)
     torch.manual_seed(99)                                   # same seed word -> same mask

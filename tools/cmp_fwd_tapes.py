@@ -7,6 +7,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sparch_b200 import functional as F  # noqa: E402
 
+F.W_TAPE_EVERY = 0   # both forward kernels write the full adaptation tape here (the checkpoint tape is tcgen05-only)
+
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 Be = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 H = int(sys.argv[3]) if len(sys.argv) > 3 else 512
