@@ -785,7 +785,7 @@ int sparch_recur_bwd_tc_ck(int kind, const float* G, const float* U, const float
   SPARCH_REQUIRE(!adapt || (W && beta && a && b && w0 && p_beta && p_a && p_b),
                  "adaptive kind needs W, beta, a, b, w0 and the partial buffers");
   const int Hp = sparch_recur_tc_padded(H), KB = Hp / (64 * TC_CL);
-  const size_t smem = rec_bwd_tc_smem(KB, adapt && w_every > 0) + (getenv("SPARCH_TC_PAD_SMEM") ? atoi(getenv("SPARCH_TC_PAD_SMEM")) : 0);
+  const size_t smem = rec_bwd_tc_smem(KB, adapt && w_every > 0);
   SPARCH_REQUIRE(KB <= 4 && smem <= 128 * 1024, "hidden size too large for the resident V0 tiles");
   SPARCH_REQUIRE((long long)Be * T * H < (1LL << 31), "tape larger than 2^31 elements: split the batch");
   cudaStream_t st = as_stream(st_);
