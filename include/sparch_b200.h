@@ -409,6 +409,15 @@ SPARCH_API int sparch_ce_bwd(const float* logits, const int64_t* target, const f
                              int C, float* dlogits, sparch_stream_t st);
 
 /* ---- on-device data path of the spiking datasets (sparch/dataloaders/spiking_datasets.py:66-78) ------------- */
+/* ---- initial states (snns.py:286-287, 423-425, 558-559, 700-702, 812) ---------------------------------------------
+ * The reference draws them with torch.rand on the default CPU generator: MT19937, one 32-bit word per float32,
+ * u = (word & (2^24 - 1)) * 2^-24, in element order.  This produces the same n numbers on the device from the generator's
+ * 624-word state (state_in, DEVICE pointer) and position pos (0..624: words of the current block already used), and
+ * writes the state afterwards to state_out[0..623] and the new position to state_out[624]; the caller puts them back
+ * into the generator (torch.set_rng_state), which is then exactly where n host draws would have left it.      */
+SPARCH_API int sparch_mt19937_uniform(const uint32_t* state_in, int pos, int64_t n, float* out, uint32_t* state_out,
+                                      sparch_stream_t st);
+
 /* A batch of B event lists, concatenated: times[e] (seconds, fp32), units[e] (int32), offsets[b] .. offsets[b+1] the
  * events of example b (offsets[B] = nev).  dense (B, nb_steps, nb_units) fp32 is zeroed and receives, per example, the
  * reference's x.to_dense(): the NUMBER of events of unit u whose time falls into bin np.digitize(t, bins) (bins:

@@ -75,6 +75,7 @@ _PROTOS = {
     "sparch_ce_fwd": "ppiippp",
     "sparch_ce_bwd": "ppppiipp",
     "sparch_events_to_dense": "ppppiiilppp",
+    "sparch_mt19937_uniform": "pilppp",
 }
 _CT = {"p": _P, "i": _I, "l": _L, "f": _F}
 

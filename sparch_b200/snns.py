@@ -17,6 +17,7 @@ import torch.nn as nn
 from .functional import (LayerNormFunction, LinearFunction, NormState, ReadoutCellFunction, SpikeFunctionBoxcar,
                          SpikingCellFunction, spike_post)
 from . import functional as _F
+from . import rng as _rng
 
 # SPARCH_B200_LAZY_SPIKES=0: the forward recurrence writes the fp32 spike tensor even where the post pass could read the
 # packed planes (comparison / debugging).
@@ -55,9 +56,18 @@ def _side_stream(device):
     return _SIDE_STREAMS[idx]
 
 
+# SPARCH_B200_DEVICE_MT=0: the "cpu" mode draws on the host (torch.rand) instead of replaying the CPU generator's MT19937
+# stream on the device (sparch_b200/rng.py: same numbers, generator left in the same state).
+_DEVICE_MT = os.environ.get("SPARCH_B200_DEVICE_MT", "1") != "0"
+
+
 def _rand_state(rows, cols, device):
     if _STATE_INIT == "device":
         return torch.rand(rows, cols, device=device)
+    if _DEVICE_MT:
+        r = _rng.cpu_generator_rand(rows * cols, device)
+        if r is not None:
+            return r.view(rows, cols)
     return torch.rand(rows, cols).to(device)
 
 
@@ -310,7 +320,9 @@ class ReadoutLayer(nn.Module):
         return self._readout_cell(Wx, gamma, bn_beta, norm)
 
     def _readout_cell(self, Wx, gamma=None, bn_beta=None, norm=None):
-        ut = _rand_state(Wx.shape[0], Wx.shape[2], Wx.device)    # snns.py:812
+        ut = _PENDING_PREP.pop(id(self), None)                   # drawn ahead by SNN.forward, in the reference's order
+        if ut is None or ut.shape != (Wx.shape[0], Wx.shape[2]):
+            ut = _rand_state(Wx.shape[0], Wx.shape[2], Wx.device)    # snns.py:812
         return ReadoutCellFunction.apply(Wx, gamma, bn_beta, self.alpha, ut,
                                          norm if norm is not None else NormState("none"))
 
@@ -391,14 +403,30 @@ class SNN(nn.Module):
             return None
         dev = x.device
         with torch.cuda.device(dev):
+            Be = x.shape[0] * (2 if self.bidirectional else 1)
+            host_draws = None
+            if _STATE_INIT == "cpu" and _DEVICE_MT:
+                # the reference's CPU-generator draws of ALL layers (ut, [wt,] st per spiking layer, then the readout's ut:
+                # the order in which the layers run) as one replay of the generator's stream on the device
+                sizes = [(3 if lay._adaptive else 2) * Be * lay.hidden_size for lay in layers]
+                ro = self.snn[-1] if isinstance(self.snn[-1], ReadoutLayer) else None
+                if ro is not None:
+                    sizes.append(x.shape[0] * ro.hidden_size)
+                flat = _rng.cpu_generator_rand(sum(sizes), dev)
+                if flat is not None:
+                    host_draws = list(torch.split(flat, sizes))
+                    if ro is not None:
+                        _PENDING_PREP[id(ro)] = host_draws.pop().view(x.shape[0], ro.hidden_size)
             main, side = torch.cuda.current_stream(), _side_stream(dev)
             side.wait_stream(main)
-            Be = x.shape[0] * (2 if self.bidirectional else 1)
             with torch.cuda.stream(side), torch.no_grad():
-                for lay in layers:
+                for li, lay in enumerate(layers):
                     H = lay.hidden_size
                     states = None
-                    if _STATE_INIT == "device":
+                    if host_draws is not None:
+                        r = host_draws[li].view(-1, Be, H)
+                        states = (r[0], (r[1] if lay._adaptive else None), r[-1])
+                    elif _STATE_INIT == "device":
                         r = torch.rand(3 if lay._adaptive else 2, Be, H, device=dev)
                         states = (r[0], (r[1] if lay._adaptive else None), r[-1])
                     pr = _F.prepare_cell(_F.KINDS[lay._kind], lay.alpha, getattr(lay, "beta", None),

@@ -1384,3 +1384,53 @@ def test_copy_free_bidirectional_equals_flip_cat(kind, norm, p, bias, precision)
         ref = gb[k.replace("W.bias", "W.weight")].abs().max() if k.endswith("W.bias") else gb[k].abs().max()
         err = float((ga[k] - gb[k]).abs().max() / ref.clamp_min(1e-30))
         assert err < tol, (k, err)
+
+
+@pytest.mark.parametrize("seed,pre,n,post", [(0, 0, 1, 5), (42, 0, 256 * 1024, 700), (7, 100, 623, 3), (7, 524, 100, 1300),
+                                             (3, 17, 3 * 256 * 1024 + 35, 40), (11, 624, 624, 624), (5, 1, 2000, 0)])
+def test_device_mt19937_equals_torch_rand(seed, pre, n, post):
+    """sparch_b200.rng.cpu_generator_rand: the reference's initial-state draws (torch.rand on the default CPU generator,
+    snns.py:700-702) replayed on the device -- the same float32 values bit for bit, from any position of the
+    generator's stream, and the generator left exactly where n host draws would have left it (what the host draws
+    next is the same, the state blobs are equal)."""
+    from sparch_b200 import rng
+    torch.manual_seed(seed)
+    torch.rand(pre)
+    want = torch.rand(n)
+    want_next = torch.rand(post)
+    want_state = torch.get_rng_state().clone()
+    torch.manual_seed(seed)
+    torch.rand(pre)
+    got = rng.cpu_generator_rand(n, torch.device(DEV))
+    assert got is not None and got.shape == (n,)
+    got_next = torch.rand(post)
+    assert torch.equal(got.cpu(), want)
+    assert torch.equal(got_next, want_next)
+    assert torch.equal(torch.get_rng_state(), want_state)
+
+
+def test_default_state_mode_draws_equal_host_draws():
+    """The drop-in's default ("cpu") state mode with the device replay of the generator against the same mode drawing on
+    the host: identical outputs, gradients and final generator state for a whole model (so every fixture written by the
+    reference, which the default mode reproduces, is reproduced by the device draws too)."""
+    import sparch_b200.snns as snns_mod
+    sp, _ = _mods()
+    res = []
+    for dev_mt in (True, False):
+        snns_mod._DEVICE_MT = dev_mt
+        try:
+            torch.manual_seed(0)
+            net = sp.SNN((16, None, 40), layer_sizes=[96, 64, 10], neuron_type="RadLIF", normalization="batchnorm",
+                         dropout=0.1).to(DEV)
+            x = torch.randn(16, 30, 40, generator=torch.Generator().manual_seed(1)).to(DEV)
+            torch.manual_seed(21)
+            out, rates = net(x)
+            (out.square().sum() + rates.sum()).backward()
+            res.append((out.detach().clone(), rates.detach().clone(), [q.grad.clone() for q in net.parameters()],
+                        torch.get_rng_state().clone()))
+        finally:
+            snns_mod._DEVICE_MT = True
+    (oa, ra, ga, sa), (ob, rb, gb, sb) = res
+    assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(sa, sb)
+    for a, b in zip(ga, gb):
+        assert torch.equal(a, b)
