@@ -156,11 +156,13 @@ class LinearFunction(torch.autograd.Function):
 
     @staticmethod
     @_on_device
-    def forward(ctx, x, weight, bias, in_scale, norm=None, x_terms=None):
+    def forward(ctx, x, weight, bias, in_scale, norm=None, x_terms=None, w_terms=None):
         """norm: the layer's NormState; in 'bn_train' mode the GEMM epilogue can also accumulate the
         BatchNorm column statistics of the output and leave them in ``norm.stats``.
         x_terms: the one-term {0,1} image of x (x = in_scale * x_terms) when the producing layer's
-        post pass already wrote it (SpikePost): no split pass over x."""
+        post pass already wrote it (SpikePost): no split pass over x.
+        w_terms: (gemm.Terms of ``weight`` in the current mode, event or None) when SNN.forward split the weights
+        ahead on its side stream (parameter-only work)."""
         _require_cuda(x, weight)
         K = x.shape[-1]
         N = weight.shape[0]
@@ -174,7 +176,12 @@ class LinearFunction(torch.autograd.Function):
                     xa, alpha = gemm.split_general(x2d), 1.0
                 else:
                     xa, alpha = gemm.split_binary(x2d, prescale=1.0 / in_scale), float(in_scale)
-                wb = gemm.split_general(_f32c(weight))
+                if w_terms is not None and w_terms[2] == (gemm.MODE, weight.data_ptr(), weight._version):
+                    wb = w_terms[0]
+                    if w_terms[1] is not None:
+                        torch.cuda.current_stream().wait_event(w_terms[1])
+                else:
+                    wb = gemm.split_general(_f32c(weight))
                 # BatchNorm statistics ride in the GEMM epilogue when the tile's main loop is long enough
                 # to dwarf it (measured: for the K=40 input layer the epilogue IS the kernel and a
                 # separate column-statistics pass over the L2-warm output is cheaper).
@@ -224,7 +231,7 @@ class LinearFunction(torch.autograd.Function):
                     dw = gemm.gemm_parts(ga, xa, M, alpha=ctx.alpha, a_mn=True, b_mn=True, M=N, N=K)
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 db = g2d.sum(dim=0)
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
 class NormState:

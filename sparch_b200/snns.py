@@ -176,7 +176,8 @@ class _SpikingLayerBase(nn.Module):
         if self.batch_size != x.shape[0]:                        # snns.py:671-672
             self.batch_size = x.shape[0]
         gamma, bn_beta, norm = _norm_args(self)
-        Wx = LinearFunction.apply(x, self.W.weight, self.W.bias, in_scale, norm, x_terms)   # snns.py:675
+        Wx = LinearFunction.apply(x, self.W.weight, self.W.bias, in_scale, norm, x_terms,
+                                  _PENDING_PREP.pop((id(self), "W"), None))                  # snns.py:675
         if norm is None:                                         # layernorm, snns.py:678-680
             if isinstance(self.norm, nn.LayerNorm) and Wx.shape[-1] <= 2048:
                 Wx = LayerNormFunction.apply(Wx, self.norm.weight, self.norm.bias, self.norm.eps)
@@ -212,7 +213,8 @@ class _SpikingLayerBase(nn.Module):
         if self.batch_size != 2 * B:                             # snns.py:671-672 (the reference sees the doubled batch)
             self.batch_size = 2 * B
         gamma, bn_beta, norm = _norm_args(self)
-        Wx = LinearFunction.apply(x, self.W.weight, self.W.bias, in_scale, norm, x_terms)   # snns.py:675, once
+        Wx = LinearFunction.apply(x, self.W.weight, self.W.bias, in_scale, norm, x_terms,
+                                  _PENDING_PREP.pop((id(self), "W"), None))                  # snns.py:675, once
         norm.bidir = B
         norm.lazy_spikes = True
         p = self.drop.p if self.drop.training else 0.0
@@ -310,7 +312,8 @@ class ReadoutLayer(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("sparch_b200 layers run on CUDA only (no CPU fallback)")
         gamma, bn_beta, norm = _norm_args(self)
-        Wx = LinearFunction.apply(x, self.W.weight, self.W.bias, in_scale, norm, x_terms)   # snns.py:796
+        Wx = LinearFunction.apply(x, self.W.weight, self.W.bias, in_scale, norm, x_terms,
+                                  _PENDING_PREP.pop((id(self), "W"), None))                  # snns.py:796
         if norm is None:
             if isinstance(self.norm, nn.LayerNorm) and Wx.shape[-1] <= 2048:
                 Wx = LayerNormFunction.apply(Wx, self.norm.weight, self.norm.bias, self.norm.eps)
@@ -388,6 +391,7 @@ class SNN(nn.Module):
             if ahead is not None:
                 for lay in self.snn:
                     _PENDING_PREP.pop(id(lay), None)
+                    _PENDING_PREP.pop((id(lay), "W"), None)
                 torch.cuda.current_stream(x.device).wait_stream(ahead)   # (every layer has already waited for its share)
 
     def _prepare_ahead(self, x):
@@ -420,7 +424,15 @@ class SNN(nn.Module):
             main, side = torch.cuda.current_stream(), _side_stream(dev)
             side.wait_stream(main)
             with torch.cuda.stream(side), torch.no_grad():
+                def split_weight(lay):     # the 16-bit operand terms of W (max|W| + split: two launches per layer)
+                    w = lay.W.weight
+                    if w.is_cuda and w.dtype == torch.float32 and w.is_contiguous():
+                        ev = torch.cuda.Event()
+                        terms = _F.gemm.split_general(w.detach())
+                        ev.record(side)
+                        _PENDING_PREP[(id(lay), "W")] = (terms, ev, (_F.gemm.MODE, w.data_ptr(), w._version))
                 for li, lay in enumerate(layers):
+                    split_weight(lay)
                     H = lay.hidden_size
                     states = None
                     if host_draws is not None:
@@ -435,6 +447,8 @@ class SNN(nn.Module):
                     pr.event = torch.cuda.Event()
                     pr.event.record(side)
                     _PENDING_PREP[id(lay)] = pr
+                if isinstance(self.snn[-1], ReadoutLayer):
+                    split_weight(self.snn[-1])
         return side
 
     def _forward_layers(self, x):
