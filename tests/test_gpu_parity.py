@@ -1328,6 +1328,17 @@ def test_packed_plane_hand_over_equals_fp32_spike_tensor(kind, H, p, B, T):
     ("RadLIF", "batchnorm", 0.25, True, "fp32"), ("RadLIF", "none", 0.0, False, "fp32"),
     ("RadLIF", "batchnorm", 0.1, False, "bf16")])
 def test_copy_free_bidirectional_equals_flip_cat(kind, norm, p, bias, precision):
+    _bidir_fused_vs_flip_cat(kind, norm, p, bias, precision, 128, 20, 256)
+
+
+@pytest.mark.parametrize("B,T,H", [(128, 1, 64), (128, 17, 264), (256, 33, 40), (128, 16, 1024), (384, 5, 96)])
+def test_copy_free_bidirectional_edge_shapes(B, T, H):
+    """The same comparison at the edges: a single timestep, T around the adaptation checkpoint distance (16), hidden
+    sizes that are multiples of 8 but not of the kernels' 16 / 32 / 256-wide slices, several 128-row groups per direction."""
+    _bidir_fused_vs_flip_cat("RadLIF", "batchnorm", 0.1, False, "fp32", B, T, H)
+
+
+def _bidir_fused_vs_flip_cat(kind, norm, p, bias, precision, B, T, H):
     """a bidirectional layer WITHOUT the reference's flipped / concatenated copies (snns.py:666-668,
     686-689) -- one projection of the un-flipped batch, the second half of the recurrence reading it time-reversed, the
     merge written by the post pass from the packed planes, the BatchNorm backward summing a row's two uses -- against
@@ -1337,7 +1348,6 @@ def test_copy_free_bidirectional_equals_flip_cat(kind, norm, p, bias, precision)
     import sparch_b200
     import sparch_b200.snns as snns_mod
     sp, _ = _mods()
-    B, T, H = 128, 20, 256
     res = []
     sparch_b200.set_precision(precision)
     try:
@@ -1372,7 +1382,7 @@ def test_copy_free_bidirectional_equals_flip_cat(kind, norm, p, bias, precision)
         snns_mod._BIDIR_FUSED = True
         sparch_b200.set_precision("fp32")
     (oa, ra, ga, sa, ea, rea), (ob, rb, gb, sb, eb, reb) = res
-    assert ra.shape == (4 * H,) and 0.005 < float(ra.mean()) < 0.9
+    assert ra.shape == (4 * H,) and 0.003 < float(ra.mean()) < 0.9
     assert torch.equal(ra, rb) and torch.equal(oa, ob)
     assert torch.equal(rea, reb) and torch.equal(ea, eb)
     for k in sa:
