@@ -1444,3 +1444,37 @@ def test_default_state_mode_draws_equal_host_draws():
     assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(sa, sb)
     for a, b in zip(ga, gb):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("kind,bidir", [("RadLIF", False), ("adLIF", False), ("RLIF", True)])
+def test_side_stream_preparation_equals_inline_order(kind, bidir):
+    """SNN.forward issues the parameter-only launches of all layers (clamps, images of V0, weight operand terms, the
+    state draws with rec_0) on a side stream at the start of the step; with SPARCH_B200_PREP_AHEAD=0 every layer issues
+    them itself, in line.  Same kernels on the same data either way: outputs, rates, gradients and the CPU generator's
+    final state are bit-identical (default state mode; two steps, so that the second step's preparation overlaps the
+    first step's tail)."""
+    import sparch_b200.snns as snns_mod
+    sp, _ = _mods()
+    res = []
+    for ahead in (True, False):
+        snns_mod._PREP_AHEAD = ahead
+        try:
+            torch.manual_seed(0)
+            net = sp.SNN((32, None, 40), layer_sizes=[128, 96, 10], neuron_type=kind, normalization="batchnorm",
+                         dropout=0.1, bidirectional=bidir).to(DEV)
+            opt = torch.optim.SGD(net.parameters(), lr=0.05)
+            x = torch.randn(32, 25, 40, generator=torch.Generator().manual_seed(1)).to(DEV)
+            torch.manual_seed(21)
+            for _ in range(2):
+                opt.zero_grad(set_to_none=True)
+                out, rates = net(x)
+                (out.square().sum() + rates.sum()).backward()
+                opt.step()
+            res.append((out.detach().clone(), rates.detach().clone(), [q.grad.clone() for q in net.parameters()],
+                        torch.get_rng_state().clone()))
+        finally:
+            snns_mod._PREP_AHEAD = True
+    (oa, ra, ga, sa), (ob, rb, gb, sb) = res
+    assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(sa, sb)
+    for a, b in zip(ga, gb):
+        assert torch.equal(a, b)
