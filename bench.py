@@ -129,6 +129,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_config(cfg, args, world):
+    """The `config` object of a bench line: the workload, identical for both arms (--impl ours / reference)."""
+    return {"workload": cfg["desc"], "bench_config": args.config, "per_gpu_batch": cfg["B"],
+            "global_batch": cfg["B"] * world, "parallelism": f"dp{world}",
+            "l2": "per-step working set (>=1 GB of activations/tapes at the headline configuration) exceeds the 126 MB L2"}
+
+
 # --------------------------------------------------------------------------- reference arm (CPU)
 def cpu_reference_steps(cfg, B, steps, warmup):
     """Oracle restatement of the reference train step on the host cores; returns samples/s."""
@@ -166,8 +173,7 @@ def run_reference(args, cfg, rank, world):
         "impl": "reference", "metric": "train samples/sec", "value": sps, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": cfg["desc"], "bench_config": args.config,
-                                        "per_step_batch": Bs},
+        "data": "synthetic", "config": workload_config(cfg, args, world),   # (the bounded sample: cpu_baseline.sample)
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -473,12 +479,11 @@ def run_ours(args, cfg, rank, local_rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.precision == "fp32" else "bf16 products, f32 state/accumulation",
         "data": "synthetic",
-        "config": {"workload": cfg["desc"], "bench_config": args.config, "per_gpu_batch": B,
-                   "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": bool(use_graph),
-                   "state_init": args.state_init + (" generator draws of u0/w0/s0 ~ U[0,1) (same distribution "
-                                                    "as the reference's CPU draws)" if args.state_init == "device"
-                                                    else " generator draws, identical to the reference's"),
-                   "l2": "per-step working set (>=1 GB of activations/tapes) exceeds the 126 MB L2"},
+        "config": workload_config(cfg, args, world),
+        "mode": {"cuda_graph": bool(use_graph),
+                 "state_init": args.state_init + (" generator draws of u0/w0/s0 ~ U[0,1) (same distribution "
+                                                  "as the reference's CPU draws)" if args.state_init == "device"
+                                                  else " generator draws, identical to the reference's")},
         "e2e": {"value": e2e_value, "unit": "samples/s",
                 "h2d_bytes_per_step": events["h2d"] if events else x_h.numel() * 4 + y_h.numel() * 8,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
