@@ -1478,3 +1478,56 @@ def test_side_stream_preparation_equals_inline_order(kind, bidir):
     assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(sa, sb)
     for a, b in zip(ga, gb):
         assert torch.equal(a, b)
+
+
+def test_copy_free_bidirectional_against_oracle():
+    """The copy-free bidirectional path (one projection, reversed TMA coordinates, merged output from the packed planes)
+    DIRECTLY against the oracle's torch restatement of snns.py:663-694 on the same device -- not only against this
+    library's own flip / cat formulation: bidirectional RadLIF [256, 256, 35] + BatchNorm, B = 128 (the smallest batch
+    the path takes: one 128-row group per direction), T = 60, a <- |a|.  Layer-0 merged spike trains (forward hook, so
+    the hidden output is materialised) within the flip tolerance, firing rates to 0.01, loss to 2 %, all gradients
+    finite and the projection's gradient within 5 % in relative L2 (free-running: a straddler reshuffles what follows)."""
+    sp, _ = _mods()
+    kw = dict(layer_sizes=[256, 256, 35], neuron_type="RadLIF", normalization="batchnorm", bidirectional=True)
+    torch.manual_seed(0)
+    net = sp.SNN((128, None, 40), **kw)
+    ref = orc.build_oracle_snn((128, None, 40), **kw)
+    ref.load_state_dict(net.state_dict())
+    for m in (net, ref):
+        with torch.no_grad():
+            for lay in m.snn:
+                if hasattr(lay, "a"):
+                    lay.a.abs_()
+                if isinstance(getattr(lay, "norm", None), torch.nn.BatchNorm1d):
+                    lay.norm.weight.fill_(3.0)
+                    lay.norm.bias.fill_(0.8)
+    net, ref = net.to(DEV), ref.to(DEV)
+    assert net.snn[0]._copy_free_bidir(torch.empty(128, 60, 40, device=DEV))
+    ref.snn[0].capture = {}
+    torch.manual_seed(1234)
+    x = torch.randn(128, 60, 40, device=DEV)
+    y = torch.randint(0, 35, (128,), device=DEV)
+    got = {}
+    h = net.snn[0].register_forward_hook(lambda m, i, o: got.__setitem__(0, o.detach()))
+    try:
+        torch.manual_seed(42)
+        out, rates = net(x)
+        loss = torch.nn.functional.cross_entropy(out, y)
+        loss.backward()
+    finally:
+        h.remove()
+    torch.manual_seed(42)
+    out_r, rates_r = ref(x)
+    loss_r = torch.nn.functional.cross_entropy(out_r, y)
+    loss_r.backward()
+    s_ref = ref.snn[0].capture["s"]                 # (2B, T, H) before the direction merge (snns.py:686-689)
+    merged = torch.cat([s_ref[:128], s_ref[128:].flip(1)], dim=2)
+    assert got[0].shape == (128, 60, 512) and 0.005 < float(merged.mean()) < 0.9
+    flips = float((got[0] != merged).float().mean())
+    assert flips <= FLIP_TOL, flips
+    lo, lr_ = float(loss.detach()), float(loss_r.detach())
+    assert abs(lo - lr_) <= 0.02 * abs(lr_), (lo, lr_)
+    assert float((rates - rates_r).abs().max()) < 0.01
+    assert all(q.grad is not None and torch.isfinite(q.grad).all() for q in net.parameters())
+    gw, gw_r = net.snn[0].W.weight.grad, ref.snn[0].W.weight.grad
+    assert float((gw - gw_r).norm() / gw_r.norm()) < 0.05
