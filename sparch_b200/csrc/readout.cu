@@ -1,6 +1,8 @@
 // ReadoutLayer cell (snns.py:807-825): non-spiking leaky integrator whose output is the sum over
 // time of softmax(u_t) across the class dimension, and its reverse pass.
 // One block per batch row; see the kernels for the decomposition.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sparch {
@@ -92,9 +94,13 @@ __global__ void __launch_bounds__(1024) readout_fwd_kernel(const float* __restri
       for (int c = lane; c < C; c += 32) m = fmaxf(m, row[c]);
       m = warp_max(m);
       float den = 0.f;
-      for (int c = lane; c < C; c += 32) den += expf(row[c] - m);
+      for (int c = lane; c < C; c += 32) {      // each lane revisits only its own entries: exp once, kept in place
+        const float e = expf(row[c] - m);
+        row[c] = e;
+        den += e;
+      }
       den = warp_sum(den);
-      for (int c = lane; c < C; c += 32) row[c] = expf(row[c] - m) / den;
+      for (int c = lane; c < C; c += 32) row[c] = row[c] / den;
     }
     __syncthreads();
     if (live)
@@ -133,12 +139,20 @@ __global__ void __launch_bounds__(1024) readout_bwd_kernel(const float* __restri
       for (int c = lane; c < C; c += 32) m = fmaxf(m, row[c]);
       m = warp_max(m);
       float den = 0.f;
-      for (int c = lane; c < C; c += 32) den += expf(row[c] - m);
+      for (int c = lane; c < C; c += 32) {      // exp once per entry, parked in the output row (own entries only)
+        const float e = expf(row[c] - m);
+        sx[t * C + c] = e;
+        den += e;
+      }
       den = warp_sum(den);
       float dot = 0.f;
-      for (int c = lane; c < C; c += 32) dot += expf(row[c] - m) / den * go[c];
+      for (int c = lane; c < C; c += 32) {
+        const float pr = sx[t * C + c] / den;
+        sx[t * C + c] = pr;
+        dot += pr * go[c];
+      }
       dot = warp_sum(dot);
-      for (int c = lane; c < C; c += 32) sx[t * C + c] = expf(row[c] - m) / den * (go[c] - dot);
+      for (int c = lane; c < C; c += 32) sx[t * C + c] = sx[t * C + c] * (go[c] - dot);
     }
     __syncthreads();
     if (live)
@@ -210,6 +224,14 @@ __global__ void ce_bwd_kernel(const float* __restrict__ X, const long long* __re
 
 using namespace sparch;
 
+// The chain phase uses one thread per class, the softmax phase one WARP per timestep of the chunk: with few classes the
+// block is sized for the softmax phase (16 warps share a chunk's ~100 timesteps instead of 4).
+static int readout_min_threads(int B) {
+  static const char* e = getenv("SPARCH_B200_READOUT_THREADS");
+  if (e) return atoi(e);
+  return B <= sm_count() ? 1024 : 512;      // one block per batch row: few rows = few blocks, make each one wide
+}
+
 extern "C" {
 
 int sparch_readout_fwd(const float* Z, const float* scale, const float* shift, const float* alpha,
@@ -219,7 +241,7 @@ int sparch_readout_fwd(const float* Z, const float* scale, const float* shift, c
   if (B == 0) return SPARCH_OK;
   SPARCH_REQUIRE(alpha && u0 && out && (T == 0 || (Z && U)), "null pointer");
   int threads = ((C + 31) / 32) * 32;
-  if (threads < 128) threads = 128;
+  if (threads < readout_min_threads(B)) threads = readout_min_threads(B);
   const int tch = readout_chunk(T, C, 1);
   readout_fwd_kernel<<<B, threads, (size_t)tch * C * sizeof(float), as_stream(st)>>>(Z, scale, shift, alpha, u0, out, U,
                                                                                       T, C, tch);
@@ -233,7 +255,7 @@ int sparch_readout_bwd(const float* gout, const float* U, const float* alpha, co
   if (B == 0) return SPARCH_OK;
   SPARCH_REQUIRE(gout && alpha && u0 && p_alpha && (T == 0 || (U && dI)), "null pointer");
   int threads = ((C + 31) / 32) * 32;
-  if (threads < 128) threads = 128;
+  if (threads < readout_min_threads(B)) threads = readout_min_threads(B);
   const int tch = readout_chunk(T, C, 2);
   readout_bwd_kernel<<<B, threads, (size_t)(2 * tch + 1) * C * sizeof(float) + 32, as_stream(st)>>>(gout, U, alpha, u0, dI,
                                                                                                 p_alpha, T, C, tch);
