@@ -83,7 +83,8 @@ SPARCH_API int sparch_bn_bwd_apply(float* dI, const float* Z, const float* mean,
  * weight- and data-gradient GEMMs read, without the fp32 tensor in between (dZ32 may be NULL; it may
  * alias dI).  amax_dI: max|dI| bits from sparch_col_dot; bound (out): bit pattern of the upper bound of
  * max|dZ| that fixed the terms' scale -- pass it to sparch_gemm_terms as the operand's amax word;
- * coef: scratch of 2*H floats (the per-column constants sum1/M, sum2/M converted once).            */
+ * coef: 4*H floats: the per-column constants sum1/M, sum2/M converted once (scratch), then sum1 and sum2 as fp32
+ * (= the gradients of the BatchNorm bias and weight, autograd of snns.py:679).                                      */
 SPARCH_API int sparch_bn_bwd_apply_f16(const float* dI, const float* Z, const float* mean, const float* rstd,
                         const float* scale, const double* sum1, const double* sum2, int64_t M, int H,
                         const uint32_t* amax_dI, uint32_t* bound, float* coef, void* P0, void* P1,

@@ -346,6 +346,8 @@ bn_bwd_bound_kernel(const float* __restrict__ scale, const double* __restrict__ 
     const float c1 = (float)(s1[h] * invM), c2 = (float)(s2[h] * invM);
     coef[h] = c1;          // the per-column constants of the apply pass, converted once
     coef[H + h] = c2;
+    coef[2 * H + h] = (float)s1[h];   // = d(beta) and d(gamma) of the BatchNorm affine as fp32 (no conversion launches)
+    coef[3 * H + h] = (float)s2[h];
     ms = fmaxf(ms, fabsf(scale[h]));
     m1 = fmaxf(m1, fabsf(c1));
     m2 = fmaxf(m2, fabsf(c2));

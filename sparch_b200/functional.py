@@ -327,8 +327,9 @@ def _norm_backward_apply(dI2d, Z2d, gamma, bn_beta, norm, scale, mean, rstd, sum
     if norm.mode == "none":
         return None, None
     M, H = dI2d.shape
-    dgamma = sums[1].float() if gamma is not None else None
-    dbeta = sums[0].float() if bn_beta is not None else None
+    f16_terms = norm.mode == "bn_train" and gemm.MODE == "f16x2"     # that path leaves the two sums as fp32 itself
+    dgamma = sums[1].float() if (gamma is not None and not f16_terms) else None
+    dbeta = sums[0].float() if (bn_beta is not None and not f16_terms) else None
     if norm.bidir:
         # dZ (B*T rows) = the sum of a row's two uses; lands in the first half of dI (and / or as operand terms)
         M = Z2d.shape[0]
@@ -337,11 +338,12 @@ def _norm_backward_apply(dI2d, Z2d, gamma, bn_beta, norm, scale, mean, rstd, sum
             ld = (H + 7) // 8 * 8
             parts = torch.empty(2, M, ld, device=dI2d.device, dtype=torch.float16)
             bound = torch.empty(1, device=dI2d.device, dtype=torch.int32)
-            coef = torch.empty(2, H, device=dI2d.device, dtype=torch.float32)
+            coef = torch.empty(4, H, device=dI2d.device, dtype=torch.float32)
             call("sparch_bn_bwd_apply_f16_bidir", ptr(dI2d), ptr(Z2d), ptr(mean), ptr(rstd), ptr(scale), ptr(sums[0]),
                  ptr(sums[1]), M, H, T, ptr(amax), ptr(bound), ptr(coef), ptr(parts[0]), ptr(parts[1]), ld,
                  ptr(dI2d) if norm.need_dz32 else None, _stream())
             norm.dz_terms = gemm.Terms(parts, bound)
+            dgamma, dbeta = (coef[3] if gamma is not None else None), (coef[2] if bn_beta is not None else None)
         elif norm.mode == "bn_train":
             call("sparch_bn_bwd_apply_bidir", ptr(dI2d), ptr(Z2d), ptr(mean), ptr(rstd), ptr(scale),
                  ptr(sums[0]), ptr(sums[1]), M, H, T, _stream())
@@ -353,11 +355,12 @@ def _norm_backward_apply(dI2d, Z2d, gamma, bn_beta, norm, scale, mean, rstd, sum
         ld = (H + 7) // 8 * 8
         parts = torch.empty(2, M, ld, device=dI2d.device, dtype=torch.float16)
         bound = torch.empty(1, device=dI2d.device, dtype=torch.int32)
-        coef = torch.empty(2, H, device=dI2d.device, dtype=torch.float32)
+        coef = torch.empty(4, H, device=dI2d.device, dtype=torch.float32)
         call("sparch_bn_bwd_apply_f16", ptr(dI2d), ptr(Z2d), ptr(mean), ptr(rstd), ptr(scale), ptr(sums[0]),
              ptr(sums[1]), M, H, ptr(amax), ptr(bound), ptr(coef), ptr(parts[0]), ptr(parts[1]), ld,
              ptr(dI2d) if norm.need_dz32 else None, _stream())
         norm.dz_terms = gemm.Terms(parts, bound)
+        dgamma, dbeta = (coef[3] if gamma is not None else None), (coef[2] if bn_beta is not None else None)
     elif norm.mode == "bn_train":
         call("sparch_bn_bwd_apply", ptr(dI2d), ptr(Z2d), ptr(mean), ptr(rstd), ptr(scale),
              ptr(sums[0]), ptr(sums[1]), M, H, None, _stream())
@@ -578,7 +581,10 @@ class SpikingCellFunction(torch.autograd.Function):
         G = _f32c(gS)
         dI = torch.empty_like(U)
         npart = 4 if adaptive else 1
-        part = torch.zeros(npart, Be, H, device=dev, dtype=torch.float32)
+        # (the streaming and the tcgen05 kernels write every entry; the stepwise path accumulates, the mma.sync kernel is
+        # left with a cleared buffer as before)
+        overwrite = (not recurrent) or (ctx.rec is not None and ctx.tc)
+        part = (torch.empty if overwrite else torch.zeros)(npart, Be, H, device=dev, dtype=torch.float32)
         pp = [ptr(part[i]) if i < npart else None for i in range(4)]
         ws = sync = None
         if recurrent and ctx.rec is not None:
@@ -679,7 +685,7 @@ class FiringRateFunction(torch.autograd.Function):
     @_on_device
     def forward(ctx, out, counts, factor):
         ctx.shape = out.shape
-        return counts.to(torch.float32) * factor
+        return counts * factor        # int32 * Python float -> float32: one launch
 
     @staticmethod
     @_on_device
