@@ -394,6 +394,11 @@ RECUR_FWD_TC_MAX_H = 1536
 W_TAPE_EVERY = int(os.environ.get("SPARCH_B200_W_EVERY", "16"))
 
 
+# Callables run right after a reverse recurrence kernel has been issued (parallel.GradSync registers its ``flush``: the
+# data-parallel all-reduces start behind the kernel instead of underneath it).
+AFTER_BPTT = []
+
+
 class CellPrep:
     """What a spiking layer's forward needs that depends on its PARAMETERS (and the initial states) only: the clamped
     neuron parameters (snns.py:706-709), the images of V0 the recurrence kernels read (snns.py:712), rec_0 = s0 @ V0.
@@ -627,6 +632,8 @@ class SpikingCellFunction(torch.autograd.Function):
                  pp[3], ptr(ws), ptr(sync), ctx.reduced, Be, T, H, st)
         if recurrent:
             region.__exit__()
+            for cb in AFTER_BPTT:
+                cb()
         # BatchNorm backward reductions first: the same pass leaves max|dI| for the dV operand split
         sums, di_amax = _norm_backward_reduce(dI.view(Be * T, H), Z.view(-1, H), norm, mean, rstd)
         if recurrent:

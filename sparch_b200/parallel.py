@@ -13,6 +13,13 @@ the backward pass.  ``average=False`` leaves the SUM in ``.grad`` (no division p
 applies 1 / world (``sparch_b200.optim.Adam(grad_scale=1 / world)``).  BatchNorm uses local (per-rank)
 batch statistics -- plain data-parallel semantics.
 
+``defer`` (default: on when the module has recurrent spiking layers on CUDA): a bucket whose last gradient exists is
+not reduced at once but at the next SAFE POINT -- right after a reverse recurrence kernel has been issued, or in
+``finish()``.  The tcgen05 reverse recurrence needs its 32 four-CTA clusters resident at the same time (four per GPC,
+exactly what a B200 holds) and lives on L2 latency: with a collective's CTAs on a few SMs underneath it, it measured
+14 % slower (1.39 vs 1.22 ms per step at 2 GPUs), more than the collectives take.  Issued after the kernel, a bucket's
+all-reduce runs under the BatchNorm-backward passes and the gradient GEMMs that follow, which do not care.
+
 Works with any backend ("nccl" on GPUs; "gloo" in the CPU tests).
 """
 import torch
@@ -20,7 +27,7 @@ import torch.distributed as dist
 
 
 class GradSync:
-    def __init__(self, module, group=None, broadcast=True, average=True):
+    def __init__(self, module, group=None, broadcast=True, average=True, defer=None):
         if not dist.is_initialized():
             raise RuntimeError("GradSync needs an initialised torch.distributed process group")
         self.group = group
@@ -45,6 +52,17 @@ class GradSync:
                 for t in list(module.parameters()) + list(module.buffers()):
                     dist.broadcast(t, src=0, group=group)
         self._handles = []
+        self._ready = []
+        if defer is None:
+            defer = any(getattr(lay, "_recurrent", False) and any(p.is_cuda for p in lay.parameters()) for lay in layers)
+        self.defer = bool(defer)
+        # reverse recurrences still to come in this backward pass: once the last one has been issued nothing is left to
+        # protect, and buckets go out the moment they are complete again
+        self._n_bptt = sum(1 for lay in layers if getattr(lay, "_recurrent", False))
+        self._bptt_left = self._n_bptt
+        if self.defer:
+            from . import functional
+            functional.AFTER_BPTT.append(self._after_bptt)
 
     def _add_bucket(self, params):
         n = sum(p.numel() for p in params)
@@ -62,12 +80,26 @@ class GradSync:
             b["views"][i].copy_(p.grad)
             b["pending"] -= 1
             if b["pending"] == 0:
-                b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group,
-                                            async_op=True)
+                if self.defer and self._bptt_left > 0:
+                    self._ready.append(b)
+                else:
+                    b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group,
+                                                async_op=True)
         return hook
+
+    def _after_bptt(self):
+        self._bptt_left -= 1
+        self.flush()
+
+    def flush(self):
+        """Start the all-reduce of every complete bucket that has not been started (safe point, see ``defer``)."""
+        ready, self._ready = self._ready, []
+        for b in ready:
+            b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def finish(self):
         """Wait for the outstanding all-reduces, average, and point .grad at the reduced values."""
+        self.flush()
         for b in self.buckets:
             if b["pending"] != 0:
                 # a parameter received no gradient this step: reduce what there is
@@ -84,3 +116,4 @@ class GradSync:
                 p.grad = v
             b["pending"] = len(b["params"])
             b["work"] = None
+        self._bptt_left = self._n_bptt
