@@ -111,6 +111,8 @@ __global__ void col_reduce_kernel(const float* __restrict__ A, const float* __re
 // four rows in flight per thread.  A row's partial products are summed in fp32 over 4 rows before they enter the
 // fp64 accumulators (the fp64 pipe is narrow; 4-term fp32 sums of same-sign-agnostic values cost <1 ulp each).
 // amax (may be NULL): bit pattern of max|A|, for the fp16 split of A that follows (dV's dI operand).
+constexpr int CR_FLY = 8;   // rows in flight per thread (4 left the kernel latency-bound at 62 % of the DRAM throughput)
+
 template <bool DOT>
 __global__ void __launch_bounds__(256)
 col_reduce4_kernel(const float* __restrict__ A, const float* __restrict__ Zn, const float* __restrict__ mean,
@@ -131,10 +133,10 @@ col_reduce4_kernel(const float* __restrict__ A, const float* __restrict__ Zn, co
       mu = *reinterpret_cast<const float4*>(mean + h);
       rs = *reinterpret_cast<const float4*>(rstd + h);
     }
-    for (int64_t r = r0 + threadIdx.y; r < r1; r += 4 * CS_ROWS) {
-      float4 v[4], z[4];
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += CR_FLY * CS_ROWS) {
+      float4 v[CR_FLY], z[CR_FLY];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < CR_FLY; ++k) {
         const int64_t rr = r + k * CS_ROWS;
         v[k] = rr < r1 ? *reinterpret_cast<const float4*>(A + rr * H + h) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (DOT) {
@@ -148,7 +150,7 @@ col_reduce4_kernel(const float* __restrict__ A, const float* __restrict__ Zn, co
       }
       float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < CR_FLY; ++k) {
         const float vv[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
         const float zz[4] = {DOT ? (z[k].x - mu.x) * rs.x : v[k].x, DOT ? (z[k].y - mu.y) * rs.y : v[k].y,
                              DOT ? (z[k].z - mu.z) * rs.z : v[k].z, DOT ? (z[k].w - mu.w) * rs.w : v[k].w};
@@ -460,6 +462,88 @@ bn_bwd_apply_f16_kernel(const float* __restrict__ dI, const float* __restrict__ 
   }
 }
 
+// The same pass for the common layout (H % 8 == 0, 16-byte aligned rows, 256 % (H / 8) == 0): a thread KEEPS its 8 columns
+// and walks rows, so the five per-column constants are loaded once instead of with every item (10 of an item's 16 load
+// instructions in the generic kernel, which ncu showed latency-bound at 48 % of the DRAM throughput), and two rows are in
+// flight per thread.
+template <bool PAIR>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_f16_rows_kernel(const float* __restrict__ dI, const float* __restrict__ Z, const float* __restrict__ mean,
+                             const float* __restrict__ rstd, const float* __restrict__ scale,
+                             const float* __restrict__ coef, int64_t M, int H, const uint32_t* __restrict__ bound,
+                             __half* __restrict__ P0, __half* __restrict__ P1, float* __restrict__ dZ32, int T) {
+  const float sc2 = ldexpf(1.0f, f16_scale_exp(*bound));
+  const int segs = H / 8, ty = 256 / segs;
+  const int c = (threadIdx.x % segs) * 8, ry = threadIdx.x / segs;
+  float pm[8], pr[8], ps[8], p1[8], p2[8];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const float4 a = *reinterpret_cast<const float4*>(mean + c + 4 * q), b = *reinterpret_cast<const float4*>(rstd + c + 4 * q);
+    const float4 e = *reinterpret_cast<const float4*>(scale + c + 4 * q), f = *reinterpret_cast<const float4*>(coef + c + 4 * q);
+    const float4 g = *reinterpret_cast<const float4*>(coef + H + c + 4 * q);
+    pm[4 * q] = a.x; pm[4 * q + 1] = a.y; pm[4 * q + 2] = a.z; pm[4 * q + 3] = a.w;
+    pr[4 * q] = b.x; pr[4 * q + 1] = b.y; pr[4 * q + 2] = b.z; pr[4 * q + 3] = b.w;
+    ps[4 * q] = e.x; ps[4 * q + 1] = e.y; ps[4 * q + 2] = e.z; ps[4 * q + 3] = e.w;
+    p1[4 * q] = f.x; p1[4 * q + 1] = f.y; p1[4 * q + 2] = f.z; p1[4 * q + 3] = f.w;
+    p2[4 * q] = g.x; p2[4 * q + 1] = g.y; p2[4 * q + 2] = g.z; p2[4 * q + 3] = g.w;
+  }
+  const int64_t stride = (int64_t)gridDim.x * ty;
+  for (int64_t r0 = (int64_t)blockIdx.x * ty + ry; r0 < M; r0 += 2 * stride) {
+    float4 dv[2][2], zv[2][2], qv[2][2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r < M) {
+        const float* dp = dI + r * H + c;
+        const float* zp = Z + r * H + c;
+        dv[u][0] = *reinterpret_cast<const float4*>(dp); dv[u][1] = *reinterpret_cast<const float4*>(dp + 4);
+        zv[u][0] = *reinterpret_cast<const float4*>(zp); zv[u][1] = *reinterpret_cast<const float4*>(zp + 4);
+        if (PAIR) {
+          const int64_t b = r / T;
+          const float* qp = dI + (M + b * T + (T - 1 - (r - b * T))) * H + c;
+          qv[u][0] = *reinterpret_cast<const float4*>(qp); qv[u][1] = *reinterpret_cast<const float4*>(qp + 4);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r >= M) continue;
+      const float d[8] = {dv[u][0].x, dv[u][0].y, dv[u][0].z, dv[u][0].w, dv[u][1].x, dv[u][1].y, dv[u][1].z, dv[u][1].w};
+      const float z[8] = {zv[u][0].x, zv[u][0].y, zv[u][0].z, zv[u][0].w, zv[u][1].x, zv[u][1].y, zv[u][1].z, zv[u][1].w};
+      float d2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (PAIR) {
+        d2[0] = qv[u][0].x; d2[1] = qv[u][0].y; d2[2] = qv[u][0].z; d2[3] = qv[u][0].w;
+        d2[4] = qv[u][1].x; d2[5] = qv[u][1].y; d2[6] = qv[u][1].z; d2[7] = qv[u][1].w;
+      }
+      float x[8];
+      __align__(16) __half h0[8], h1[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {   // the generic kernel's expressions, operation for operation
+        const float xh = (z[j] - pm[j]) * pr[j];
+        x[j] = PAIR ? ps[j] * ((d[j] - p1[j] - xh * p2[j]) + (d2[j] - p1[j] - xh * p2[j])) : ps[j] * (d[j] - p1[j] - xh * p2[j]);
+        const float v = x[j] * sc2;
+        h0[j] = __float2half_rn(v);
+        h1[j] = __float2half_rn(v - __half2float(h0[j]));
+      }
+      *reinterpret_cast<uint4*>(P0 + r * H + c) = *reinterpret_cast<const uint4*>(h0);
+      *reinterpret_cast<uint4*>(P1 + r * H + c) = *reinterpret_cast<const uint4*>(h1);
+      if (dZ32) {
+        float* op = dZ32 + r * H + c;
+        *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
+        *reinterpret_cast<float4*>(op + 4) = make_float4(x[4], x[5], x[6], x[7]);
+      }
+    }
+  }
+}
+
+static bool bn_apply_rows_ok(const void* dI, const void* Z, const void* P0, const void* P1, const void* dZ32, int H,
+                             int64_t ldp) {
+  const uintptr_t al = reinterpret_cast<uintptr_t>(dI) | reinterpret_cast<uintptr_t>(Z) | reinterpret_cast<uintptr_t>(P0) |
+                       reinterpret_cast<uintptr_t>(P1) | reinterpret_cast<uintptr_t>(dZ32);
+  return (H % 8) == 0 && ldp == H && H / 8 <= 256 && 256 % (H / 8) == 0 && (al & 15) == 0;
+}
+
 static int ew_grid(int64_t n, int block) {
   int64_t g = (n + block - 1) / block;
   int64_t cap = (int64_t)sm_count() * 16;
@@ -660,8 +744,15 @@ int sparch_bn_bwd_apply_f16(const float* dI, const float* Z, const float* mean, 
   SPARCH_REQUIRE((ldp % 8) == 0 && ldp >= H, "ldp must be a multiple of 8 covering a row");
   bn_bwd_bound_kernel<<<1, 1024, 0, as_stream(st)>>>(scale, sum1, sum2, M, H, amax_dI, bound, coef);
   SPARCH_LAUNCH_OK();
-  bn_bwd_apply_f16_kernel<<<ew_grid(M * (ldp / 8), 256), 256, 0, as_stream(st)>>>(
-      dI, Z, mean, rstd, scale, coef, M, H, bound, (__half*)P0, (__half*)P1, ldp, dZ32);
+  if (bn_apply_rows_ok(dI, Z, P0, P1, dZ32, H, ldp)) {
+    const int ty = 256 / (H / 8);
+    int64_t nb = (M + 2 * ty - 1) / (2 * ty), cap = (int64_t)sm_count() * 8;
+    bn_bwd_apply_f16_rows_kernel<false><<<(unsigned)(nb < cap ? nb : cap), 256, 0, as_stream(st)>>>(
+        dI, Z, mean, rstd, scale, coef, M, H, bound, (__half*)P0, (__half*)P1, dZ32, 1);
+  } else {
+    bn_bwd_apply_f16_kernel<<<ew_grid(M * (ldp / 8), 256), 256, 0, as_stream(st)>>>(
+        dI, Z, mean, rstd, scale, coef, M, H, bound, (__half*)P0, (__half*)P1, ldp, dZ32);
+  }
   SPARCH_LAUNCH_OK();
   return SPARCH_OK;
 }
@@ -686,8 +777,15 @@ int sparch_bn_bwd_apply_f16_bidir(const float* dI, const float* Z, const float* 
   // column means over all 2 M rows of the two passes
   bn_bwd_bound_kernel<<<1, 1024, 0, as_stream(st)>>>(scale, sum1, sum2, 2 * M, H, amax_dI, bound, coef, 2.0f);
   SPARCH_LAUNCH_OK();
-  bn_bwd_apply_f16_kernel<<<ew_grid(M * (ldp / 8), 256), 256, 0, as_stream(st)>>>(
-      dI, Z, mean, rstd, scale, coef, M, H, bound, (__half*)P0, (__half*)P1, ldp, dZ32, T);
+  if (bn_apply_rows_ok(dI, Z, P0, P1, dZ32, H, ldp)) {
+    const int ty = 256 / (H / 8);
+    int64_t nb = (M + 2 * ty - 1) / (2 * ty), cap = (int64_t)sm_count() * 8;
+    bn_bwd_apply_f16_rows_kernel<true><<<(unsigned)(nb < cap ? nb : cap), 256, 0, as_stream(st)>>>(
+        dI, Z, mean, rstd, scale, coef, M, H, bound, (__half*)P0, (__half*)P1, dZ32, T);
+  } else {
+    bn_bwd_apply_f16_kernel<<<ew_grid(M * (ldp / 8), 256), 256, 0, as_stream(st)>>>(
+        dI, Z, mean, rstd, scale, coef, M, H, bound, (__half*)P0, (__half*)P1, ldp, dZ32, T);
+  }
   SPARCH_LAUNCH_OK();
   return SPARCH_OK;
 }
