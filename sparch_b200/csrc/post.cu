@@ -6,6 +6,8 @@
 //     tensor is stored) + the row maxima of the gradient that the tcgen05 reverse recurrence scales with;
 //   * neuron_params / param_grads: the clamp of alpha, beta, a, b (snns.py:706-709) and its backward (batch
 //     reduction of the per-(b,h) partial gradients + clamp mask) as one launch each instead of ~25 ATen ops.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sparch {
@@ -135,6 +137,126 @@ spike_post_fwd_kernel(const float* __restrict__ S, const SpikeBits sb_, long lon
     }
   }
   if (counts && use_hist) {
+    __syncthreads();
+    for (int h = threadIdx.x; h < Hc; h += blockDim.x)
+      if (hist[h]) atomicAdd(&counts[h], hist[h]);
+  }
+}
+
+// The same pass for the packed-plane input as MASK arithmetic.  The generic kernel above spends ~930 warp instructions
+// per 8-element item (ncu: issue slots 67 % busy, DRAM 29 %), most of them per-element selects, compares and
+// reconverging branches around the count atomics; here an item is an 8-bit spike mask AND an 8-bit keep mask, the
+// outputs are selected from the mask bits, and the per-neuron counts live in registers: every launch makes the grid
+// stride a multiple of the segments per row, so a thread keeps its 8 columns for all its rows and adds them to the
+// block's histogram once, at the end.  Same item numbering, mask stream and results as the generic kernel.
+__global__ void __launch_bounds__(256)
+spike_post_bits_kernel(const SpikeBits sb_, long long M, int H, long long ld, float scale, uint32_t thresh,
+                       const unsigned long long* __restrict__ seed, float* __restrict__ out, uint16_t* __restrict__ term,
+                       uint16_t* __restrict__ sterm, uint16_t one_bits, int* __restrict__ counts) {
+  extern __shared__ int hist[];
+  const bool bidir = sb_.rev_from > 0;
+  const int Hc = bidir ? 2 * H : H;
+  if (counts) {
+    for (int h = threadIdx.x; h < Hc; h += blockDim.x) hist[h] = 0;
+    __syncthreads();
+  }
+  const long long segs = ld / 8, n = M * segs;
+  const long long stride = (long long)gridDim.x * blockDim.x;          // a multiple of segs (host)
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (int)(i0 % segs) * 8;                                   // this thread's columns, for all its items
+  const int nvalid = max(0, min(8, H - c));
+  const uint32_t vmask = (1u << nvalid) - 1u;
+  const bool vec = ((H & 3) == 0) && (!out || (reinterpret_cast<uintptr_t>(out) & 15) == 0) && nvalid == 8;
+  const uint32_t one2 = (uint32_t)one_bits * 0x00010001u;
+  const unsigned long long sd = thresh ? *seed : 0ull;
+  const uint2 key = make_uint2((uint32_t)sd, (uint32_t)(sd >> 32));
+  const long long ldo = bidir ? 2 * ld : ld, Ho = bidir ? 2 * (long long)H : H;
+  int cnt0[8], cnt1[8];                                                 // counts of the two directions' columns
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cnt0[j] = cnt1[j] = 0;
+  // row, batch row and timestep of an item advance by constants (the stride is a whole number of rows): no division in
+  // the loop
+  const long long rstep = stride / segs;
+  const long long bstep = rstep / sb_.T;
+  const int tstep = (int)(rstep - bstep * sb_.T);
+  long long r = i0 / segs, b = r / sb_.T;
+  int t = (int)(r - b * sb_.T);
+  for (long long i = i0; i < n; i += stride, r += rstep, b += bstep, t += tstep) {
+    if (t >= sb_.T) {
+      t -= sb_.T;
+      ++b;
+    }
+    const uint32_t w = c < H ? sb_.words[(((size_t)t * sb_.groups + (size_t)(b >> 7)) * sb_.nsl + (c >> 4)) * 128 + (b & 127)] : 0u;
+    uint32_t m = (w >> (2 * (c & 15))) & 0x5555u;                       // 8 spikes at the even bits -> 8 adjacent bits
+    m = (m | (m >> 1)) & 0x3333u;
+    m = (m | (m >> 2)) & 0x0f0fu;
+    m = (m | (m >> 4)) & vmask;
+    if (sb_.s_last && t == sb_.T - 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nvalid) sb_.s_last[b * H + c + j] = (float)((m >> j) & 1u);
+    }
+    long long ro = r, io = i;
+    int co = c;
+    const bool second = bidir && b >= sb_.rev_from;
+    if (bidir) {
+      if (second) {
+        ro = (b - sb_.rev_from) * sb_.T + (sb_.T - 1 - t);
+        co = c + H;
+      }
+      io = ro * (ldo / 8) + co / 8;
+    }
+    uint32_t y = m;
+    if (thresh) {
+      const uint4 a = philox4x32_10(make_uint4((uint32_t)io, (uint32_t)((unsigned long long)io >> 32), 0u, 0u), key);
+      const uint4 q = philox4x32_10(make_uint4((uint32_t)io, (uint32_t)((unsigned long long)io >> 32), 1u, 0u), key);
+      const uint32_t k = (a.x >= thresh ? 1u : 0u) | (a.y >= thresh ? 2u : 0u) | (a.z >= thresh ? 4u : 0u) |
+                         (a.w >= thresh ? 8u : 0u) | (q.x >= thresh ? 16u : 0u) | (q.y >= thresh ? 32u : 0u) |
+                         (q.z >= thresh ? 64u : 0u) | (q.w >= thresh ? 128u : 0u);
+      y &= k;
+    }
+    if (out) {
+      float* dst = out + ro * Ho + co;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = ((y >> j) & 1u) ? scale : 0.f;
+      if (vec) {
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < nvalid) dst[j] = v[j];
+      }
+    }
+    // bit pair (2 p, 2 p + 1) -> two 16-bit patterns: (bit ? one : 0) | (bit' ? one : 0) << 16
+    auto halves = [&](uint32_t bits) {
+      uint4 h;
+      uint32_t e[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const uint32_t lo = 0u - ((bits >> (2 * p)) & 1u), hi = 0u - ((bits >> (2 * p + 1)) & 1u);
+        e[p] = one2 & ((lo & 0x0000ffffu) | (hi & 0xffff0000u));
+      }
+      h.x = e[0]; h.y = e[1]; h.z = e[2]; h.w = e[3];
+      return h;
+    };
+    if (term) *reinterpret_cast<uint4*>(term + ro * ldo + co) = halves(y);
+    if (sterm) *reinterpret_cast<uint4*>(sterm + r * ld + c) = halves(m);
+    if (second) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cnt1[j] += (int)((y >> j) & 1u);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cnt0[j] += (int)((y >> j) & 1u);
+    }
+  }
+  if (counts) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < nvalid && cnt0[j]) atomicAdd(&hist[c + j], cnt0[j]);
+      if (bidir && j < nvalid && cnt1[j]) atomicAdd(&hist[H + c + j], cnt1[j]);
+    }
     __syncthreads();
     for (int h = threadIdx.x; h < Hc; h += blockDim.x)
       if (hist[h]) atomicAdd(&counts[h], hist[h]);
@@ -320,6 +442,23 @@ int sparch_spike_post_fwd_bits_bidir(const uint32_t* bits, int Be, int T, int H,
   const int use_hist = counts && Hc <= 8192;
   const uint32_t thresh = p_drop > 0.f ? (uint32_t)fmin((double)p_drop * 4294967296.0, 4294967295.0) : 0u;
   const SpikeBits sb{bits, T, (Be + 127) / 128, (H + 15) / 16, s_last, rev_from};
+  static const bool generic = getenv("SPARCH_B200_POST_GENERIC") != nullptr;
+  if ((use_hist || !counts) && !generic) {
+    // mask-arithmetic kernel: the grid stride must be a multiple of the segments per row (a thread keeps its columns)
+    const int64_t segs = ld / 8;
+    int64_t unit = segs;                           // smallest block count whose 256 * blocks is a multiple of segs
+    for (int64_t x = 256, y = segs; y;) { const int64_t tq = x % y; x = y; y = tq; unit = segs / x; }
+    int64_t nb = g < cap ? g : cap;
+    nb = (nb / unit) * unit;
+    if (nb >= unit && nb >= 1) {
+      spike_post_bits_kernel<<<(unsigned)nb, 256, counts ? sizeof(int) * Hc : 0, st>>>(
+          sb, M, H, ld, 1.0f / (1.0f - p_drop), thresh, reinterpret_cast<const unsigned long long*>(seed), out,
+          reinterpret_cast<uint16_t*>(term), reinterpret_cast<uint16_t*>(sterm), fp16_terms ? (uint16_t)0x3C00 : (uint16_t)0x3F80,
+          counts);
+      SPARCH_LAUNCH_OK();
+      return SPARCH_OK;
+    }
+  }
   spike_post_fwd_kernel<<<(unsigned)(g < cap ? g : cap), 256, use_hist ? sizeof(int) * Hc : 0, st>>>(
       nullptr, sb, M, H, ld, 1.0f / (1.0f - p_drop), thresh, reinterpret_cast<const unsigned long long*>(seed), out,
       reinterpret_cast<uint16_t*>(term), reinterpret_cast<uint16_t*>(sterm), fp16_terms ? (uint16_t)0x3C00 : (uint16_t)0x3F80,
