@@ -639,9 +639,18 @@ int sparch_split_bf16_transpose(const float* X, int R, int C, int nparts, int T,
   return SPARCH_OK;
 }
 
+// Split-K factor allowed for an (M, N) output: 8 sets of fp32 partials, up to 32 while they stay under 16 MB (the weight
+// gradients of narrow layers -- dW of the 40-input first layer, of the 35-class readout -- contract over all Be*T frames
+// into 8 output tiles: with 8 splits they ran on 64 CTAs and took longer than the full-width GEMMs next to them).
+static int gemm_max_splits(int M, int N) {
+  const size_t per = (size_t)M * (((size_t)N + 3) / 4 * 4) * sizeof(float);
+  int cap = 8;
+  while (cap < 32 && (size_t)(2 * cap) * per <= ((size_t)16 << 20)) cap *= 2;
+  return cap;
+}
+
 size_t sparch_gemm_workspace(int M, int N, int K) {
-  // room for up to 8 fp32 split-K partial tiles sets
-  return (size_t)8 * M * (((size_t)N + 3) / 4 * 4) * sizeof(float);
+  return (size_t)gemm_max_splits(M, N) * M * (((size_t)N + 3) / 4 * 4) * sizeof(float);
 }
 
 int sparch_absmax(const float* X, int64_t ldx, int64_t M, int K, uint32_t* amax, sparch_stream_t st) {
@@ -728,7 +737,7 @@ int sparch_gemm_terms(int fp16, const void* const* A_parts, int na, const uint32
   int splits = 1;
   if (workspace && tiles < sm_count() && !stat_sum) {  // statistics need the finished tile in one epilogue
     splits = sm_count() / tiles;
-    if (splits > 8) splits = 8;
+    if (splits > gemm_max_splits(M, N)) splits = gemm_max_splits(M, N);
     if (splits > p.kblocks) splits = p.kblocks;
     if (splits < 1) splits = 1;
   }
