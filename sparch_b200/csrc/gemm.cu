@@ -461,7 +461,16 @@ __global__ void absmax_kernel(const float* __restrict__ X, long long ldx, long l
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax, __float_as_uint(m));
+  // one atomic per BLOCK (a thousand blocks x 8 warps on one word serialised: 9.6 us for a 4 MB tensor)
+  __shared__ float wm[32];
+  if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? wm[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0 && m > 0.f) atomicMax(amax, __float_as_uint(m));
+  }
 }
 
 // parts[i][r][c] = i-th fp16 term of prescale * 2^k * X[r][c], k = f16_scale_exp(*amax) (0 without amax).

@@ -177,7 +177,7 @@ static int readout_chunk(int T, int C, int arrays) {
 
 // ---- cross-entropy of the readout's output (exp.py:83 nn.CrossEntropyLoss(), exp.py:362): mean over the batch of
 // logsumexp(x_b) - x_b[y_b], and its gradient (softmax(x_b) - onehot(y_b)) * gloss / B.  One block; a warp per row
-// (lane-strided classes, shuffle reductions), the B row losses are summed in row order by thread 0: deterministic.
+// (lane-strided classes, shuffle reductions), the B row losses are summed by one warp in a fixed order: deterministic.
 __global__ void ce_fwd_kernel(const float* __restrict__ X, const long long* __restrict__ y, int B, int C,
                               float* __restrict__ loss, float* __restrict__ lse) {
   extern __shared__ float row_loss[];
@@ -200,10 +200,14 @@ __global__ void ce_fwd_kernel(const float* __restrict__ X, const long long* __re
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
+    // lane l sums rows l, l + 32, ... in row order, then a fixed shuffle tree: deterministic, without the 256-step serial
+    // chain of a single thread
     float sum = 0.f;
-    for (int b = 0; b < B; ++b) sum += row_loss[b];
-    *loss = sum / (float)B;
+    for (int b = lane; b < B; b += 32) sum += row_loss[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) *loss = sum / (float)B;
   }
 }
 
