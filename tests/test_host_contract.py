@@ -328,3 +328,53 @@ def test_spiking_batcher_is_cuda_only():
     from sparch_b200.data import SpikingBatcher
     with pytest.raises(RuntimeError):
         SpikingBatcher(device="cpu")
+
+
+def test_cpu_generator_state_layout_behind_the_device_draws():
+    """sparch_b200/rng.py replays torch's default CPU generator on the device from its state blob.  This pins, on the CPU,
+    everything that code assumes about the blob and the stream: 5056 bytes, `left` at byte 8, `next` at 16, 624 state words
+    as uint64 from byte 24; torch.rand(n) = one MT19937 word per element, (word & (2^24 - 1)) * 2^-24, in element order;
+    and that writing position / state back into the blob moves the generator to exactly that point."""
+    import struct
+    import numpy as np
+    from sparch_b200 import rng
+
+    def mt_block(mt):                      # one regeneration of the 624-word state (Matsumoto & Nishimura 1998)
+        mt = mt.copy()
+        for i in range(624):
+            y = (int(mt[i]) & 0x80000000) | (int(mt[(i + 1) % 624]) & 0x7fffffff)
+            mt[i] = int(mt[(i + 397) % 624]) ^ (y >> 1) ^ (0x9908b0df if y & 1 else 0)
+        return mt
+
+    def temper(y):
+        y ^= y >> 11
+        y ^= (y << 7) & 0x9d2c5680
+        y ^= (y << 15) & 0xefc60000
+        y ^= y >> 18
+        return y & 0xffffffff
+
+    torch.manual_seed(1234)
+    torch.rand(100)                                            # somewhere inside a block
+    blob = torch.get_rng_state()
+    assert blob.numel() == rng._STATE_BYTES
+    raw = bytearray(blob.numpy().tobytes())
+    left, = struct.unpack_from("<i", raw, rng._OFF_LEFT)
+    nxt, = struct.unpack_from("<Q", raw, rng._OFF_NEXT)
+    pos = rng._MT_N + 1 - left
+    assert pos == nxt == 100
+    mt = np.frombuffer(raw, dtype=np.uint64, count=rng._MT_N, offset=rng._OFF_STATE).astype(np.uint64)
+    n = 700                                                    # crosses into the next block
+    want = torch.rand(n)
+    got, words, p = [], mt, pos
+    while len(got) < n:
+        if p == 624:
+            words, p = mt_block(words), 0
+        got.append((temper(int(words[p])) & 0xffffff) * 2.0 ** -24)
+        p += 1
+    assert np.array_equal(np.asarray(got, dtype=np.float32), want.numpy())
+    # the blob the device path would write back: new state words, position p
+    struct.pack_into("<i", raw, rng._OFF_LEFT, rng._MT_N + 1 - p)
+    struct.pack_into("<Q", raw, rng._OFF_NEXT, p)
+    raw[rng._OFF_STATE:rng._OFF_STATE + 8 * rng._MT_N] = words.astype(np.uint64).tobytes()
+    after = torch.get_rng_state()
+    assert bytes(raw) == after.numpy().tobytes()

@@ -45,16 +45,46 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out, average=True):
+class _BpttMark(torch.autograd.Function):
+    """Identity whose backward plays the role of a reverse recurrence kernel having been issued: it runs the callbacks
+    sparch_b200.functional.AFTER_BPTT (GradSync's safe point)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        from sparch_b200 import functional
+        for cb in functional.AFTER_BPTT:
+            cb()
+        return g
+
+
+class _RecLay(_Lay):
+    _recurrent = True       # what GradSync counts to know how many safe points a backward pass has
+
+    def forward(self, x):
+        return _BpttMark.apply(super().forward(x))
+
+
+class _ToyDeferred(_Toy):
+    def __init__(self):
+        super().__init__()
+        self.snn = torch.nn.ModuleList([_RecLay(6, 5), torch.nn.Linear(5, 4), _RecLay(4, 3)])
+
+
+def _worker(rank, world, port, out, average=True, defer=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from sparch_b200.parallel import GradSync
         torch.manual_seed(100 + rank)          # different init per rank: broadcast must fix it
-        net = _Toy()
+        net = _ToyDeferred() if defer else _Toy()
         net.stat.fill_(float(rank + 1))
-        sync = GradSync(net, average=average)
+        sync = GradSync(net, average=average, defer=defer)
         assert len(sync.buckets) == 6   # (gain | W) x 2 layers + one plain layer + the module's own parameter
+        assert sync.defer == defer and sync._n_bptt == (2 if defer else 0)
         torch.manual_seed(7)
         ref = _Toy()                            # what rank 0 had (seed 100) is unknown here; compare via gather
         p0 = [p.detach().clone() for p in net.parameters()]
@@ -68,6 +98,11 @@ def _worker(rank, world, port, out, average=True):
             net.zero_grad()                     # set_to_none=True, like exp.py:375
             loss = net(x).square().sum()
             loss.backward()
+            if defer:
+                # both safe points passed: the buckets completed before / between them went out there, the last
+                # layer's (complete only after the last safe point) at once; nothing is left queued
+                assert sync._bptt_left == 0 and not sync._ready
+                assert all(b["work"] is not None for b in sync.buckets if b["pending"] == 0)
             local = [None if p.grad is None else p.grad.detach().clone() for p in net.parameters()]
             sync.finish()
             for p, lg in zip(net.parameters(), local):
@@ -85,12 +120,14 @@ def _worker(rank, world, port, out, average=True):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("average", [True, False])
-def test_gradsync_world2_gloo(average):
+@pytest.mark.parametrize("average,defer", [(True, False), (False, False), (True, True)])
+def test_gradsync_world2_gloo(average, defer):
+    """defer=True: buckets are reduced at the safe points (behind a reverse recurrence, sparch_b200.functional.AFTER_BPTT)
+    and at once after the last one; same reduced gradients as the immediate mode."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, average)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, average, defer)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
