@@ -632,7 +632,7 @@ class SpikingCellFunction(torch.autograd.Function):
                  pp[3], ptr(ws), ptr(sync), ctx.reduced, Be, T, H, st)
         if recurrent:
             region.__exit__()
-            for cb in AFTER_BPTT:
+            for cb in list(AFTER_BPTT):
                 cb()
         # BatchNorm backward reductions first: the same pass leaves max|dI| for the dV operand split
         sums, di_amax = _norm_backward_reduce(dI.view(Be * T, H), Z.view(-1, H), norm, mean, rstd)

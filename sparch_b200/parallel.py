@@ -61,8 +61,17 @@ class GradSync:
         self._n_bptt = sum(1 for lay in layers if getattr(lay, "_recurrent", False))
         self._bptt_left = self._n_bptt
         if self.defer:
+            import weakref
             from . import functional
-            functional.AFTER_BPTT.append(self._after_bptt)
+            ref = weakref.WeakMethod(self._after_bptt)      # the registry must not keep a discarded GradSync alive
+
+            def after_bptt():
+                cb = ref()
+                if cb is not None:
+                    cb()
+                elif after_bptt in functional.AFTER_BPTT:
+                    functional.AFTER_BPTT.remove(after_bptt)
+            functional.AFTER_BPTT.append(after_bptt)
 
     def _add_bucket(self, params):
         n = sum(p.numel() for p in params)
