@@ -409,6 +409,13 @@ class CellPrep:
                  "event", "key")
 
 
+def _param_versions(*ts):
+    """(storage address, version counter) of every given parameter: a CellPrep made ahead is only used for the very
+    tensors, in the very state, it was made from (an in-place change in between -- a hook, an optimizer step -- bumps
+    the version and the layer prepares again in line)."""
+    return tuple((t.data_ptr(), t._version) for t in ts if t is not None)
+
+
 def prepare_cell(k, alpha, beta, a, b, V, Be, H, states=None):
     """The parameter-only launches of SpikingCellFunction.forward (same kernels, same order); ``states`` = (u0, w0, s0)
     when they are already drawn (rec_0 needs s0)."""
@@ -418,7 +425,7 @@ def prepare_cell(k, alpha, beta, a, b, V, Be, H, states=None):
     pr = CellPrep()
     pr.event = None
     pr.states = states
-    pr.key = (k, Be, H, _PRECISION, RECUR_BWD, RECUR_FWD)
+    pr.key = (k, Be, H, _PRECISION, RECUR_BWD, RECUR_FWD) + _param_versions(alpha, beta, a, b, V)
     with torch.no_grad():
         alpha, beta, a, b = _f32c(alpha), _f32c(beta), _f32c(a), _f32c(b)
         cl = torch.empty(4 if adaptive else 1, H, device=dev, dtype=torch.float32)   # snns.py:706-709
@@ -496,7 +503,8 @@ class SpikingCellFunction(torch.autograd.Function):
             # call (functional.CellPrep), issued here otherwise
             pr = norm.prep
             norm.prep = None
-            if pr is not None and (pr.key != (k, Be, H, _PRECISION, RECUR_BWD, RECUR_FWD) or
+            if pr is not None and (pr.key != (k, Be, H, _PRECISION, RECUR_BWD, RECUR_FWD) +
+                                   _param_versions(alpha, beta, a, b, V) or
                                    (pr.states is not None and pr.states[2].data_ptr() != s0.data_ptr())):
                 pr = None
             if pr is None:
